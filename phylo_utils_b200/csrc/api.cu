@@ -1,0 +1,681 @@
+// C ABI of the engine: context life cycle, input upload, schedule resolution, orchestration.
+// Every function maps to a piece of TreeModel (see include/phylo_b200.h for the file:line map).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace phb {
+
+static thread_local std::string g_thread_error;
+void set_thread_error(const std::string& msg) { g_thread_error = msg; }
+const char* thread_error() { return g_thread_error.c_str(); }
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+struct Plan {
+    size_t codes, lut, weights, clv, scale, up, up_scale, root_clv, root_scale, pmats, dmats, model, lengths, rows,
+        pattern_lnl, cat_lnl, partial, result, total;
+};
+
+Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
+    Plan p;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += align_up(bytes ? bytes : 1);
+        return at;
+    };
+    const size_t n_int = n_tips > 2 ? (size_t)(n_tips - 2) : 0;
+    const size_t max_rows = n_int > 0 ? n_int : 1;
+    const bool store = !(flags & PHB_FLAG_NO_PARTIALS);
+    const bool up = store && (flags & PHB_FLAG_UP_PARTIALS);
+    const size_t node_doubles = (size_t)S * K * A;
+    p.codes = take((size_t)n_tips * S);
+    p.lut = take(256 * (size_t)A * 8);
+    p.weights = take((size_t)S * 8);
+    p.clv = take(store ? n_int * node_doubles * 8 : 0);
+    p.scale = take(store ? n_int * (size_t)S * 4 : 0);
+    p.up = take(up ? n_int * node_doubles * 8 : 0);
+    p.up_scale = take(up ? n_int * (size_t)S * 4 : 0);
+    p.root_clv = take(store ? node_doubles * 8 : 0);
+    p.root_scale = take(store ? (size_t)S * 4 : 0);
+    p.pmats = take((2 * max_rows + 2) * (size_t)K * A * A * 8);
+    p.dmats = take((size_t)kMaxEdgeBatch * 3 * K * A * A * 8);
+    p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
+    p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
+    p.rows = take(max_rows * sizeof(OpRow));
+    p.pattern_lnl = take((size_t)S * 8);
+    p.cat_lnl = take((size_t)S * K * 8);
+    p.partial = take((size_t)kMaxReduceBlocks * 4 * 8);
+    p.result = take((size_t)kMaxEdgeBatch * 4 * 8);
+    p.total = off;
+    return p;
+}
+
+bool shape_ok(int n_tips, int64_t S, int K, int A, std::string* why) {
+    if (n_tips < 2) { *why = "need at least two tips"; return false; }
+    if (S < 1) { *why = "need at least one pattern"; return false; }
+    if (K < 1 || K > 16) { *why = "number of rate categories must be in 1..16"; return false; }
+    if (A < 2 || A > 64) { *why = "number of states must be in 2..64"; return false; }
+    return true;
+}
+
+int activate(Ctx* c) {
+    PHB_CUDA(c, cudaSetDevice(c->device));
+    return PHB_OK;
+}
+
+// Turn the raw (PAR, CH1, CH2) rows into kernel rows; validates dependencies.
+int resolve_schedule(Ctx* c) {
+    const int n_rows = (int)c->rows_raw.size() / 3;
+    PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_set_tips must be called before the schedule can be resolved");
+    c->node_slot.assign(c->n_nodes, -1);
+    c->node_row.assign(c->n_nodes, -1);
+    c->node_parent.assign(c->n_nodes, -1);
+    c->rows.assign(n_rows, OpRow{});
+    auto rank = [](int kind) { return kind == SRC_TIP ? 0 : (kind == SRC_PREV ? 1 : 2); };
+    for (int r = 0; r < n_rows; ++r) {
+        const int par = c->rows_raw[3 * r], ch[2] = {c->rows_raw[3 * r + 1], c->rows_raw[3 * r + 2]};
+        PHB_REQUIRE(c, par >= 0 && par < c->n_nodes, PHB_ERR_INVALID, "schedule: parent node id out of range");
+        PHB_REQUIRE(c, c->node_tip[par] < 0, PHB_ERR_INVALID, "schedule: a tip appears as a parent");
+        PHB_REQUIRE(c, c->node_row[par] < 0, PHB_ERR_INVALID, "schedule: a node is computed twice");
+        OpRow row{};
+        row.dst = r;
+        for (int i = 0; i < 2; ++i) {
+            PHB_REQUIRE(c, ch[i] >= 0 && ch[i] < c->n_nodes && ch[i] != par, PHB_ERR_INVALID,
+                        "schedule: child node id out of range");
+            PHB_REQUIRE(c, c->node_parent[ch[i]] < 0, PHB_ERR_INVALID, "schedule: a node has two parents");
+            c->node_parent[ch[i]] = par;
+            if (c->node_tip[ch[i]] >= 0) {
+                row.kind[i] = SRC_TIP;
+                row.src[i] = c->node_tip[ch[i]];
+            } else {
+                PHB_REQUIRE(c, c->node_row[ch[i]] >= 0, PHB_ERR_INVALID,
+                            "schedule: a child is used before the row that computes it");
+                row.src[i] = c->node_slot[ch[i]];
+                row.kind[i] = (c->node_row[ch[i]] == r - 1) ? SRC_PREV : SRC_GLOBAL;
+            }
+            row.pidx[i] = 2 * r + i;
+        }
+        PHB_REQUIRE(c, ch[0] != ch[1], PHB_ERR_INVALID, "schedule: both children are the same node");
+        if (rank(row.kind[0]) > rank(row.kind[1])) {
+            std::swap(row.kind[0], row.kind[1]);
+            std::swap(row.src[0], row.src[1]);
+            std::swap(row.pidx[0], row.pidx[1]);
+        }
+        c->rows[r] = row;
+        c->node_slot[par] = r;
+        c->node_row[par] = r;
+    }
+    if (!c->level_offsets.empty()) {
+        const int n_levels = (int)c->level_offsets.size() - 1;
+        PHB_REQUIRE(c, c->level_offsets.front() == 0 && c->level_offsets.back() == n_rows, PHB_ERR_INVALID,
+                    "schedule: level offsets must start at 0 and end at n_rows");
+        std::vector<int> level_of_row(n_rows, 0);
+        for (int l = 0; l < n_levels; ++l) {
+            PHB_REQUIRE(c, c->level_offsets[l] <= c->level_offsets[l + 1], PHB_ERR_INVALID,
+                        "schedule: level offsets must be non-decreasing");
+            for (int r = c->level_offsets[l]; r < c->level_offsets[l + 1]; ++r) level_of_row[r] = l;
+        }
+        for (int r = 0; r < n_rows; ++r)
+            for (int i = 0; i < 2; ++i) {
+                const int child = c->rows_raw[3 * r + 1 + i];
+                if (c->node_tip[child] < 0)
+                    PHB_REQUIRE(c, level_of_row[c->node_row[child]] < level_of_row[r], PHB_ERR_INVALID,
+                                "schedule: a row depends on a row of the same or a later level");
+            }
+    }
+    if (n_rows > 0)
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_rows, c->rows.data(), (size_t)n_rows * sizeof(OpRow),
+                                    cudaMemcpyHostToDevice, c->stream));
+    c->have_schedule = true;
+    c->have_partials = false;
+    c->have_up = false;
+    return PHB_OK;
+}
+
+int node_operand_ok(Ctx* c, int node) {
+    PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "node id out of range");
+    if (c->node_tip[node] >= 0) return PHB_OK;
+    PHB_REQUIRE(c, c->have_schedule && c->node_slot[node] >= 0, PHB_ERR_INVALID,
+                "node is neither a tip nor computed by the schedule");
+    return PHB_OK;
+}
+
+}  // namespace
+}  // namespace phb
+
+using namespace phb;
+
+extern "C" {
+
+int phb_version(void) { return PHB_VERSION; }
+
+const char* phb_status_name(int status) {
+    switch (status) {
+        case PHB_OK: return "PHB_OK";
+        case PHB_ERR_INVALID: return "PHB_ERR_INVALID";
+        case PHB_ERR_CUDA: return "PHB_ERR_CUDA";
+        case PHB_ERR_NO_DEVICE: return "PHB_ERR_NO_DEVICE";
+        case PHB_ERR_STATE: return "PHB_ERR_STATE";
+        case PHB_ERR_NOMEM: return "PHB_ERR_NOMEM";
+        case PHB_ERR_UNSUPPORTED: return "PHB_ERR_UNSUPPORTED";
+    }
+    return "PHB_ERR_UNKNOWN";
+}
+
+const char* phb_last_error(const phb_ctx* ctx) { return ctx ? ctx->err.c_str() : thread_error(); }
+
+int64_t phb_launch_count(const phb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+size_t phb_workspace_bytes(int n_tips, int64_t n_patterns, int n_cat, int n_states, unsigned flags) {
+    std::string why;
+    if (!shape_ok(n_tips, n_patterns, n_cat, n_states, &why)) return 0;
+    return make_plan(n_tips, n_patterns, n_cat, n_states, flags).total;
+}
+
+int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_states, unsigned flags, void* workspace,
+               size_t workspace_bytes, void* stream, phb_ctx** out) {
+    if (out == nullptr) {
+        set_thread_error("phb_create: out is NULL");
+        return PHB_ERR_INVALID;
+    }
+    *out = nullptr;
+    std::string why;
+    if (!shape_ok(n_tips, n_patterns, n_cat, n_states, &why)) {
+        set_thread_error("phb_create: " + why);
+        return PHB_ERR_INVALID;
+    }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        set_thread_error(std::string("phb_create: no CUDA device available (") + cudaGetErrorString(e) +
+                         "); this engine has no CPU fallback");
+        cudaGetLastError();
+        return PHB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n_dev) {
+        set_thread_error("phb_create: device index out of range");
+        return PHB_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess || (e = cudaSetDevice(device)) != cudaSuccess) {
+        set_thread_error(std::string("phb_create: ") + cudaGetErrorString(e));
+        return PHB_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        set_thread_error("phb_create: device is not sm_100 or newer (kernels are built for sm_100a only)");
+        return PHB_ERR_NO_DEVICE;
+    }
+    phb_ctx* c = new (std::nothrow) phb_ctx();
+    if (!c) {
+        set_thread_error("phb_create: out of host memory");
+        return PHB_ERR_NOMEM;
+    }
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    c->n_tips = n_tips;
+    c->S = n_patterns;
+    c->K = n_cat;
+    c->A = n_states;
+    c->flags = flags;
+    c->n_nodes = 2 * n_tips - 2;
+    c->n_internal = n_tips > 2 ? n_tips - 2 : 0;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    const Plan p = make_plan(n_tips, n_patterns, n_cat, n_states, flags);
+    if (workspace != nullptr) {
+        if (workspace_bytes < p.total || ((uintptr_t)workspace % kAlign) != 0) {
+            set_thread_error("phb_create: workspace too small or not 256-byte aligned");
+            delete c;
+            return PHB_ERR_NOMEM;
+        }
+        c->ws = (uint8_t*)workspace;
+        c->owns_ws = false;
+    } else {
+        void* ptr = nullptr;
+        if ((e = cudaMalloc(&ptr, p.total)) != cudaSuccess) {
+            set_thread_error(std::string("phb_create: cudaMalloc of workspace failed: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+            delete c;
+            return PHB_ERR_NOMEM;
+        }
+        c->ws = (uint8_t*)ptr;
+        c->owns_ws = true;
+    }
+    c->ws_bytes = p.total;
+    uint8_t* w = c->ws;
+    c->d_codes_ws = w + p.codes;
+    c->d_codes = c->d_codes_ws;
+    c->d_lut = (double*)(w + p.lut);
+    c->d_weights = nullptr;  // all ones until phb_set_pattern_weights
+    const bool store = !(flags & PHB_FLAG_NO_PARTIALS);
+    c->d_clv = store ? (double*)(w + p.clv) : nullptr;
+    c->d_scale = store ? (int32_t*)(w + p.scale) : nullptr;
+    const bool up = store && (flags & PHB_FLAG_UP_PARTIALS);
+    c->d_up = up ? (double*)(w + p.up) : nullptr;
+    c->d_up_scale = up ? (int32_t*)(w + p.up_scale) : nullptr;
+    c->d_root_clv = store ? (double*)(w + p.root_clv) : nullptr;
+    c->d_root_scale = store ? (int32_t*)(w + p.root_scale) : nullptr;
+    c->d_pmats = (double*)(w + p.pmats);
+    c->d_dmats = (double*)(w + p.dmats);
+    c->d_model = (double*)(w + p.model);
+    c->d_lengths = (double*)(w + p.lengths);
+    c->d_rows = (OpRow*)(w + p.rows);
+    c->d_pattern_lnl = (double*)(w + p.pattern_lnl);
+    c->d_cat_lnl = (double*)(w + p.cat_lnl);
+    c->d_partial_sums = (double*)(w + p.partial);
+    c->d_result = (double*)(w + p.result);
+    c->node_tip.assign(c->n_nodes, -1);
+    *out = c;
+    return PHB_OK;
+}
+
+int phb_destroy(phb_ctx* c) {
+    if (!c) return PHB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->owns_ws && c->ws) cudaFree(c->ws);
+    delete c;
+    return PHB_OK;
+}
+
+int phb_sync(phb_ctx* c) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_codes, const double* lut,
+                 const int32_t* tip_nodes) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, codes && lut && tip_nodes, PHB_ERR_INVALID, "phb_set_tips: NULL argument");
+    PHB_REQUIRE(c, n_codes >= 1 && n_codes <= 256, PHB_ERR_INVALID, "phb_set_tips: n_codes must be in 1..256");
+    std::vector<int32_t> node_tip(c->n_nodes, -1);
+    for (int t = 0; t < c->n_tips; ++t) {
+        const int node = tip_nodes[t];
+        PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "phb_set_tips: tip node id out of range");
+        PHB_REQUIRE(c, node_tip[node] < 0, PHB_ERR_INVALID, "phb_set_tips: two tips share a node id");
+        node_tip[node] = t;
+    }
+    for (int i = 0; i < n_codes * c->A; ++i)
+        PHB_REQUIRE(c, lut[i] >= 0.0 && std::isfinite(lut[i]), PHB_ERR_INVALID,
+                    "phb_set_tips: look-up table entries must be finite and non-negative");
+    if (!codes_on_device) {
+        // codes are validated on the host: an out-of-range code would index past the table
+        const size_t n = (size_t)c->n_tips * c->S;
+        uint8_t worst = 0;
+        for (size_t i = 0; i < n; ++i) worst = codes[i] > worst ? codes[i] : worst;
+        PHB_REQUIRE(c, worst < n_codes, PHB_ERR_INVALID, "phb_set_tips: a code is >= n_codes");
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_codes_ws, codes, n, cudaMemcpyHostToDevice, c->stream));
+        c->d_codes = c->d_codes_ws;
+    } else {
+        c->d_codes = codes;
+    }
+    std::vector<double> full(256 * (size_t)c->A, 0.0);
+    std::memcpy(full.data(), lut, (size_t)n_codes * c->A * sizeof(double));
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_lut, full.data(), full.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));  // `full` is a stack-lifetime staging buffer
+    const bool remap = node_tip != c->node_tip;
+    c->node_tip.swap(node_tip);
+    c->n_codes = n_codes;
+    c->have_tips = true;
+    c->have_partials = false;
+    c->have_up = false;
+    if (remap && !c->rows_raw.empty()) return resolve_schedule(c);
+    return PHB_OK;
+}
+
+int phb_set_pattern_weights(phb_ctx* c, const int64_t* weights) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    if (weights == nullptr) {
+        c->d_weights = nullptr;
+        return PHB_OK;
+    }
+    std::vector<double> w((size_t)c->S);
+    for (int64_t i = 0; i < c->S; ++i) {
+        PHB_REQUIRE(c, weights[i] >= 0, PHB_ERR_INVALID, "phb_set_pattern_weights: negative weight");
+        w[i] = (double)weights[i];
+    }
+    const Plan p = make_plan(c->n_tips, c->S, c->K, c->A, c->flags);
+    c->d_weights = (double*)(c->ws + p.weights);
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_weights, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice,
+                                c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+static int upload_mixture(phb_ctx* c, const double* freqs, const double* rates, const double* cat_weights) {
+    const int A = c->A, K = c->K;
+    std::vector<double> buf(2 * (size_t)A + 2 * K, 0.0);  // evals | freqs | rates | catw  (evals untouched here)
+    for (int i = 0; i < A; ++i) {
+        PHB_REQUIRE(c, std::isfinite(freqs[i]), PHB_ERR_INVALID, "model: non-finite state frequency");
+        buf[i] = freqs[i];
+    }
+    for (int k = 0; k < K; ++k) {
+        PHB_REQUIRE(c, rates[k] >= 0 && std::isfinite(rates[k]), PHB_ERR_INVALID, "model: category rates must be >= 0");
+        PHB_REQUIRE(c, cat_weights[k] >= 0 && std::isfinite(cat_weights[k]), PHB_ERR_INVALID,
+                    "model: category weights must be >= 0");
+        buf[A + k] = rates[k];
+        buf[A + K + k] = cat_weights[k];
+    }
+    PHB_CUDA(c, cudaMemcpyAsync(c->model_freqs(), buf.data(), ((size_t)A + 2 * K) * sizeof(double),
+                                cudaMemcpyHostToDevice, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_mixture = true;
+    return PHB_OK;
+}
+
+int phb_set_model(phb_ctx* c, const double* evecs, const double* evals, const double* ivecs, const double* freqs,
+                  const double* rates, const double* cat_weights) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, evecs && evals && ivecs && freqs && rates && cat_weights, PHB_ERR_INVALID,
+                "phb_set_model: NULL argument");
+    const size_t AA = (size_t)c->A * c->A;
+    std::vector<double> buf(2 * AA + c->A);
+    std::memcpy(buf.data(), evecs, AA * 8);
+    std::memcpy(buf.data() + AA, evals, (size_t)c->A * 8);
+    std::memcpy(buf.data() + AA + c->A, ivecs, AA * 8);
+    for (double v : buf) PHB_REQUIRE(c, std::isfinite(v), PHB_ERR_INVALID, "phb_set_model: non-finite eigen-system");
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_model, buf.data(), buf.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    st = upload_mixture(c, freqs, rates, cat_weights);
+    if (st) return st;
+    c->have_model = true;
+    c->have_pmats = false;
+    c->have_partials = false;
+    c->have_up = false;
+    return PHB_OK;
+}
+
+int phb_set_mixture(phb_ctx* c, const double* freqs, const double* rates, const double* cat_weights) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, freqs && rates && cat_weights, PHB_ERR_INVALID, "phb_set_mixture: NULL argument");
+    return upload_mixture(c, freqs, rates, cat_weights);
+}
+
+int phb_set_schedule(phb_ctx* c, int n_rows, const int32_t* rows, int n_levels, const int32_t* level_offsets) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, n_rows >= 0 && n_rows <= c->max_rows() && (n_rows == 0 || rows), PHB_ERR_INVALID,
+                "phb_set_schedule: row count must be in 0..n_tips-2");
+    PHB_REQUIRE(c, n_rows <= c->n_internal, PHB_ERR_INVALID, "phb_set_schedule: more rows than internal nodes");
+    c->rows_raw.assign(rows, rows + 3 * (size_t)n_rows);
+    c->level_offsets.clear();
+    if (level_offsets != nullptr && n_levels > 0) c->level_offsets.assign(level_offsets, level_offsets + n_levels + 1);
+    c->have_lengths = false;
+    c->have_pmats = false;
+    c->have_schedule = false;
+    if (c->have_tips) return resolve_schedule(c);
+    return PHB_OK;
+}
+
+int phb_set_edge_lengths(phb_ctx* c, const double* lengths) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    const size_t n = c->rows_raw.size() / 3 * 2;
+    PHB_REQUIRE(c, n == 0 || lengths, PHB_ERR_INVALID, "phb_set_edge_lengths: NULL lengths");
+    for (size_t i = 0; i < n; ++i)
+        PHB_REQUIRE(c, lengths[i] >= 0 && std::isfinite(lengths[i]), PHB_ERR_INVALID,
+                    "phb_set_edge_lengths: branch lengths must be finite and >= 0");
+    c->lengths.assign(lengths, lengths + n);
+    if (n) {
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_lengths, c->lengths.data(), n * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->have_lengths = true;
+    c->have_pmats = false;
+    c->have_partials = false;
+    c->have_up = false;
+    return PHB_OK;
+}
+
+int phb_build_pmatrices(phb_ctx* c) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, c->have_model, PHB_ERR_STATE, "phb_build_pmatrices: no eigen-system set (phb_set_model)");
+    PHB_REQUIRE(c, c->have_lengths, PHB_ERR_STATE, "phb_build_pmatrices: no edge lengths set");
+    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
+    if (st) return st;
+    c->have_pmats = true;
+    c->have_partials = false;
+    c->have_up = false;
+    return PHB_OK;
+}
+
+int phb_set_pmatrices(phb_ctx* c, const double* pmats) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    const size_t n = c->rows_raw.size() / 3 * 2 * (size_t)c->K * c->A * c->A;
+    PHB_REQUIRE(c, n == 0 || pmats, PHB_ERR_INVALID, "phb_set_pmatrices: NULL matrices");
+    if (n) {
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_pmats, pmats, n * 8, cudaMemcpyHostToDevice, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->have_pmats = true;
+    c->have_partials = false;
+    c->have_up = false;
+    return PHB_OK;
+}
+
+int phb_get_pmatrix(phb_ctx* c, int row, int child, double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, c->have_pmats, PHB_ERR_STATE, "phb_get_pmatrix: matrices have not been built");
+    PHB_REQUIRE(c, out && row >= 0 && row < (int)c->rows_raw.size() / 3 && (child == 0 || child == 1), PHB_ERR_INVALID,
+                "phb_get_pmatrix: bad row / child");
+    const size_t blk = (size_t)c->K * c->A * c->A;
+    PHB_CUDA(c, cudaMemcpyAsync(out, c->d_pmats + (size_t)(2 * row + child) * blk, blk * 8, cudaMemcpyDeviceToHost,
+                                c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+int phb_compute_partials(phb_ctx* c, int mode) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS), PHB_ERR_STATE,
+                "phb_compute_partials: context was created without partial storage");
+    PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_compute_partials: no tip data");
+    PHB_REQUIRE(c, c->have_schedule, PHB_ERR_STATE, "phb_compute_partials: no schedule");
+    PHB_REQUIRE(c, c->have_pmats, PHB_ERR_STATE, "phb_compute_partials: transition matrices not built");
+    if (mode == PHB_MODE_AUTO) mode = c->level_offsets.empty() ? PHB_MODE_TILE : PHB_MODE_LEVEL;
+    PHB_REQUIRE(c, mode == PHB_MODE_TILE || mode == PHB_MODE_LEVEL, PHB_ERR_INVALID, "phb_compute_partials: bad mode");
+    PHB_REQUIRE(c, mode != PHB_MODE_LEVEL || !c->level_offsets.empty(), PHB_ERR_STATE,
+                "phb_compute_partials: level mode needs level offsets in the schedule");
+    st = dna_supported(c) ? dna_compute_partials(c, mode) : generic_compute_partials(c, mode);
+    if (st) return st;
+    c->have_partials = true;
+    c->have_up = false;
+    return PHB_OK;
+}
+
+static int prepare_root(phb_ctx* c, int node_a, int node_b, double length, const double* root_pmats) {
+    int st = node_operand_ok(c, node_a);
+    if (st) return st;
+    st = node_operand_ok(c, node_b);
+    if (st) return st;
+    PHB_REQUIRE(c, node_a != node_b, PHB_ERR_INVALID, "root edge: both ends are the same node");
+    PHB_REQUIRE(c, c->have_mixture, PHB_ERR_STATE, "root edge: frequencies / mixture not set");
+    const size_t blk = (size_t)c->K * c->A * c->A;
+    double* d_root_p = c->d_pmats + (size_t)(2 * c->max_rows()) * blk;
+    if (root_pmats != nullptr) {
+        PHB_CUDA(c, cudaMemcpyAsync(d_root_p, root_pmats, 2 * blk * 8, cudaMemcpyHostToDevice, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    } else {
+        PHB_REQUIRE(c, c->have_model, PHB_ERR_STATE, "root edge: no eigen-system set and no matrices given");
+        PHB_REQUIRE(c, length >= 0 && std::isfinite(length), PHB_ERR_INVALID, "root edge: bad length");
+        const double two[2] = {0.0, length};  // P(0) on a's side, P(length) on b's: tree_model.py:189-190
+        double* d_len = c->d_lengths + 2 * (size_t)c->max_rows();
+        PHB_CUDA(c, cudaMemcpyAsync(d_len, two, sizeof two, cudaMemcpyHostToDevice, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        st = launch_build_pmatrices(c, d_len, 2, d_root_p, 0, 0);
+        if (st) return st;
+    }
+    c->root_a = node_a;
+    c->root_b = node_b;
+    c->root_len = length;
+    return PHB_OK;
+}
+
+int phb_root_lnl(phb_ctx* c, int node_a, int node_b, double length, const double* root_pmats, double* total,
+                 double* pattern_lnl, double* cat_lnl) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, total != nullptr, PHB_ERR_INVALID, "phb_root_lnl: total is NULL");
+    PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS), PHB_ERR_STATE,
+                "phb_root_lnl: context has no partial storage, use phb_lnl_resident");
+    PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_root_lnl: no tip data");
+    PHB_REQUIRE(c, c->have_partials || c->n_rows() == 0, PHB_ERR_STATE,
+                "phb_root_lnl: partials are stale, call phb_compute_partials first");
+    st = prepare_root(c, node_a, node_b, length, root_pmats);
+    if (st) return st;
+    const bool want_cat = cat_lnl != nullptr;
+    st = dna_supported(c) ? dna_root(c, node_a, node_b, want_cat, true)
+                          : generic_root(c, node_a, node_b, want_cat, true);
+    if (st) return st;
+    c->have_root = true;
+    PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pattern_lnl)
+        PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (cat_lnl)
+        PHB_CUDA(c, cudaMemcpyAsync(cat_lnl, c->d_cat_lnl, (size_t)c->S * c->K * 8, cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* total, double* pattern_lnl) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, total != nullptr, PHB_ERR_INVALID, "phb_lnl_resident: total is NULL");
+    PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
+                "phb_lnl_resident: tips, schedule, model and edge lengths must be set");
+    PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_resident: only 4-state models with K in {1,2,4,8}");
+    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
+    if (st) return st;
+    c->have_pmats = true;
+    st = prepare_root(c, node_a, node_b, length, nullptr);
+    if (st) return st;
+    st = dna_lnl_resident(c, node_a, node_b);
+    if (st) return st;
+    PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pattern_lnl)
+        PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+int phb_get_partials(phb_ctx* c, int node, double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, out != nullptr, PHB_ERR_INVALID, "phb_get_partials: out is NULL");
+    PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "phb_get_partials: node id out of range");
+    const size_t S = (size_t)c->S, K = c->K, A = c->A;
+    if (c->node_tip[node] >= 0) {
+        PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_get_partials: no tip data");
+        std::vector<uint8_t> codes(S);
+        std::vector<double> lut(256 * A);
+        PHB_CUDA(c, cudaMemcpyAsync(codes.data(), c->d_codes + (size_t)c->node_tip[node] * S, S, cudaMemcpyDeviceToHost,
+                                    c->stream));
+        PHB_CUDA(c, cudaMemcpyAsync(lut.data(), c->d_lut, lut.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t s = 0; s < S; ++s)
+            for (size_t k = 0; k < K; ++k) std::memcpy(out + (s * K + k) * A, lut.data() + (size_t)codes[s] * A, A * 8);
+        return PHB_OK;
+    }
+    PHB_REQUIRE(c, c->have_partials && c->node_slot[node] >= 0, PHB_ERR_STATE,
+                "phb_get_partials: partials of this node have not been computed");
+    PHB_CUDA(c, cudaMemcpyAsync(out, c->d_clv + (size_t)c->node_slot[node] * c->clv_stride(), c->clv_stride() * 8,
+                                cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+static int scalers_to_host(phb_ctx* c, const int32_t* d_exp, double* out) {
+    const size_t S = (size_t)c->S, K = c->K;
+    std::vector<int32_t> e(S);
+    PHB_CUDA(c, cudaMemcpyAsync(e.data(), d_exp, S * 4, cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t s = 0; s < S; ++s)
+        for (size_t k = 0; k < K; ++k) out[s * K + k] = (double)e[s] * kLn2;
+    return PHB_OK;
+}
+
+int phb_get_scalers(phb_ctx* c, int node, double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, out != nullptr, PHB_ERR_INVALID, "phb_get_scalers: out is NULL");
+    PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "phb_get_scalers: node id out of range");
+    if (c->node_tip[node] >= 0) {
+        std::memset(out, 0, (size_t)c->S * c->K * 8);
+        return PHB_OK;
+    }
+    PHB_REQUIRE(c, c->have_partials && c->node_slot[node] >= 0, PHB_ERR_STATE,
+                "phb_get_scalers: partials of this node have not been computed");
+    return scalers_to_host(c, c->d_scale + (size_t)c->node_slot[node] * c->S, out);
+}
+
+int phb_get_root_partials(phb_ctx* c, double* out_partials, double* out_scalers) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, c->have_root, PHB_ERR_STATE, "phb_get_root_partials: phb_root_lnl has not run");
+    if (out_partials) {
+        PHB_CUDA(c, cudaMemcpyAsync(out_partials, c->d_root_clv, c->clv_stride() * 8, cudaMemcpyDeviceToHost, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    if (out_scalers) return scalers_to_host(c, c->d_root_scale, out_scalers);
+    return PHB_OK;
+}
+
+int phb_compute_up_partials(phb_ctx* c) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, c->d_up != nullptr, PHB_ERR_STATE, "phb_compute_up_partials: context lacks PHB_FLAG_UP_PARTIALS");
+    PHB_REQUIRE(c, c->have_partials, PHB_ERR_STATE, "phb_compute_up_partials: run phb_compute_partials first");
+    PHB_REQUIRE(c, c->have_model, PHB_ERR_STATE, "phb_compute_up_partials: needs the eigen-system (reversible model)");
+    st = launch_up_partials(c);
+    if (st) return st;
+    c->have_up = true;
+    return PHB_OK;
+}
+
+int phb_edge_derivatives(phb_ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
+                         double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, n_edges >= 0 && (n_edges == 0 || (nodes && lengths && out)), PHB_ERR_INVALID,
+                "phb_edge_derivatives: NULL argument");
+    PHB_REQUIRE(c, c->have_up, PHB_ERR_STATE, "phb_edge_derivatives: run phb_compute_up_partials first");
+    return launch_edge_derivatives(c, n_edges, nodes, lengths, chain_rule, out);
+}
+
+}  // extern "C"

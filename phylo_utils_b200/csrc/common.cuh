@@ -1,0 +1,181 @@
+// Shared declarations of the phylo_b200 engine: context, schedule rows, launch helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/phylo_b200.h"
+
+namespace phb {
+
+// Partials smaller than this get rescaled (same threshold as the reference's SCALE_THRESHOLD,
+// likelihood/numba_likelihood_engine.py:7); rescaling multiplies by an exact power of two.
+constexpr double kScaleThreshold = 2.938735877055718769921841343056e-39;  // 2^-128
+constexpr int kScaleThresholdHi = 0x37F00000;                              // high word of 2^-128
+constexpr double kLn2 = 0.693147180559945309417232121458;
+
+// One row of the pruning schedule as the kernels see it.
+// kind: where a child's partial comes from.  SRC_PREV = "the block written by the row just before
+// this one" (src still holds its slot): tile-resident kernels read it from on-chip storage,
+// level-order kernels treat it as SRC_GLOBAL.  The host canonicalises every row so that
+// rank(kind[0]) <= rank(kind[1]) with TIP < PREV < GLOBAL (children commute), which leaves five
+// row shapes: TT, TP, TG, PG, GG.
+enum : int32_t { SRC_GLOBAL = 0, SRC_TIP = 1, SRC_PREV = 2 };
+struct __align__(16) OpRow {
+    int32_t dst;      // internal slot written by this row
+    int32_t src[2];   // tip row or internal slot of each child
+    int32_t kind[2];  // SRC_*
+    int32_t pidx[2];  // index of each child's P matrix block ([K][A][A]) in the P buffer
+    int32_t pad;
+};
+static_assert(sizeof(OpRow) == 32, "OpRow must stay 32 bytes");
+
+struct Ctx;
+
+// launch bookkeeping ------------------------------------------------------------------------
+#define PHB_CUDA(ctx, expr)                                                                     \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return (ctx)->fail_cuda(_e, #expr, __FILE__, __LINE__);          \
+    } while (0)
+
+#define PHB_REQUIRE(ctx, cond, code, msg)                                                       \
+    do {                                                                                        \
+        if (!(cond)) return (ctx)->fail((code), (msg));                                         \
+    } while (0)
+
+void set_thread_error(const std::string& msg);
+const char* thread_error();
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n_tips = 0, K = 0, A = 0, n_codes = 0;
+    int64_t S = 0;
+    unsigned flags = 0;
+    int n_nodes = 0, n_internal = 0, sm_count = 148;
+    size_t smem_optin = 0;
+
+    // workspace
+    bool owns_ws = false;
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+
+    // device views (all inside ws unless noted)
+    const uint8_t* d_codes = nullptr;  // may point outside ws when the caller keeps codes on the device
+    uint8_t* d_codes_ws = nullptr;
+    double* d_lut = nullptr;           // [256][A]
+    double* d_weights = nullptr;       // [S]
+    double* d_clv = nullptr;           // [n_internal][S][K][A]
+    int32_t* d_scale = nullptr;        // [n_internal][S]
+    double* d_up = nullptr;            // [n_internal][S][K][A] (optional)
+    int32_t* d_up_scale = nullptr;
+    double* d_root_clv = nullptr;      // [S][K][A]
+    int32_t* d_root_scale = nullptr;   // [S]
+    double* d_pmats = nullptr;         // [2*max_rows + 2][K][A][A]
+    double* d_dmats = nullptr;         // derivative scratch [3][K][A][A] per edge chunk
+    double* d_model = nullptr;         // evecs | evals | ivecs | freqs | rates | catw
+    double* d_lengths = nullptr;       // [2*max_rows + 2]
+    OpRow* d_rows = nullptr;           // [max_rows]
+    double* d_pattern_lnl = nullptr;   // [S]
+    double* d_cat_lnl = nullptr;       // [S][K]
+    double* d_partial_sums = nullptr;  // [kMaxReduceBlocks * 4]
+    double* d_result = nullptr;        // [4 * kMaxEdgeBatch]
+
+    // host mirrors
+    std::vector<int32_t> node_tip;     // node id -> tip row, or -1
+    std::vector<int32_t> node_slot;    // node id -> internal slot, or -1
+    std::vector<int32_t> node_parent;  // node id -> parent node id (-1 for root children)
+    std::vector<int32_t> node_row;     // node id -> schedule row that computes it (-1 for tips)
+    std::vector<OpRow> rows;
+    std::vector<int32_t> rows_raw;     // PAR, CH1, CH2 as given
+    std::vector<int32_t> level_offsets;
+    std::vector<double> lengths;       // [n_rows][2]
+    bool have_tips = false, have_model = false, have_mixture = false, have_schedule = false;
+    bool have_lengths = false, have_pmats = false, have_partials = false, have_up = false;
+    bool have_root = false;
+    int root_a = -1, root_b = -1;
+    double root_len = 0;
+
+    std::string err;
+    int64_t launches = 0;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+    int fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+        err = buf;
+        return PHB_ERR_CUDA;
+    }
+    int max_rows() const { return n_internal > 0 ? n_internal : 1; }
+    int n_rows() const { return (int)rows.size(); }
+    size_t clv_stride() const { return (size_t)S * K * A; }  // doubles per node
+    double* model_evecs() const { return d_model; }
+    double* model_evals() const { return d_model + (size_t)A * A; }
+    double* model_ivecs() const { return d_model + (size_t)A * A + A; }
+    double* model_freqs() const { return d_model + 2 * (size_t)A * A + A; }
+    double* model_rates() const { return d_model + 2 * (size_t)A * A + 2 * A; }
+    double* model_catw() const { return d_model + 2 * (size_t)A * A + 2 * A + K; }
+};
+
+constexpr int kMaxReduceBlocks = 4096;
+constexpr int kMaxEdgeBatch = 64;
+
+// kernel families (each returns a phb_status) ---------------------------------------------------
+// pmatrix.cu
+int launch_build_pmatrices(Ctx* c, const double* d_lengths, int n_mats, double* d_out, int order, int chain_rule);
+cudaError_t launch_pmatrix_raw(cudaStream_t stream, const double* evecs, const double* evals, const double* ivecs,
+                               const double* rates, const double* d_lengths, double* d_out, int A, int K, int n_mats,
+                               int order, int chain_rule);
+// clv_dna.cu  (A == 4, K in {1,2,4,8})
+bool dna_supported(const Ctx* c);
+int dna_compute_partials(Ctx* c, int mode);
+int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
+int dna_lnl_resident(Ctx* c, int a, int b);
+// clv_generic.cu (any A <= 64, any K <= 16)
+int generic_compute_partials(Ctx* c, int mode);
+int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
+// derivs.cu
+int launch_up_partials(Ctx* c);
+int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
+                            double* out);
+// reduce (in clv_generic.cu): sums n_parts partial sums (stride 1) into d_result[0..n_out)
+int launch_final_reduce(Ctx* c, const double* d_parts, int n_parts, int n_out, double* d_out);
+
+// device helpers ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void ld256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void ld256_nc(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st256(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3])
+                 : "memory");
+}
+// 2^e as a double, e in [-1022, 1023]
+__device__ __forceinline__ double pow2i(int e) { return __hiloint2double((e + 1023) << 20, 0); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+}  // namespace phb
+
+struct phb_ctx : phb::Ctx {};

@@ -1,0 +1,68 @@
+// Batched transition-probability matrices.
+//
+//   P[m][k] = V . diag( g(lambda) . exp(lambda . t_m . r_k) ) . V^-1
+//
+// for every branch length t_m (all edges of the schedule, plus the root edge) and every rate
+// category r_k in ONE launch; g = 1 for P, lambda (or lambda r_k) for dP/dt, its square for
+// d2P/dt2.  This is the device form of Eigen.exp / Eigen.fn_apply behind Model.p, dp_dt, d2p_dt2
+// (/root/reference/phylo_utils/substitution_models/abstract.py:49-77, 99-122), which the reference
+// calls 2(N-2) times per evaluation from Python (tree_model.py:168-169).
+//
+// The matrices are tiny (A = 4, 20, 61): one CTA per (matrix, category), the scaled eigenvector
+// matrix staged in shared memory, one output element per thread-iteration.  Traffic is KBs; the
+// kernel only has to stay off the critical path of the pruning kernels that follow it in-stream.
+#include "common.cuh"
+
+namespace phb {
+
+__global__ void pmatrix_kernel(const double* __restrict__ evecs, const double* __restrict__ evals,
+                               const double* __restrict__ ivecs, const double* __restrict__ rates,
+                               const double* __restrict__ lengths, double* __restrict__ out, int A, int K,
+                               int order, int chain_rule) {
+    extern __shared__ double sm[];
+    double* scaledV = sm;          // [A][A]  V[i][m] * g_m * exp(lambda_m s)
+    double* fac = sm + A * A;      // [A]
+    const int m = blockIdx.x, k = blockIdx.y;
+    const double r = rates ? rates[k] : 1.0;
+    const double s = lengths[m] * r;  // same association as the reference: exp(evals * (t * rate))
+    for (int j = threadIdx.x; j < A; j += blockDim.x) {
+        const double lam = evals[j];
+        double g = 1.0;
+        const double base = chain_rule ? lam * r : lam;
+        if (order >= 1) g = base;
+        if (order >= 2) g = base * base;
+        fac[j] = g * exp(lam * s);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < A * A; e += blockDim.x) scaledV[e] = evecs[e] * fac[e % A];
+    __syncthreads();
+    double* dst = out + ((size_t)m * K + k) * A * A;
+    for (int e = threadIdx.x; e < A * A; e += blockDim.x) {
+        const int i = e / A, j = e % A;
+        double acc = 0.0;
+        for (int q = 0; q < A; ++q) acc += scaledV[i * A + q] * ivecs[q * A + j];
+        dst[e] = acc;
+    }
+}
+
+cudaError_t launch_pmatrix_raw(cudaStream_t stream, const double* evecs, const double* evals, const double* ivecs,
+                               const double* rates, const double* d_lengths, double* d_out, int A, int K, int n_mats,
+                               int order, int chain_rule) {
+    if (n_mats <= 0) return cudaSuccess;
+    const int threads = A * A >= 256 ? 256 : (A * A >= 64 ? 128 : 32);
+    const size_t smem = (size_t)(A * A + A) * sizeof(double);
+    dim3 grid(n_mats, K);
+    pmatrix_kernel<<<grid, threads, smem, stream>>>(evecs, evals, ivecs, rates, d_lengths, d_out, A, K, order,
+                                                    chain_rule);
+    return cudaGetLastError();
+}
+
+int launch_build_pmatrices(Ctx* c, const double* d_lengths, int n_mats, double* d_out, int order, int chain_rule) {
+    if (n_mats <= 0) return PHB_OK;
+    c->launches++;
+    PHB_CUDA(c, launch_pmatrix_raw(c->stream, c->model_evecs(), c->model_evals(), c->model_ivecs(), c->model_rates(),
+                                   d_lengths, d_out, c->A, c->K, n_mats, order, chain_rule));
+    return PHB_OK;
+}
+
+}  // namespace phb

@@ -1,0 +1,219 @@
+"""
+Thin object wrapper over the C ABI (include/phylo_b200.h): one ``LikelihoodEngine`` = one
+``phb_ctx`` = one GPU.  All arithmetic happens in libphylo_b200.so; this class only marshals
+numpy arrays and owns the device workspace (a torch uint8 tensor when torch is importable, so
+that torch's caching allocator, streams and ``torch.cuda.Event`` timing see the same memory and
+stream; otherwise the library allocates for itself).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, dptr, iptr
+
+__all__ = ["LikelihoodEngine"]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.double)
+
+
+class LikelihoodEngine(object):
+    def __init__(self, n_tips, n_patterns, n_cat, n_states, device=0, up_partials=False, store_partials=True,
+                 use_torch=True):
+        self.n_tips, self.n_patterns, self.n_cat, self.n_states = int(n_tips), int(n_patterns), int(n_cat), int(n_states)
+        self.device = int(device)
+        self._ctx = ctypes.c_void_p()
+        self._keep = {}            # host/device buffers that must outlive the ctx
+        self._lib = lib()
+        flags = 0
+        if up_partials:
+            flags |= _lib.PHB_FLAG_UP_PARTIALS
+        if not store_partials:
+            flags |= _lib.PHB_FLAG_NO_PARTIALS
+        self.flags = flags
+        nbytes = self._lib.phb_workspace_bytes(self.n_tips, self.n_patterns, self.n_cat, self.n_states, flags)
+        if nbytes == 0:
+            raise ValueError("unsupported problem shape: tips={} patterns={} categories={} states={}".format(
+                n_tips, n_patterns, n_cat, n_states))
+        self.workspace_bytes = int(nbytes)
+        ws_ptr, stream = None, None
+        if use_torch:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    ws = torch.empty(self.workspace_bytes + 256, dtype=torch.uint8, device="cuda:{}".format(self.device))
+                    base = ws.data_ptr()
+                    ws_ptr = (base + 255) // 256 * 256
+                    self._keep["workspace"] = ws
+                    stream = torch.cuda.current_stream(self.device).cuda_stream
+            except ImportError:
+                pass
+        check(self._lib.phb_create(self.device, self.n_tips, self.n_patterns, self.n_cat, self.n_states, flags,
+                                   ctypes.c_void_p(ws_ptr), self.workspace_bytes if ws_ptr else 0,
+                                   ctypes.c_void_p(stream), ctypes.byref(self._ctx)))
+
+    # ---- life cycle -------------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            self._lib.phb_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+        self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ok(self, status):
+        check(status, self._ctx)
+
+    def sync(self):
+        self._ok(self._lib.phb_sync(self._ctx))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.phb_launch_count(self._ctx))
+
+    # ---- inputs -----------------------------------------------------------------------------
+    def set_tips(self, codes, lut, tip_nodes):
+        """codes: uint8 (n_tips, n_patterns) numpy array (host) or a torch CUDA uint8 tensor (kept on device)."""
+        lut = _f64(lut)
+        tip_nodes = np.ascontiguousarray(tip_nodes, dtype=np.int32)
+        if lut.ndim != 2 or lut.shape[1] != self.n_states:
+            raise ValueError("lut must be (n_codes, n_states)")
+        if tip_nodes.shape != (self.n_tips,):
+            raise ValueError("tip_nodes must have one entry per tip")
+        on_device = hasattr(codes, "data_ptr")
+        if on_device:
+            if tuple(codes.shape) != (self.n_tips, self.n_patterns) or not codes.is_contiguous():
+                raise ValueError("device codes must be a contiguous (n_tips, n_patterns) uint8 tensor")
+            self._keep["codes"] = codes
+            ptr = ctypes.c_void_p(codes.data_ptr())
+        else:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            if codes.shape != (self.n_tips, self.n_patterns):
+                raise ValueError("codes must be (n_tips, n_patterns)")
+            ptr = ctypes.c_void_p(codes.ctypes.data)
+        self._ok(self._lib.phb_set_tips(self._ctx, ptr, 1 if on_device else 0, lut.shape[0], dptr(lut), iptr(tip_nodes)))
+
+    def set_pattern_weights(self, weights):
+        if weights is None:
+            self._ok(self._lib.phb_set_pattern_weights(self._ctx, None))
+            return
+        w = np.ascontiguousarray(weights, dtype=np.int64)
+        if w.shape != (self.n_patterns,):
+            raise ValueError("weights must have one entry per pattern")
+        self._ok(self._lib.phb_set_pattern_weights(self._ctx, w.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))))
+
+    def set_model(self, evecs, evals, ivecs, freqs, rates, cat_weights):
+        A, K = self.n_states, self.n_cat
+        evecs, evals, ivecs = _f64(evecs), _f64(evals), _f64(ivecs)
+        freqs, rates, cat_weights = _f64(freqs), _f64(rates), _f64(cat_weights)
+        if evecs.shape != (A, A) or ivecs.shape != (A, A) or evals.shape != (A,) or freqs.shape != (A,):
+            raise ValueError("eigen-system / frequencies do not match the number of states")
+        if rates.shape != (K,) or cat_weights.shape != (K,):
+            raise ValueError("rates / weights do not match the number of categories")
+        self._ok(self._lib.phb_set_model(self._ctx, dptr(evecs), dptr(evals), dptr(ivecs), dptr(freqs), dptr(rates),
+                                         dptr(cat_weights)))
+
+    def set_mixture(self, freqs, rates, cat_weights):
+        freqs, rates, cat_weights = _f64(freqs), _f64(rates), _f64(cat_weights)
+        if freqs.shape != (self.n_states,) or rates.shape != (self.n_cat,) or cat_weights.shape != (self.n_cat,):
+            raise ValueError("frequencies / rates / weights have the wrong length")
+        self._ok(self._lib.phb_set_mixture(self._ctx, dptr(freqs), dptr(rates), dptr(cat_weights)))
+
+    def set_schedule(self, rows, level_offsets=None):
+        rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, 3)
+        if level_offsets is None:
+            self._ok(self._lib.phb_set_schedule(self._ctx, rows.shape[0], iptr(rows), 0, None))
+        else:
+            lo = np.ascontiguousarray(level_offsets, dtype=np.int32)
+            self._ok(self._lib.phb_set_schedule(self._ctx, rows.shape[0], iptr(rows), lo.shape[0] - 1, iptr(lo)))
+        self.n_rows = rows.shape[0]
+
+    def set_edge_lengths(self, lengths):
+        lengths = _f64(lengths).reshape(-1, 2)
+        if lengths.shape[0] != getattr(self, "n_rows", -1):
+            raise ValueError("need one (len1, len2) pair per schedule row")
+        self._ok(self._lib.phb_set_edge_lengths(self._ctx, dptr(lengths)))
+
+    # ---- transition matrices ----------------------------------------------------------------
+    def build_pmatrices(self):
+        self._ok(self._lib.phb_build_pmatrices(self._ctx))
+
+    def set_pmatrices(self, pmats):
+        pmats = _f64(pmats)
+        want = (getattr(self, "n_rows", 0), 2, self.n_cat, self.n_states, self.n_states)
+        if pmats.shape != want:
+            raise ValueError("pmats must be {}".format(want))
+        self._ok(self._lib.phb_set_pmatrices(self._ctx, dptr(pmats)))
+
+    def get_pmatrix(self, row, child):
+        out = np.empty((self.n_cat, self.n_states, self.n_states))
+        self._ok(self._lib.phb_get_pmatrix(self._ctx, int(row), int(child), dptr(out)))
+        return out
+
+    # ---- hot path ---------------------------------------------------------------------------
+    def compute_partials(self, mode=_lib.PHB_MODE_AUTO):
+        self._ok(self._lib.phb_compute_partials(self._ctx, int(mode)))
+
+    def root_lnl(self, node_a, node_b, length, want_pattern=False, want_cat=False, root_pmats=None):
+        total = ctypes.c_double(0.0)
+        pattern = np.empty(self.n_patterns) if want_pattern else None
+        cat = np.empty((self.n_patterns, self.n_cat)) if want_cat else None
+        rp = None
+        if root_pmats is not None:
+            rp = _f64(root_pmats)
+            if rp.shape != (2, self.n_cat, self.n_states, self.n_states):
+                raise ValueError("root_pmats must be (2, K, A, A)")
+        self._ok(self._lib.phb_root_lnl(self._ctx, int(node_a), int(node_b), float(length),
+                                        dptr(rp) if rp is not None else None, ctypes.byref(total),
+                                        dptr(pattern) if want_pattern else None, dptr(cat) if want_cat else None))
+        return total.value, pattern, cat
+
+    def lnl_resident(self, node_a, node_b, length, want_pattern=False):
+        total = ctypes.c_double(0.0)
+        pattern = np.empty(self.n_patterns) if want_pattern else None
+        self._ok(self._lib.phb_lnl_resident(self._ctx, int(node_a), int(node_b), float(length), ctypes.byref(total),
+                                            dptr(pattern) if want_pattern else None))
+        return total.value, pattern
+
+    # ---- read-back --------------------------------------------------------------------------
+    def get_partials(self, node):
+        out = np.empty((self.n_patterns, self.n_cat, self.n_states))
+        self._ok(self._lib.phb_get_partials(self._ctx, int(node), dptr(out)))
+        return out
+
+    def get_scalers(self, node):
+        out = np.empty((self.n_patterns, self.n_cat))
+        self._ok(self._lib.phb_get_scalers(self._ctx, int(node), dptr(out)))
+        return out
+
+    def get_root_partials(self):
+        part = np.empty((self.n_patterns, self.n_cat, self.n_states))
+        scal = np.empty((self.n_patterns, self.n_cat))
+        self._ok(self._lib.phb_get_root_partials(self._ctx, dptr(part), dptr(scal)))
+        return part, scal
+
+    # ---- derivatives ------------------------------------------------------------------------
+    def compute_up_partials(self):
+        self._ok(self._lib.phb_compute_up_partials(self._ctx))
+
+    def edge_derivatives(self, nodes, lengths, chain_rule=True):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        lengths = _f64(lengths)
+        if nodes.shape != lengths.shape or nodes.ndim != 1:
+            raise ValueError("nodes and lengths must be 1-D and of equal length")
+        out = np.empty((nodes.shape[0], 3))
+        self._ok(self._lib.phb_edge_derivatives(self._ctx, nodes.shape[0], iptr(nodes), dptr(lengths),
+                                                1 if chain_rule else 0, dptr(out)))
+        return out

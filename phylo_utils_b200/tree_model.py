@@ -1,0 +1,339 @@
+"""
+TreeModel - the reference's orchestration object, re-backed by the GPU engine.
+
+Same methods and attributes as /root/reference/phylo_utils/tree_model.py:12-217:
+
+    set_alignment, get_empirical_freqs, set_substitution_model, set_rate_model, set_tree,
+    set_ascertainment_bias_correction, initialise, compute_partials, compute_partials_at_edge,
+    compute_likelihood_at_edge;  attributes alignment, siteweights, inverse_index, names,
+    traversal, partials, scale, root_partials, root_scale.
+
+What differs underneath:
+
+* tips live on the device as one uint8 state-set code per (taxon, pattern); ``alignment`` /
+  ``partials`` / ``scale`` are materialised as numpy arrays only when somebody reads them
+* all 2(N-2) transition matrices x K categories come from one kernel launch, not from
+  2(N-2) ``model.p`` calls
+* the post-order loop is one launch (pattern-tile resident) or one launch per tree level
+* scalers are one cumulative binary exponent per pattern; ``scale[node]`` reports it as a
+  natural log replicated over the categories, so ``partials * exp(scale)`` is comparable with the
+  reference's ``partials * exp(scale)``
+* ``compute_likelihood_at_edge`` runs root combine + lnl_node + mixture + log on the device
+
+Extras for the derivative path (no counterpart in TreeModel, composed from lnl_branch_derivs):
+``compute_up_partials`` and ``edge_derivatives``.
+"""
+import numpy as np
+from scipy.special import logsumexp
+
+from . import _lib
+from .alignment.alignment import alignment_to_codes, invariant_sites
+from .engine import LikelihoodEngine
+from .traversal import Traversal
+from .utils import deepcopy_tree, setup_logger
+
+logger = setup_logger()
+
+# below this many patterns the pattern axis alone cannot occupy the GPU: schedule level by level
+_TILE_MODE_MIN_PATTERNS = 16384
+
+
+class TreeModel(object):
+    alignment_codes = None
+    ascbias = False
+
+    def __init__(self, device=0, up_partials=False, mode="auto"):
+        self.device = device
+        self.want_up_partials = up_partials
+        self.mode = mode
+        self.engine = None
+        self.substitution_model = None
+        self.rate_model = None
+        self.traversal = None
+        self.tree = None
+        self._lut = None
+        self.siteweights = None
+        self.inverse_index = None
+        self.names = None
+        self._rows = None
+        self._n_dummy = 0
+
+    # ------------------------------------------------------------------------------------------
+    # inputs (reference: tree_model.py:42-98)
+    # ------------------------------------------------------------------------------------------
+    def set_alignment(self, alignment, alphabet, compress=True):
+        """``alignment``: iterable of records with ``.name`` and ``.seq`` (Biopython alignment or alignment.SeqRecord list)."""
+        codes, lut, sw, ii, names = alignment_to_codes(alignment, alphabet, compress)
+        self.set_tip_codes(codes, lut, names, sw, ii)
+
+    def set_tip_codes(self, codes, lut, names, siteweights=None, inverse_index=None):
+        """Direct entry for already-encoded data: ``codes`` uint8 (ntax, npat) indexing ``lut`` (ncodes, A)."""
+        self.alignment_codes = codes
+        self._lut = np.ascontiguousarray(lut, dtype=np.double)
+        npat = codes.shape[1]
+        self.siteweights = np.ones(npat, dtype=np.int64) if siteweights is None else np.asarray(siteweights, dtype=np.int64)
+        self.inverse_index = np.arange(npat, dtype=np.int64) if inverse_index is None else np.asarray(inverse_index, dtype=np.int64)
+        self.names = dict(names)
+        self.engine = None
+
+    @property
+    def alignment(self):
+        """(ntax, npat, A) float array, as the reference stores it (materialised on demand)."""
+        if self.alignment_codes is None:
+            return None
+        codes = self.alignment_codes
+        if hasattr(codes, "cpu"):
+            codes = codes.cpu().numpy()
+        return np.ascontiguousarray(self._lut[codes])
+
+    def get_empirical_freqs(self, pseudocount=None, include_ambiguous=False):
+        if self.alignment_codes is None:
+            logger.error("No alignment has been set")
+            return 0
+        if include_ambiguous:
+            logger.warning("Not implemented")
+        counts = (self.alignment * self.siteweights[np.newaxis, :, np.newaxis]).sum((0, 1))
+        if pseudocount is not None:
+            try:
+                counts += np.array(pseudocount)
+            except TypeError:
+                logger.warning("Pseudocount {} caused Type error. Carrying on without pseudocount.".format(pseudocount))
+            except ValueError:
+                logger.warning("Pseudocount {} caused Value error (probably the wrong length). "
+                               "Carrying on without pseudocount.".format(pseudocount))
+        return counts / counts.sum()
+
+    def set_substitution_model(self, model):
+        self.substitution_model = model
+        if self.engine is not None:
+            self._upload_model()
+
+    def set_rate_model(self, rate_model):
+        if self.engine is not None and self.rate_model is not None and rate_model.ncat != self.rate_model.ncat:
+            self.engine = None          # category count is baked into the device layout
+        self.rate_model = rate_model
+        if self.engine is not None:
+            self._upload_model()
+
+    def set_tree(self, dpytree):
+        self.tree = deepcopy_tree(dpytree)
+        self.traversal = Traversal(self.tree)
+        self.engine = None
+
+    def set_ascertainment_bias_correction(self):
+        """Lewis (2001) correction with one dummy constant pattern per state (reference: tree_model.py:92-98)."""
+        if np.any(invariant_sites(self.alignment)):
+            logger.warning("Using Lewis ascertainment bias correction on an alignment with invariant sites!")
+        self.ascbias = True
+        self.engine = None
+
+    # ------------------------------------------------------------------------------------------
+    # device set-up (reference: initialise, tree_model.py:101-158)
+    # ------------------------------------------------------------------------------------------
+    def _tip_rows(self):
+        missing = [name for name in self.traversal.names if name not in self.names]
+        if missing:
+            raise ValueError("taxa in the tree but not in the alignment: {}".format(missing[:5]))
+        order = sorted(self.traversal.names, key=lambda nm: self.names[nm])
+        rows = [self.names[nm] for nm in order]
+        nodes = [self.traversal.names[nm] for nm in order]
+        return np.asarray(rows), np.asarray(nodes, dtype=np.int32)
+
+    def _choose_mode(self, n_patterns):
+        if self.mode == "tile":
+            return _lib.PHB_MODE_TILE
+        if self.mode == "level":
+            return _lib.PHB_MODE_LEVEL
+        return _lib.PHB_MODE_TILE if n_patterns >= _TILE_MODE_MIN_PATTERNS else _lib.PHB_MODE_LEVEL
+
+    def initialise(self):
+        """Allocate device storage, upload tips / model / schedule, run one post-order pass."""
+        if self.alignment_codes is None or self.traversal is None:
+            raise ValueError("alignment and tree must be set before initialise()")
+        if self.substitution_model is None or self.rate_model is None:
+            raise ValueError("substitution model and rate model must be set before initialise()")
+        codes, lut = self.alignment_codes, self._lut
+        weights = self.siteweights
+        n_states = lut.shape[1]
+        rows_in_aln, tip_nodes = self._tip_rows()
+        on_device = hasattr(codes, "data_ptr")
+        if on_device:
+            if len(rows_in_aln) != codes.shape[0] or np.any(rows_in_aln != np.arange(codes.shape[0])):
+                codes = codes[rows_in_aln.tolist()].contiguous()
+        else:
+            if len(rows_in_aln) != codes.shape[0] or np.any(rows_in_aln != np.arange(codes.shape[0])):
+                codes = np.ascontiguousarray(codes[rows_in_aln])
+        self._n_dummy = 0
+        if self.ascbias:
+            if on_device:
+                raise ValueError("ascertainment-bias correction needs host-resident codes")
+            # one constant pattern per state, appended after the real patterns (tree_model.py:151-156);
+            # weight 0 keeps them out of the total
+            lut = lut.copy()
+            single = []
+            for st in range(n_states):
+                onehot = np.zeros(n_states)
+                onehot[st] = 1.0
+                hit = np.flatnonzero((lut == onehot).all(axis=1))
+                if hit.size:
+                    single.append(int(hit[0]))
+                else:
+                    lut = np.vstack([lut, onehot])
+                    single.append(lut.shape[0] - 1)
+            dummy = np.repeat(np.asarray(single, dtype=np.uint8)[None, :], codes.shape[0], axis=0)
+            codes = np.ascontiguousarray(np.hstack([codes, dummy]))
+            weights = np.concatenate([weights, np.zeros(n_states, dtype=np.int64)])
+            self._n_dummy = n_states
+        n_tips, n_patterns = codes.shape
+        self._mode = self._choose_mode(n_patterns)
+        self.engine = LikelihoodEngine(n_tips, n_patterns, self.rate_model.ncat, n_states, device=self.device,
+                                       up_partials=self.want_up_partials)
+        self.engine.set_tips(codes, lut, tip_nodes)
+        self.engine.set_pattern_weights(weights)
+        if self._mode == _lib.PHB_MODE_LEVEL:
+            rows, offsets = self.traversal.level_order()
+            self.engine.set_schedule(rows, offsets)
+        else:
+            rows = self.traversal.locality_order()
+            self.engine.set_schedule(rows)
+        self._rows = rows
+        self._upload_model()
+        self.compute_partials()
+
+    def _upload_model(self):
+        m, r = self.substitution_model, self.rate_model
+        if m is None or r is None or self.engine is None:
+            return
+        if r.ncat != self.engine.n_cat:
+            raise ValueError("rate model has {} categories, device layout was built for {}".format(r.ncat, self.engine.n_cat))
+        if m.size != self.engine.n_states:
+            raise ValueError("substitution model has {} states, alignment has {}".format(m.size, self.engine.n_states))
+        if getattr(m, "has_real_eigensystem", True):
+            e = m.eigen
+            self.engine.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), m.freqs, r.rates, r.weights)
+        else:
+            self.engine.set_mixture(m.freqs, r.rates, r.weights)
+
+    def _row_lengths(self):
+        br = self.traversal.brlens
+        out = np.empty((len(self._rows), 2))
+        for i, (par, c1, c2) in enumerate(self._rows):
+            out[i, 0] = br[(int(par), int(c1))]
+            out[i, 1] = br[(int(par), int(c2))]
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # the hot path
+    # ------------------------------------------------------------------------------------------
+    def compute_partials(self):
+        """One post-order traversal over all internal nodes (reference: tree_model.py:160-176)."""
+        if self.engine is None:
+            raise ValueError("call initialise() first")
+        lengths = self._row_lengths()
+        self.engine.set_edge_lengths(lengths)
+        m = self.substitution_model
+        if getattr(m, "has_real_eigensystem", True):
+            self.engine.build_pmatrices()
+        else:
+            rates = self.rate_model.rates
+            pm = np.empty((len(self._rows), 2, self.engine.n_cat, m.size, m.size))
+            for i in range(len(self._rows)):
+                pm[i, 0] = m.p(lengths[i, 0], rates)
+                pm[i, 1] = m.p(lengths[i, 1], rates)
+            self.engine.set_pmatrices(pm)
+        self.engine.compute_partials(self._mode)
+
+    def _edge_length(self, node_a, node_b):
+        try:
+            return self.traversal.brlens[node_a, node_b]
+        except KeyError:
+            raise ValueError('There is no edge connecting nodes {} and {}'.format(node_a, node_b))
+
+    def _root_pmats(self, length):
+        m = self.substitution_model
+        if getattr(m, "has_real_eigensystem", True):
+            return None
+        rates = self.rate_model.rates
+        return np.stack([m.p(0, rates), m.p(length, rates)])
+
+    def compute_partials_at_edge(self, node_a, node_b):
+        """Root the tree on edge (a, b); -> (root_partials (S,K,A), root_scale (S,K)) (reference: tree_model.py:178-198)."""
+        length = self._edge_length(node_a, node_b)
+        self.engine.root_lnl(node_a, node_b, length, root_pmats=self._root_pmats(length))
+        return self.engine.get_root_partials()
+
+    def _pattern_lnl(self, node_a, node_b):
+        length = self._edge_length(node_a, node_b)
+        rp = self._root_pmats(length)
+        if not self.ascbias:
+            total, pattern, _ = self.engine.root_lnl(node_a, node_b, length, want_pattern=True, root_pmats=rp)
+            return total, pattern
+        # Lewis correction exactly as the reference composes it (tree_model.py:209-216): subtract
+        # log(1 - sum over dummy patterns and categories of exp(lnl)) from every per-category value
+        _, _, cat = self.engine.root_lnl(node_a, node_b, length, want_cat=True, root_pmats=rp)
+        n = self._n_dummy
+        correction = np.log(1 - np.exp(logsumexp(cat[-n:])))
+        cat[:-n] -= correction
+        pattern = logsumexp(cat + np.log(self.rate_model.weights), axis=1)
+        total = float(np.dot(pattern[:-n], self.siteweights))
+        return total, pattern
+
+    def compute_likelihood_at_edge(self, node_a, node_b):
+        """Per ORIGINAL site log-likelihoods, gathered through ``inverse_index`` (reference: tree_model.py:200-217)."""
+        _, pattern = self._pattern_lnl(node_a, node_b)
+        return pattern[self.inverse_index]
+
+    def lnl(self, node_a=None, node_b=None):
+        """Total log-likelihood = sum_p siteweights_p * lnl_p (what bin/phy.py:146 prints), reduced on the device."""
+        if node_a is None:
+            node_a, node_b = self.traversal.root_edge
+        total, _ = self._pattern_lnl(node_a, node_b)
+        return total
+
+    # ------------------------------------------------------------------------------------------
+    # attribute views of device state (reference attributes partials / scale / root_partials / root_scale)
+    # ------------------------------------------------------------------------------------------
+    @property
+    def partials(self):
+        n_nodes = 2 * self.engine.n_tips - 2
+        return np.stack([self.engine.get_partials(i) for i in range(n_nodes)])
+
+    @property
+    def scale(self):
+        n_nodes = 2 * self.engine.n_tips - 2
+        return np.stack([self.engine.get_scalers(i) for i in range(n_nodes)])
+
+    @property
+    def root_partials(self):
+        return self.engine.get_root_partials()[0]
+
+    @property
+    def root_scale(self):
+        return self.engine.get_root_partials()[1]
+
+    # ------------------------------------------------------------------------------------------
+    # derivatives (composition of lnl_branch_derivs over the Gamma mixture)
+    # ------------------------------------------------------------------------------------------
+    def compute_up_partials(self):
+        self.engine.compute_up_partials()
+
+    def edge_derivatives(self, nodes, lengths=None, chain_rule=True):
+        """
+        For each node id (meaning the edge above it), (lnL, dlnL/dt, d2lnL/dt2) at ``lengths`` (default:
+        the current branch lengths).  ``chain_rule=False`` reproduces Model.dp_dt's convention.
+        """
+        nodes = np.asarray(nodes, dtype=np.int32)
+        if lengths is None:
+            lengths = np.asarray([self.branch_length_above(int(n)) for n in nodes])
+        return self.engine.edge_derivatives(nodes, lengths, chain_rule)
+
+    def branch_length_above(self, node):
+        a, b = self.traversal.root_edge
+        if node == a:
+            return self.traversal.brlens[(a, b)]
+        if node == b:
+            return self.traversal.brlens[(a, b)]
+        for par, c1, c2 in self.traversal.postorder_traversal:
+            if node == c1 or node == c2:
+                return self.traversal.brlens[(int(par), int(node))]
+        raise ValueError("node {} has no edge above it".format(node))
