@@ -1,0 +1,75 @@
+"""Shared test helpers: load golden fixtures and rebuild the same problem with phylo_utils_b200 / the oracle."""
+import os
+
+import numpy as np
+
+import phylo_utils_b200 as phy
+from phylo_utils_b200.alignment.alignment import SeqRecord, alignment_to_codes
+from phylo_utils_b200.tree import parse_newick
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-10   # BASELINE.json north_star: total and per-site lnL within 1e-10 relative in fp64
+
+
+def load(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def records(g):
+    return [SeqRecord(str(n), bytes(row).decode("ascii")) for n, row in zip(g["names"], g["seqs"])]
+
+
+def tree(g):
+    return parse_newick(str(g["newick"]))
+
+
+sm = phy.substitution_models
+rm = phy.rate_models
+_GTR = lambda: sm.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+_UNREST = lambda: sm.Unrest(rates=[[0., 1., 2., 3.], [4., 0., 5., 6.], [7., 8., 0., 9.], [10., 11., 12., 0.]])
+
+# name -> (substitution model factory, rate model factory); must match oracle/make_golden.py
+CASES = {
+    "cfg1_gtr_g4": (_GTR, lambda: rm.GammaRateModel(4, 0.5)),
+    "cfg1_jc_g4": (lambda: sm.GTR(), lambda: rm.GammaRateModel(4, 0.5)),
+    "cfg1_gtr_uniform": (_GTR, lambda: rm.UniformRateModel()),
+    "ambig_hky_ig": (lambda: sm.HKY85(2.5, [0.3, 0.2, 0.15, 0.35]), lambda: rm.InvariantGammaModel(0.2, 4, 0.7)),
+    "ambig_tn93_inv": (lambda: sm.TN93(2.0, 3.0, 1.0, [0.25, 0.2, 0.3, 0.25]), lambda: rm.InvariantSitesModel(0.3)),
+    "deep300_gtr_g4": (_GTR, lambda: rm.GammaRateModel(4, 0.5)),
+    "ladder120_k80_g4": (lambda: sm.K80(2.0), lambda: rm.GammaRateModel(4, 1.3)),
+    "prot12_lg_g4": (lambda: sm.LG(), lambda: rm.GammaRateModel(4, 0.8)),
+    "prot12_wag_g4": (lambda: sm.WAG(), lambda: rm.GammaRateModel(4, 0.8)),
+    "prot150_jtt_g4": (lambda: sm.JTT(), lambda: rm.GammaRateModel(4, 0.6)),
+    "nonrev_unrest_g4": (_UNREST, lambda: rm.GammaRateModel(4, 0.5)),
+}
+ASC_CASES = {
+    "ascbias_gtr_uniform": (_GTR, lambda: rm.UniformRateModel()),
+    "ascbias_gtr_g4": (_GTR, lambda: rm.GammaRateModel(4, 2.0)),
+}
+
+
+def problem(name):
+    """-> (golden dict, traversal, codes, lut, siteweights, inverse_index, names, model, rate_model)"""
+    g = load(name)
+    factories = CASES.get(name) or ASC_CASES[name]
+    model, rate = factories[0](), factories[1]()
+    tr = phy.traversal.Traversal(phy.utils.deepcopy_tree(tree(g)))
+    codes, lut, sw, ii, names = alignment_to_codes(records(g), int(g["alphabet"]))
+    return g, tr, codes, lut, sw, ii, names, model, rate
+
+
+def tip_partials(tr, codes, lut, names):
+    return {tr.names[nm]: np.ascontiguousarray(lut[codes[names[nm]]]) for nm in tr.names}
+
+
+def assert_lnl_close(got, want, rtol=RTOL, what="lnL"):
+    got, want = np.asarray(got, dtype=float), np.asarray(want, dtype=float)
+    assert got.shape == want.shape, "{}: shape {} vs {}".format(what, got.shape, want.shape)
+    finite = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), finite), "{}: finiteness pattern differs".format(what)
+    if finite.any():
+        err = np.abs(got[finite] - want[finite]) / np.maximum(np.abs(want[finite]), 1e-300)
+        assert err.max() <= rtol, "{}: max relative error {:.3e} > {:.1e}".format(what, err.max(), rtol)
+    if (~finite).any():
+        assert np.array_equal(got[~finite], want[~finite]) or np.all(np.isnan(want[~finite]) == np.isnan(got[~finite]))

@@ -1,0 +1,87 @@
+"""The C-ABI library loads and exports exactly what include/phylo_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from phylo_utils_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "phylo_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(phb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_functions():
+    names = declared_functions()
+    assert "phb_create" in names and "phb_compute_partials" in names and len(names) >= 25
+
+
+def test_every_declared_symbol_is_exported():
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(handle, name), "libphylo_b200.so does not export " + name
+
+
+def test_python_binding_table_matches_header():
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+
+
+def test_header_cites_reference_interfaces():
+    text = open(HEADER).read()
+    for cite in ("tree_model.py:160-176", "numba_likelihood_engine.py:10-46", "abstract.py:49-59",
+                 "c_discrete_gamma.c:285-321", "tree_model.py:178-217"):
+        assert cite in text
+
+
+def test_version_and_status_names():
+    lib = _lib.lib()
+    assert lib.phb_version() == 100
+    assert lib.phb_status_name(0) == b"PHB_OK"
+    assert lib.phb_status_name(3) == b"PHB_ERR_NO_DEVICE"
+
+
+def test_workspace_size_of_headline_config():
+    # 1000 taxa x 1M patterns x 4 categories x 4 states: 998 internal nodes x 128 MB + scalers + tips
+    lib = _lib.lib()
+    n = lib.phb_workspace_bytes(1000, 1000000, 4, 4, 0)
+    partials = 998 * 1000000 * 16 * 8
+    assert partials < n < partials * 1.06
+    assert n < 180e9            # fits one B200
+    assert lib.phb_workspace_bytes(1000, 1000000, 4, 4, _lib.PHB_FLAG_NO_PARTIALS) < 1.2e9
+    assert lib.phb_workspace_bytes(1, 10, 4, 4, 0) == 0          # invalid shape
+    assert lib.phb_workspace_bytes(10, 10, 4, 65, 0) == 0
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_a_device():
+    from phylo_utils_b200.engine import LikelihoodEngine
+    with pytest.raises(RuntimeError) as exc:
+        LikelihoodEngine(4, 10, 4, 4)
+    assert "no CPU fallback" in str(exc.value) or "NO_DEVICE" in str(exc.value)
+    import numpy as np
+    from phylo_utils_b200.likelihood import clv
+    p = np.eye(4)[None]
+    with pytest.raises(RuntimeError):
+        clv(p, p, np.ones((3, 1, 4)), np.ones((3, 1, 4)), np.zeros((3, 1)), np.zeros((3, 1)), np.zeros((3, 1)))
+
+
+def test_bad_arguments_are_value_errors():
+    from phylo_utils_b200.engine import LikelihoodEngine
+    with pytest.raises(ValueError):
+        LikelihoodEngine(1, 10, 4, 4)
+    with pytest.raises(ValueError):
+        LikelihoodEngine(4, 10, 4, 100)
