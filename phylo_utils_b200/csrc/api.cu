@@ -311,16 +311,20 @@ int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_co
     for (int i = 0; i < n_codes * c->A; ++i)
         PHB_REQUIRE(c, lut[i] >= 0.0 && std::isfinite(lut[i]), PHB_ERR_INVALID,
                     "phb_set_tips: look-up table entries must be finite and non-negative");
+    const size_t n_code_bytes = (size_t)c->n_tips * c->S;
     if (!codes_on_device) {
-        // codes are validated on the host: an out-of-range code would index past the table
-        const size_t n = (size_t)c->n_tips * c->S;
-        uint8_t worst = 0;
-        for (size_t i = 0; i < n; ++i) worst = codes[i] > worst ? codes[i] : worst;
-        PHB_REQUIRE(c, worst < n_codes, PHB_ERR_INVALID, "phb_set_tips: a code is >= n_codes");
-        PHB_CUDA(c, cudaMemcpyAsync(c->d_codes_ws, codes, n, cudaMemcpyHostToDevice, c->stream));
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_codes_ws, codes, n_code_bytes, cudaMemcpyHostToDevice, c->stream));
         c->d_codes = c->d_codes_ws;
     } else {
         c->d_codes = codes;
+    }
+    // The look-up table always has 256 rows on the device (unused rows are zero), so a stray code can
+    // never index out of bounds; it is still an input error, detected on the device in one pass.
+    {
+        int worst = 0;
+        int st2 = launch_max_code(c, c->d_codes, n_code_bytes, &worst);
+        if (st2) return st2;
+        PHB_REQUIRE(c, worst < n_codes, PHB_ERR_INVALID, "phb_set_tips: a code is >= n_codes");
     }
     std::vector<double> full(256 * (size_t)c->A, 0.0);
     std::memcpy(full.data(), lut, (size_t)n_codes * c->A * sizeof(double));
@@ -501,6 +505,10 @@ int phb_compute_partials(phb_ctx* c, int mode) {
     PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_compute_partials: no tip data");
     PHB_REQUIRE(c, c->have_schedule, PHB_ERR_STATE, "phb_compute_partials: no schedule");
     PHB_REQUIRE(c, c->have_pmats, PHB_ERR_STATE, "phb_compute_partials: transition matrices not built");
+    if (c->n_rows() == 0) {  // two-tip tree: nothing to prune
+        c->have_partials = true;
+        return PHB_OK;
+    }
     if (mode == PHB_MODE_AUTO) mode = c->level_offsets.empty() ? PHB_MODE_TILE : PHB_MODE_LEVEL;
     PHB_REQUIRE(c, mode == PHB_MODE_TILE || mode == PHB_MODE_LEVEL, PHB_ERR_INVALID, "phb_compute_partials: bad mode");
     PHB_REQUIRE(c, mode != PHB_MODE_LEVEL || !c->level_offsets.empty(), PHB_ERR_STATE,

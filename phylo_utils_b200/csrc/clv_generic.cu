@@ -254,6 +254,26 @@ __global__ void final_reduce_kernel(const double* __restrict__ parts, int n_part
     if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
+// largest byte of an array: validates tip codes without a host pass over N x S bytes.
+// `head` bytes are handled one by one until the pointer is 16-byte aligned, then 16 at a time.
+__global__ void max_code_kernel(const uint8_t* __restrict__ codes, size_t n, size_t head, int* __restrict__ out) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    unsigned b = 0;
+    for (size_t i = gtid; i < head; i += gsz) b = max(b, (unsigned)codes[i]);
+    const size_t n16 = (n - head) / 16;
+    const uint4* v = reinterpret_cast<const uint4*>(codes + head);
+    unsigned m = 0;
+    for (size_t i = gtid; i < n16; i += gsz) {
+        const uint4 q = v[i];
+        m = __vmaxu4(m, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+    }
+    b = max(b, max(max(m & 0xff, (m >> 8) & 0xff), max((m >> 16) & 0xff, m >> 24)));
+    for (size_t i = head + n16 * 16 + gtid; i < n; i += gsz) b = max(b, (unsigned)codes[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b > 0) atomicMax(out, (int)b);
+}
+
 int tile_sites_for(const Ctx* c, size_t* smem_out, int* ld_out) {
     const int A = c->A;
     const int ld = A | 1;
@@ -359,6 +379,22 @@ int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root) {
     c->launches++;
     PHB_CUDA(c, cudaGetLastError());
     return launch_final_reduce(c, c->d_partial_sums, (int)grid, 1, c->d_result);
+}
+
+int launch_max_code(Ctx* c, const uint8_t* d_codes, size_t n, int* worst) {
+    int* d_flag = reinterpret_cast<int*>(c->d_result + 4 * kMaxEdgeBatch - 1);
+    PHB_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+    size_t head = (16 - reinterpret_cast<uintptr_t>(d_codes) % 16) % 16;
+    if (head > n) head = n;
+    size_t blocks = (n / 16 + 255) / 256;
+    if (blocks > (size_t)c->sm_count * 16) blocks = (size_t)c->sm_count * 16;
+    if (blocks < 1) blocks = 1;
+    max_code_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(d_codes, n, head, d_flag);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    PHB_CUDA(c, cudaMemcpyAsync(worst, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
 }
 
 int launch_final_reduce(Ctx* c, const double* d_parts, int n_parts, int n_out, double* d_out) {

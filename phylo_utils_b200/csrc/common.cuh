@@ -146,6 +146,8 @@ int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 int launch_up_partials(Ctx* c);
 int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
                             double* out);
+// max over a byte array (in clv_generic.cu); synchronises the stream
+int launch_max_code(Ctx* c, const uint8_t* d_codes, size_t n, int* worst);
 // reduce (in clv_generic.cu): sums n_parts partial sums (stride 1) into d_result[0..n_out)
 int launch_final_reduce(Ctx* c, const double* d_parts, int n_parts, int n_out, double* d_out);
 
