@@ -150,8 +150,9 @@ int phb_get_root_partials(phb_ctx* ctx, double* out_partials, double* out_scaler
 /* Pre-order pass: for every non-root-child node the partial of everything outside its subtree
  * ("up" partial), the operand lnl_branch_derivs needs at the far end of each edge; device-side
  * equivalent of walking Traversal.optimising_traversal (utils.py:137-188) without re-rooting in place.
- * Needs PHB_FLAG_UP_PARTIALS and a reversible model. */
-int phb_compute_up_partials(phb_ctx* ctx);
+ * (node_a, node_b, length) is the root edge the down partials were computed for
+ * (Traversal.root_edge).  Needs PHB_FLAG_UP_PARTIALS and a reversible model. */
+int phb_compute_up_partials(phb_ctx* ctx, int node_a, int node_b, double length);
 /* For each listed node (edge above it; for a root child: the root edge), at the given trial length:
  * out[i] = { lnL, d lnL / dt, d2 lnL / dt2 } summed over patterns with their weights, Gamma mixture
  * composed as in SURVEY.md 8(a) row a12 from lnl_branch_derivs (numba_likelihood_engine.py:49-57).

@@ -50,7 +50,7 @@ SIGNATURES = {
     "phb_get_partials": (c_int, [c_void_p, c_int, _dp]),
     "phb_get_scalers": (c_int, [c_void_p, c_int, _dp]),
     "phb_get_root_partials": (c_int, [c_void_p, _dp, _dp]),
-    "phb_compute_up_partials": (c_int, [c_void_p]),
+    "phb_compute_up_partials": (c_int, [c_void_p, c_int, c_int, c_double]),
     "phb_edge_derivatives": (c_int, [c_void_p, c_int, _ip, _dp, c_int, _dp]),
     "phb_op_clv": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "phb_op_lnl_node": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp]),

@@ -19,7 +19,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, root_clv, root_scale, pmats, dmats, model, lengths, rows,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows,
         pattern_lnl, cat_lnl, partial, result, total;
 };
 
@@ -39,10 +39,14 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.codes = take((size_t)n_tips * S);
     p.lut = take(256 * (size_t)A * 8);
     p.weights = take((size_t)S * 8);
-    p.clv = take(store ? n_int * node_doubles * 8 : 0);
-    p.scale = take(store ? n_int * (size_t)S * 4 : 0);
-    p.up = take(up ? n_int * node_doubles * 8 : 0);
-    p.up_scale = take(up ? n_int * (size_t)S * 4 : 0);
+    // down partials [n_int blocks] immediately followed by up partials [n_nodes blocks] (if requested)
+    const size_t n_nodes = 2 * (size_t)n_tips - 2;
+    const size_t n_blocks = n_int + (up ? n_nodes : 0);
+    p.clv = take(store ? n_blocks * node_doubles * 8 : 0);
+    p.scale = take(store ? n_blocks * (size_t)S * 4 : 0);
+    p.up = p.clv + n_int * node_doubles * 8;
+    p.up_scale = p.scale + n_int * (size_t)S * 4;
+    p.up_rows = take(up ? 2 * max_rows * sizeof(OpRow) : 0);
     p.root_clv = take(store ? node_doubles * 8 : 0);
     p.root_scale = take(store ? (size_t)S * 4 : 0);
     p.pmats = take((2 * max_rows + 2) * (size_t)K * A * A * 8);
@@ -261,6 +265,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     const bool up = store && (flags & PHB_FLAG_UP_PARTIALS);
     c->d_up = up ? (double*)(w + p.up) : nullptr;
     c->d_up_scale = up ? (int32_t*)(w + p.up_scale) : nullptr;
+    c->d_up_rows = up ? (OpRow*)(w + p.up_rows) : nullptr;
     c->d_root_clv = store ? (double*)(w + p.root_clv) : nullptr;
     c->d_root_scale = store ? (int32_t*)(w + p.root_scale) : nullptr;
     c->d_pmats = (double*)(w + p.pmats);
@@ -513,7 +518,8 @@ int phb_compute_partials(phb_ctx* c, int mode) {
     PHB_REQUIRE(c, mode == PHB_MODE_TILE || mode == PHB_MODE_LEVEL, PHB_ERR_INVALID, "phb_compute_partials: bad mode");
     PHB_REQUIRE(c, mode != PHB_MODE_LEVEL || !c->level_offsets.empty(), PHB_ERR_STATE,
                 "phb_compute_partials: level mode needs level offsets in the schedule");
-    st = dna_supported(c) ? dna_compute_partials(c, mode) : generic_compute_partials(c, mode);
+    const RowSet rs{c->d_rows, c->n_rows(), &c->level_offsets};
+    st = dna_supported(c) ? dna_run_rows(c, rs, mode) : generic_run_rows(c, rs, mode);
     if (st) return st;
     c->have_partials = true;
     c->have_up = false;
@@ -662,14 +668,17 @@ int phb_get_root_partials(phb_ctx* c, double* out_partials, double* out_scalers)
     return PHB_OK;
 }
 
-int phb_compute_up_partials(phb_ctx* c) {
+int phb_compute_up_partials(phb_ctx* c, int node_a, int node_b, double length) {
     if (!c) return PHB_ERR_INVALID;
     int st = activate(c);
     if (st) return st;
     PHB_REQUIRE(c, c->d_up != nullptr, PHB_ERR_STATE, "phb_compute_up_partials: context lacks PHB_FLAG_UP_PARTIALS");
     PHB_REQUIRE(c, c->have_partials, PHB_ERR_STATE, "phb_compute_up_partials: run phb_compute_partials first");
     PHB_REQUIRE(c, c->have_model, PHB_ERR_STATE, "phb_compute_up_partials: needs the eigen-system (reversible model)");
-    st = launch_up_partials(c);
+    PHB_REQUIRE(c, c->have_pmats, PHB_ERR_STATE, "phb_compute_up_partials: transition matrices not built");
+    st = prepare_root(c, node_a, node_b, length, nullptr);   // builds P(length) for the root edge
+    if (st) return st;
+    st = launch_up_partials(c, node_a, node_b);
     if (st) return st;
     c->have_up = true;
     return PHB_OK;

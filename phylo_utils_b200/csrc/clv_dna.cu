@@ -225,10 +225,10 @@ __global__ void __launch_bounds__(kThreads) dna_prune_kernel(const DnaArgs p) {
 }
 
 template <int K, int U, bool LEVEL>
-int launch_prune(Ctx* c, int row_begin, int row_end) {
+int launch_prune(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     constexpr int TS = (kThreads / K) * U;
     DnaArgs a;
-    a.rows = c->d_rows;
+    a.rows = d_rows;
     a.row_begin = row_begin;
     a.row_end = row_end;
     a.pmats = c->d_pmats;
@@ -260,31 +260,32 @@ int launch_prune(Ctx* c, int row_begin, int row_end) {
 
 // pick the unroll (tile size) so that there are enough tiles to occupy the chip
 template <int K, bool LEVEL>
-int launch_prune_u(Ctx* c, int row_begin, int row_end, int64_t parallel_rows) {
+int launch_prune_u(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, int64_t parallel_rows) {
     const int64_t want = (int64_t)c->sm_count * 4;
     const int spi = kThreads / K;
     auto tiles = [&](int u) { return ((c->S + (int64_t)spi * u - 1) / ((int64_t)spi * u)) * parallel_rows; };
-    if (tiles(8) >= want) return launch_prune<K, 8, LEVEL>(c, row_begin, row_end);
-    if (tiles(4) >= want) return launch_prune<K, 4, LEVEL>(c, row_begin, row_end);
-    if (tiles(2) >= want) return launch_prune<K, 2, LEVEL>(c, row_begin, row_end);
-    return launch_prune<K, 1, LEVEL>(c, row_begin, row_end);
+    if (tiles(8) >= want) return launch_prune<K, 8, LEVEL>(c, d_rows, row_begin, row_end);
+    if (tiles(4) >= want) return launch_prune<K, 4, LEVEL>(c, d_rows, row_begin, row_end);
+    if (tiles(2) >= want) return launch_prune<K, 2, LEVEL>(c, d_rows, row_begin, row_end);
+    return launch_prune<K, 1, LEVEL>(c, d_rows, row_begin, row_end);
 }
 
 template <int K>
-int compute_partials_k(Ctx* c, int mode) {
-    const int n = c->n_rows();
+int run_rows_k(Ctx* c, const RowSet& rs, int mode) {
+    const int n = rs.n_rows;
     if (n == 0) return PHB_OK;
     if (mode == PHB_MODE_LEVEL) {
-        const int n_levels = (int)c->level_offsets.size() - 1;
+        const std::vector<int32_t>& lv = *rs.levels;
+        const int n_levels = (int)lv.size() - 1;
         for (int l = 0; l < n_levels; ++l) {
-            const int b = c->level_offsets[l], e = c->level_offsets[l + 1];
+            const int b = lv[l], e = lv[l + 1];
             if (e <= b) continue;
-            int st = launch_prune_u<K, true>(c, b, e, e - b);
+            int st = launch_prune_u<K, true>(c, rs.d_rows, b, e, e - b);
             if (st != PHB_OK) return st;
         }
         return PHB_OK;
     }
-    return launch_prune_u<K, false>(c, 0, n, 1);
+    return launch_prune_u<K, false>(c, rs.d_rows, 0, n, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -428,12 +429,12 @@ int root_k(Ctx* c, int a, int b, bool want_cat, bool store_root) {
 
 bool dna_supported(const Ctx* c) { return c->A == 4 && (c->K == 1 || c->K == 2 || c->K == 4 || c->K == 8); }
 
-int dna_compute_partials(Ctx* c, int mode) {
+int dna_run_rows(Ctx* c, const RowSet& rs, int mode) {
     switch (c->K) {
-        case 1: return compute_partials_k<1>(c, mode);
-        case 2: return compute_partials_k<2>(c, mode);
-        case 4: return compute_partials_k<4>(c, mode);
-        case 8: return compute_partials_k<8>(c, mode);
+        case 1: return run_rows_k<1>(c, rs, mode);
+        case 2: return run_rows_k<2>(c, rs, mode);
+        case 4: return run_rows_k<4>(c, rs, mode);
+        case 8: return run_rows_k<8>(c, rs, mode);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "dna kernels need K in {1,2,4,8}");
 }

@@ -288,12 +288,12 @@ int tile_sites_for(const Ctx* c, size_t* smem_out, int* ld_out) {
 }
 
 template <bool LEVEL>
-int launch_generic(Ctx* c, int row_begin, int row_end) {
+int launch_generic(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     size_t smem;
     int ld;
     const int ts = tile_sites_for(c, &smem, &ld);
     GenArgs a;
-    a.rows = c->d_rows;
+    a.rows = d_rows;
     a.row_begin = row_begin;
     a.row_end = row_end;
     a.pmats = c->d_pmats;
@@ -323,20 +323,21 @@ int launch_generic(Ctx* c, int row_begin, int row_end) {
 
 }  // namespace
 
-int generic_compute_partials(Ctx* c, int mode) {
-    const int n = c->n_rows();
+int generic_run_rows(Ctx* c, const RowSet& rs, int mode) {
+    const int n = rs.n_rows;
     if (n == 0) return PHB_OK;
     if (mode == PHB_MODE_LEVEL) {
-        const int n_levels = (int)c->level_offsets.size() - 1;
+        const std::vector<int32_t>& lv = *rs.levels;
+        const int n_levels = (int)lv.size() - 1;
         for (int l = 0; l < n_levels; ++l) {
-            const int b = c->level_offsets[l], e = c->level_offsets[l + 1];
+            const int b = lv[l], e = lv[l + 1];
             if (e <= b) continue;
-            int st = launch_generic<true>(c, b, e);
+            int st = launch_generic<true>(c, rs.d_rows, b, e);
             if (st != PHB_OK) return st;
         }
         return PHB_OK;
     }
-    return launch_generic<false>(c, 0, n);
+    return launch_generic<false>(c, rs.d_rows, 0, n);
 }
 
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root) {

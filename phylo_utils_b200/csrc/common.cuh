@@ -72,8 +72,13 @@ struct Ctx {
     double* d_weights = nullptr;       // [S]
     double* d_clv = nullptr;           // [n_internal][S][K][A]
     int32_t* d_scale = nullptr;        // [n_internal][S]
-    double* d_up = nullptr;            // [n_internal][S][K][A] (optional)
-    int32_t* d_up_scale = nullptr;
+    // "up" (pre-order) partials live in the SAME block array as the down partials, right behind them:
+    // block n_internal + node_id.  One array, one kernel family.
+    double* d_up = nullptr;            // = d_clv + n_internal * stride, [n_nodes][S][K][A] (optional)
+    int32_t* d_up_scale = nullptr;     // = d_scale + n_internal * S
+    OpRow* d_up_rows = nullptr;        // [2 * max_rows]
+    std::vector<OpRow> up_rows;
+    std::vector<int32_t> up_levels;
     double* d_root_clv = nullptr;      // [S][K][A]
     int32_t* d_root_scale = nullptr;   // [S]
     double* d_pmats = nullptr;         // [2*max_rows + 2][K][A][A]
@@ -135,15 +140,21 @@ cudaError_t launch_pmatrix_raw(cudaStream_t stream, const double* evecs, const d
                                const double* rates, const double* d_lengths, double* d_out, int A, int K, int n_mats,
                                int order, int chain_rule);
 // clv_dna.cu  (A == 4, K in {1,2,4,8})
+// A set of rows to execute: device array, count and (for PHB_MODE_LEVEL) offsets of independent groups.
+struct RowSet {
+    const OpRow* d_rows;
+    int n_rows;
+    const std::vector<int32_t>* levels;  // may be null / empty in tile mode
+};
 bool dna_supported(const Ctx* c);
-int dna_compute_partials(Ctx* c, int mode);
+int dna_run_rows(Ctx* c, const RowSet& rs, int mode);
 int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 int dna_lnl_resident(Ctx* c, int a, int b);
 // clv_generic.cu (any A <= 64, any K <= 16)
-int generic_compute_partials(Ctx* c, int mode);
+int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 // derivs.cu
-int launch_up_partials(Ctx* c);
+int launch_up_partials(Ctx* c, int node_a, int node_b);
 int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
                             double* out);
 // max over a byte array (in clv_generic.cu); synchronises the stream

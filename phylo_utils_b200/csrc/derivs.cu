@@ -1,13 +1,280 @@
-// Pre-order ("up") partials and per-edge likelihood derivatives.  Filled in after the pruning
-// path is validated on hardware; until then the entry points report PHB_ERR_UNSUPPORTED.
+// Pre-order ("up") partials and per-edge likelihood derivatives.
+//
+// The reference ships only the per-site, single-category primitive
+// (lnl_branch_derivs, /root/reference/phylo_utils/likelihood/numba_likelihood_engine.py:49-57) and a
+// re-rooting sweep table nobody consumes (utils.py:137-188): row [PAR,SIB,GPA,NOD,PAR] = "rebuild PAR's
+// partial from SIB and GPA so that it faces NOD, then optimise edge NOD-PAR".  Here the same quantity -
+// the partial of everything OUTSIDE NOD's subtree, seen from PAR's end of the edge - is computed for
+// all nodes at once in a pre-order pass and kept next to the post-order partials:
+//
+//     up[c] = (P(len(p,sib)) . down[sib]) * (P(len(p,gpa)) . X),    X = up[p], or for a root child p
+//                                                                    the other root child's down partial
+//
+// which is again a `clv` row, so the pass re-uses the pruning kernels (clv_dna.cu / clv_generic.cu) on a
+// second row table whose destinations are blocks n_internal + node of the shared block array.  Valid for
+// reversible models (pulley principle), exactly like the reference's re-rooting.
+//
+// Edge derivatives: for the edge above node c at trial length t, with a = down[c], b = up[c]:
+//     f_k  = sum_i pi_i b_ki (P_k(t) a_k)_i,   f'_k, f''_k with dP/dt, d2P/dt2
+//     L    = sum_k w_k f_k        (the per-pattern exponents of a and b are common to all k and cancel)
+//     lnL  = sum_s wt_s [ log L_s + (e_a + e_b) ln 2 ]
+//     dlnL = sum_s wt_s L'_s / L_s ,   d2lnL = sum_s wt_s [ L''_s / L_s - (L'_s / L_s)^2 ]
+// i.e. lnl_branch_derivs composed over the Gamma mixture.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace phb {
 
-int launch_up_partials(Ctx* c) { return c->fail(PHB_ERR_UNSUPPORTED, "up partials: not built yet"); }
+namespace {
 
-int launch_edge_derivatives(Ctx* c, int, const int32_t*, const double*, int, double*) {
-    return c->fail(PHB_ERR_UNSUPPORTED, "edge derivatives: not built yet");
+struct DerivArgs {
+    const double* mats;     // [3][batch_cap][K][A][A]
+    const uint8_t* codes;
+    const double* lut;
+    const double* clv;      // shared block array (down blocks, then up blocks)
+    const int32_t* scale;
+    const double* freqs;
+    const double* catw;
+    const double* weights;
+    int64_t S;
+    int A, K, batch_cap, n_parts;
+    int src_a[kMaxEdgeBatch], kind_a[kMaxEdgeBatch];
+    int src_b[kMaxEdgeBatch], kind_b[kMaxEdgeBatch];
+    double* partial_sums;   // [n_edges * 3][n_parts]
+};
+
+constexpr int kDerivThreads = 128;
+constexpr int kSitesPerThread = 4;
+
+// grid = (n_parts, n_edges); thread = up to kSitesPerThread patterns; one category's three matrices in smem at a time
+__global__ void __launch_bounds__(kDerivThreads) edge_deriv_kernel(const DerivArgs p) {
+    extern __shared__ double sm[];
+    const int A = p.A, K = p.K, e = blockIdx.y;
+    double* M = sm;                       // [3][A][A]
+    __shared__ double s_red[3][kDerivThreads / 32];
+    const size_t S = (size_t)p.S;
+    const int64_t span = (int64_t)kDerivThreads * kSitesPerThread;
+    double tot[3] = {0.0, 0.0, 0.0};
+    for (int64_t base = (int64_t)blockIdx.x * span; base < p.S; base += (int64_t)gridDim.x * span) {
+        double acc[kSitesPerThread][3];
+        const double* va[kSitesPerThread];
+        const double* vb[kSitesPerThread];
+        int ex[kSitesPerThread];
+#pragma unroll
+        for (int q = 0; q < kSitesPerThread; ++q) {
+            acc[q][0] = acc[q][1] = acc[q][2] = 0.0;
+            const int64_t s = base + (int64_t)q * kDerivThreads + threadIdx.x;
+            const size_t ss = s < p.S ? (size_t)s : 0;
+            ex[q] = 0;
+            if (p.kind_a[e] == SRC_TIP) {
+                va[q] = p.lut + (size_t)p.codes[(size_t)p.src_a[e] * S + ss] * A;
+            } else {
+                va[q] = p.clv + ((size_t)p.src_a[e] * S + ss) * K * A;
+                ex[q] += p.scale[(size_t)p.src_a[e] * S + ss];
+            }
+            if (p.kind_b[e] == SRC_TIP) {
+                vb[q] = p.lut + (size_t)p.codes[(size_t)p.src_b[e] * S + ss] * A;
+            } else {
+                vb[q] = p.clv + ((size_t)p.src_b[e] * S + ss) * K * A;
+                ex[q] += p.scale[(size_t)p.src_b[e] * S + ss];
+            }
+        }
+        for (int k = 0; k < K; ++k) {
+            __syncthreads();
+            for (int d = 0; d < 3; ++d) {
+                const double* src = p.mats + (((size_t)d * p.batch_cap + e) * K + k) * A * A;
+                for (int idx = threadIdx.x; idx < A * A; idx += kDerivThreads) M[d * A * A + idx] = src[idx];
+            }
+            __syncthreads();
+            const double wk = p.catw[k];
+#pragma unroll
+            for (int q = 0; q < kSitesPerThread; ++q) {
+                const double* a = va[q] + (p.kind_a[e] == SRC_TIP ? 0 : (size_t)k * A);
+                const double* b = vb[q] + (p.kind_b[e] == SRC_TIP ? 0 : (size_t)k * A);
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+                for (int i = 0; i < A; ++i) {
+                    double x0 = 0.0, x1 = 0.0, x2 = 0.0;
+                    for (int j = 0; j < A; ++j) {
+                        const double aj = a[j];
+                        x0 = fma(M[i * A + j], aj, x0);
+                        x1 = fma(M[A * A + i * A + j], aj, x1);
+                        x2 = fma(M[2 * A * A + i * A + j], aj, x2);
+                    }
+                    const double pb = p.freqs[i] * b[i];
+                    f0 = fma(pb, x0, f0);
+                    f1 = fma(pb, x1, f1);
+                    f2 = fma(pb, x2, f2);
+                }
+                acc[q][0] = fma(wk, f0, acc[q][0]);
+                acc[q][1] = fma(wk, f1, acc[q][1]);
+                acc[q][2] = fma(wk, f2, acc[q][2]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kSitesPerThread; ++q) {
+            const int64_t s = base + (int64_t)q * kDerivThreads + threadIdx.x;
+            if (s < p.S) {
+                const double w = p.weights ? p.weights[s] : 1.0;
+                const double L = acc[q][0];
+                const double g = acc[q][1] / L;
+                tot[0] += w * (L > 0 ? log(L) + (double)ex[q] * kLn2 : -INFINITY);
+                tot[1] += w * g;
+                tot[2] += w * (acc[q][2] / L - g * g);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double v = warp_sum(tot[d]);
+        if ((threadIdx.x & 31) == 0) s_red[d][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int w = 0; w < kDerivThreads / 32; ++w) t += s_red[threadIdx.x][w];
+        p.partial_sums[((size_t)e * 3 + threadIdx.x) * p.n_parts + blockIdx.x] = t;
+    }
+}
+
+void fill_operand(const Ctx* c, int node, int* src, int* kind) {
+    if (c->node_tip[node] >= 0) {
+        *kind = SRC_TIP;
+        *src = c->node_tip[node];
+    } else {
+        *kind = SRC_GLOBAL;
+        *src = c->node_slot[node];
+    }
+}
+
+}  // namespace
+
+int launch_up_partials(Ctx* c, int node_a, int node_b) {
+    const int n_rows = c->n_rows();
+    c->up_rows.clear();
+    c->up_levels.clear();
+    if (n_rows == 0) return PHB_OK;
+    const int root_p = 2 * c->max_rows() + 1;  // P(root length), built by prepare_root
+    std::vector<int> depth(c->n_nodes, 0), level_of;
+    auto rank = [](int kind) { return kind == SRC_TIP ? 0 : 2; };
+    for (int r = n_rows - 1; r >= 0; --r) {
+        const int par = c->rows_raw[3 * r];
+        const int ch[2] = {c->rows_raw[3 * r + 1], c->rows_raw[3 * r + 2]};
+        // X: what sits "above" par
+        int x_src, x_kind, x_pidx;
+        if (par == node_a || par == node_b) {
+            fill_operand(c, par == node_a ? node_b : node_a, &x_src, &x_kind);
+            x_pidx = root_p;
+            depth[par] = 0;
+        } else {
+            const int q = c->node_parent[par];
+            PHB_REQUIRE(c, q >= 0, PHB_ERR_STATE, "up partials: the given root edge does not match the schedule");
+            const int rq = c->node_row[q];
+            x_src = c->n_internal + par;
+            x_kind = SRC_GLOBAL;
+            x_pidx = 2 * rq + (c->rows_raw[3 * rq + 1] == par ? 0 : 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            const int child = ch[i], sib = ch[1 - i];
+            OpRow row{};
+            row.dst = c->n_internal + child;
+            fill_operand(c, sib, &row.src[0], &row.kind[0]);
+            row.pidx[0] = 2 * r + (1 - i);
+            row.src[1] = x_src;
+            row.kind[1] = x_kind;
+            row.pidx[1] = x_pidx;
+            if (rank(row.kind[0]) > rank(row.kind[1])) {
+                std::swap(row.kind[0], row.kind[1]);
+                std::swap(row.src[0], row.src[1]);
+                std::swap(row.pidx[0], row.pidx[1]);
+            }
+            depth[child] = depth[par] + 1;
+            c->up_rows.push_back(row);
+            level_of.push_back(depth[par]);
+        }
+    }
+    const int n_up = (int)c->up_rows.size();
+    int mode = c->level_offsets.empty() ? PHB_MODE_TILE : PHB_MODE_LEVEL;
+    if (mode == PHB_MODE_LEVEL) {
+        std::vector<int> order(n_up);
+        for (int i = 0; i < n_up; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level_of[x] < level_of[y]; });
+        std::vector<OpRow> sorted(n_up);
+        const int n_levels = level_of[order.back()] + 1;
+        c->up_levels.assign(n_levels + 1, 0);
+        for (int i = 0; i < n_up; ++i) {
+            sorted[i] = c->up_rows[order[i]];
+            c->up_levels[level_of[order[i]] + 1]++;
+        }
+        for (int l = 0; l < n_levels; ++l) c->up_levels[l + 1] += c->up_levels[l];
+        c->up_rows.swap(sorted);
+    }
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_up_rows, c->up_rows.data(), (size_t)n_up * sizeof(OpRow), cudaMemcpyHostToDevice,
+                                c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const RowSet rs{c->d_up_rows, n_up, &c->up_levels};
+    return dna_supported(c) ? dna_run_rows(c, rs, mode) : generic_run_rows(c, rs, mode);
+}
+
+int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
+                            double* out) {
+    const int A = c->A, K = c->K;
+    const size_t blk = (size_t)K * A * A;
+    double* d_len = c->d_lengths + 2 * (size_t)c->max_rows() + 2;
+    for (int start = 0; start < n_edges; start += kMaxEdgeBatch) {
+        const int n = std::min(kMaxEdgeBatch, n_edges - start);
+        DerivArgs p;
+        for (int i = 0; i < n; ++i) {
+            const int node = nodes[start + i];
+            PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "edge derivatives: node id out of range");
+            PHB_REQUIRE(c, lengths[start + i] >= 0, PHB_ERR_INVALID, "edge derivatives: negative branch length");
+            fill_operand(c, node, &p.src_a[i], &p.kind_a[i]);
+            if (node == c->root_a || node == c->root_b) {
+                fill_operand(c, node == c->root_a ? c->root_b : c->root_a, &p.src_b[i], &p.kind_b[i]);
+            } else {
+                PHB_REQUIRE(c, c->node_parent[node] >= 0, PHB_ERR_INVALID, "edge derivatives: node has no edge above it");
+                p.src_b[i] = c->n_internal + node;
+                p.kind_b[i] = SRC_GLOBAL;
+            }
+        }
+        PHB_CUDA(c, cudaMemcpyAsync(d_len, lengths + start, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int order = 0; order < 3; ++order) {
+            int st = launch_build_pmatrices(c, d_len, n, c->d_dmats + (size_t)order * kMaxEdgeBatch * blk, order,
+                                            chain_rule);
+            if (st) return st;
+        }
+        p.mats = c->d_dmats;
+        p.codes = c->d_codes;
+        p.lut = c->d_lut;
+        p.clv = c->d_clv;
+        p.scale = c->d_scale;
+        p.freqs = c->model_freqs();
+        p.catw = c->model_catw();
+        p.weights = c->d_weights;
+        p.S = c->S;
+        p.A = A;
+        p.K = K;
+        p.batch_cap = kMaxEdgeBatch;
+        const int64_t span = (int64_t)kDerivThreads * kSitesPerThread;
+        int64_t parts = (c->S + span - 1) / span;
+        const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(kMaxReduceBlocks * 4 / (3 * n), (int64_t)c->sm_count * 8));
+        if (parts > cap) parts = cap;
+        p.n_parts = (int)parts;
+        p.partial_sums = c->d_partial_sums;
+        const size_t smem = 3 * (size_t)A * A * sizeof(double);
+        PHB_CUDA(c, cudaFuncSetAttribute(edge_deriv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)parts, (unsigned)n);
+        edge_deriv_kernel<<<grid, kDerivThreads, smem, c->stream>>>(p);
+        c->launches++;
+        PHB_CUDA(c, cudaGetLastError());
+        int st = launch_final_reduce(c, c->d_partial_sums, (int)parts, 3 * n, c->d_result);
+        if (st) return st;
+        PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, c->d_result, (size_t)3 * n * 8, cudaMemcpyDeviceToHost,
+                                    c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return PHB_OK;
 }
 
 }  // namespace phb

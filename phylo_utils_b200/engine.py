@@ -205,8 +205,8 @@ class LikelihoodEngine(object):
         return part, scal
 
     # ---- derivatives ------------------------------------------------------------------------
-    def compute_up_partials(self):
-        self._ok(self._lib.phb_compute_up_partials(self._ctx))
+    def compute_up_partials(self, node_a, node_b, length):
+        self._ok(self._lib.phb_compute_up_partials(self._ctx, int(node_a), int(node_b), float(length)))
 
     def edge_derivatives(self, nodes, lengths, chain_rule=True):
         nodes = np.ascontiguousarray(nodes, dtype=np.int32)

@@ -1,0 +1,147 @@
+"""
+Site-pattern sharding across the GPUs of one box (BASELINE north_star subsystem 5).
+
+Patterns are independent through the whole pruning recursion (the reference's `clv` simply broadcasts
+over sites), so each rank owns a contiguous block of patterns - tip codes, partials, scalers and weights
+are sliced on the pattern axis; tree schedule, eigen-system and P matrices are replicated (KBs).  No data
+moves between GPUs inside an evaluation: the only exchange is an all-reduce of the scalar lnL (or of the
+3 x n_edges derivative sums), issued through torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU
+tests).  Per-site output, when asked for, is an all-gather of the per-pattern vector.
+
+One process per GPU; launch with ``python -m torch.distributed.run --nproc-per-node N ...``.
+"""
+import numpy as np
+
+from .tree_model import TreeModel
+
+__all__ = ["shard_bounds", "shard_slices", "allreduce_sum", "allgather_concat", "ShardedTreeModel"]
+
+
+def shard_bounds(n_patterns, rank, world):
+    """Contiguous, balanced block [lo, hi) of the pattern axis owned by ``rank`` (sizes differ by at most one)."""
+    if not 0 <= rank < world:
+        raise ValueError("rank {} outside world of size {}".format(rank, world))
+    base, extra = divmod(int(n_patterns), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_slices(n_patterns, world):
+    return [shard_bounds(n_patterns, r, world) for r in range(world)]
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if dist.is_available() and dist.is_initialized() else None
+
+
+def allreduce_sum(values, device=None):
+    """Sum a small float64 array over all ranks (identity when torch.distributed is not initialised)."""
+    arr = np.atleast_1d(np.asarray(values, dtype=np.double))
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return arr.copy()
+    import torch
+    t = torch.from_numpy(arr.copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def allgather_concat(local, sizes, device=None):
+    """Concatenate per-rank 1-D float64 arrays of known ``sizes`` in rank order."""
+    local = np.ascontiguousarray(local, dtype=np.double)
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return local.copy()
+    import torch
+    width = max(sizes)
+    pad = np.zeros(width)
+    pad[:local.shape[0]] = local
+    mine = torch.from_numpy(pad)
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.empty_like(mine) for _ in sizes]
+    dist.all_gather(parts, mine)
+    return np.concatenate([p.cpu().numpy()[:n] for p, n in zip(parts, sizes)])
+
+
+class ShardedTreeModel(object):
+    """
+    TreeModel whose pattern axis is split over the ranks of the current torch.distributed group.
+    Every rank calls every method (SPMD); scalar results are identical on all ranks.
+    """
+
+    def __init__(self, device=None, up_partials=False, mode="auto"):
+        dist = _dist()
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+        self.local = TreeModel(device=device, up_partials=up_partials, mode=mode)
+        self._torch_device = None
+        self.n_patterns = None
+
+    def _comm_device(self):
+        dist = _dist()
+        if dist is not None and dist.get_backend() == "nccl":
+            import torch
+            return torch.device("cuda", self.device)
+        return None
+
+    # -- inputs: same calls as TreeModel; the alignment is given in full and sliced here ------------------
+    def set_tree(self, tree):
+        self.local.set_tree(tree)
+
+    def set_substitution_model(self, model):
+        self.local.set_substitution_model(model)
+
+    def set_rate_model(self, rate_model):
+        self.local.set_rate_model(rate_model)
+
+    def set_tip_codes(self, codes, lut, names, siteweights=None, inverse_index=None):
+        """``codes`` (ntax, npat) is the FULL compressed alignment; this rank keeps patterns [lo, hi)."""
+        npat = codes.shape[1]
+        self.n_patterns = npat
+        self.sizes = [hi - lo for lo, hi in shard_slices(npat, self.world)]
+        lo, hi = shard_bounds(npat, self.rank, self.world)
+        if hi <= lo:
+            raise ValueError("more ranks than site patterns")
+        self.lo, self.hi = lo, hi
+        self.inverse_index = np.arange(npat) if inverse_index is None else np.asarray(inverse_index)
+        w = None if siteweights is None else np.asarray(siteweights)[lo:hi]
+        self.local.set_tip_codes(np.ascontiguousarray(codes[:, lo:hi]), lut, names, w)
+
+    def set_alignment(self, alignment, alphabet, compress=True):
+        from .alignment.alignment import alignment_to_codes
+        codes, lut, sw, ii, names = alignment_to_codes(alignment, alphabet, compress)
+        self.set_tip_codes(codes, lut, names, sw, ii)
+
+    def initialise(self):
+        self.local.initialise()
+
+    def compute_partials(self):
+        self.local.compute_partials()
+
+    @property
+    def traversal(self):
+        return self.local.traversal
+
+    # -- results ----------------------------------------------------------------------------------------------
+    def lnl(self, node_a=None, node_b=None):
+        return float(allreduce_sum([self.local.lnl(node_a, node_b)], self._comm_device())[0])
+
+    def compute_likelihood_at_edge(self, node_a, node_b):
+        _, pattern = self.local._pattern_lnl(node_a, node_b)
+        full = allgather_concat(pattern, self.sizes, self._comm_device())
+        return full[self.inverse_index]
+
+    def compute_up_partials(self):
+        self.local.compute_up_partials()
+
+    def edge_derivatives(self, nodes, lengths=None, chain_rule=True):
+        part = self.local.edge_derivatives(nodes, lengths, chain_rule)
+        return allreduce_sum(part.ravel(), self._comm_device()).reshape(part.shape)

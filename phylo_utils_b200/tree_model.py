@@ -315,7 +315,9 @@ class TreeModel(object):
     # derivatives (composition of lnl_branch_derivs over the Gamma mixture)
     # ------------------------------------------------------------------------------------------
     def compute_up_partials(self):
-        self.engine.compute_up_partials()
+        """Pre-order pass: partial of everything outside each node's subtree (needs ``up_partials=True``)."""
+        a, b = self.traversal.root_edge
+        self.engine.compute_up_partials(a, b, self.traversal.brlens[(a, b)])
 
     def edge_derivatives(self, nodes, lengths=None, chain_rule=True):
         """

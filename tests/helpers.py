@@ -73,3 +73,59 @@ def assert_lnl_close(got, want, rtol=RTOL, what="lnL"):
         assert err.max() <= rtol, "{}: max relative error {:.3e} > {:.1e}".format(what, err.max(), rtol)
     if (~finite).any():
         assert np.array_equal(got[~finite], want[~finite]) or np.all(np.isnan(want[~finite]) == np.isnan(got[~finite]))
+
+
+# ---- derivative oracle by composition (SURVEY.md 8(c) "not in the reference at all") ---------------------------
+def oracle_up_partials(tr, ot, model, rates):
+    """
+    Pre-order partials composed from the oracle's clv: up[c] = clv(P(p,sib), P(p,gpa), down[sib], X)
+    following the reference's re-rooting rows [PAR,SIB,GPA,NOD,PAR] (utils.py:169).  Returns
+    {node: (partials (S,K,A), scale (S,K))}.
+    """
+    from oracle import oracle
+    a, b = tr.root_edge
+    up = {}
+    for par, c1, c2 in tr.postorder_traversal[::-1]:
+        par, c1, c2 = int(par), int(c1), int(c2)
+        if par in (a, b):
+            other = b if par == a else a
+            x_part, x_scale, x_len = ot.partials[other], ot.scale[other], tr.brlens[(a, b)]
+        else:
+            gpa = [int(r[0]) for r in tr.postorder_traversal if par in (int(r[1]), int(r[2]))][0]
+            x_part, x_scale = up[par]
+            x_len = tr.brlens[(par, gpa)]
+        for child, sib in ((c1, c2), (c2, c1)):
+            sc = np.zeros_like(ot.scale[0])
+            part = oracle.clv(model.p(tr.brlens[(par, sib)], rates), model.p(x_len, rates), ot.partials[sib], x_part,
+                              ot.scale[sib], x_scale, sc)
+            up[child] = (part, sc)
+    return up
+
+
+def oracle_edge_derivatives(tr, ot, up, model, rate, node, t, siteweights, chain_rule=True):
+    """(lnL, dlnL/dt, d2lnL/dt2) for the edge above ``node`` from per-category lnl_branch_derivs outputs."""
+    from oracle import oracle
+    from scipy.special import logsumexp
+    a, b = tr.root_edge
+    if node in (a, b):
+        other = b if node == a else a
+        pb, sb = ot.partials[other], ot.scale[other]
+    else:
+        pb, sb = up[node]
+    pa, sa = ot.partials[node], ot.scale[node]
+    S, K = sa.shape
+    lnf = np.empty((S, K))
+    g1 = np.empty((S, K))
+    g2 = np.empty((S, K))
+    for k, r in enumerate(rate.rates):
+        c1, c2 = (r, r * r) if chain_rule else (1.0, 1.0)
+        probs = np.stack([model.p(t * r), model.dp_dt(t * r) * c1, model.d2p_dt2(t * r) * c2])
+        d = oracle.lnl_branch_derivs(probs, model.freqs, pa[:, k], pb[:, k], sa[:, k], sb[:, k])
+        lnf[:, k], g1[:, k], g2[:, k] = d[:, 0], d[:, 1], d[:, 2]
+    logw = np.log(rate.weights)
+    lnL = logsumexp(lnf + logw, axis=1)
+    post = np.exp(lnf + logw - lnL[:, None])              # w_k f_k / L
+    d1 = (post * g1).sum(axis=1)                           # L'/L
+    d2 = (post * (g2 + g1 * g1)).sum(axis=1) - d1 * d1     # L''/L - (L'/L)^2
+    w = np.asarray(siteweights, dtype=float)
+    return np.array([np.dot(w, lnL), np.dot(w, d1), np.dot(w, d2)])

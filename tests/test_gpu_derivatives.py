@@ -1,0 +1,118 @@
+"""
+Edge derivatives and the pre-order pass (BASELINE configs 3 and 5).  The reference only ships the
+single-category primitive lnl_branch_derivs; the oracle here is its composition over the Gamma mixture
+(helpers.oracle_edge_derivatives), cross-checked by finite differences of the oracle lnL.
+"""
+import numpy as np
+import pytest
+
+import phylo_utils_b200 as phy
+from phylo_utils_b200.tree import random_tree, caterpillar_tree
+from helpers import (problem, records, tree, tip_partials, oracle_up_partials, oracle_edge_derivatives, assert_lnl_close)
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def setup_case(name, mode):
+    g, tr, codes, lut, sw, ii, names, model, rate = problem(name)
+    tm = phy.TreeModel(mode=mode, up_partials=True)
+    tm.set_tree(tree(g))
+    tm.set_alignment(records(g), int(g["alphabet"]))
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    tm.compute_up_partials()
+    _, ot = oracle.tree_lnl(tr, tip_partials(tr, codes, lut, names), model.p, model.freqs, rate.rates, rate.weights,
+                            return_tree=True)
+    up = oracle_up_partials(tr, ot, model, rate.rates)
+    return tm, tr, ot, up, model, rate, sw
+
+
+@pytest.mark.parametrize("mode", ["level", "tile"])
+@pytest.mark.parametrize("name", ["cfg1_gtr_g4", "ambig_hky_ig", "prot12_lg_g4", "ladder120_k80_g4"])
+def test_all_edges_match_the_composed_oracle(name, mode):
+    tm, tr, ot, up, model, rate, sw = setup_case(name, mode)
+    nodes = [n for n in range(2 * len(tr.names) - 2) if n != tr.root_edge[1]]
+    if len(nodes) > 40:
+        nodes = nodes[::7] + list(tr.root_edge[:1])
+    lengths = np.array([tm.branch_length_above(n) for n in nodes])
+    got = tm.edge_derivatives(nodes, lengths)
+    base = tm.lnl()
+    for (node, t), row in zip(zip(nodes, lengths), got):
+        want = oracle_edge_derivatives(tr, ot, up, model, rate, node, t, sw)
+        assert abs(row[0] - want[0]) <= 1e-10 * abs(want[0]), (node, row, want)
+        assert abs(row[1] - want[1]) <= 1e-8 * max(1.0, abs(want[1])), (node, row, want)
+        assert abs(row[2] - want[2]) <= 1e-8 * max(1.0, abs(want[2])), (node, row, want)
+        # the likelihood is the same whichever edge it is evaluated on (pulley principle)
+        assert abs(row[0] - base) <= 1e-10 * abs(base)
+
+
+def test_derivatives_agree_with_finite_differences_of_the_oracle_lnl():
+    g, tr, codes, lut, sw, ii, names, model, rate = problem("cfg1_gtr_g4")
+    tm, tr, ot, up, model, rate, sw = setup_case("cfg1_gtr_g4", "tile")
+    tips = tip_partials(tr, codes, lut, names)
+    key = sorted(tr.brlens.keys())[5]
+    node = key[0] if tm.traversal.is_leaf(key[0]) or key[0] < key[1] else key[1]
+    # node must be the child end of the edge
+    rows = tr.postorder_traversal
+    child = [c for par, c1, c2 in rows for c in (int(c1), int(c2)) if {int(par), c} == set(key)]
+    node = child[0] if child else tr.root_edge[0]
+    t0 = tr.brlens[key]
+    h = 1e-4
+
+    def lnl_at(t):
+        tr.brlens[tr.brlens.canonical_key(key)] = t
+        pat = oracle.tree_lnl(tr, tips, model.p, model.freqs, rate.rates, rate.weights)
+        return float(np.dot(pat, sw))
+    f_plus, f_0, f_minus = lnl_at(t0 + h), lnl_at(t0), lnl_at(t0 - h)
+    tr.brlens[tr.brlens.canonical_key(key)] = t0
+    got = tm.edge_derivatives([node], [t0])[0]
+    assert abs(got[0] - f_0) <= 1e-10 * abs(f_0)
+    assert abs(got[1] - (f_plus - f_minus) / (2 * h)) < 1e-4 * max(1.0, abs(got[1]))
+    assert abs(got[2] - (f_plus - 2 * f_0 + f_minus) / (h * h)) < 1e-2 * max(1.0, abs(got[2]))
+
+
+def test_trial_lengths_and_reference_convention_flag():
+    tm, tr, ot, up, model, rate, sw = setup_case("cfg1_gtr_g4", "level")
+    node = int(tr.postorder_traversal[0][1])
+    for t in (0.01, 0.2, 1.5):
+        for chain in (True, False):
+            got = tm.edge_derivatives([node], [t], chain_rule=chain)[0]
+            want = oracle_edge_derivatives(tr, ot, up, model, rate, node, t, sw, chain_rule=chain)
+            assert np.allclose(got, want, rtol=1e-8, atol=1e-8)
+
+
+def test_up_partials_larger_tree_vs_oracle_total():
+    rng = np.random.default_rng(12)
+    n_taxa, n_pat = 80, 20000
+    tr_tree = random_tree(n_taxa, 12)
+    names = [l.taxon.label for l in tr_tree.leaf_node_iter()]
+    lut = np.vstack([np.eye(4)[::-1], np.ones((1, 4))])
+    codes = rng.integers(0, 5, size=(n_taxa, n_pat)).astype(np.uint8)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(mode="tile", up_partials=True)
+    tm.set_tree(tr_tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    tm.compute_up_partials()
+    base = tm.lnl()
+    nodes = np.arange(2 * n_taxa - 2)
+    out = tm.edge_derivatives(nodes)
+    assert np.all(np.abs(out[:, 0] - base) <= 1e-10 * abs(base))          # every edge reproduces the same lnL
+    assert np.all(np.isfinite(out))
+
+
+def test_derivatives_need_the_up_pass():
+    g, tr, codes, lut, sw, ii, names, model, rate = problem("cfg1_gtr_g4")
+    tm = phy.TreeModel()
+    tm.set_tree(tree(g))
+    tm.set_alignment(records(g), 0)
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    with pytest.raises(RuntimeError):
+        tm.compute_up_partials()                   # context built without up_partials=True
