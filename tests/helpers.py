@@ -122,6 +122,12 @@ def oracle_edge_derivatives(tr, ot, up, model, rate, node, t, siteweights, chain
         probs = np.stack([model.p(t * r), model.dp_dt(t * r) * c1, model.d2p_dt2(t * r) * c2])
         d = oracle.lnl_branch_derivs(probs, model.freqs, pa[:, k], pb[:, k], sa[:, k], sb[:, k])
         lnf[:, k], g1[:, k], g2[:, k] = d[:, 0], d[:, 1], d[:, 2]
+    # a rate-0 (invariant) category has f_k = 0 at variable patterns: log f = -inf, the ratios are 0/0.
+    # Its f'_k and f''_k vanish too (dP/dt carries the factor r_k = 0), so it contributes nothing.
+    dead = ~np.isfinite(lnf)
+    lnf = np.where(dead, -np.inf, lnf)
+    g1 = np.where(dead | ~np.isfinite(g1), 0.0, g1)
+    g2 = np.where(dead | ~np.isfinite(g2), 0.0, g2)
     logw = np.log(rate.weights)
     lnL = logsumexp(lnf + logw, axis=1)
     post = np.exp(lnf + logw - lnL[:, None])              # w_k f_k / L

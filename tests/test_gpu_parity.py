@@ -203,6 +203,9 @@ def test_two_tip_tree_has_no_internal_nodes():
     tm.set_substitution_model(k80)
     tm.initialise()
     site = tm.compute_likelihood_at_edge(*tm.traversal.root_edge)
-    p = k80.p(0.3)
+    # a two-leaf tree is left alone by deroot(), so the reference's root-edge rule (utils.py:205-207) takes
+    # the LARGER of the two root branches, not their sum
+    assert tm.traversal.brlens[tm.traversal.root_edge] == 0.2
+    p = k80.p(0.2)
     want = np.log(0.25 * np.array([p[0, 0], p[1, 1], p[2, 2], p[3, 3], p[0, 3], p[1, 3]]))
     assert_lnl_close(site, want, rtol=1e-12)
