@@ -55,7 +55,11 @@ def parse_args():
     ap.add_argument("--patterns", type=int, default=1000000, help="site patterns per GPU")
     ap.add_argument("--cpu-patterns", type=int, default=20000, help="pattern sample for the CPU baseline")
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--mode", choices=["auto", "tile", "level"], default="auto")
+    ap.add_argument("--mode", choices=["auto", "tile", "level", "resident"], default="auto",
+                    help="how the rows are walked when per-node partials are stored")
+    ap.add_argument("--lnl-only", action="store_true",
+                    help="evaluate with the operand-resident kernel without storing per-node partials")
+    ap.add_argument("--resident-u", type=int, default=0, help="tuning: force the resident kernel's tile multiplier")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -286,14 +290,16 @@ def main():
     tip_nodes = np.asarray([trav.names[n] for n in names], dtype=np.int32)
 
     mode = {"auto": _lib.PHB_MODE_TILE if n_pat >= 16384 else _lib.PHB_MODE_LEVEL, "tile": _lib.PHB_MODE_TILE,
-            "level": _lib.PHB_MODE_LEVEL}[args.mode]
-    eng = phy.LikelihoodEngine(n_taxa, n_pat, NCAT, 4, device=local_rank)
+            "level": _lib.PHB_MODE_LEVEL, "resident": _lib.PHB_MODE_RESIDENT}[args.mode]
+    eng = phy.LikelihoodEngine(n_taxa, n_pat, NCAT, 4, device=local_rank, store_partials=not args.lnl_only)
     if mode == _lib.PHB_MODE_LEVEL:
         rows, offsets = trav.level_order()
         eng.set_schedule(rows, offsets)
     else:
         rows = trav.locality_order()
         eng.set_schedule(rows)
+    if args.resident_u:
+        os.environ["PHB_RESIDENT_U"] = str(args.resident_u)
     e = model.eigen
     eng.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), model.freqs, rate.rates, rate.weights)
     lengths = np.asarray([[trav.brlens[(int(p), int(c1))], trav.brlens[(int(p), int(c2))]] for p, c1, c2 in rows])
@@ -305,6 +311,8 @@ def main():
 
     def eval_resident():
         eng.set_edge_lengths(lengths)
+        if args.lnl_only:
+            return eng.lnl_resident(a, b, root_len)[0]
         eng.build_pmatrices()
         eng.compute_partials(mode)
         return eng.root_lnl(a, b, root_len)[0]
@@ -352,22 +360,31 @@ def main():
 
     # dominant kernel alone (pruning), CUDA events on the launching stream
     eng.set_edge_lengths(lengths)
-    eng.build_pmatrices()
+    if not args.lnl_only:
+        eng.build_pmatrices()
     torch.cuda.synchronize(dev)
     k_start, k_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k_start.record()
     for _ in range(args.steps):
-        eng.compute_partials(mode)
+        if args.lnl_only:
+            eng.lnl_resident(a, b, root_len)        # P build (tiny) + the resident kernel + reduction
+        else:
+            eng.compute_partials(mode)
     k_stop.record()
     torch.cuda.synchronize(dev)
     kernel_ms = k_start.elapsed_time(k_stop) / args.steps
     prune_bytes, eval_bytes = algorithmic_bytes(n_taxa, n_pat)
     peak, peak_src = measured_peak()
     achieved = prune_bytes / (kernel_ms * 1e-3) / 1e9
-    workload_key = "dna_prune_{}x{}".format(n_taxa, n_pat)
+    if args.lnl_only:
+        kernel_name = "dna_resident_kernel<K=4,STORE=0,ROOT=1> (operands on chip, no partials stored)"
+    else:
+        kernel_name = {_lib.PHB_MODE_TILE: "dna_prune_kernel<K=4> (tile mode)",
+                       _lib.PHB_MODE_LEVEL: "dna_prune_kernel<K=4> (level mode)",
+                       _lib.PHB_MODE_RESIDENT: "dna_resident_kernel<K=4,STORE=1> (operands on chip, blocks streamed out)"}[mode]
+    workload_key = "{}_{}x{}".format("lnl_only" if args.lnl_only else args.mode, n_taxa, n_pat)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(workload_key), "kernel": "dna_prune_kernel<K=4> ({} mode)".format(
-                    "tile" if mode == _lib.PHB_MODE_TILE else "level"),
+                "traffic": ncu_traffic(workload_key), "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": prune_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_per_step}
 

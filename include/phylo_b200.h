@@ -56,6 +56,7 @@ enum phb_status {
 #define PHB_MODE_AUTO 0
 #define PHB_MODE_TILE 1  /* one launch: every CTA owns a pattern tile and walks the whole schedule */
 #define PHB_MODE_LEVEL 2 /* one launch per tree level (all rows of a level are independent)        */
+#define PHB_MODE_RESIDENT 3 /* 4-state only: one launch, operands stay on chip, blocks streamed out   */
 
 typedef struct phb_ctx phb_ctx;
 
@@ -90,7 +91,7 @@ int phb_sync(phb_ctx* ctx);
  * (tree_model.py:142-148).  codes[n_tips][n_patterns] indexes lut[n_codes][n_states]
  * (rows are usually 0/1 state sets but any non-negative doubles are allowed).
  * tip_nodes[n_tips] gives the node id of each codes row (Traversal.names ∘ TreeModel.names).
- * `codes_on_device` != 0: codes is already a device pointer (no copy is made; caller keeps it alive). */
+ * `codes_on_device` != 0: codes is a device pointer (copied device-to-device into the pitched workspace buffer). */
 int phb_set_tips(phb_ctx* ctx, const uint8_t* codes, int codes_on_device, int n_codes, const double* lut,
                  const int32_t* tip_nodes);
 /* pattern multiplicities (alignment.py:48-51 `siteweights`); NULL = all ones */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libphylo_b200.so")
 PHB_OK, PHB_ERR_INVALID, PHB_ERR_CUDA, PHB_ERR_NO_DEVICE, PHB_ERR_STATE, PHB_ERR_NOMEM, PHB_ERR_UNSUPPORTED = range(7)
 PHB_FLAG_UP_PARTIALS = 0x1
 PHB_FLAG_NO_PARTIALS = 0x2
-PHB_MODE_AUTO, PHB_MODE_TILE, PHB_MODE_LEVEL = 0, 1, 2
+PHB_MODE_AUTO, PHB_MODE_TILE, PHB_MODE_LEVEL, PHB_MODE_RESIDENT = 0, 1, 2, 3
 
 _dp = POINTER(c_double)
 _ip = POINTER(c_int32)

@@ -19,9 +19,11 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows,
         pattern_lnl, cat_lnl, partial, result, total;
 };
+
+inline size_t code_pitch_for(int64_t S) { return ((size_t)S + 127) / 128 * 128; }
 
 Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     Plan p;
@@ -36,7 +38,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     const bool store = !(flags & PHB_FLAG_NO_PARTIALS);
     const bool up = store && (flags & PHB_FLAG_UP_PARTIALS);
     const size_t node_doubles = (size_t)S * K * A;
-    p.codes = take((size_t)n_tips * S);
+    p.codes = take((size_t)n_tips * code_pitch_for(S));
     p.lut = take(256 * (size_t)A * 8);
     p.weights = take((size_t)S * 8);
     // down partials [n_int blocks] immediately followed by up partials [n_nodes blocks] (if requested)
@@ -54,6 +56,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
     p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
     p.rows = take(max_rows * sizeof(OpRow));
+    p.res_rows = take((max_rows + 1) * 16);
     p.pattern_lnl = take((size_t)S * 8);
     p.cat_lnl = take((size_t)S * K * 8);
     p.partial = take((size_t)kMaxReduceBlocks * 4 * 8);
@@ -257,6 +260,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     uint8_t* w = c->ws;
     c->d_codes_ws = w + p.codes;
     c->d_codes = c->d_codes_ws;
+    c->code_pitch = code_pitch_for(n_patterns);
     c->d_lut = (double*)(w + p.lut);
     c->d_weights = nullptr;  // all ones until phb_set_pattern_weights
     const bool store = !(flags & PHB_FLAG_NO_PARTIALS);
@@ -273,6 +277,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->d_model = (double*)(w + p.model);
     c->d_lengths = (double*)(w + p.lengths);
     c->d_rows = (OpRow*)(w + p.rows);
+    c->d_res_rows = (void*)(w + p.res_rows);
     c->d_pattern_lnl = (double*)(w + p.pattern_lnl);
     c->d_cat_lnl = (double*)(w + p.cat_lnl);
     c->d_partial_sums = (double*)(w + p.partial);
@@ -316,13 +321,13 @@ int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_co
     for (int i = 0; i < n_codes * c->A; ++i)
         PHB_REQUIRE(c, lut[i] >= 0.0 && std::isfinite(lut[i]), PHB_ERR_INVALID,
                     "phb_set_tips: look-up table entries must be finite and non-negative");
-    const size_t n_code_bytes = (size_t)c->n_tips * c->S;
-    if (!codes_on_device) {
-        PHB_CUDA(c, cudaMemcpyAsync(c->d_codes_ws, codes, n_code_bytes, cudaMemcpyHostToDevice, c->stream));
-        c->d_codes = c->d_codes_ws;
-    } else {
-        c->d_codes = codes;
-    }
+    // host or device source, always copied into the pitched workspace buffer (padding stays zero)
+    const size_t n_code_bytes = (size_t)c->n_tips * c->code_pitch;
+    if (c->code_pitch != (size_t)c->S && !c->have_tips)
+        PHB_CUDA(c, cudaMemsetAsync(c->d_codes_ws, 0, n_code_bytes, c->stream));
+    PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws, c->code_pitch, codes, (size_t)c->S, (size_t)c->S, (size_t)c->n_tips,
+                                  codes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    c->d_codes = c->d_codes_ws;
     // The look-up table always has 256 rows on the device (unused rows are zero), so a stray code can
     // never index out of bounds; it is still an input error, detected on the device in one pass.
     {
@@ -515,7 +520,17 @@ int phb_compute_partials(phb_ctx* c, int mode) {
         return PHB_OK;
     }
     if (mode == PHB_MODE_AUTO) mode = c->level_offsets.empty() ? PHB_MODE_TILE : PHB_MODE_LEVEL;
-    PHB_REQUIRE(c, mode == PHB_MODE_TILE || mode == PHB_MODE_LEVEL, PHB_ERR_INVALID, "phb_compute_partials: bad mode");
+    PHB_REQUIRE(c, mode == PHB_MODE_TILE || mode == PHB_MODE_LEVEL || mode == PHB_MODE_RESIDENT, PHB_ERR_INVALID,
+                "phb_compute_partials: bad mode");
+    if (mode == PHB_MODE_RESIDENT) {
+        PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED,
+                    "phb_compute_partials: resident mode covers 4-state models with K in {1,2,4,8}");
+        st = dna_resident(c, -1, -1, true, false);
+        if (st) return st;
+        c->have_partials = true;
+        c->have_up = false;
+        return PHB_OK;
+    }
     PHB_REQUIRE(c, mode != PHB_MODE_LEVEL || !c->level_offsets.empty(), PHB_ERR_STATE,
                 "phb_compute_partials: level mode needs level offsets in the schedule");
     const RowSet rs{c->d_rows, c->n_rows(), &c->level_offsets};
@@ -594,7 +609,7 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
     c->have_pmats = true;
     st = prepare_root(c, node_a, node_b, length, nullptr);
     if (st) return st;
-    st = dna_lnl_resident(c, node_a, node_b);
+    st = dna_resident(c, node_a, node_b, false, true);
     if (st) return st;
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)
@@ -614,7 +629,7 @@ int phb_get_partials(phb_ctx* c, int node, double* out) {
         PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_get_partials: no tip data");
         std::vector<uint8_t> codes(S);
         std::vector<double> lut(256 * A);
-        PHB_CUDA(c, cudaMemcpyAsync(codes.data(), c->d_codes + (size_t)c->node_tip[node] * S, S, cudaMemcpyDeviceToHost,
+        PHB_CUDA(c, cudaMemcpyAsync(codes.data(), c->d_codes + (size_t)c->node_tip[node] * c->code_pitch, S, cudaMemcpyDeviceToHost,
                                     c->stream));
         PHB_CUDA(c, cudaMemcpyAsync(lut.data(), c->d_lut, lut.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         PHB_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -38,7 +38,8 @@ struct DnaArgs {
     const OpRow* rows;
     int row_begin, row_end;
     const double* pmats;    // [pidx][K][16]
-    const uint8_t* codes;   // [tip][S]
+    const uint8_t* codes;   // [tip][pitch]
+    size_t pitch;
     const double* lut;      // [256][4]
     double* clv;            // [slot][S][K][4]
     int32_t* scale;         // [slot][S]
@@ -103,8 +104,8 @@ __device__ __forceinline__ void process_row(const DnaArgs& p, const OpRow& row, 
     const double* gb = (KB == SRC_GLOBAL) ? p.clv + (size_t)row.src[1] * S * (K * 4) : nullptr;
     const int32_t* ea_ptr = (KA == SRC_GLOBAL) ? p.scale + (size_t)row.src[0] * S : nullptr;
     const int32_t* eb_ptr = (KB == SRC_GLOBAL) ? p.scale + (size_t)row.src[1] * S : nullptr;
-    const uint8_t* ta = (KA == SRC_TIP) ? p.codes + (size_t)row.src[0] * S : nullptr;
-    const uint8_t* tb = (KB == SRC_TIP) ? p.codes + (size_t)row.src[1] * S : nullptr;
+    const uint8_t* ta = (KA == SRC_TIP) ? p.codes + (size_t)row.src[0] * p.pitch : nullptr;
+    const uint8_t* tb = (KB == SRC_TIP) ? p.codes + (size_t)row.src[1] * p.pitch : nullptr;
     double* out = p.clv + (size_t)row.dst * S * (K * 4);
     int32_t* out_e = p.scale + (size_t)row.dst * S;
 
@@ -233,6 +234,7 @@ int launch_prune(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     a.row_end = row_end;
     a.pmats = c->d_pmats;
     a.codes = c->d_codes;
+    a.pitch = c->code_pitch;
     a.lut = c->d_lut;
     a.clv = c->d_clv;
     a.scale = c->d_scale;
@@ -295,6 +297,7 @@ int run_rows_k(Ctx* c, const RowSet& rs, int mode) {
 struct DnaRootArgs {
     const double* pmats;  // [2][K][16]: P for child a, P for child b
     const uint8_t* codes;
+    size_t pitch;
     const double* lut;
     const double* clv;
     const int32_t* scale;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(kThreads) dna_root_kernel(const DnaRootArgs p)
         double a[4], b[4];
         int ea = 0, eb = 0;
         if (p.kind[0] == SRC_TIP) {
-            const int code = p.codes[(size_t)p.src[0] * S + ss];
+            const int code = p.codes[(size_t)p.src[0] * p.pitch + ss];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = s_lut[code][i];
         } else {
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(kThreads) dna_root_kernel(const DnaRootArgs p)
             ea = p.scale[(size_t)p.src[0] * S + ss];
         }
         if (p.kind[1] == SRC_TIP) {
-            const int code = p.codes[(size_t)p.src[1] * S + ss];
+            const int code = p.codes[(size_t)p.src[1] * p.pitch + ss];
 #pragma unroll
             for (int i = 0; i < 4; ++i) b[i] = s_lut[code][i];
         } else {
@@ -392,6 +395,7 @@ int root_k(Ctx* c, int a, int b, bool want_cat, bool store_root) {
     DnaRootArgs p;
     p.pmats = c->d_pmats + (size_t)(2 * c->max_rows()) * c->K * 16;
     p.codes = c->d_codes;
+    p.pitch = c->code_pitch;
     p.lut = c->d_lut;
     p.clv = c->d_clv;
     p.scale = c->d_scale;
@@ -447,12 +451,6 @@ int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root) {
         case 8: return root_k<8>(c, a, b, want_cat, store_root);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "dna kernels need K in {1,2,4,8}");
-}
-
-int dna_lnl_resident(Ctx* c, int a, int b) {
-    (void)a;
-    (void)b;
-    return c->fail(PHB_ERR_UNSUPPORTED, "resident lnL kernel not built yet");
 }
 
 }  // namespace phb

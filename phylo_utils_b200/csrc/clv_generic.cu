@@ -26,6 +26,7 @@ struct GenArgs {
     int row_begin, row_end;
     const double* pmats;  // [pidx][K][A][A]
     const uint8_t* codes;
+    size_t pitch;
     const double* lut;    // [256][A]
     double* clv;
     int32_t* scale;
@@ -39,7 +40,7 @@ __device__ __forceinline__ void stage_child(const GenArgs& p, int kind, int src,
     const int A = p.A;
     const size_t S = (size_t)p.S;
     if (kind == SRC_TIP) {
-        const uint8_t* codes = p.codes + (size_t)src * S;
+        const uint8_t* codes = p.codes + (size_t)src * p.pitch;
         for (int idx = threadIdx.x; idx < ts * A; idx += blockDim.x) {
             const int sl = idx / A, j = idx - sl * A;
             const int64_t s = site0 + sl;
@@ -136,6 +137,7 @@ __global__ void generic_prune_kernel(const GenArgs p) {
 struct GenRootArgs {
     const double* pmats;  // [2][K][A][A]
     const uint8_t* codes;
+    size_t pitch;
     const double* lut;
     const double* clv;
     const int32_t* scale;
@@ -172,7 +174,7 @@ __global__ void generic_root_kernel(const GenRootArgs p) {
         int e = 0;
         for (int c = 0; c < 2; ++c) {
             if (p.kind[c] == SRC_TIP) {
-                va[c] = p.lut + (size_t)p.codes[(size_t)p.src[c] * S + ss] * A;
+                va[c] = p.lut + (size_t)p.codes[(size_t)p.src[c] * p.pitch + ss] * A;
             } else {
                 va[c] = p.clv + ((size_t)p.src[c] * S + ss) * K * A;
                 e += p.scale[(size_t)p.src[c] * S + ss];
@@ -298,6 +300,7 @@ int launch_generic(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     a.row_end = row_end;
     a.pmats = c->d_pmats;
     a.codes = c->d_codes;
+    a.pitch = c->code_pitch;
     a.lut = c->d_lut;
     a.clv = c->d_clv;
     a.scale = c->d_scale;
@@ -344,6 +347,7 @@ int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root) {
     GenRootArgs p;
     p.pmats = c->d_pmats + (size_t)(2 * c->max_rows()) * c->K * c->A * c->A;
     p.codes = c->d_codes;
+    p.pitch = c->code_pitch;
     p.lut = c->d_lut;
     p.clv = c->d_clv;
     p.scale = c->d_scale;

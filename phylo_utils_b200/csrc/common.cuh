@@ -66,8 +66,11 @@ struct Ctx {
     size_t ws_bytes = 0;
 
     // device views (all inside ws unless noted)
-    const uint8_t* d_codes = nullptr;  // may point outside ws when the caller keeps codes on the device
+    // tip codes, one row per tip with a 128-byte multiple pitch (rows padded with zeros) so that tiles can
+    // be fetched with aligned 16-byte asynchronous copies and may over-read up to the pitch
+    const uint8_t* d_codes = nullptr;
     uint8_t* d_codes_ws = nullptr;
+    size_t code_pitch = 0;
     double* d_lut = nullptr;           // [256][A]
     double* d_weights = nullptr;       // [S]
     double* d_clv = nullptr;           // [n_internal][S][K][A]
@@ -86,6 +89,9 @@ struct Ctx {
     double* d_model = nullptr;         // evecs | evals | ivecs | freqs | rates | catw
     double* d_lengths = nullptr;       // [2*max_rows + 2]
     OpRow* d_rows = nullptr;           // [max_rows]
+    void* d_res_rows = nullptr;        // [max_rows + 1] 16-byte descriptors of the resident kernel
+    int resident_u = 0;                // 0 = choose, else forced patterns-per-warp multiplier (tuning / tests)
+    int resident_slots = 0;            // shared-memory slots the last resident launch needed
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
     double* d_partial_sums = nullptr;  // [kMaxReduceBlocks * 4]
@@ -149,7 +155,7 @@ struct RowSet {
 bool dna_supported(const Ctx* c);
 int dna_run_rows(Ctx* c, const RowSet& rs, int mode);
 int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
-int dna_lnl_resident(Ctx* c, int a, int b);
+int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root);   // clv_dna_resident.cu
 // clv_generic.cu (any A <= 64, any K <= 16)
 int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);

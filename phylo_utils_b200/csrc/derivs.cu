@@ -31,6 +31,7 @@ namespace {
 struct DerivArgs {
     const double* mats;     // [3][batch_cap][K][A][A]
     const uint8_t* codes;
+    size_t pitch;
     const double* lut;
     const double* clv;      // shared block array (down blocks, then up blocks)
     const int32_t* scale;
@@ -68,13 +69,13 @@ __global__ void __launch_bounds__(kDerivThreads) edge_deriv_kernel(const DerivAr
             const size_t ss = s < p.S ? (size_t)s : 0;
             ex[q] = 0;
             if (p.kind_a[e] == SRC_TIP) {
-                va[q] = p.lut + (size_t)p.codes[(size_t)p.src_a[e] * S + ss] * A;
+                va[q] = p.lut + (size_t)p.codes[(size_t)p.src_a[e] * p.pitch + ss] * A;
             } else {
                 va[q] = p.clv + ((size_t)p.src_a[e] * S + ss) * K * A;
                 ex[q] += p.scale[(size_t)p.src_a[e] * S + ss];
             }
             if (p.kind_b[e] == SRC_TIP) {
-                vb[q] = p.lut + (size_t)p.codes[(size_t)p.src_b[e] * S + ss] * A;
+                vb[q] = p.lut + (size_t)p.codes[(size_t)p.src_b[e] * p.pitch + ss] * A;
             } else {
                 vb[q] = p.clv + ((size_t)p.src_b[e] * S + ss) * K * A;
                 ex[q] += p.scale[(size_t)p.src_b[e] * S + ss];
@@ -246,6 +247,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
         }
         p.mats = c->d_dmats;
         p.codes = c->d_codes;
+        p.pitch = c->code_pitch;
         p.lut = c->d_lut;
         p.clv = c->d_clv;
         p.scale = c->d_scale;

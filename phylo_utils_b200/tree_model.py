@@ -42,10 +42,17 @@ class TreeModel(object):
     alignment_codes = None
     ascbias = False
 
-    def __init__(self, device=0, up_partials=False, mode="auto"):
+    def __init__(self, device=0, up_partials=False, mode="auto", store_partials=True):
+        """
+        mode: "auto" | "tile" | "level" | "resident" - how the post-order rows are walked on the device.
+        store_partials=False builds an lnL-only model: no per-node partials are kept in HBM (``partials`` /
+        ``scale`` / derivatives are unavailable), every likelihood call runs the operand-resident kernel
+        (4-state models only).
+        """
         self.device = device
         self.want_up_partials = up_partials
         self.mode = mode
+        self.store_partials = store_partials
         self.engine = None
         self.substitution_model = None
         self.rate_model = None
@@ -144,6 +151,8 @@ class TreeModel(object):
             return _lib.PHB_MODE_TILE
         if self.mode == "level":
             return _lib.PHB_MODE_LEVEL
+        if self.mode == "resident" or not self.store_partials:
+            return _lib.PHB_MODE_RESIDENT
         return _lib.PHB_MODE_TILE if n_patterns >= _TILE_MODE_MIN_PATTERNS else _lib.PHB_MODE_LEVEL
 
     def initialise(self):
@@ -186,8 +195,10 @@ class TreeModel(object):
             self._n_dummy = n_states
         n_tips, n_patterns = codes.shape
         self._mode = self._choose_mode(n_patterns)
+        if not self.store_partials and (self.ascbias or self.want_up_partials):
+            raise ValueError("store_partials=False supports plain likelihood evaluation only")
         self.engine = LikelihoodEngine(n_tips, n_patterns, self.rate_model.ncat, n_states, device=self.device,
-                                       up_partials=self.want_up_partials)
+                                       up_partials=self.want_up_partials, store_partials=self.store_partials)
         self.engine.set_tips(codes, lut, tip_nodes)
         self.engine.set_pattern_weights(weights)
         if self._mode == _lib.PHB_MODE_LEVEL:
@@ -231,6 +242,8 @@ class TreeModel(object):
             raise ValueError("call initialise() first")
         lengths = self._row_lengths()
         self.engine.set_edge_lengths(lengths)
+        if not self.store_partials:
+            return                      # lnL-only: the walk happens inside every likelihood call
         m = self.substitution_model
         if getattr(m, "has_real_eigensystem", True):
             self.engine.build_pmatrices()
@@ -264,6 +277,10 @@ class TreeModel(object):
 
     def _pattern_lnl(self, node_a, node_b):
         length = self._edge_length(node_a, node_b)
+        if not self.store_partials:
+            if not getattr(self.substitution_model, "has_real_eigensystem", True):
+                raise ValueError("store_partials=False needs a model with a real eigen-system")
+            return self.engine.lnl_resident(node_a, node_b, length, want_pattern=True)
         rp = self._root_pmats(length)
         if not self.ascbias:
             total, pattern, _ = self.engine.root_lnl(node_a, node_b, length, want_pattern=True, root_pmats=rp)

@@ -125,3 +125,45 @@ def test_repeated_blocks_property_at_scale():
     assert np.array_equal(pattern.reshape(reps, block), np.tile(pattern[:block], (reps, 1)))   # bitwise periodic
     assert_lnl_close(pattern[:block], want)
     assert_lnl_close(total, reps * want.sum())
+
+
+@pytest.mark.parametrize("tree_fn,n_taxa,n_pat", [(random_tree, 300, 40000), (caterpillar_tree, 200, 10000),
+                                                  (balanced_tree, 256, 9000), (random_tree, 64, 33), (random_tree, 7, 1)])
+def test_resident_kernels_vs_oracle(tree_fn, n_taxa, n_pat):
+    tree, names, codes, lut = synthetic(n_taxa, n_pat, 4, seed=n_taxa * 7 + n_pat, tree_fn=tree_fn)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    w = np.random.default_rng(2).integers(1, 4, size=n_pat)
+    want = None
+    for store in (False, True):
+        tm = phy.TreeModel(mode="resident", store_partials=store)
+        tm.set_tree(tree)
+        tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, siteweights=w)
+        tm.set_rate_model(rate)
+        tm.set_substitution_model(model)
+        tm.initialise()
+        total, pattern = tm._pattern_lnl(*tm.traversal.root_edge)
+        if want is None:
+            tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+            want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights)
+        assert_lnl_close(pattern, want)
+        assert_lnl_close(total, float(np.dot(want, w)))
+
+
+@pytest.mark.parametrize("K,rate", [(1, lambda: phy.rate_models.UniformRateModel()),
+                                    (2, lambda: phy.rate_models.InvariantSitesModel(0.2)),
+                                    (8, lambda: phy.rate_models.GammaRateModel(8, 0.4))])
+def test_resident_other_category_counts(K, rate):
+    tree, names, codes, lut = synthetic(90, 6000, 4, seed=40 + K)
+    model = phy.substitution_models.HKY85(2.0, [0.3, 0.2, 0.2, 0.3])
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    r = rate()
+    tm.set_rate_model(r)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    total, pattern = tm._pattern_lnl(*tm.traversal.root_edge)
+    tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+    want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, r.rates, r.weights)
+    assert_lnl_close(pattern, want)

@@ -209,3 +209,49 @@ def test_two_tip_tree_has_no_internal_nodes():
     p = k80.p(0.2)
     want = np.log(0.25 * np.array([p[0, 0], p[1, 1], p[2, 2], p[3, 3], p[0, 3], p[1, 3]]))
     assert_lnl_close(site, want, rtol=1e-12)
+
+
+# ---- operand-resident kernel (4-state models): lnL-only and streaming-store variants ------------------------
+DNA_CASES = ["cfg1_gtr_g4", "cfg1_jc_g4", "cfg1_gtr_uniform", "ambig_hky_ig", "ambig_tn93_inv", "deep300_gtr_g4",
+             "ladder120_k80_g4"]
+
+
+@pytest.mark.parametrize("name", [n for n in DNA_CASES if n != "ambig_hky_ig"])      # K=5 is not a resident shape
+def test_resident_lnl_only_matches_reference(name):
+    g, tr, codes, lut, sw, ii, names, model, rate = problem(name)
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree(g))
+    tm.set_alignment(records(g), int(g["alphabet"]))
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    site = tm.compute_likelihood_at_edge(*tm.traversal.root_edge)
+    assert_lnl_close(site, g["site_lnl"], what=name + " per-site lnL (resident)")
+    assert_lnl_close(tm.lnl(), g["total_lnl"], what=name + " total (resident)")
+    assert tm.engine.workspace_bytes < 4e6          # no per-node storage at all
+    with pytest.raises(RuntimeError):
+        tm.engine.compute_partials()
+
+
+@pytest.mark.parametrize("name", ["cfg1_gtr_g4", "deep300_gtr_g4", "ladder120_k80_g4"])
+def test_resident_store_mode_writes_the_same_partials(name):
+    g, tm = make_tm(name, "resident")
+    tm.initialise()
+    site = tm.compute_likelihood_at_edge(*tm.traversal.root_edge)
+    assert_lnl_close(site, g["site_lnl"], what=name)
+    g2, tm2 = make_tm(name, "level")
+    tm2.initialise()
+    tm2.compute_likelihood_at_edge(*tm2.traversal.root_edge)
+    assert np.array_equal(tm.partials, tm2.partials) and np.array_equal(tm.scale, tm2.scale)   # bitwise
+
+
+def test_resident_rejects_unsupported_shapes():
+    g, tr, codes, lut, sw, ii, names, model, rate = problem("prot12_lg_g4")
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree(g))
+    tm.set_alignment(records(g), 1)
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    with pytest.raises(ValueError):
+        tm.lnl()
