@@ -6,8 +6,8 @@
 // larger child subtree finished first, a 1000-taxon tree never has more than ~6 finished-but-unconsumed
 // partial blocks alive (9 for a perfectly balanced 1024-taxon tree).  So:
 //
-//   * every WARP owns a tile of (32/K)*U patterns and walks ALL rows for it, independently of every other
-//     warp (no block barrier in the row loop);
+//   * every WARP owns a tile of 32 patterns (lane = pattern, the K categories are looped inside the thread)
+//     and walks ALL rows for it, independently of every other warp (no block barrier in the row loop);
 //   * the result of a row stays in REGISTERS when the next row consumes it (2/3 of the internal operands),
 //     otherwise it is parked in one of a few per-warp SHARED-MEMORY slots allotted by the host like a
 //     register allocator;
@@ -20,7 +20,9 @@
 //   * ROOT = true appends the virtual-root step (root combine, pi-dot, Gamma mixture, log, weighted
 //     sum) as a final pseudo-row, so one launch yields the per-pattern lnL and the block sums.
 //
-// Thread mapping inside a warp is the one of clv_dna.cu: lane = (pattern g, category k), 4 doubles each.
+// One thread per pattern means the per-pattern maximum / exponent is thread-local (no shuffles), P rows are
+// warp-wide broadcast reads, and all bookkeeping (descriptor, prefetch, exponents) is paid once per 32
+// pattern-node updates.
 #include <algorithm>
 #include <cstdlib>
 
@@ -110,16 +112,18 @@ __device__ __forceinline__ int combine_scale(const double (&x)[4], const double 
     return -shift;
 }
 
-// geometry of one warp's shared memory
-template <int K, int U>
+// geometry of one warp's shared memory.  A warp tile is 32 patterns: lane = pattern, the K categories
+// are looped inside the thread.
+template <int K>
 struct WarpLayout {
-    static constexpr int SPI = 32 / K;                 // patterns per warp iteration
-    static constexpr int SPW = SPI * U;                // patterns per warp tile
-    static constexpr int P_BYTES = 2 * K * 128;        // both P blocks
-    static constexpr int CODE_BYTES = SPW < 16 ? 16 : (SPW + 15) / 16 * 16;   // per operand, padded
+    static constexpr int SPW = 32;                      // patterns per warp tile
+    static constexpr int P_BYTES = 2 * K * 128;         // both P blocks, [operand][k][16 doubles]
+    static constexpr int CODE_BYTES = 32;               // per operand
     static constexpr int STAGE_BYTES = P_BYTES + 2 * CODE_BYTES;
     static constexpr int DESC_BYTES = kND * 16;
-    static constexpr int SLOT_BYTES = U * 32 * 32 + U * 32 * 4;   // vectors + exponents
+    // a parked block: [k][half][lane] 16-byte pieces (every LDS.128/STS.128 touches 512 contiguous bytes)
+    // followed by one exponent per lane
+    static constexpr int SLOT_BYTES = K * 2 * 32 * 16 + 32 * 4;
     static constexpr int FIXED_BYTES = DESC_BYTES + kNS * STAGE_BYTES;
 };
 
@@ -128,9 +132,91 @@ struct Cursor {
     int64_t wt;
 };
 
-template <int K, int U, bool STORE, bool ROOT>
+// o[k] = (P1[k] . a[k]) * (P2[k] . b[k]) for one pattern; operands per kind; result left in `prev`
+template <int K, int KA, int KB>
+__device__ __forceinline__ int row_update(const unsigned char* st, const unsigned char* s_slots, int src_a, int src_b,
+                                          const double (*s_lut)[4], int lane, double (&prev)[K][4], int prev_e) {
+    using L = WarpLayout<K>;
+    double ta[4], tb[4];
+    int e = 0;
+    if (KA == KIND_TIP) {
+        const int code = st[L::P_BYTES + lane];
+        const double2 lo = *reinterpret_cast<const double2*>(&s_lut[code][0]);
+        const double2 hi = *reinterpret_cast<const double2*>(&s_lut[code][2]);
+        ta[0] = lo.x; ta[1] = lo.y; ta[2] = hi.x; ta[3] = hi.y;
+    }
+    if (KB == KIND_TIP) {
+        const int code = st[L::P_BYTES + L::CODE_BYTES + lane];
+        const double2 lo = *reinterpret_cast<const double2*>(&s_lut[code][0]);
+        const double2 hi = *reinterpret_cast<const double2*>(&s_lut[code][2]);
+        tb[0] = lo.x; tb[1] = lo.y; tb[2] = hi.x; tb[3] = hi.y;
+    }
+    if (KA == KIND_PREV || KB == KIND_PREV) e += prev_e;
+    const unsigned char* sa = s_slots + (size_t)src_a * L::SLOT_BYTES;
+    const unsigned char* sb = s_slots + (size_t)src_b * L::SLOT_BYTES;
+    if (KA == KIND_SLOT) e += *reinterpret_cast<const int*>(sa + K * 1024 + lane * 4);
+    if (KB == KIND_SLOT) e += *reinterpret_cast<const int*>(sb + K * 1024 + lane * 4);
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double a[4], b[4], x[4], y[4];
+        if (KA == KIND_TIP) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = ta[i];
+        } else if (KA == KIND_PREV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = prev[k][i];
+        } else {
+            const double2 lo = *reinterpret_cast<const double2*>(sa + (k * 2 + 0) * 512 + lane * 16);
+            const double2 hi = *reinterpret_cast<const double2*>(sa + (k * 2 + 1) * 512 + lane * 16);
+            a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+        }
+        if (KB == KIND_TIP) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = tb[i];
+        } else if (KB == KIND_PREV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = prev[k][i];
+        } else {
+            const double2 lo = *reinterpret_cast<const double2*>(sb + (k * 2 + 0) * 512 + lane * 16);
+            const double2 hi = *reinterpret_cast<const double2*>(sb + (k * 2 + 1) * 512 + lane * 16);
+            b[0] = lo.x; b[1] = lo.y; b[2] = hi.x; b[3] = hi.y;
+        }
+        // P rows are read as warp-wide broadcasts (every lane, same address)
+        const double2* q1 = reinterpret_cast<const double2*>(st + k * 128);
+        const double2* q2 = reinterpret_cast<const double2*>(st + K * 128 + k * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 r0 = q1[2 * i], r1 = q1[2 * i + 1];
+            x[i] = fma(r1.y, a[3], fma(r1.x, a[2], fma(r0.y, a[1], r0.x * a[0])));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 r0 = q2[2 * i], r1 = q2[2 * i + 1];
+            y[i] = fma(r1.y, b[3], fma(r1.x, b[2], fma(r0.y, b[1], r0.x * b[0])));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            prev[k][i] = x[i] * y[i];
+            m = fmax(m, prev[k][i]);
+        }
+    }
+    const int hi = __double2hiint(m);
+    if (hi < kScaleThresholdHi && hi >= 0x00100000) {   // 0 < max < 2^-128: rescale the whole pattern
+        const int shift = 1023 - (hi >> 20);
+        const double f = pow2i(shift);
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prev[k][i] *= f;
+        e -= shift;
+    }
+    return e;
+}
+
+template <int K, bool STORE, bool ROOT>
 __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs p) {
-    using L = WarpLayout<K, U>;
+    using L = WarpLayout<K>;
     extern __shared__ __align__(128) unsigned char smem[];
     double(*s_lut)[4] = reinterpret_cast<double(*)[4]>(smem);
     __shared__ double s_red[kWarps];
@@ -143,7 +229,6 @@ __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs
     unsigned char* s_stage = wbase + L::DESC_BYTES;
     unsigned char* s_slots = wbase + L::FIXED_BYTES;
 
-    const int g = lane / K, k = lane % K;
     const int64_t n_wt = (p.S + L::SPW - 1) / L::SPW;
     const int64_t wstride = (int64_t)gridDim.x * kWarps;
     const int n_steps = p.n_steps;
@@ -152,7 +237,7 @@ __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs
     Cursor cd{0, (int64_t)blockIdx.x * kWarps + warp};   // descriptor prefetch cursor
     Cursor cp = cd;                                      // data prefetch cursor
     Cursor cc = cd;                                      // compute cursor
-    int qd = 0, qp = 0, qc = 0;                          // ring positions (step counters mod ring size)
+    int qd = 0, qp = 0, qc = 0;
 
     auto advance = [&](Cursor& c) {
         if (++c.row == n_steps) {
@@ -173,28 +258,21 @@ __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs
             const char* pa = reinterpret_cast<const char*>(p.pmats + (size_t)d.pidx_a * K * 16);
             const char* pb = reinterpret_cast<const char*>(p.pmats + (size_t)pidx_b * K * 16);
             constexpr int CH = K * 128 / 16;   // 16-byte chunks per P block
-            for (int c = lane; c < CH; c += 32) {
-                cp_async16(st + c * 16, pa + c * 16);
-                cp_async16(st + K * 128 + c * 16, pb + c * 16);
+            for (int c = lane; c < 2 * CH; c += 32) {
+                const char* src = c < CH ? pa + c * 16 : pb + (c - CH) * 16;
+                cp_async16(st + c * 16, src);
             }
             const int64_t site0 = cp.wt * L::SPW;
-            constexpr int CC = L::SPW < 16 ? 1 : L::CODE_BYTES / 16;
-            if (kind_a == KIND_TIP && lane < CC) {
-                const uint8_t* src = p.codes + (size_t)d.src_a * p.pitch + site0 + lane * 16;
-                if (L::SPW >= 16) cp_async16(st + L::P_BYTES + lane * 16, src);
-                else cp_async8(st + L::P_BYTES, src);
-            }
-            if (kind_b == KIND_TIP && lane >= 16 && lane < 16 + CC) {
-                const uint8_t* src = p.codes + (size_t)d.src_b * p.pitch + site0 + (lane - 16) * 16;
-                if (L::SPW >= 16) cp_async16(st + L::P_BYTES + L::CODE_BYTES + (lane - 16) * 16, src);
-                else cp_async8(st + L::P_BYTES + L::CODE_BYTES, src);
-            }
+            if (kind_a == KIND_TIP && lane < 2)
+                cp_async16(st + L::P_BYTES + lane * 16, p.codes + (size_t)d.src_a * p.pitch + site0 + lane * 16);
+            if (kind_b == KIND_TIP && lane >= 2 && lane < 4)
+                cp_async16(st + L::P_BYTES + L::CODE_BYTES + (lane - 2) * 16,
+                           p.codes + (size_t)d.src_b * p.pitch + site0 + (lane - 2) * 16);
         }
         ++qp;
         advance(cp);
     };
 
-    // ---- prologue: fill the descriptor ring, then the data ring ------------------------------------------
     for (int i = 0; i < kND - 1; ++i) prefetch_desc();
     cp_async_commit();
     cp_async_wait<0>();
@@ -204,14 +282,12 @@ __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs
         cp_async_commit();
     }
 
-    double prev[U][4];
-    int prev_e[U];
+    double prev[K][4];
+    int prev_e = 0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        prev_e[u] = 0;
+    for (int k = 0; k < K; ++k)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) prev[u][i] = 0.0;
-    }
+        for (int i = 0; i < 4; ++i) prev[k][i] = 0.0;
     double acc = 0.0;
 
     while (cc.wt < n_wt) {
@@ -223,98 +299,58 @@ __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs
 
         const ResRow d = s_desc[qc % kND];
         const unsigned char* st = s_stage + (size_t)(qc % kNS) * L::STAGE_BYTES;
-        const int kind_a = (d.packed >> 24) & 3, kind_b = (d.packed >> 26) & 3, dst_slot = d.packed >> 28;
-        double P1[16], P2[16];
-        {
-            const double* q1 = reinterpret_cast<const double*>(st) + k * 16;
-            const double* q2 = reinterpret_cast<const double*>(st + K * 128) + k * 16;
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                const double2 v1 = *reinterpret_cast<const double2*>(q1 + i);
-                const double2 v2 = *reinterpret_cast<const double2*>(q2 + i);
-                P1[i] = v1.x; P1[i + 1] = v1.y;
-                P2[i] = v2.x; P2[i + 1] = v2.y;
-            }
+        const int kinds = (d.packed >> 24) & 15, dst_slot = d.packed >> 28;   // kind_a | kind_b << 2
+        int e;
+        switch (kinds) {
+            case KIND_TIP | (KIND_TIP << 2):
+                e = row_update<K, KIND_TIP, KIND_TIP>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
+                break;
+            case KIND_TIP | (KIND_PREV << 2):
+                e = row_update<K, KIND_TIP, KIND_PREV>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
+                break;
+            case KIND_TIP | (KIND_SLOT << 2):
+                e = row_update<K, KIND_TIP, KIND_SLOT>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
+                break;
+            case KIND_PREV | (KIND_SLOT << 2):
+                e = row_update<K, KIND_PREV, KIND_SLOT>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
+                break;
+            default:
+                e = row_update<K, KIND_SLOT, KIND_SLOT>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
+                break;
         }
-        const uint8_t* codes_a = st + L::P_BYTES;
-        const uint8_t* codes_b = st + L::P_BYTES + L::CODE_BYTES;
-        const int64_t site0 = cc.wt * L::SPW;
+        prev_e = e;
+        const int64_t s = cc.wt * L::SPW + lane;
         const bool is_root = ROOT && cc.row == n_steps - 1;
-
-        auto operand = [&](int kind, int src, const uint8_t* codes, int u, double (&v)[4], int& e) {
-            if (kind == KIND_TIP) {
-                const int code = codes[u * L::SPI + g];
-                const double2 lo = *reinterpret_cast<const double2*>(&s_lut[code][0]);
-                const double2 hi = *reinterpret_cast<const double2*>(&s_lut[code][2]);
-                v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-                e = 0;
-            } else if (kind == KIND_PREV) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = prev[u][i];
-                e = prev_e[u];
-            } else {
-                const unsigned char* sl = s_slots + (size_t)src * L::SLOT_BYTES;
-                const double2 lo = *reinterpret_cast<const double2*>(sl + (u * 32 + lane) * 32);
-                const double2 hi = *reinterpret_cast<const double2*>(sl + (u * 32 + lane) * 32 + 16);
-                v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-                e = *reinterpret_cast<const int*>(sl + U * 32 * 32 + (u * 32 + lane) * 4);
-            }
-        };
-
         if (!is_root) {
+            if (dst_slot != 15) {
+                unsigned char* sl = s_slots + (size_t)dst_slot * L::SLOT_BYTES;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                double a[4], b[4], x[4], y[4], o[4];
-                int ea, eb;
-                operand(kind_a, d.src_a, codes_a, u, a, ea);
-                operand(kind_b, d.src_b, codes_b, u, b, eb);
-                matvec4r(P1, a, x);
-                matvec4r(P2, b, y);
-                const int e = ea + eb + combine_scale<K>(x, y, o);
+                for (int k = 0; k < K; ++k) {
+                    *reinterpret_cast<double2*>(sl + (k * 2 + 0) * 512 + lane * 16) = make_double2(prev[k][0], prev[k][1]);
+                    *reinterpret_cast<double2*>(sl + (k * 2 + 1) * 512 + lane * 16) = make_double2(prev[k][2], prev[k][3]);
+                }
+                *reinterpret_cast<int*>(sl + K * 1024 + lane * 4) = e;
+            }
+            if (STORE && s < p.S) {
+                double* out = p.clv + ((size_t)cc.row * S + (size_t)s) * (K * 4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) prev[u][i] = o[i];
-                prev_e[u] = e;
-                if (dst_slot != 15) {
-                    unsigned char* sl = s_slots + (size_t)dst_slot * L::SLOT_BYTES;
-                    *reinterpret_cast<double2*>(sl + (u * 32 + lane) * 32) = make_double2(o[0], o[1]);
-                    *reinterpret_cast<double2*>(sl + (u * 32 + lane) * 32 + 16) = make_double2(o[2], o[3]);
-                    *reinterpret_cast<int*>(sl + U * 32 * 32 + (u * 32 + lane) * 4) = e;
-                }
-                if (STORE) {
-                    const int64_t s = site0 + u * L::SPI + g;
-                    if (s < p.S) {
-                        st256_stream(p.clv + (((size_t)cc.row * S + (size_t)s) * K + k) * 4, o);
-                        if (k == 0) p.scale[(size_t)cc.row * S + s] = e;
-                    }
-                }
+                for (int k = 0; k < K; ++k) st256_stream(out + k * 4, prev[k]);
+                p.scale[(size_t)cc.row * S + s] = e;
             }
         } else {
-            double pi[4];
+            double mix = 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pi[i] = p.freqs[i];
-            const double wk = p.catw[k];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                double a[4], b[4], x[4], y[4], o[4];
-                int ea, eb;
-                operand(kind_a, d.src_a, codes_a, u, a, ea);
-                operand(kind_b, d.src_b, codes_b, u, b, eb);
-                matvec4r(P1, a, x);
-                matvec4r(P2, b, y);
-                const int e = ea + eb + combine_scale<K>(x, y, o);
-                double f = pi[0] * o[0];
-                f = fma(pi[1], o[1], f);
-                f = fma(pi[2], o[2], f);
-                f = fma(pi[3], o[3], f);
-                double mix = f > 0 ? wk * f : 0.0;
-#pragma unroll
-                for (int dd = K / 2; dd > 0; dd >>= 1) mix += __shfl_xor_sync(0xffffffffu, mix, dd);
-                const int64_t s = site0 + u * L::SPI + g;
-                if (k == 0 && s < p.S) {
-                    const double lnl = mix > 0 ? log(mix) + (double)e * kLn2 : -INFINITY;
-                    p.pattern_lnl[s] = lnl;
-                    acc += (p.weights ? p.weights[s] : 1.0) * lnl;
-                }
+            for (int k = 0; k < K; ++k) {
+                double f = p.freqs[0] * prev[k][0];
+                f = fma(p.freqs[1], prev[k][1], f);
+                f = fma(p.freqs[2], prev[k][2], f);
+                f = fma(p.freqs[3], prev[k][3], f);
+                if (f > 0) mix = fma(p.catw[k], f, mix);
+            }
+            if (s < p.S) {
+                const double lnl = mix > 0 ? log(mix) + (double)e * kLn2 : -INFINITY;
+                p.pattern_lnl[s] = lnl;
+                acc += (p.weights ? p.weights[s] : 1.0) * lnl;
             }
         }
         ++qc;
@@ -408,9 +444,9 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, ResPlan* out) {
     return PHB_OK;
 }
 
-template <int K, int U, bool STORE, bool ROOT>
+template <int K, bool STORE, bool ROOT>
 int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
-    using L = WarpLayout<K, U>;
+    using L = WarpLayout<K>;
     ResArgs a;
     a.rows = static_cast<const ResRow*>(c->d_res_rows);
     a.n_rows = c->n_rows();
@@ -430,8 +466,9 @@ int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
     a.n_slots = plan.n_slots;
     a.warp_bytes = (L::FIXED_BYTES + std::max(plan.n_slots, 1) * L::SLOT_BYTES + 127) / 128 * 128;
     const size_t smem = 256 * 32 + (size_t)kWarps * a.warp_bytes;
-    if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel: operand stack does not fit in shared memory");
-    auto kern = dna_resident_kernel<K, U, STORE, ROOT>;
+    if (smem > c->smem_optin)
+        return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel: operand stack does not fit in shared memory");
+    auto kern = dna_resident_kernel<K, STORE, ROOT>;
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 0;
@@ -449,35 +486,13 @@ int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
     return PHB_OK;
 }
 
-template <int K, bool STORE, bool ROOT>
-int launch_resident_u(Ctx* c, const ResPlan& plan, int* grid_out) {
-    // Larger U amortises the P reload of a row over more patterns, smaller U leaves room for more warps.
-    // Take the largest U that still lets >= 8 warps per SM live with this tree's slot count and keeps the
-    // chip busy.
-    int force = c->resident_u;
-    if (const char* env = getenv("PHB_RESIDENT_U")) force = atoi(env);
-    auto fits = [&](int u, int sites_per_iter) {
-        const int slot = u * 32 * 32 + u * 32 * 4;
-        const int spw = sites_per_iter * u;
-        const int code = spw < 16 ? 16 : (spw + 15) / 16 * 16;
-        const size_t warp_bytes = kND * 16 + kNS * (2 * K * 128 + 2 * code) + (size_t)std::max(plan.n_slots, 1) * slot;
-        const size_t cta = 256 * 32 + kWarps * warp_bytes;
-        const bool enough_tiles = (c->S + spw - 1) / spw >= (int64_t)c->sm_count * 8;
-        return cta * 2 <= c->smem_optin && enough_tiles;
-    };
-    const int spi = 32 / K;
-    if (force == 4 || (force == 0 && fits(4, spi))) return launch_resident<K, 4, STORE, ROOT>(c, plan, grid_out);
-    if (force == 2 || (force == 0 && (fits(2, spi) || spi * 1 < 8))) return launch_resident<K, 2, STORE, ROOT>(c, plan, grid_out);
-    return launch_resident<K, 1, STORE, ROOT>(c, plan, grid_out);
-}
-
 template <bool STORE, bool ROOT>
 int launch_resident_k(Ctx* c, const ResPlan& plan, int* grid_out) {
     switch (c->K) {
-        case 1: return launch_resident_u<1, STORE, ROOT>(c, plan, grid_out);
-        case 2: return launch_resident_u<2, STORE, ROOT>(c, plan, grid_out);
-        case 4: return launch_resident_u<4, STORE, ROOT>(c, plan, grid_out);
-        case 8: return launch_resident_u<8, STORE, ROOT>(c, plan, grid_out);
+        case 1: return launch_resident<1, STORE, ROOT>(c, plan, grid_out);
+        case 2: return launch_resident<2, STORE, ROOT>(c, plan, grid_out);
+        case 4: return launch_resident<4, STORE, ROOT>(c, plan, grid_out);
+        case 8: return launch_resident<8, STORE, ROOT>(c, plan, grid_out);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel needs K in {1,2,4,8}");
 }

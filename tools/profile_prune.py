@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--evals", type=int, default=3)
     ap.add_argument("--mode", default="tile")
     ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--lnl-only", action="store_true")
     args = ap.parse_args()
     import torch
     tree, names = bench.make_tree(args.taxa, args.seed)
@@ -29,8 +30,8 @@ def main():
     model = phy.substitution_models.GTR(bench.GTR_RATES, bench.GTR_FREQS)
     rate = phy.rate_models.GammaRateModel(4, 0.5)
     codes = torch.from_numpy(bench.make_codes(args.taxa, args.patterns, args.seed)).cuda()
-    eng = phy.LikelihoodEngine(args.taxa, args.patterns, 4, 4)
-    mode = _lib.PHB_MODE_TILE if args.mode == "tile" else _lib.PHB_MODE_LEVEL
+    eng = phy.LikelihoodEngine(args.taxa, args.patterns, 4, 4, store_partials=not args.lnl_only)
+    mode = {"tile": _lib.PHB_MODE_TILE, "level": _lib.PHB_MODE_LEVEL, "resident": _lib.PHB_MODE_RESIDENT}[args.mode]
     if mode == _lib.PHB_MODE_LEVEL:
         rows, off = trav.level_order()
         eng.set_schedule(rows, off)
@@ -44,6 +45,9 @@ def main():
     a, b = trav.root_edge
     for _ in range(args.evals):
         eng.set_edge_lengths(lengths)
+        if args.lnl_only:
+            lnl = eng.lnl_resident(a, b, trav.brlens[(a, b)])[0]
+            continue
         eng.build_pmatrices()
         eng.compute_partials(mode)
         lnl = eng.root_lnl(a, b, trav.brlens[(a, b)])[0]
