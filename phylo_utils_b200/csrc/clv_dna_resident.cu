@@ -314,8 +314,11 @@ __global__ void __launch_bounds__(kWarps * 32) dna_resident_kernel(const ResArgs
             case KIND_PREV | (KIND_SLOT << 2):
                 e = row_update<K, KIND_PREV, KIND_SLOT>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
                 break;
-            default:
+            case KIND_SLOT | (KIND_SLOT << 2):
                 e = row_update<K, KIND_SLOT, KIND_SLOT>(st, s_slots, d.src_a, d.src_b, s_lut, lane, prev, prev_e);
+                break;
+            default:   // not a canonical row shape: the host plan is broken, do not touch memory
+                e = 0;
                 break;
         }
         prev_e = e;
@@ -414,6 +417,11 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, ResPlan* out) {
                 if (src[i] < 0) return c->fail(PHB_ERR_STATE, "resident plan: operand was never parked");
                 busy[src[i]] = 0;   // free after this row has read it
             }
+        }
+        if (kind[0] > kind[1]) {   // canonical operand order TIP <= PREV <= SLOT (children commute): 5 row shapes
+            std::swap(kind[0], kind[1]);
+            std::swap(src[0], src[1]);
+            std::swap(pidx[0], pidx[1]);
         }
         int dst = 15;
         if (dst_node >= 0 && consumer_row[dst_node] != r + 1 && consumer_row[dst_node] >= 0) {
