@@ -19,7 +19,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size,
         pattern_lnl, cat_lnl, partial, result, total;
 };
 
@@ -57,6 +57,9 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
     p.rows = take(max_rows * sizeof(OpRow));
     p.res_rows = take((max_rows + 1) * 16);
+    // parking area of the lnL-only resident kernel (4-state models): 160 SMs x 16 warps x 15 blocks
+    p.scratch_size = A == 4 ? (size_t)160 * 16 * 15 * ((size_t)K * 1024 + 128) : 0;
+    p.scratch = take(p.scratch_size);
     p.pattern_lnl = take((size_t)S * 8);
     p.cat_lnl = take((size_t)S * K * 8);
     p.partial = take((size_t)kMaxReduceBlocks * 4 * 8);
@@ -236,6 +239,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->n_internal = n_tips > 2 ? n_tips - 2 : 0;
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = prop.sharedMemPerMultiprocessor;
     const Plan p = make_plan(n_tips, n_patterns, n_cat, n_states, flags);
     if (workspace != nullptr) {
         if (workspace_bytes < p.total || ((uintptr_t)workspace % kAlign) != 0) {
@@ -278,6 +282,8 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->d_lengths = (double*)(w + p.lengths);
     c->d_rows = (OpRow*)(w + p.rows);
     c->d_res_rows = (void*)(w + p.res_rows);
+    c->d_scratch = p.scratch_size ? w + p.scratch : nullptr;
+    c->scratch_bytes = p.scratch_size;
     c->d_pattern_lnl = (double*)(w + p.pattern_lnl);
     c->d_cat_lnl = (double*)(w + p.cat_lnl);
     c->d_partial_sums = (double*)(w + p.partial);

@@ -91,7 +91,11 @@ struct Ctx {
     OpRow* d_rows = nullptr;           // [max_rows]
     void* d_res_rows = nullptr;        // [max_rows + 1] 16-byte descriptors of the resident kernel
     int resident_u = 0;                // 0 = choose, else forced patterns-per-warp multiplier (tuning / tests)
-    int resident_slots = 0;            // shared-memory slots the last resident launch needed
+    int resident_slots = 0;            // parked blocks the last resident launch needed
+    int resident_warps = 0;            // warps per SM of the last resident launch
+    unsigned char* d_scratch = nullptr;  // L2-resident parking area of the lnL-only resident kernel
+    size_t scratch_bytes = 0;
+    size_t smem_per_sm = 0;
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
     double* d_partial_sums = nullptr;  // [kMaxReduceBlocks * 4]
