@@ -33,7 +33,8 @@ namespace phb {
 namespace {
 
 constexpr int KIND_TIP = 0, KIND_PREV = 1, KIND_SLOT = 2;
-constexpr int kMaxWarps = 12;
+constexpr int kMaxWarps = 1;      // one warp per CTA: warps share nothing but the (tiny) look-up table
+constexpr int kMinCtas = 16;      // register budget: 65536 / (16 * 32) = 128 per thread
 constexpr int kScratchSlots = 15;
 
 // 16-byte row descriptor
@@ -89,7 +90,9 @@ struct WarpLayout {
     static constexpr int BLOCK_BYTES = 32 * K * 32;          // a parked block in global memory (dense)
     static constexpr int SCRATCH_SLOT = BLOCK_BYTES + 128;
     static constexpr int CHUNKS = BLOCK_BYTES / 16;          // 16-byte chunks per block
-    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + 3 * OPIN_BYTES;   // 2 operand tiles + staging
+    // two operand tiles; the tile of the row being computed doubles as its output staging tile once the
+    // operand has been consumed
+    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + 2 * OPIN_BYTES;
 };
 
 struct Cursor {
@@ -175,7 +178,7 @@ __device__ __forceinline__ int row_update(const unsigned char* st, const unsigne
 }
 
 template <int K, bool STORE, bool ROOT>
-__global__ void __launch_bounds__(kMaxWarps * 32) dna_resident_kernel(const ResArgs p) {
+__global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(const ResArgs p) {
     using L = WarpLayout<K>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double s_red[kMaxWarps];
@@ -188,7 +191,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dna_resident_kernel(const ResA
     ResRow* s_desc = reinterpret_cast<ResRow*>(wbase);
     unsigned char* s_stage = wbase + L::DESC_BYTES;
     unsigned char* s_opin = s_stage + 2 * L::STAGE_BYTES;
-    unsigned char* s_out = s_opin + 2 * L::OPIN_BYTES;
 
     const int64_t n_wt = (p.S + 31) / 32;
     const int64_t gwarp = (int64_t)blockIdx.x * n_warps + warp;
@@ -299,20 +301,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dna_resident_kernel(const ResA
             case KIND_TIP | (KIND_SLOT << 2):
                 e = row_update<K, KIND_TIP, KIND_SLOT>(st, opin, opin, s_lut, lane, prev, prev_e);
                 break;
-            case KIND_SLOT | (KIND_SLOT << 2): {
-                // never produced by a post-order schedule (the second child is always the previous row); kept for
-                // arbitrary user schedules: fetch both blocks now and wait for them
-                // (the staging tile is idle until this row parks its own result, so it holds operand b)
-                fetch_block(d.src_a, site0, opin);
-                fetch_block(d.src_b, site0, s_out);
-                cp_async_commit();
-                cp_async_wait_all();
-                __syncwarp();
-                e = row_update<K, KIND_SLOT, KIND_SLOT>(st, opin, s_out, s_lut, lane, prev, prev_e);
-                __syncwarp();
-                break;
-            }
-            default:   // not a canonical row shape: the host plan is broken, do not touch memory
+            default:   // not a row shape the host plan may emit (it rejects SLOT/SLOT rows): do not touch memory
                 e = 0;
                 break;
         }
@@ -321,7 +310,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) dna_resident_kernel(const ResA
         const bool is_root = ROOT && cc.row == n_steps - 1;
         if (!is_root) {
             if (STORE || dst_slot != 15) {
-                // park: registers -> padded staging tile -> coalesced 128-bit stores
+                // park: registers -> padded staging tile -> coalesced 128-bit stores.  The operand tile of this
+                // row is dead by now and serves as the staging tile.
+                unsigned char* s_out = opin;
+                __syncwarp();
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     *reinterpret_cast<double2*>(s_out + lane * L::ROWB + k * 32) = make_double2(prev[k][0], prev[k][1]);
@@ -420,6 +412,10 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPla
                 if (!store) busy[src[i]] = 0;   // recycled after this row has read it
             }
         }
+        if (kind[0] == KIND_SLOT && kind[1] == KIND_SLOT)
+            return c->fail(PHB_ERR_UNSUPPORTED,
+                           "resident kernel needs a post-order schedule (second child = previous row); "
+                           "use Traversal.locality_order() or another mode");
         if (kind[0] > kind[1]) {   // canonical operand order TIP <= PREV <= SLOT (children commute)
             std::swap(kind[0], kind[1]);
             std::swap(src[0], src[1]);

@@ -228,7 +228,7 @@ def test_resident_lnl_only_matches_reference(name):
     site = tm.compute_likelihood_at_edge(*tm.traversal.root_edge)
     assert_lnl_close(site, g["site_lnl"], what=name + " per-site lnL (resident)")
     assert_lnl_close(tm.lnl(), g["total_lnl"], what=name + " total (resident)")
-    assert tm.engine.workspace_bytes < 4e6          # no per-node storage at all
+    assert tm.engine.workspace_bytes < 2e8          # no per-node storage: only the fixed L2 parking area
     with pytest.raises(RuntimeError):
         tm.engine.compute_partials()
 
