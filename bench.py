@@ -56,12 +56,14 @@ def parse_args():
     ap.add_argument("--cpu-patterns", type=int, default=20000, help="pattern sample for the CPU baseline")
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--mode", choices=["auto", "tile", "level", "resident"], default="auto",
-                    help="how the rows are walked when per-node partials are stored")
-    ap.add_argument("--lnl-only", action="store_true",
-                    help="evaluate with the operand-resident kernel without storing per-node partials")
-    ap.add_argument("--resident-u", type=int, default=0, help="tuning: force the resident kernel's tile multiplier")
+                    help="how the rows are walked when per-node partials are stored (--store-partials)")
+    ap.add_argument("--store-partials", action="store_true",
+                    help="headline path keeps every node's partials in HBM (TreeModel.partials / derivatives); "
+                         "default is the pure lnL evaluation with the operand-resident kernel")
+    ap.add_argument("--chunks", type=int, default=8, help="host->device pipeline depth of the e2e path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stored", action="store_true", help="skip the extra 'partials stored' measurements")
     return ap.parse_args()
 
 
@@ -289,7 +291,8 @@ def main():
     codes_np = codes_host.numpy()
     tip_nodes = np.asarray([trav.names[n] for n in names], dtype=np.int32)
 
-    mode = {"auto": _lib.PHB_MODE_TILE if n_pat >= 16384 else _lib.PHB_MODE_LEVEL, "tile": _lib.PHB_MODE_TILE,
+    args.lnl_only = not args.store_partials
+    mode = {"auto": _lib.PHB_MODE_RESIDENT if n_pat >= 16384 else _lib.PHB_MODE_LEVEL, "tile": _lib.PHB_MODE_TILE,
             "level": _lib.PHB_MODE_LEVEL, "resident": _lib.PHB_MODE_RESIDENT}[args.mode]
     eng = phy.LikelihoodEngine(n_taxa, n_pat, NCAT, 4, device=local_rank, store_partials=not args.lnl_only)
     if mode == _lib.PHB_MODE_LEVEL:
@@ -298,8 +301,6 @@ def main():
     else:
         rows = trav.locality_order()
         eng.set_schedule(rows)
-    if args.resident_u:
-        os.environ["PHB_RESIDENT_U"] = str(args.resident_u)
     e = model.eigen
     eng.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), model.freqs, rate.rates, rate.weights)
     lengths = np.asarray([[trav.brlens[(int(p), int(c1))], trav.brlens[(int(p), int(c2))]] for p, c1, c2 in rows])
@@ -318,8 +319,14 @@ def main():
         return eng.root_lnl(a, b, root_len)[0]
 
     def eval_e2e():
+        eng.set_edge_lengths(lengths)
+        if args.lnl_only:
+            # pinned host codes -> device in chunks, overlapped with the pruning of the previous chunk
+            return eng.lnl_from_host(codes_np, a, b, root_len, n_chunks=args.chunks)[0]
         eng.set_tips(codes_np, lut, tip_nodes)          # pinned host -> device, N x S bytes
-        return eval_resident()
+        eng.build_pmatrices()
+        eng.compute_partials(mode)
+        return eng.root_lnl(a, b, root_len)[0]
 
     def allreduce(x):
         if world == 1:
@@ -387,6 +394,39 @@ def main():
                 "traffic": ncu_traffic(workload_key), "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": prune_bytes, "peak_source": peak_src,
                 "share_of_step": kernel_ms / ms_per_step}
+    if args.lnl_only or mode == _lib.PHB_MODE_RESIDENT:
+        # 64 fp64 FMA/clk/SM on B200: (N-2) * S * K * (2*16 + 4) FMA-pipe instructions-worth of work
+        fma_ops = (n_taxa - 2) * n_pat * NCAT * 36.0
+        roofline["fp64_pipe_frac_at_max_clock"] = fma_ops / (kernel_ms * 1e-3) / (64.0 * 148 * 1.965e9)
+        roofline["note"] = ("operand-resident kernel: intermediate partials stay in registers / shared memory / L2, so the "
+                            "kernel moves far fewer DRAM bytes than the algorithmic count (see `traffic` and "
+                            "profiles/); frac > 1 is expected here (SURVEY.md 8(d): 'kernels that fuse levels on-chip "
+                            "may legitimately exceed 100 %'), the binding resources are instruction issue and the FP64 pipe")
+
+    # the same evaluation while ALSO keeping every node's partials in HBM (what TreeModel.partials and the
+    # derivative path need): reported next to the headline so that both costs are on record
+    stored = None
+    if args.lnl_only and world == 1 and not args.no_stored:
+        eng2 = phy.LikelihoodEngine(n_taxa, n_pat, NCAT, 4, device=local_rank)
+        eng2.set_schedule(rows)
+        eng2.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), model.freqs, rate.rates, rate.weights)
+        eng2.set_tips(codes_dev, lut, tip_nodes)
+        stored = {}
+        for label, m2 in (("resident_store", _lib.PHB_MODE_RESIDENT), ("tile", _lib.PHB_MODE_TILE)):
+            def eval_stored():
+                eng2.set_edge_lengths(lengths)
+                eng2.build_pmatrices()
+                eng2.compute_partials(m2)
+                return eng2.root_lnl(a, b, root_len)[0]
+            for _ in range(2):
+                eval_stored()
+            s_ms, s_lnl = timed(eval_stored, max(2, args.steps // 2))
+            s_ms /= max(2, args.steps // 2)
+            stored[label] = {"evals_per_s": 1e3 / s_ms, "ms_per_step": s_ms, "lnl": s_lnl,
+                             "algorithmic_gbs": eval_bytes / (s_ms * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": eval_bytes / (s_ms * 1e-3) / 1e9 / peak}
+        eng2.close()
+        del eng2
 
     e2e = None
     if not args.no_e2e:
@@ -396,8 +436,10 @@ def main():
         e_ms /= args.steps
         e2e = {"value": world * 1e3 / e_ms, "unit": "lnL evals/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": int(n_taxa * n_pat + lengths.nbytes + 16), "d2h_bytes_per_step": 8,
-               "api": "LikelihoodEngine.set_tips(host codes) + set_edge_lengths + build_pmatrices + "
-                      "compute_partials + root_lnl (C ABI, pinned host buffers)", "lnl": e_lnl}
+               "api": ("LikelihoodEngine.set_edge_lengths + lnl_from_host (C ABI phb_lnl_from_host: pinned host codes, "
+                       "{} chunks, copy overlapped with compute)".format(args.chunks) if args.lnl_only else
+                       "LikelihoodEngine.set_tips(host codes) + set_edge_lengths + build_pmatrices + "
+                       "compute_partials + root_lnl (C ABI, pinned host buffers)"), "lnl": e_lnl}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -410,6 +452,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "path": "lnL only (no per-node partials stored)" if args.lnl_only else "partials stored ({})".format(args.mode),
+            "with_stored_partials": stored,
             "clocks": clocks.summary(), "lnl": lnl,
             "site_node_updates_per_s": world * (n_taxa - 2) * n_pat * 1e3 / ms_per_step,
             "eval_algorithmic_gbytes": eval_bytes / 1e9,

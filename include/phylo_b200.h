@@ -139,6 +139,13 @@ int phb_root_lnl(phb_ctx* ctx, int node_a, int node_b, double length, const doub
  * phb_root_lnl.  Works on contexts created with or without PHB_FLAG_NO_PARTIALS. */
 int phb_lnl_resident(phb_ctx* ctx, int node_a, int node_b, double length, double* total, double* pattern_lnl);
 
+/* The same evaluation starting from HOST tip codes (same layout and look-up table as the last phb_set_tips):
+ * the pattern axis is cut into n_chunks pieces (0 = default) and the host->device copy of piece i+1 overlaps
+ * the pruning of piece i.  Pass pinned memory for the copies to be truly asynchronous.  Replaces
+ * "TreeModel.set_alignment + initialise + compute_likelihood_at_edge" for a changed alignment. */
+int phb_lnl_from_host(phb_ctx* ctx, const uint8_t* codes, int n_chunks, int node_a, int node_b, double length,
+                      double* total, double* pattern_lnl);
+
 /* ---- read-back for parity tests (TreeModel.partials / .scale / .root_partials attributes) --- */
 /* out[S][K][A]; tips are expanded from their codes */
 int phb_get_partials(phb_ctx* ctx, int node, double* out);

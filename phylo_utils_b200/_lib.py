@@ -47,6 +47,7 @@ SIGNATURES = {
     "phb_compute_partials": (c_int, [c_void_p, c_int]),
     "phb_root_lnl": (c_int, [c_void_p, c_int, c_int, c_double, _dp, _dp, _dp, _dp]),
     "phb_lnl_resident": (c_int, [c_void_p, c_int, c_int, c_double, _dp, _dp]),
+    "phb_lnl_from_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, _dp, _dp]),
     "phb_get_partials": (c_int, [c_void_p, c_int, _dp]),
     "phb_get_scalers": (c_int, [c_void_p, c_int, _dp]),
     "phb_get_root_partials": (c_int, [c_void_p, _dp, _dp]),

@@ -297,6 +297,12 @@ int phb_destroy(phb_ctx* c) {
     if (!c) return PHB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventDestroy(c->chunk_events[i]);
+        cudaEventDestroy(c->start_event);
+        cudaStreamDestroy(c->copy_stream);
+    }
     if (c->owns_ws && c->ws) cudaFree(c->ws);
     delete c;
     return PHB_OK;
@@ -616,6 +622,31 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
     st = prepare_root(c, node_a, node_b, length, nullptr);
     if (st) return st;
     st = dna_resident(c, node_a, node_b, false, true);
+    if (st) return st;
+    PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pattern_lnl)
+        PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+int phb_lnl_from_host(phb_ctx* c, const uint8_t* codes, int n_chunks, int node_a, int node_b, double length,
+                      double* total, double* pattern_lnl) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, codes != nullptr && total != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host: NULL argument");
+    PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
+                "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
+    PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
+    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
+    if (st) return st;
+    c->have_pmats = true;
+    st = prepare_root(c, node_a, node_b, length, nullptr);
+    if (st) return st;
+    c->have_partials = false;
+    c->have_up = false;
+    st = dna_resident_from_host(c, codes, n_chunks > 0 ? n_chunks : 8, node_a, node_b);
     if (st) return st;
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)

@@ -63,6 +63,7 @@ struct ResArgs {
     double* pattern_lnl;
     double* partial_sums;
     int64_t S;
+    int64_t wt_begin, wt_end;   // warp tiles (32 patterns each) covered by this launch
     int warp_bytes;
 };
 
@@ -192,14 +193,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(
     unsigned char* s_stage = wbase + L::DESC_BYTES;
     unsigned char* s_opin = s_stage + 2 * L::STAGE_BYTES;
 
-    const int64_t n_wt = (p.S + 31) / 32;
+    const int64_t n_wt = p.wt_end;
     const int64_t gwarp = (int64_t)blockIdx.x * n_warps + warp;
     const int64_t wstride = (int64_t)gridDim.x * n_warps;
     const int n_steps = p.n_steps;
     const size_t S = (size_t)p.S;
     unsigned char* my_scratch = STORE ? nullptr : p.scratch + (size_t)gwarp * p.n_slots * L::SCRATCH_SLOT;
 
-    Cursor cd{0, gwarp};   // descriptor prefetch cursor (two rows ahead)
+    Cursor cd{0, p.wt_begin + gwarp};   // descriptor prefetch cursor (two rows ahead)
     Cursor cp = cd;        // data prefetch cursor (one row ahead)
     Cursor cc = cd;        // compute cursor
     int qd = 0, qp = 0, qc = 0;
@@ -451,7 +452,7 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPla
 }
 
 template <int K, bool STORE, bool ROOT>
-int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
+int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_end, double* partial_sums, int* grid_out) {
     using L = WarpLayout<K>;
     ResArgs a;
     a.rows = static_cast<const ResRow*>(c->d_res_rows);
@@ -469,8 +470,10 @@ int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
     a.catw = c->model_catw();
     a.weights = c->d_weights;
     a.pattern_lnl = c->d_pattern_lnl;
-    a.partial_sums = c->d_partial_sums;
+    a.partial_sums = partial_sums;
     a.S = c->S;
+    a.wt_begin = wt_begin;
+    a.wt_end = wt_end;
     a.warp_bytes = (L::WARP_BYTES + 127) / 128 * 128;
     auto kern = dna_resident_kernel<K, STORE, ROOT>;
     cudaFuncAttributes fa;
@@ -500,7 +503,7 @@ int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, best_w * 32, smem));
     if (per_sm < 1) per_sm = 1;
     per_sm = std::min(per_sm, best_ctas);
-    const int64_t n_wt = (c->S + 31) / 32;
+    const int64_t n_wt = wt_end - wt_begin;
     const int64_t blocks_needed = (n_wt + best_w - 1) / best_w;
     int64_t grid = std::min<int64_t>(blocks_needed, (int64_t)c->sm_count * per_sm);
     grid = std::min<int64_t>(grid, kMaxReduceBlocks);
@@ -519,17 +522,24 @@ int launch_resident(Ctx* c, const ResPlan& plan, int* grid_out) {
 }
 
 template <bool STORE, bool ROOT>
-int launch_resident_k(Ctx* c, const ResPlan& plan, int* grid_out) {
+int launch_resident_k(Ctx* c, const ResPlan& plan, int64_t b, int64_t e, double* ps, int* grid_out) {
     switch (c->K) {
-        case 1: return launch_resident<1, STORE, ROOT>(c, plan, grid_out);
-        case 2: return launch_resident<2, STORE, ROOT>(c, plan, grid_out);
-        case 4: return launch_resident<4, STORE, ROOT>(c, plan, grid_out);
-        case 8: return launch_resident<8, STORE, ROOT>(c, plan, grid_out);
+        case 1: return launch_resident<1, STORE, ROOT>(c, plan, b, e, ps, grid_out);
+        case 2: return launch_resident<2, STORE, ROOT>(c, plan, b, e, ps, grid_out);
+        case 4: return launch_resident<4, STORE, ROOT>(c, plan, b, e, ps, grid_out);
+        case 8: return launch_resident<8, STORE, ROOT>(c, plan, b, e, ps, grid_out);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel needs K in {1,2,4,8}");
 }
 
 }  // namespace
+
+int upload_plan(Ctx* c, const ResPlan& plan) {
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_res_rows, plan.rows.data(), plan.rows.size() * sizeof(ResRow),
+                                cudaMemcpyHostToDevice, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // plan.rows is a stack object
+    return PHB_OK;
+}
 
 // store = write every node block to the partials array; with_root = append the root step and reduce the lnL
 int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root) {
@@ -537,18 +547,58 @@ int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root) {
     int st = plan_rows(c, root_a, root_b, with_root, store, &plan);
     if (st) return st;
     if (plan.rows.empty()) return PHB_OK;
-    PHB_CUDA(c, cudaMemcpyAsync(c->d_res_rows, plan.rows.data(), plan.rows.size() * sizeof(ResRow),
-                                cudaMemcpyHostToDevice, c->stream));
-    PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // plan.rows is a stack object
+    st = upload_plan(c, plan);
+    if (st) return st;
     int grid = 0;
-    if (store && with_root) st = launch_resident_k<true, true>(c, plan, &grid);
-    else if (store) st = launch_resident_k<true, false>(c, plan, &grid);
-    else if (with_root) st = launch_resident_k<false, true>(c, plan, &grid);
+    const int64_t n_wt = (c->S + 31) / 32;
+    if (store && with_root) st = launch_resident_k<true, true>(c, plan, 0, n_wt, c->d_partial_sums, &grid);
+    else if (store) st = launch_resident_k<true, false>(c, plan, 0, n_wt, c->d_partial_sums, &grid);
+    else if (with_root) st = launch_resident_k<false, true>(c, plan, 0, n_wt, c->d_partial_sums, &grid);
     else return c->fail(PHB_ERR_INVALID, "resident kernel: nothing to produce");
     if (st) return st;
     c->resident_slots = plan.n_slots;
     if (with_root) return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
     return PHB_OK;
+}
+
+// Whole evaluation starting from HOST tip codes: the pattern axis is cut into chunks; chunk i+1 is copied
+// host->device on a second stream while the resident kernel walks chunk i (patterns are independent, so a
+// chunk can be evaluated as soon as its codes have landed).  One synchronisation at the very end.
+int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int root_a, int root_b) {
+    ResPlan plan;
+    int st = plan_rows(c, root_a, root_b, true, false, &plan);
+    if (st) return st;
+    st = upload_plan(c, plan);
+    if (st) return st;
+    if (c->copy_stream == nullptr) {
+        PHB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) PHB_CUDA(c, cudaEventCreateWithFlags(&c->chunk_events[i], cudaEventDisableTiming));
+        PHB_CUDA(c, cudaEventCreateWithFlags(&c->start_event, cudaEventDisableTiming));
+    }
+    const int64_t n_wt = (c->S + 31) / 32;
+    n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_chunks, kMaxChunks), n_wt));
+    // the copy stream must not overtake work already queued on the compute stream (previous evaluation)
+    PHB_CUDA(c, cudaEventRecord(c->start_event, c->stream));
+    PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
+    int* d_flag = reinterpret_cast<int*>(c->d_result + 4 * kMaxEdgeBatch - 1);
+    PHB_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
+    int parts = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+        const int64_t b = n_wt * i / n_chunks, e = n_wt * (i + 1) / n_chunks;
+        const int64_t s0 = b * 32, s1 = std::min<int64_t>(e * 32, c->S);
+        PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws + s0, c->code_pitch, codes_host + s0, (size_t)c->S, (size_t)(s1 - s0),
+                                      (size_t)c->n_tips, cudaMemcpyHostToDevice, c->copy_stream));
+        PHB_CUDA(c, cudaEventRecord(c->chunk_events[i], c->copy_stream));
+        PHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[i], 0));
+        int grid = 0;
+        st = launch_resident_k<false, true>(c, plan, b, e, c->d_partial_sums + parts, &grid);
+        if (st) return st;
+        parts += grid;
+        if (parts + grid > kMaxReduceBlocks * 4) return c->fail(PHB_ERR_UNSUPPORTED, "too many chunks for the reduction buffer");
+    }
+    c->d_codes = c->d_codes_ws;
+    c->resident_slots = plan.n_slots;
+    return launch_final_reduce(c, c->d_partial_sums, parts, 1, c->d_result);
 }
 
 }  // namespace phb

@@ -96,6 +96,10 @@ struct Ctx {
     unsigned char* d_scratch = nullptr;  // L2-resident parking area of the lnL-only resident kernel
     size_t scratch_bytes = 0;
     size_t smem_per_sm = 0;
+    // host->device pipelining of phb_lnl_from_host
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_events[32] = {};
+    cudaEvent_t start_event = nullptr;
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
     double* d_partial_sums = nullptr;  // [kMaxReduceBlocks * 4]
@@ -142,6 +146,7 @@ struct Ctx {
 
 constexpr int kMaxReduceBlocks = 4096;
 constexpr int kMaxEdgeBatch = 64;
+constexpr int kMaxChunks = 32;
 
 // kernel families (each returns a phb_status) ---------------------------------------------------
 // pmatrix.cu
@@ -160,6 +165,7 @@ bool dna_supported(const Ctx* c);
 int dna_run_rows(Ctx* c, const RowSet& rs, int mode);
 int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root);   // clv_dna_resident.cu
+int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int root_a, int root_b);
 // clv_generic.cu (any A <= 64, any K <= 16)
 int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);

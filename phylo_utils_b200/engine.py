@@ -187,6 +187,18 @@ class LikelihoodEngine(object):
                                             dptr(pattern) if want_pattern else None))
         return total.value, pattern
 
+    def lnl_from_host(self, codes, node_a, node_b, length, n_chunks=0, want_pattern=False):
+        """Evaluate starting from host tip codes (numpy uint8 (n_tips, n_patterns), ideally pinned); copy and compute overlap."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if codes.shape != (self.n_tips, self.n_patterns):
+            raise ValueError("codes must be (n_tips, n_patterns)")
+        total = ctypes.c_double(0.0)
+        pattern = np.empty(self.n_patterns) if want_pattern else None
+        self._ok(self._lib.phb_lnl_from_host(self._ctx, ctypes.c_void_p(codes.ctypes.data), int(n_chunks), int(node_a),
+                                             int(node_b), float(length), ctypes.byref(total),
+                                             dptr(pattern) if want_pattern else None))
+        return total.value, pattern
+
     # ---- read-back --------------------------------------------------------------------------
     def get_partials(self, node):
         out = np.empty((self.n_patterns, self.n_cat, self.n_states))

@@ -167,3 +167,32 @@ def test_resident_other_category_counts(K, rate):
     tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
     want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, r.rates, r.weights)
     assert_lnl_close(pattern, want)
+
+
+def test_pipelined_evaluation_from_host_codes_matches_resident():
+    import torch
+    tree, names, codes, lut = synthetic(120, 70000, 4, seed=77)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    a, b = tm.traversal.root_edge
+    length = tm.traversal.brlens[(a, b)]
+    total, pattern = tm.engine.lnl_resident(a, b, length, want_pattern=True)
+    # a different alignment arrives on the host (pinned): evaluate it with copy/compute overlap
+    rng = np.random.default_rng(5)
+    other = rng.integers(0, 5, size=codes.shape).astype(np.uint8)
+    pinned = torch.from_numpy(other).pin_memory().numpy()
+    for chunks in (1, 3, 8, 32):
+        t2, p2 = tm.engine.lnl_from_host(pinned, a, b, length, n_chunks=chunks, want_pattern=True)
+        tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[other[i]]) for i, n in enumerate(names)}
+        want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights)
+        assert_lnl_close(p2, want)
+        assert_lnl_close(t2, want.sum())
+    # and the original alignment again, through the same path
+    t3, p3 = tm.engine.lnl_from_host(codes, a, b, length, want_pattern=True)
+    assert np.array_equal(p3, pattern) and t3 == total
