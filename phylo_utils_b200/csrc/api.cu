@@ -62,7 +62,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.scratch = take(p.scratch_size);
     p.pattern_lnl = take((size_t)S * 8);
     p.cat_lnl = take((size_t)S * K * 8);
-    p.partial = take((size_t)kMaxReduceBlocks * 4 * 8);
+    p.partial = take((size_t)kPartialCap * 8);
     p.result = take((size_t)kMaxEdgeBatch * 4 * 8);
     p.total = off;
     return p;

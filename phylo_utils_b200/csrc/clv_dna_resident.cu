@@ -452,7 +452,8 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPla
 }
 
 template <int K, bool STORE, bool ROOT>
-int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_end, double* partial_sums, int* grid_out) {
+int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_end, double* partial_sums, int max_grid,
+                    int* grid_out) {
     using L = WarpLayout<K>;
     ResArgs a;
     a.rows = static_cast<const ResRow*>(c->d_res_rows);
@@ -506,7 +507,7 @@ int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_en
     const int64_t n_wt = wt_end - wt_begin;
     const int64_t blocks_needed = (n_wt + best_w - 1) / best_w;
     int64_t grid = std::min<int64_t>(blocks_needed, (int64_t)c->sm_count * per_sm);
-    grid = std::min<int64_t>(grid, kMaxReduceBlocks);
+    grid = std::min<int64_t>(grid, max_grid);
     if (!STORE) {   // every resident warp needs its own scratch stripe
         const int64_t cap = (int64_t)(c->scratch_bytes / ((size_t)plan.n_slots * L::SCRATCH_SLOT)) / best_w;
         if (cap < 1) return c->fail(PHB_ERR_NOMEM, "resident kernel: scratch area too small");
@@ -522,12 +523,12 @@ int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_en
 }
 
 template <bool STORE, bool ROOT>
-int launch_resident_k(Ctx* c, const ResPlan& plan, int64_t b, int64_t e, double* ps, int* grid_out) {
+int launch_resident_k(Ctx* c, const ResPlan& plan, int64_t b, int64_t e, double* ps, int max_grid, int* grid_out) {
     switch (c->K) {
-        case 1: return launch_resident<1, STORE, ROOT>(c, plan, b, e, ps, grid_out);
-        case 2: return launch_resident<2, STORE, ROOT>(c, plan, b, e, ps, grid_out);
-        case 4: return launch_resident<4, STORE, ROOT>(c, plan, b, e, ps, grid_out);
-        case 8: return launch_resident<8, STORE, ROOT>(c, plan, b, e, ps, grid_out);
+        case 1: return launch_resident<1, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 2: return launch_resident<2, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 4: return launch_resident<4, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 8: return launch_resident<8, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel needs K in {1,2,4,8}");
 }
@@ -551,9 +552,9 @@ int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root) {
     if (st) return st;
     int grid = 0;
     const int64_t n_wt = (c->S + 31) / 32;
-    if (store && with_root) st = launch_resident_k<true, true>(c, plan, 0, n_wt, c->d_partial_sums, &grid);
-    else if (store) st = launch_resident_k<true, false>(c, plan, 0, n_wt, c->d_partial_sums, &grid);
-    else if (with_root) st = launch_resident_k<false, true>(c, plan, 0, n_wt, c->d_partial_sums, &grid);
+    if (store && with_root) st = launch_resident_k<true, true>(c, plan, 0, n_wt, c->d_partial_sums, kPartialCap, &grid);
+    else if (store) st = launch_resident_k<true, false>(c, plan, 0, n_wt, c->d_partial_sums, kPartialCap, &grid);
+    else if (with_root) st = launch_resident_k<false, true>(c, plan, 0, n_wt, c->d_partial_sums, kPartialCap, &grid);
     else return c->fail(PHB_ERR_INVALID, "resident kernel: nothing to produce");
     if (st) return st;
     c->resident_slots = plan.n_slots;
@@ -591,10 +592,9 @@ int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int 
         PHB_CUDA(c, cudaEventRecord(c->chunk_events[i], c->copy_stream));
         PHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[i], 0));
         int grid = 0;
-        st = launch_resident_k<false, true>(c, plan, b, e, c->d_partial_sums + parts, &grid);
+        st = launch_resident_k<false, true>(c, plan, b, e, c->d_partial_sums + parts, kPartialCap / n_chunks, &grid);
         if (st) return st;
         parts += grid;
-        if (parts + grid > kMaxReduceBlocks * 4) return c->fail(PHB_ERR_UNSUPPORTED, "too many chunks for the reduction buffer");
     }
     c->d_codes = c->d_codes_ws;
     c->resident_slots = plan.n_slots;

@@ -102,7 +102,7 @@ struct Ctx {
     cudaEvent_t start_event = nullptr;
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
-    double* d_partial_sums = nullptr;  // [kMaxReduceBlocks * 4]
+    double* d_partial_sums = nullptr;  // [kPartialCap]
     double* d_result = nullptr;        // [4 * kMaxEdgeBatch]
 
     // host mirrors
@@ -145,6 +145,7 @@ struct Ctx {
 };
 
 constexpr int kMaxReduceBlocks = 4096;
+constexpr int kPartialCap = 65536;   // doubles in the block-sum buffer
 constexpr int kMaxEdgeBatch = 64;
 constexpr int kMaxChunks = 32;
 
