@@ -2,6 +2,7 @@
 // Every function maps to a piece of TreeModel (see include/phylo_b200.h for the file:line map).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -75,6 +76,16 @@ bool shape_ok(int n_tips, int64_t S, int K, int A, std::string* why) {
     if (A < 2 || A > 64) { *why = "number of states must be in 2..64"; return false; }
     return true;
 }
+
+}  // namespace
+
+int run_rows(Ctx* c, const RowSet& rs, int mode) {
+    if (dna_supported(c)) return dna_run_rows(c, rs, mode);
+    if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr) return mma_run_rows(c, rs, mode);
+    return generic_run_rows(c, rs, mode);
+}
+
+namespace {
 
 int activate(Ctx* c) {
     PHB_CUDA(c, cudaSetDevice(c->device));
@@ -546,7 +557,7 @@ int phb_compute_partials(phb_ctx* c, int mode) {
     PHB_REQUIRE(c, mode != PHB_MODE_LEVEL || !c->level_offsets.empty(), PHB_ERR_STATE,
                 "phb_compute_partials: level mode needs level offsets in the schedule");
     const RowSet rs{c->d_rows, c->n_rows(), &c->level_offsets};
-    st = dna_supported(c) ? dna_run_rows(c, rs, mode) : generic_run_rows(c, rs, mode);
+    st = run_rows(c, rs, mode);
     if (st) return st;
     c->have_partials = true;
     c->have_up = false;

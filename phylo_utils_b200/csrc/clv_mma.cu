@@ -1,0 +1,263 @@
+// Felsenstein pruning on the FP64 tensor cores (DMMA) for the two large alphabets:
+// amino acids (A = 20) and sense codons (A = 61).
+//
+// With 20 or 61 states, P . L is a real dense contraction (BASELINE north_star, subsystem 3): for one
+// category and one child
+//
+//     X[i][s] = sum_j P[i][j] . L[s][j]              i, j = states, s = pattern
+//
+// is a (A x A) . (A x N) product over a tile of N patterns.  It is issued as
+// mma.sync.aligned.m8n8k4.row.col.f64 (SASS DMMA; tcgen05 has no FP64 kind):
+//     A operand = P       (row-major, 8 states x 4 states per instruction)
+//     B operand = L^T     ("column-major": the 4 states of one pattern are contiguous)
+//     C/D       = X       (8 states x 8 patterns, two doubles per lane)
+// States are padded to MT*8 rows and KS*4 columns with zeros (20 -> 24 x 20, 61 -> 64 x 64).
+//
+// A CTA owns a tile of patterns; each warp owns NT * 8 of them and keeps both children's accumulators in
+// registers, multiplies them element-wise (same fragment layout), finds the per-pattern maximum with three
+// shuffles, and writes the result through its own rows of the shared child tile back to global memory with
+// coalesced stores.  P[k] for the two children is staged in shared memory once per (row, category) and
+// shared by all warps; all shared arrays use a row pitch = 4 (mod 16) doubles so that the 8 x 4 fragment
+// loads are bank-conflict free.  Semantics (reference `clv`, numba_likelihood_engine.py:10-46, with the
+// per-pattern binary exponent of clv_dna.cu) and data layout are those of clv_generic.cu, which remains the
+// fallback for every other state count.
+#include "common.cuh"
+
+namespace phb {
+
+namespace {
+
+struct MmaArgs {
+    const OpRow* rows;
+    int row_begin, row_end;
+    const double* pmats;  // [pidx][K][A][A]
+    const uint8_t* codes;
+    size_t pitch;
+    const double* lut;    // [256][A]
+    double* clv;
+    int32_t* scale;
+    int64_t S;
+    int64_t n_tiles;
+    int A, K;
+};
+
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+constexpr int pad_pitch(int cols) {   // smallest pitch >= cols with pitch % 16 == 4
+    int p = cols;
+    while (p % 16 != 4) ++p;
+    return p;
+}
+
+template <int MT, int KS, int NT, int WARPS, bool LEVEL>
+__global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) {
+    constexpr int MROWS = MT * 8, KCOLS = KS * 4;
+    constexpr int LDP = pad_pitch(KCOLS);
+    constexpr int LDL = pad_pitch(KCOLS > MROWS ? KCOLS : MROWS);
+    constexpr int TS = WARPS * NT * 8;
+    extern __shared__ double sm[];
+    double* P1 = sm;                     // [MROWS][LDP]
+    double* P2 = P1 + MROWS * LDP;
+    double* La = P2 + MROWS * LDP;       // [TS][LDL]   child 1 rows, later the output rows
+    double* Lb = La + TS * LDL;
+    const int A = p.A, K = p.K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fr = lane >> 2, fc = lane & 3;          // fragment row / column
+    const size_t S = (size_t)p.S;
+    double* myLa = La + (size_t)warp * NT * 8 * LDL;
+    double* myLb = Lb + (size_t)warp * NT * 8 * LDL;
+
+    const int64_t items = LEVEL ? (int64_t)(p.row_end - p.row_begin) * p.n_tiles : p.n_tiles;
+    for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const int64_t tile = LEVEL ? it % p.n_tiles : it;
+        const int r0 = LEVEL ? p.row_begin + (int)(it / p.n_tiles) : p.row_begin;
+        const int r1 = LEVEL ? r0 + 1 : p.row_end;
+        const int64_t wsite0 = tile * TS + (int64_t)warp * NT * 8;   // first pattern of this warp
+        for (int r = r0; r < r1; ++r) {
+            const OpRow row = p.rows[r];
+            double* out = p.clv + (size_t)row.dst * S * K * A;
+            double mx[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mx[nt][0] = mx[nt][1] = 0.0;
+
+            for (int k = 0; k < K; ++k) {
+                __syncthreads();   // every warp is done with the previous P
+                {
+                    const double* q1 = p.pmats + ((size_t)row.pidx[0] * K + k) * A * A;
+                    const double* q2 = p.pmats + ((size_t)row.pidx[1] * K + k) * A * A;
+                    for (int e = threadIdx.x; e < MROWS * KCOLS; e += WARPS * 32) {
+                        const int i = e / KCOLS, j = e - i * KCOLS;
+                        const bool in = i < A && j < A;
+                        P1[i * LDP + j] = in ? __ldg(q1 + i * A + j) : 0.0;
+                        P2[i * LDP + j] = in ? __ldg(q2 + i * A + j) : 0.0;
+                    }
+                }
+                // this warp's child rows (zero padded up to KCOLS)
+                for (int c = 0; c < 2; ++c) {
+                    double* tileL = c == 0 ? myLa : myLb;
+                    if (row.kind[c] == SRC_TIP) {
+                        const uint8_t* codes = p.codes + (size_t)row.src[c] * p.pitch;
+                        for (int e = lane; e < NT * 8 * KCOLS; e += 32) {
+                            const int n = e / KCOLS, j = e - n * KCOLS;
+                            const int64_t s = wsite0 + n;
+                            tileL[n * LDL + j] = (s < p.S && j < A) ? __ldg(p.lut + (size_t)codes[s] * A + j) : 0.0;
+                        }
+                    } else {
+                        const double* base = p.clv + (size_t)row.src[c] * S * K * A;
+                        for (int e = lane; e < NT * 8 * KCOLS; e += 32) {
+                            const int n = e / KCOLS, j = e - n * KCOLS;
+                            const int64_t s = wsite0 + n;
+                            tileL[n * LDL + j] = (s < p.S && j < A) ? base[((size_t)s * K + k) * A + j] : 0.0;
+                        }
+                    }
+                }
+                __syncthreads();   // P staged (and, within the warp, its own child rows)
+
+                double acc1[MT][NT][2], acc2[MT][NT][2];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) acc1[mt][nt][0] = acc1[mt][nt][1] = acc2[mt][nt][0] = acc2[mt][nt][1] = 0.0;
+#pragma unroll 2
+                for (int ks = 0; ks < KS; ++ks) {
+                    double b1[NT], b2[NT];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        b1[nt] = myLa[(nt * 8 + fr) * LDL + ks * 4 + fc];
+                        b2[nt] = myLb[(nt * 8 + fr) * LDL + ks * 4 + fc];
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const double a1 = P1[(mt * 8 + fr) * LDP + ks * 4 + fc];
+                        const double a2 = P2[(mt * 8 + fr) * LDP + ks * 4 + fc];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            dmma(acc1[mt][nt], a1, b1[nt]);
+                            dmma(acc2[mt][nt], a2, b2[nt]);
+                        }
+                    }
+                }
+                __syncwarp();      // all lanes have read their child rows; they now become the output rows
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const double o = acc1[mt][nt][q] * acc2[mt][nt][q];
+                            const int i = mt * 8 + fr, n = nt * 8 + 2 * fc + q;
+                            myLa[n * LDL + i] = o;
+                            if (i < A) mx[nt][q] = fmax(mx[nt][q], o);
+                        }
+                __syncwarp();
+                for (int e = lane; e < NT * 8 * A; e += 32) {   // coalesced: A contiguous doubles per pattern
+                    const int n = e / A, i = e - n * A;
+                    const int64_t s = wsite0 + n;
+                    if (s < p.S) out[((size_t)s * K + k) * A + i] = myLa[n * LDL + i];
+                }
+                __syncwarp();
+            }
+            // per-pattern maximum over states (lanes sharing fc) and categories (already folded into mx)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double m = mx[nt][q];
+                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                    mx[nt][q] = m;
+                }
+            // lanes 0..3 (fr == 0) finalise the patterns 2*fc + q of every n-tile
+            if (fr == 0) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int64_t s = wsite0 + nt * 8 + 2 * fc + q;
+                        if (s >= p.S) continue;
+                        int e = 0;
+                        if (row.kind[0] != SRC_TIP) e += p.scale[(size_t)row.src[0] * S + s];
+                        if (row.kind[1] != SRC_TIP) e += p.scale[(size_t)row.src[1] * S + s];
+                        const int hi = __double2hiint(mx[nt][q]);
+                        if (hi < kScaleThresholdHi && hi >= 0x00100000) {
+                            const int shift = 1023 - (hi >> 20);
+                            const double f = pow2i(shift);
+                            double* mine = out + (size_t)s * K * A;
+                            for (int z = 0; z < K * A; ++z) mine[z] *= f;
+                            e -= shift;
+                        }
+                        p.scale[(size_t)row.dst * S + s] = e;
+                    }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int MT, int KS, int NT, int WARPS, bool LEVEL>
+int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
+    constexpr int MROWS = MT * 8, KCOLS = KS * 4;
+    constexpr int LDP = pad_pitch(KCOLS);
+    constexpr int LDL = pad_pitch(KCOLS > MROWS ? KCOLS : MROWS);
+    constexpr int TS = WARPS * NT * 8;
+    MmaArgs a;
+    a.rows = d_rows;
+    a.row_begin = row_begin;
+    a.row_end = row_end;
+    a.pmats = c->d_pmats;
+    a.codes = c->d_codes;
+    a.pitch = c->code_pitch;
+    a.lut = c->d_lut;
+    a.clv = c->d_clv;
+    a.scale = c->d_scale;
+    a.S = c->S;
+    a.n_tiles = (c->S + TS - 1) / TS;
+    a.A = c->A;
+    a.K = c->K;
+    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double);
+    auto kern = mma_prune_kernel<MT, KS, NT, WARPS, LEVEL>;
+    PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t items = LEVEL ? (int64_t)(row_end - row_begin) * a.n_tiles : a.n_tiles;
+    const int64_t cap = (int64_t)c->sm_count * per_sm;
+    const int grid = (int)(items < cap ? items : cap);
+    if (grid <= 0) return PHB_OK;
+    kern<<<grid, WARPS * 32, smem, c->stream>>>(a);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    return PHB_OK;
+}
+
+template <int MT, int KS, int NT, int WARPS>
+int run_rows_mma(Ctx* c, const RowSet& rs, int mode) {
+    if (rs.n_rows == 0) return PHB_OK;
+    if (mode == PHB_MODE_LEVEL) {
+        const std::vector<int32_t>& lv = *rs.levels;
+        for (int l = 0; l + 1 < (int)lv.size(); ++l) {
+            if (lv[l + 1] <= lv[l]) continue;
+            int st = launch_mma<MT, KS, NT, WARPS, true>(c, rs.d_rows, lv[l], lv[l + 1]);
+            if (st) return st;
+        }
+        return PHB_OK;
+    }
+    return launch_mma<MT, KS, NT, WARPS, false>(c, rs.d_rows, 0, rs.n_rows);
+}
+
+}  // namespace
+
+bool mma_supported(const Ctx* c) { return c->A == 20 || c->A == 61; }
+
+int mma_run_rows(Ctx* c, const RowSet& rs, int mode) {
+    if (c->A == 20) return run_rows_mma<3, 5, 4, 4>(c, rs, mode);    // 24 x 20 P, 128 patterns per CTA
+    if (c->A == 61) return run_rows_mma<8, 16, 1, 8>(c, rs, mode);   // 64 x 64 P, 64 patterns per CTA
+    return c->fail(PHB_ERR_UNSUPPORTED, "DMMA kernels cover 20 and 61 states");
+}
+
+}  // namespace phb

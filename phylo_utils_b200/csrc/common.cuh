@@ -169,6 +169,11 @@ int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root);   
 int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int root_a, int root_b);
 // clv_generic.cu (any A <= 64, any K <= 16)
 int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
+// clv_mma.cu (A == 20 or 61, FP64 tensor cores)
+bool mma_supported(const Ctx* c);
+int mma_run_rows(Ctx* c, const RowSet& rs, int mode);
+// picks the kernel family for this context's shape
+int run_rows(Ctx* c, const RowSet& rs, int mode);
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 // derivs.cu
 int launch_up_partials(Ctx* c, int node_a, int node_b);

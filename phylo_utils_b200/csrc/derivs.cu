@@ -214,7 +214,7 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
                                 c->stream));
     PHB_CUDA(c, cudaStreamSynchronize(c->stream));
     const RowSet rs{c->d_up_rows, n_up, &c->up_levels};
-    return dna_supported(c) ? dna_run_rows(c, rs, mode) : generic_run_rows(c, rs, mode);
+    return run_rows(c, rs, mode);
 }
 
 int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
