@@ -64,6 +64,11 @@ def report(name, tm, n_taxa, n_pat, A, reps, derivs=False):
         d_ms, d = timed(lambda: tm.edge_derivatives(all_nodes), max(1, reps // 2))
         out.update(up_pass_ms=up_ms, all_edge_derivatives_ms=d_ms, n_edges=int(len(all_nodes)),
                    sweep_ms=ms + up_ms + d_ms, max_abs_dlnl=float(np.abs(d[:, 1]).max()))
+        if "--newton" in sys.argv:
+            from phylo_utils_b200.optimise import optimise_branch_lengths
+            t0 = time.perf_counter()
+            res = optimise_branch_lengths(tm, max_sweeps=3, inner_iterations=2, tol=0.0)
+            out.update(newton_sweeps=res["sweeps"], newton_wall_s=time.perf_counter() - t0, newton_trace=res["trace"])
     print(json.dumps(out), flush=True)
 
 
