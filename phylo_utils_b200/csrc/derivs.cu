@@ -138,6 +138,88 @@ __global__ void __launch_bounds__(kDerivThreads) edge_deriv_kernel(const DerivAr
     }
 }
 
+// 4-state specialisation: lane = (pattern, category) as in clv_dna.cu, one 256-bit load per end of the
+// edge, the edge's three 4x4 matrices for this lane's category in registers, mixture by width-K shuffles.
+// HBM-bound: 2 x K x 32 B per pattern and edge.
+template <int K>
+__global__ void __launch_bounds__(128) dna_edge_deriv_kernel(const DerivArgs p) {
+    constexpr int SPI = 128 / K;
+    __shared__ double s_lut[256][4];
+    __shared__ double s_red[3][4];
+    const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
+    for (int i = tid; i < 256 * 4; i += 128) (&s_lut[0][0])[i] = p.lut[i];
+    __syncthreads();
+    double M[3][16];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double* src = p.mats + (((size_t)d * p.batch_cap + e) * K + k) * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M[d][i] = src[i];
+    }
+    double pi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pi[i] = p.freqs[i];
+    const double wk = p.catw[k];
+    const size_t S = (size_t)p.S;
+    const int ka = p.kind_a[e], kb = p.kind_b[e];
+    const size_t sa = (size_t)p.src_a[e], sb = (size_t)p.src_b[e];
+    double tot[3] = {0.0, 0.0, 0.0};
+    const int64_t n_iter = (p.S + SPI - 1) / SPI;
+    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
+        const int64_t s = it * SPI + g;
+        const bool ok = s < p.S;
+        const size_t ss = ok ? (size_t)s : 0;
+        double a[4], b[4];
+        int ex = 0;
+        if (ka == SRC_TIP) {
+            const int code = p.codes[sa * p.pitch + ss];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = s_lut[code][i];
+        } else {
+            ld256(p.clv + ((sa * S + ss) * K + k) * 4, a);
+            ex += p.scale[sa * S + ss];
+        }
+        if (kb == SRC_TIP) {
+            const int code = p.codes[sb * p.pitch + ss];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = s_lut[code][i];
+        } else {
+            ld256(p.clv + ((sb * S + ss) * K + k) * 4, b);
+            ex += p.scale[sb * S + ss];
+        }
+        double f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double x = M[d][4 * i] * a[0];
+                x = fma(M[d][4 * i + 1], a[1], x);
+                x = fma(M[d][4 * i + 2], a[2], x);
+                x = fma(M[d][4 * i + 3], a[3], x);
+                acc = fma(pi[i] * b[i], x, acc);
+            }
+            f[d] = wk * acc;
+#pragma unroll
+            for (int o = K / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+        }
+        if (ok && k == 0) {
+            const double w = p.weights ? p.weights[ss] : 1.0;
+            const double gq = f[1] / f[0];
+            tot[0] += w * (f[0] > 0 ? log(f[0]) + (double)ex * kLn2 : -INFINITY);
+            tot[1] += w * gq;
+            tot[2] += w * (f[2] / f[0] - gq * gq);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double v = warp_sum(tot[d]);
+        if ((tid & 31) == 0) s_red[d][tid >> 5] = v;
+    }
+    __syncthreads();
+    if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
+}
+
 void fill_operand(const Ctx* c, int node, int* src, int* kind) {
     if (c->node_tip[node] >= 0) {
         *kind = SRC_TIP;
@@ -258,16 +340,27 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
         p.A = A;
         p.K = K;
         p.batch_cap = kMaxEdgeBatch;
-        const int64_t span = (int64_t)kDerivThreads * kSitesPerThread;
+        const bool dna = dna_supported(c);
+        const int64_t span = dna ? 128 / K : (int64_t)kDerivThreads * kSitesPerThread;
         int64_t parts = (c->S + span - 1) / span;
-        const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(kMaxReduceBlocks * 4 / (3 * n), (int64_t)c->sm_count * 8));
+        // enough CTAs per edge to fill the chip across the whole batch, few enough for the block-sum buffer
+        const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(kPartialCap / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 8 / n)));
         if (parts > cap) parts = cap;
         p.n_parts = (int)parts;
         p.partial_sums = c->d_partial_sums;
-        const size_t smem = 3 * (size_t)A * A * sizeof(double);
-        PHB_CUDA(c, cudaFuncSetAttribute(edge_deriv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)parts, (unsigned)n);
-        edge_deriv_kernel<<<grid, kDerivThreads, smem, c->stream>>>(p);
+        if (dna) {
+            switch (K) {
+                case 1: dna_edge_deriv_kernel<1><<<grid, 128, 0, c->stream>>>(p); break;
+                case 2: dna_edge_deriv_kernel<2><<<grid, 128, 0, c->stream>>>(p); break;
+                case 4: dna_edge_deriv_kernel<4><<<grid, 128, 0, c->stream>>>(p); break;
+                default: dna_edge_deriv_kernel<8><<<grid, 128, 0, c->stream>>>(p); break;
+            }
+        } else {
+            const size_t smem = 3 * (size_t)A * A * sizeof(double);
+            PHB_CUDA(c, cudaFuncSetAttribute(edge_deriv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            edge_deriv_kernel<<<grid, kDerivThreads, smem, c->stream>>>(p);
+        }
         c->launches++;
         PHB_CUDA(c, cudaGetLastError());
         int st = launch_final_reduce(c, c->d_partial_sums, (int)parts, 3 * n, c->d_result);
