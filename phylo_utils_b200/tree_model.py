@@ -347,12 +347,17 @@ class TreeModel(object):
         return self.engine.edge_derivatives(nodes, lengths, chain_rule)
 
     def branch_length_above(self, node):
+        """Length of the edge above ``node`` (the root edge for either root child)."""
         a, b = self.traversal.root_edge
-        if node == a:
+        if node == a or node == b:
             return self.traversal.brlens[(a, b)]
-        if node == b:
-            return self.traversal.brlens[(a, b)]
-        for par, c1, c2 in self.traversal.postorder_traversal:
-            if node == c1 or node == c2:
-                return self.traversal.brlens[(int(par), int(node))]
-        raise ValueError("node {} has no edge above it".format(node))
+        parents = getattr(self, "_parent_map", None)
+        if parents is None or getattr(self, "_parent_map_for", None) is not self.traversal:
+            parents = {}
+            for par, c1, c2 in self.traversal.postorder_traversal:
+                parents[int(c1)] = int(par)
+                parents[int(c2)] = int(par)
+            self._parent_map, self._parent_map_for = parents, self.traversal
+        if int(node) not in parents:
+            raise ValueError("node {} has no edge above it".format(node))
+        return self.traversal.brlens[(int(node), parents[int(node)])]
