@@ -542,7 +542,24 @@ int phb_compute_partials(phb_ctx* c, int mode) {
         c->have_partials = true;
         return PHB_OK;
     }
-    if (mode == PHB_MODE_AUTO) mode = c->level_offsets.empty() ? PHB_MODE_TILE : PHB_MODE_LEVEL;
+    if (mode == PHB_MODE_AUTO) {
+        if (!c->level_offsets.empty()) {
+            mode = PHB_MODE_LEVEL;
+        } else if (dna_supported(c) && c->S >= 16384) {
+            // operand-resident walk with streamed stores; needs a post-order schedule - if the caller's row order
+            // is not one, fall back to the plain tile walk
+            st = dna_resident(c, -1, -1, true, false);
+            if (st == PHB_OK) {
+                c->have_partials = true;
+                c->have_up = false;
+                return PHB_OK;
+            }
+            if (st != PHB_ERR_UNSUPPORTED) return st;
+            mode = PHB_MODE_TILE;
+        } else {
+            mode = PHB_MODE_TILE;
+        }
+    }
     PHB_REQUIRE(c, mode == PHB_MODE_TILE || mode == PHB_MODE_LEVEL || mode == PHB_MODE_RESIDENT, PHB_ERR_INVALID,
                 "phb_compute_partials: bad mode");
     if (mode == PHB_MODE_RESIDENT) {

@@ -153,7 +153,9 @@ class TreeModel(object):
             return _lib.PHB_MODE_LEVEL
         if self.mode == "resident" or not self.store_partials:
             return _lib.PHB_MODE_RESIDENT
-        return _lib.PHB_MODE_TILE if n_patterns >= _TILE_MODE_MIN_PATTERNS else _lib.PHB_MODE_LEVEL
+        if n_patterns < _TILE_MODE_MIN_PATTERNS:
+            return _lib.PHB_MODE_LEVEL
+        return _lib.PHB_MODE_AUTO       # library picks: operand-resident walk for 4-state models, tile walk otherwise
 
     def initialise(self):
         """Allocate device storage, upload tips / model / schedule, run one post-order pass."""
