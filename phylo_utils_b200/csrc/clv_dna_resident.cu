@@ -101,64 +101,86 @@ struct Cursor {
     int64_t wt;
 };
 
+// One operand's contribution x[i] = sum_j P[k][i][j] . v[j] for this lane's pattern.
+//   TIP : if every lane of the warp holds an unambiguous state, P . onehot is a column of P - four 8-byte
+//         gathers and no arithmetic (the usual case: a tip operand appears in 2/3 of all rows);
+//         otherwise the generic product with the look-up-table row.
+//   PREV: operand in registers.   SLOT: operand in this warp's shared-memory tile.
+template <int K, int KIND>
+struct Operand {
+    double t[4];        // TIP, generic path: the look-up-table row
+    int col;            // TIP, gather path: the state index
+    bool gather;
+    const unsigned char* tile;
+
+    __device__ __forceinline__ int init(const unsigned char* st, int code_off, const unsigned char* opin,
+                                        const unsigned char* s_lut, const signed char* s_col, int lane, int prev_e) {
+        using L = WarpLayout<K>;
+        tile = opin;
+        gather = false;
+        col = 0;
+        if (KIND == KIND_TIP) {
+            const int code = st[L::P_BYTES + code_off + lane];
+            col = s_col[code];
+            gather = !__any_sync(0xffffffffu, col < 0);
+            if (!gather) {
+                const double2 lo = *reinterpret_cast<const double2*>(s_lut + code * 32);
+                const double2 hi = *reinterpret_cast<const double2*>(s_lut + code * 32 + 16);
+                t[0] = lo.x; t[1] = lo.y; t[2] = hi.x; t[3] = hi.y;
+            }
+            return 0;
+        }
+        if (KIND == KIND_PREV) return prev_e;
+        return *reinterpret_cast<const int*>(opin + L::TILE_BYTES + lane * 4);
+    }
+
+    __device__ __forceinline__ void apply(const unsigned char* pk, int k, int lane, const double (&prev_k)[4],
+                                          double (&x)[4]) const {
+        using L = WarpLayout<K>;
+        if (KIND == KIND_TIP && gather) {
+            const double* q = reinterpret_cast<const double*>(pk) + col;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = q[4 * i];
+            return;
+        }
+        double v[4];
+        if (KIND == KIND_TIP) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = t[i];
+        } else if (KIND == KIND_PREV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = prev_k[i];
+        } else {
+            const double2 lo = *reinterpret_cast<const double2*>(tile + lane * L::ROWB + k * 32);
+            const double2 hi = *reinterpret_cast<const double2*>(tile + lane * L::ROWB + k * 32 + 16);
+            v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+        }
+        const double2* q = reinterpret_cast<const double2*>(pk);   // P rows: warp-wide broadcast reads
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 r0 = q[2 * i], r1 = q[2 * i + 1];
+            x[i] = fma(r1.y, v[3], fma(r1.x, v[2], fma(r0.y, v[1], r0.x * v[0])));
+        }
+    }
+};
+
 // prev[k] <- (P1[k] . a[k]) * (P2[k] . b[k]) for this lane's pattern; returns the cumulative exponent
 template <int K, int KA, int KB>
 __device__ __forceinline__ int row_update(const unsigned char* st, const unsigned char* oa, const unsigned char* ob,
-                                          const unsigned char* s_lut, int lane, double (&prev)[K][4], int prev_e) {
-    using L = WarpLayout<K>;
-    double ta[4], tb[4];
-    int e = 0;
-    if (KA == KIND_TIP) {
-        const unsigned char* row = s_lut + (int)st[L::P_BYTES + lane] * 32;
-        const double2 lo = *reinterpret_cast<const double2*>(row);
-        const double2 hi = *reinterpret_cast<const double2*>(row + 16);
-        ta[0] = lo.x; ta[1] = lo.y; ta[2] = hi.x; ta[3] = hi.y;
-    }
-    if (KB == KIND_TIP) {
-        const unsigned char* row = s_lut + (int)st[L::P_BYTES + 32 + lane] * 32;
-        const double2 lo = *reinterpret_cast<const double2*>(row);
-        const double2 hi = *reinterpret_cast<const double2*>(row + 16);
-        tb[0] = lo.x; tb[1] = lo.y; tb[2] = hi.x; tb[3] = hi.y;
-    }
-    if (KA == KIND_PREV || KB == KIND_PREV) e += prev_e;
-    if (KA == KIND_SLOT) e += *reinterpret_cast<const int*>(oa + L::TILE_BYTES + lane * 4);
-    if (KB == KIND_SLOT) e += *reinterpret_cast<const int*>(ob + L::TILE_BYTES + lane * 4);
+                                          const unsigned char* s_lut, const signed char* s_col, int lane,
+                                          double (&prev)[K][4], int prev_e) {
+    Operand<K, KA> A;
+    Operand<K, KB> B;
+    int e = A.init(st, 0, oa, s_lut, s_col, lane, prev_e) + B.init(st, 32, ob, s_lut, s_col, lane, prev_e);
     int mh = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        double a[4], b[4];
-        if (KA == KIND_TIP) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = ta[i];
-        } else if (KA == KIND_PREV) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = prev[k][i];
-        } else {
-            const double2 lo = *reinterpret_cast<const double2*>(oa + lane * L::ROWB + k * 32);
-            const double2 hi = *reinterpret_cast<const double2*>(oa + lane * L::ROWB + k * 32 + 16);
-            a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
-        }
-        if (KB == KIND_TIP) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) b[i] = tb[i];
-        } else if (KB == KIND_PREV) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) b[i] = prev[k][i];
-        } else {
-            const double2 lo = *reinterpret_cast<const double2*>(ob + lane * L::ROWB + k * 32);
-            const double2 hi = *reinterpret_cast<const double2*>(ob + lane * L::ROWB + k * 32 + 16);
-            b[0] = lo.x; b[1] = lo.y; b[2] = hi.x; b[3] = hi.y;
-        }
-        // P rows are read as warp-wide broadcasts (every lane, same address)
-        const double2* q1 = reinterpret_cast<const double2*>(st + k * 128);
-        const double2* q2 = reinterpret_cast<const double2*>(st + K * 128 + k * 128);
+        double x[4], y[4];
+        A.apply(st + k * 128, k, lane, prev[k], x);
+        B.apply(st + K * 128 + k * 128, k, lane, prev[k], y);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double2 r0 = q1[2 * i], r1 = q1[2 * i + 1];
-            const double2 t0 = q2[2 * i], t1 = q2[2 * i + 1];
-            const double x = fma(r1.y, a[3], fma(r1.x, a[2], fma(r0.y, a[1], r0.x * a[0])));
-            const double y = fma(t1.y, b[3], fma(t1.x, b[2], fma(t0.y, b[1], t0.x * b[0])));
-            const double o = x * y;
+            const double o = x[i] * y[i];
             prev[k][i] = o;
             mh = max(mh, __double2hiint(o));   // partials are >= 0: the high word orders them
         }
@@ -185,10 +207,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(
     __shared__ double s_red[kMaxWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     unsigned char* s_lut = smem;
+    signed char* s_col = reinterpret_cast<signed char*>(smem + p.lut_rows * 32);
     for (int i = threadIdx.x; i < p.lut_rows * 4; i += blockDim.x) reinterpret_cast<double*>(s_lut)[i] = p.lut[i];
+    for (int i = threadIdx.x; i < p.lut_rows; i += blockDim.x) {
+        // a row that is exactly one unit entry is an unambiguous state: remember which one
+        int col = -1, ones = 0, others = 0;
+        for (int j = 0; j < 4; ++j) {
+            const double v = p.lut[i * 4 + j];
+            if (v == 1.0) { col = j; ++ones; } else if (v != 0.0) ++others;
+        }
+        s_col[i] = (ones == 1 && others == 0) ? (signed char)col : (signed char)-1;
+    }
     __syncthreads();
 
-    unsigned char* wbase = smem + p.lut_rows * 32 + (size_t)warp * p.warp_bytes;
+    unsigned char* wbase = smem + p.lut_rows * 32 + 256 + (size_t)warp * p.warp_bytes;
     ResRow* s_desc = reinterpret_cast<ResRow*>(wbase);
     unsigned char* s_stage = wbase + L::DESC_BYTES;
     unsigned char* s_opin = s_stage + 2 * L::STAGE_BYTES;
@@ -291,16 +323,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(
         int e;
         switch (kinds) {
             case KIND_TIP | (KIND_TIP << 2):
-                e = row_update<K, KIND_TIP, KIND_TIP>(st, opin, opin, s_lut, lane, prev, prev_e);
+                e = row_update<K, KIND_TIP, KIND_TIP>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
                 break;
             case KIND_TIP | (KIND_PREV << 2):
-                e = row_update<K, KIND_TIP, KIND_PREV>(st, opin, opin, s_lut, lane, prev, prev_e);
+                e = row_update<K, KIND_TIP, KIND_PREV>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
                 break;
             case KIND_PREV | (KIND_SLOT << 2):
-                e = row_update<K, KIND_PREV, KIND_SLOT>(st, opin, opin, s_lut, lane, prev, prev_e);
+                e = row_update<K, KIND_PREV, KIND_SLOT>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
                 break;
             case KIND_TIP | (KIND_SLOT << 2):
-                e = row_update<K, KIND_TIP, KIND_SLOT>(st, opin, opin, s_lut, lane, prev, prev_e);
+                e = row_update<K, KIND_TIP, KIND_SLOT>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
                 break;
             default:   // not a row shape the host plan may emit (it rejects SLOT/SLOT rows): do not touch memory
                 e = 0;
@@ -480,7 +512,7 @@ int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_en
     cudaFuncAttributes fa;
     PHB_CUDA(c, cudaFuncGetAttributes(&fa, kern));
     // pick the CTA width that keeps the most warps resident per SM
-    const size_t lut_bytes = (size_t)a.lut_rows * 32, budget = c->smem_optin, sm_total = c->smem_per_sm;
+    const size_t lut_bytes = (size_t)a.lut_rows * 32 + 256, budget = c->smem_optin, sm_total = c->smem_per_sm;
     int best_w = 1, best_total = 0, best_ctas = 1;
     const int force_w = getenv("PHB_RESIDENT_WARPS") ? atoi(getenv("PHB_RESIDENT_WARPS")) : 0;
     for (int w = 1; w <= kMaxWarps; ++w) {
