@@ -20,7 +20,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab,
         pattern_lnl, cat_lnl, partial, result, total;
 };
 
@@ -54,6 +54,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.root_scale = take(store ? (size_t)S * 4 : 0);
     p.pmats = take((2 * max_rows + 2) * (size_t)K * A * A * 8);
     p.dmats = take((size_t)kMaxEdgeBatch * 3 * K * A * A * 8);
+    p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32 : 0);
     p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
     p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
     p.rows = take(max_rows * sizeof(OpRow));
@@ -289,6 +290,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->d_root_scale = store ? (int32_t*)(w + p.root_scale) : nullptr;
     c->d_pmats = (double*)(w + p.pmats);
     c->d_dmats = (double*)(w + p.dmats);
+    c->d_tiptab = n_states == 4 ? (double*)(w + p.tiptab) : nullptr;
     c->d_model = (double*)(w + p.model);
     c->d_lengths = (double*)(w + p.lengths);
     c->d_rows = (OpRow*)(w + p.rows);
@@ -493,6 +495,8 @@ int phb_build_pmatrices(phb_ctx* c) {
     PHB_REQUIRE(c, c->have_lengths, PHB_ERR_STATE, "phb_build_pmatrices: no edge lengths set");
     st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
     if (st) return st;
+    st = launch_tip_tables(c, 0, (int)c->lengths.size());
+    if (st) return st;
     c->have_pmats = true;
     c->have_partials = false;
     c->have_up = false;
@@ -508,6 +512,8 @@ int phb_set_pmatrices(phb_ctx* c, const double* pmats) {
     if (n) {
         PHB_CUDA(c, cudaMemcpyAsync(c->d_pmats, pmats, n * 8, cudaMemcpyHostToDevice, c->stream));
         PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        st = launch_tip_tables(c, 0, (int)(c->rows_raw.size() / 3 * 2));
+        if (st) return st;
     }
     c->have_pmats = true;
     c->have_partials = false;
@@ -603,6 +609,8 @@ static int prepare_root(phb_ctx* c, int node_a, int node_b, double length, const
         st = launch_build_pmatrices(c, d_len, 2, d_root_p, 0, 0);
         if (st) return st;
     }
+    st = launch_tip_tables(c, 2 * c->max_rows(), 2);
+    if (st) return st;
     c->root_a = node_a;
     c->root_b = node_b;
     c->root_len = length;
@@ -646,6 +654,8 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_resident: only 4-state models with K in {1,2,4,8}");
     st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
     if (st) return st;
+    st = launch_tip_tables(c, 0, (int)c->lengths.size());
+    if (st) return st;
     c->have_pmats = true;
     st = prepare_root(c, node_a, node_b, length, nullptr);
     if (st) return st;
@@ -668,6 +678,8 @@ int phb_lnl_from_host(phb_ctx* c, const uint8_t* codes, int n_chunks, int node_a
                 "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
     st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
+    if (st) return st;
+    st = launch_tip_tables(c, 0, (int)c->lengths.size());
     if (st) return st;
     c->have_pmats = true;
     st = prepare_root(c, node_a, node_b, length, nullptr);

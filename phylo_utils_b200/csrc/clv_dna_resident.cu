@@ -49,10 +49,9 @@ struct ResArgs {
     const ResRow* rows;     // [n_steps]
     int n_steps;            // rows walked per tile (n_rows, +1 with ROOT)
     const double* pmats;
+    const double* tiptab;   // [pidx][K][NC][4]: P . lut[code], what a tip operand contributes
     const uint8_t* codes;
     size_t pitch;
-    const double* lut;
-    int lut_rows;
     double* clv;            // STORE: partials [row][S][K][4]
     int32_t* scale;         // STORE: exponents [row][S]
     unsigned char* scratch; // !STORE: [warp][slot][block | 32 exponents]
@@ -79,10 +78,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // geometry of one warp's shared memory.  A warp tile is 32 patterns.
-template <int K>
+template <int K, int NC>
 struct WarpLayout {
     static constexpr int SPW = 32;
-    static constexpr int P_BYTES = 2 * K * 128;              // both P blocks, [operand][k][16 doubles]
+    static constexpr int TAB_BYTES = K * NC * 32;            // tip table of one operand: [k][code][4 doubles]
+    static constexpr int OPER_BYTES = TAB_BYTES > K * 128 ? TAB_BYTES : K * 128;   // ... or its P block [k][16 doubles]
+    static constexpr int P_BYTES = 2 * OPER_BYTES;
     static constexpr int STAGE_BYTES = P_BYTES + 2 * 32;     // + 32 codes per operand
     static constexpr int DESC_BYTES = 4 * 16;                // descriptor ring (two rows ahead, double use)
     static constexpr int ROWB = K * 32 + 16;                 // one pattern's block row, padded: conflict-free LDS.128
@@ -101,83 +102,63 @@ struct Cursor {
     int64_t wt;
 };
 
-// One operand's contribution x[i] = sum_j P[k][i][j] . v[j] for this lane's pattern.
-//   TIP : if every lane of the warp holds an unambiguous state, P . onehot is a column of P - four 8-byte
-//         gathers and no arithmetic (the usual case: a tip operand appears in 2/3 of all rows);
-//         otherwise the generic product with the look-up-table row.
-//   PREV: operand in registers.   SLOT: operand in this warp's shared-memory tile.
-template <int K, int KIND>
-struct Operand {
-    double t[4];        // TIP, generic path: the look-up-table row
-    int col;            // TIP, gather path: the state index
-    bool gather;
-    const unsigned char* tile;
-
-    __device__ __forceinline__ int init(const unsigned char* st, int code_off, const unsigned char* opin,
-                                        const unsigned char* s_lut, const signed char* s_col, int lane, int prev_e) {
-        using L = WarpLayout<K>;
-        tile = opin;
-        gather = false;
-        col = 0;
-        if (KIND == KIND_TIP) {
-            const int code = st[L::P_BYTES + code_off + lane];
-            col = s_col[code];
-            gather = !__any_sync(0xffffffffu, col < 0);
-            if (!gather) {
-                const double2 lo = *reinterpret_cast<const double2*>(s_lut + code * 32);
-                const double2 hi = *reinterpret_cast<const double2*>(s_lut + code * 32 + 16);
-                t[0] = lo.x; t[1] = lo.y; t[2] = hi.x; t[3] = hi.y;
-            }
-            return 0;
-        }
-        if (KIND == KIND_PREV) return prev_e;
-        return *reinterpret_cast<const int*>(opin + L::TILE_BYTES + lane * 4);
-    }
-
-    __device__ __forceinline__ void apply(const unsigned char* pk, int k, int lane, const double (&prev_k)[4],
-                                          double (&x)[4]) const {
-        using L = WarpLayout<K>;
-        if (KIND == KIND_TIP && gather) {
-            const double* q = reinterpret_cast<const double*>(pk) + col;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = q[4 * i];
-            return;
-        }
-        double v[4];
-        if (KIND == KIND_TIP) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = t[i];
-        } else if (KIND == KIND_PREV) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = prev_k[i];
-        } else {
-            const double2 lo = *reinterpret_cast<const double2*>(tile + lane * L::ROWB + k * 32);
-            const double2 hi = *reinterpret_cast<const double2*>(tile + lane * L::ROWB + k * 32 + 16);
-            v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-        }
-        const double2* q = reinterpret_cast<const double2*>(pk);   // P rows: warp-wide broadcast reads
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double2 r0 = q[2 * i], r1 = q[2 * i + 1];
-            x[i] = fma(r1.y, v[3], fma(r1.x, v[2], fma(r0.y, v[1], r0.x * v[0])));
-        }
-    }
-};
-
 // prev[k] <- (P1[k] . a[k]) * (P2[k] . b[k]) for this lane's pattern; returns the cumulative exponent
-template <int K, int KA, int KB>
+template <int K, int NC, int KA, int KB>
 __device__ __forceinline__ int row_update(const unsigned char* st, const unsigned char* oa, const unsigned char* ob,
-                                          const unsigned char* s_lut, const signed char* s_col, int lane,
-                                          double (&prev)[K][4], int prev_e) {
-    Operand<K, KA> A;
-    Operand<K, KB> B;
-    int e = A.init(st, 0, oa, s_lut, s_col, lane, prev_e) + B.init(st, 32, ob, s_lut, s_col, lane, prev_e);
+                                          int lane, double (&prev)[K][4], int prev_e) {
+    using L = WarpLayout<K, NC>;
+    // a tip operand contributes the row `code` of its staged table T[k] = P[k] . lut - no arithmetic
+    int e = 0;
+    const unsigned char* ta = st + (KA == KIND_TIP ? (int)st[L::P_BYTES + lane] * 32 : 0);
+    const unsigned char* tb = st + L::OPER_BYTES + (KB == KIND_TIP ? (int)st[L::P_BYTES + 32 + lane] * 32 : 0);
+    if (KA == KIND_PREV || KB == KIND_PREV) e += prev_e;
+    if (KA == KIND_SLOT) e += *reinterpret_cast<const int*>(oa + L::TILE_BYTES + lane * 4);
+    if (KB == KIND_SLOT) e += *reinterpret_cast<const int*>(ob + L::TILE_BYTES + lane * 4);
     int mh = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        double x[4], y[4];
-        A.apply(st + k * 128, k, lane, prev[k], x);
-        B.apply(st + K * 128 + k * 128, k, lane, prev[k], y);
+        double a[4], b[4], x[4], y[4];
+        if (KA == KIND_TIP) {
+            const double2 lo = *reinterpret_cast<const double2*>(ta + k * NC * 32);
+            const double2 hi = *reinterpret_cast<const double2*>(ta + k * NC * 32 + 16);
+            x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+        } else if (KA == KIND_PREV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = prev[k][i];
+        } else {
+            const double2 lo = *reinterpret_cast<const double2*>(oa + lane * L::ROWB + k * 32);
+            const double2 hi = *reinterpret_cast<const double2*>(oa + lane * L::ROWB + k * 32 + 16);
+            a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+        }
+        if (KB == KIND_TIP) {
+            const double2 lo = *reinterpret_cast<const double2*>(tb + k * NC * 32);
+            const double2 hi = *reinterpret_cast<const double2*>(tb + k * NC * 32 + 16);
+            y[0] = lo.x; y[1] = lo.y; y[2] = hi.x; y[3] = hi.y;
+        } else if (KB == KIND_PREV) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b[i] = prev[k][i];
+        } else {
+            const double2 lo = *reinterpret_cast<const double2*>(ob + lane * L::ROWB + k * 32);
+            const double2 hi = *reinterpret_cast<const double2*>(ob + lane * L::ROWB + k * 32 + 16);
+            b[0] = lo.x; b[1] = lo.y; b[2] = hi.x; b[3] = hi.y;
+        }
+        // P rows are read as warp-wide broadcasts (every lane, same address)
+        if (KA != KIND_TIP) {
+            const double2* q1 = reinterpret_cast<const double2*>(st + k * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 r0 = q1[2 * i], r1 = q1[2 * i + 1];
+                x[i] = fma(r1.y, a[3], fma(r1.x, a[2], fma(r0.y, a[1], r0.x * a[0])));
+            }
+        }
+        if (KB != KIND_TIP) {
+            const double2* q2 = reinterpret_cast<const double2*>(st + L::OPER_BYTES + k * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 t0 = q2[2 * i], t1 = q2[2 * i + 1];
+                y[i] = fma(t1.y, b[3], fma(t1.x, b[2], fma(t0.y, b[1], t0.x * b[0])));
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const double o = x[i] * y[i];
@@ -200,27 +181,13 @@ __device__ __forceinline__ int row_update(const unsigned char* st, const unsigne
     return e;
 }
 
-template <int K, bool STORE, bool ROOT>
+template <int K, int NC, bool STORE, bool ROOT>
 __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(const ResArgs p) {
-    using L = WarpLayout<K>;
+    using L = WarpLayout<K, NC>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double s_red[kMaxWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    unsigned char* s_lut = smem;
-    signed char* s_col = reinterpret_cast<signed char*>(smem + p.lut_rows * 32);
-    for (int i = threadIdx.x; i < p.lut_rows * 4; i += blockDim.x) reinterpret_cast<double*>(s_lut)[i] = p.lut[i];
-    for (int i = threadIdx.x; i < p.lut_rows; i += blockDim.x) {
-        // a row that is exactly one unit entry is an unambiguous state: remember which one
-        int col = -1, ones = 0, others = 0;
-        for (int j = 0; j < 4; ++j) {
-            const double v = p.lut[i * 4 + j];
-            if (v == 1.0) { col = j; ++ones; } else if (v != 0.0) ++others;
-        }
-        s_col[i] = (ones == 1 && others == 0) ? (signed char)col : (signed char)-1;
-    }
-    __syncthreads();
-
-    unsigned char* wbase = smem + p.lut_rows * 32 + 256 + (size_t)warp * p.warp_bytes;
+    unsigned char* wbase = smem + (size_t)warp * p.warp_bytes;
     ResRow* s_desc = reinterpret_cast<ResRow*>(wbase);
     unsigned char* s_stage = wbase + L::DESC_BYTES;
     unsigned char* s_opin = s_stage + 2 * L::STAGE_BYTES;
@@ -274,10 +241,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(
             const ResRow d = s_desc[qp & 3];
             unsigned char* st = s_stage + (size_t)(qp & 1) * L::STAGE_BYTES;
             const int pidx_b = d.packed & 0xffffff, kind_a = (d.packed >> 24) & 3, kind_b = (d.packed >> 26) & 3;
-            const char* pa = reinterpret_cast<const char*>(p.pmats + (size_t)d.pidx_a * K * 16);
-            const char* pb = reinterpret_cast<const char*>(p.pmats + (size_t)pidx_b * K * 16);
-            constexpr int CH = K * 128 / 16;
-            for (int c = lane; c < 2 * CH; c += 32) cp_async16(st + c * 16, c < CH ? pa + c * 16 : pb + (c - CH) * 16);
+            // per operand: its tip table (tip) or its P block (anything else)
+            const char* pa = kind_a == KIND_TIP ? reinterpret_cast<const char*>(p.tiptab + (size_t)d.pidx_a * K * NC * 4)
+                                                : reinterpret_cast<const char*>(p.pmats + (size_t)d.pidx_a * K * 16);
+            const char* pb = kind_b == KIND_TIP ? reinterpret_cast<const char*>(p.tiptab + (size_t)pidx_b * K * NC * 4)
+                                                : reinterpret_cast<const char*>(p.pmats + (size_t)pidx_b * K * 16);
+            const int cha = kind_a == KIND_TIP ? L::TAB_BYTES / 16 : K * 8, chb = kind_b == KIND_TIP ? L::TAB_BYTES / 16 : K * 8;
+            for (int c = lane; c < cha; c += 32) cp_async16(st + c * 16, pa + c * 16);
+            for (int c = lane; c < chb; c += 32) cp_async16(st + L::OPER_BYTES + c * 16, pb + c * 16);
             const int64_t site0 = cp.wt * 32;
             if (kind_a == KIND_TIP && lane < 2)
                 cp_async16(st + L::P_BYTES + lane * 16, p.codes + (size_t)d.src_a * p.pitch + site0 + lane * 16);
@@ -323,16 +294,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(
         int e;
         switch (kinds) {
             case KIND_TIP | (KIND_TIP << 2):
-                e = row_update<K, KIND_TIP, KIND_TIP>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
+                e = row_update<K, NC, KIND_TIP, KIND_TIP>(st, opin, opin, lane, prev, prev_e);
                 break;
             case KIND_TIP | (KIND_PREV << 2):
-                e = row_update<K, KIND_TIP, KIND_PREV>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
+                e = row_update<K, NC, KIND_TIP, KIND_PREV>(st, opin, opin, lane, prev, prev_e);
                 break;
             case KIND_PREV | (KIND_SLOT << 2):
-                e = row_update<K, KIND_PREV, KIND_SLOT>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
+                e = row_update<K, NC, KIND_PREV, KIND_SLOT>(st, opin, opin, lane, prev, prev_e);
                 break;
             case KIND_TIP | (KIND_SLOT << 2):
-                e = row_update<K, KIND_TIP, KIND_SLOT>(st, opin, opin, s_lut, s_col, lane, prev, prev_e);
+                e = row_update<K, NC, KIND_TIP, KIND_SLOT>(st, opin, opin, lane, prev, prev_e);
                 break;
             default:   // not a row shape the host plan may emit (it rejects SLOT/SLOT rows): do not touch memory
                 e = 0;
@@ -483,18 +454,17 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPla
     return PHB_OK;
 }
 
-template <int K, bool STORE, bool ROOT>
+template <int K, int NC, bool STORE, bool ROOT>
 int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_end, double* partial_sums, int max_grid,
                     int* grid_out) {
-    using L = WarpLayout<K>;
+    using L = WarpLayout<K, NC>;
     ResArgs a;
     a.rows = static_cast<const ResRow*>(c->d_res_rows);
     a.n_steps = (int)plan.rows.size();
     a.pmats = c->d_pmats;
+    a.tiptab = c->d_tiptab;
     a.codes = c->d_codes;
     a.pitch = c->code_pitch;
-    a.lut = c->d_lut;
-    a.lut_rows = (c->n_codes + 7) / 8 * 8;
     a.clv = c->d_clv;
     a.scale = c->d_scale;
     a.scratch = c->d_scratch;
@@ -508,11 +478,11 @@ int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_en
     a.wt_begin = wt_begin;
     a.wt_end = wt_end;
     a.warp_bytes = (L::WARP_BYTES + 127) / 128 * 128;
-    auto kern = dna_resident_kernel<K, STORE, ROOT>;
+    auto kern = dna_resident_kernel<K, NC, STORE, ROOT>;
     cudaFuncAttributes fa;
     PHB_CUDA(c, cudaFuncGetAttributes(&fa, kern));
     // pick the CTA width that keeps the most warps resident per SM
-    const size_t lut_bytes = (size_t)a.lut_rows * 32 + 256, budget = c->smem_optin, sm_total = c->smem_per_sm;
+    const size_t lut_bytes = 0, budget = c->smem_optin, sm_total = c->smem_per_sm;
     int best_w = 1, best_total = 0, best_ctas = 1;
     const int force_w = getenv("PHB_RESIDENT_WARPS") ? atoi(getenv("PHB_RESIDENT_WARPS")) : 0;
     for (int w = 1; w <= kMaxWarps; ++w) {
@@ -556,11 +526,19 @@ int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_en
 
 template <bool STORE, bool ROOT>
 int launch_resident_k(Ctx* c, const ResPlan& plan, int64_t b, int64_t e, double* ps, int max_grid, int* grid_out) {
-    switch (c->K) {
-        case 1: return launch_resident<1, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
-        case 2: return launch_resident<2, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
-        case 4: return launch_resident<4, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
-        case 8: return launch_resident<8, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+    if (c->n_codes > kTipTabCodes)
+        return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel: look-up tables of more than 16 rows are not covered");
+    static_assert(kTipTabCodes == 16, "tip tables are staged with 8 or 16 rows per category");
+    const int key = c->K * 100 + tip_table_rows(c);
+    switch (key) {
+        case 108: return launch_resident<1, 8, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 116: return launch_resident<1, 16, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 208: return launch_resident<2, 8, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 216: return launch_resident<2, 16, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 408: return launch_resident<4, 8, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 416: return launch_resident<4, 16, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 808: return launch_resident<8, 8, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
+        case 816: return launch_resident<8, 16, STORE, ROOT>(c, plan, b, e, ps, max_grid, grid_out);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "resident kernel needs K in {1,2,4,8}");
 }

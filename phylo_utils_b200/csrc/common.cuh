@@ -86,6 +86,9 @@ struct Ctx {
     int32_t* d_root_scale = nullptr;   // [S]
     double* d_pmats = nullptr;         // [2*max_rows + 2][K][A][A]
     double* d_dmats = nullptr;         // derivative scratch [3][K][A][A] per edge chunk
+    // 4-state models: T[m][k][code][:] = P[m][k] . lut[code] for every P block m, so that a tip operand is
+    // a 32-byte table look-up instead of a matrix-vector product (codes padded to kTipTabCodes rows)
+    double* d_tiptab = nullptr;
     double* d_model = nullptr;         // evecs | evals | ivecs | freqs | rates | catw
     double* d_lengths = nullptr;       // [2*max_rows + 2]
     OpRow* d_rows = nullptr;           // [max_rows]
@@ -148,10 +151,13 @@ constexpr int kMaxReduceBlocks = 4096;
 constexpr int kPartialCap = 65536;   // doubles in the block-sum buffer
 constexpr int kMaxEdgeBatch = 64;
 constexpr int kMaxChunks = 32;
+constexpr int kTipTabCodes = 16;     // tip tables cover look-up tables of up to 16 rows (IUPAC DNA has 15)
 
 // kernel families (each returns a phb_status) ---------------------------------------------------
 // pmatrix.cu
 int launch_build_pmatrices(Ctx* c, const double* d_lengths, int n_mats, double* d_out, int order, int chain_rule);
+int launch_tip_tables(Ctx* c, int first_mat, int n_mats);
+inline int tip_table_rows(const Ctx* c) { return c->n_codes <= 8 ? 8 : kTipTabCodes; }   // rows per category block
 cudaError_t launch_pmatrix_raw(cudaStream_t stream, const double* evecs, const double* evals, const double* ivecs,
                                const double* rates, const double* d_lengths, double* d_out, int A, int K, int n_mats,
                                int order, int chain_rule);

@@ -57,6 +57,34 @@ cudaError_t launch_pmatrix_raw(cudaStream_t stream, const double* evecs, const d
     return cudaGetLastError();
 }
 
+// T[m][k][code][i] = sum_j P[m][k][i][j] . lut[code][j]   (4-state models; one CTA per P block m)
+__global__ void tip_table_kernel(const double* __restrict__ pmats, const double* __restrict__ lut, int n_codes, int nc,
+                                 int K, int first_mat, double* __restrict__ out) {
+    const int m = first_mat + blockIdx.x;
+    for (int idx = threadIdx.x; idx < K * nc * 4; idx += blockDim.x) {
+        const int i = idx & 3, code = (idx >> 2) % nc, k = idx / (4 * nc);
+        double acc = 0.0;
+        if (code < n_codes) {
+            const double* P = pmats + ((size_t)m * K + k) * 16 + i * 4;
+            const double* v = lut + code * 4;
+            acc = P[0] * v[0];
+            acc = fma(P[1], v[1], acc);
+            acc = fma(P[2], v[2], acc);
+            acc = fma(P[3], v[3], acc);
+        }
+        out[((size_t)m * K + k) * nc * 4 + code * 4 + i] = acc;
+    }
+}
+
+int launch_tip_tables(Ctx* c, int first_mat, int n_mats) {
+    if (c->d_tiptab == nullptr || n_mats <= 0 || !c->have_tips || c->n_codes > kTipTabCodes) return PHB_OK;
+    tip_table_kernel<<<n_mats, 128, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->K, first_mat,
+                                                    c->d_tiptab);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    return PHB_OK;
+}
+
 int launch_build_pmatrices(Ctx* c, const double* d_lengths, int n_mats, double* d_out, int order, int chain_rule) {
     if (n_mats <= 0) return PHB_OK;
     c->launches++;
