@@ -53,94 +53,115 @@ constexpr int pad_pitch(int cols) {   // smallest pitch >= cols with pitch % 16 
     return p;
 }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_all() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// A row is processed as 2K "phases" (category k, child c).  While the warps issue the DMMAs of phase ph out of
+// one P buffer and one child-row buffer, the P block and the child rows of phase ph+1 stream into the other
+// pair with cp.async (8-byte pieces: rows of 20 or 61 doubles are only 8-byte aligned).  Padding rows and
+// columns are zeroed once and never touched again.
 template <int MT, int KS, int NT, int WARPS, bool LEVEL>
 __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
     constexpr int LDL = pad_pitch(KCOLS > MROWS ? KCOLS : MROWS);
-    constexpr int TS = WARPS * NT * 8;
+    constexpr int TS = WARPS * NT * 8, WR = NT * 8;   // patterns per CTA / per warp
     extern __shared__ double sm[];
-    double* P1 = sm;                     // [MROWS][LDP]
-    double* P2 = P1 + MROWS * LDP;
-    double* La = P2 + MROWS * LDP;       // [TS][LDL]   child 1 rows, later the output rows
-    double* Lb = La + TS * LDL;
+    double* Pbuf = sm;                               // [2][MROWS][LDP]
+    double* Lbuf = Pbuf + 2 * MROWS * LDP;           // [2][TS][LDL]
+    unsigned char* s_codes = reinterpret_cast<unsigned char*>(Lbuf + 2 * TS * LDL);   // [2 children][TS]
     const int A = p.A, K = p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / column
     const size_t S = (size_t)p.S;
-    double* myLa = La + (size_t)warp * NT * 8 * LDL;
-    double* myLb = Lb + (size_t)warp * NT * 8 * LDL;
+    for (int e = threadIdx.x; e < 2 * MROWS * LDP + 2 * TS * LDL; e += WARPS * 32) sm[e] = 0.0;
+    __syncthreads();
 
     const int64_t items = LEVEL ? (int64_t)(p.row_end - p.row_begin) * p.n_tiles : p.n_tiles;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
         const int64_t tile = LEVEL ? it % p.n_tiles : it;
         const int r0 = LEVEL ? p.row_begin + (int)(it / p.n_tiles) : p.row_begin;
         const int r1 = LEVEL ? r0 + 1 : p.row_end;
-        const int64_t wsite0 = tile * TS + (int64_t)warp * NT * 8;   // first pattern of this warp
+        const int64_t wsite0 = tile * TS + (int64_t)warp * WR;   // first pattern of this warp
         for (int r = r0; r < r1; ++r) {
             const OpRow row = p.rows[r];
             double* out = p.clv + (size_t)row.dst * S * K * A;
+            const int n_phases = 2 * K;
+
+            // tip codes of this warp's patterns (same for every category)
+            for (int c = 0; c < 2; ++c)
+                if (row.kind[c] == SRC_TIP && lane < WR) {
+                    const int64_t s = wsite0 + lane;
+                    s_codes[c * TS + warp * WR + lane] = s < p.S ? p.codes[(size_t)row.src[c] * p.pitch + s] : 0;
+                }
+            __syncwarp();
+
+            auto prefetch = [&](int ph) {
+                const int k = ph >> 1, c = ph & 1, buf = ph & 1;
+                double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
+                const double* q = p.pmats + ((size_t)row.pidx[c] * K + k) * A * A;
+                for (int e = threadIdx.x; e < A * A; e += WARPS * 32) {
+                    const int i = e / A, j = e - i * A;
+                    cp_async8(Pd + i * LDP + j, q + e);
+                }
+                double* Ld = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
+                if (row.kind[c] == SRC_TIP) {
+                    for (int e = lane; e < WR * A; e += 32) {
+                        const int n = e / A, j = e - n * A;
+                        Ld[n * LDL + j] = __ldg(p.lut + (size_t)s_codes[c * TS + warp * WR + n] * A + j);
+                    }
+                } else {
+                    const double* base = p.clv + (size_t)row.src[c] * S * K * A;
+                    for (int e = lane; e < WR * A; e += 32) {
+                        const int n = e / A, j = e - n * A;
+                        const int64_t s = wsite0 + n;
+                        if (s < p.S) cp_async8(Ld + n * LDL + j, base + ((size_t)s * K + k) * A + j);
+                    }
+                }
+                cp_async_commit_all();
+            };
+
             double mx[NT][2];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) mx[nt][0] = mx[nt][1] = 0.0;
-
-            for (int k = 0; k < K; ++k) {
-                __syncthreads();   // every warp is done with the previous P
-                {
-                    const double* q1 = p.pmats + ((size_t)row.pidx[0] * K + k) * A * A;
-                    const double* q2 = p.pmats + ((size_t)row.pidx[1] * K + k) * A * A;
-                    for (int e = threadIdx.x; e < MROWS * KCOLS; e += WARPS * 32) {
-                        const int i = e / KCOLS, j = e - i * KCOLS;
-                        const bool in = i < A && j < A;
-                        P1[i * LDP + j] = in ? __ldg(q1 + i * A + j) : 0.0;
-                        P2[i * LDP + j] = in ? __ldg(q2 + i * A + j) : 0.0;
-                    }
-                }
-                // this warp's child rows (zero padded up to KCOLS)
-                for (int c = 0; c < 2; ++c) {
-                    double* tileL = c == 0 ? myLa : myLb;
-                    if (row.kind[c] == SRC_TIP) {
-                        const uint8_t* codes = p.codes + (size_t)row.src[c] * p.pitch;
-                        for (int e = lane; e < NT * 8 * KCOLS; e += 32) {
-                            const int n = e / KCOLS, j = e - n * KCOLS;
-                            const int64_t s = wsite0 + n;
-                            tileL[n * LDL + j] = (s < p.S && j < A) ? __ldg(p.lut + (size_t)codes[s] * A + j) : 0.0;
-                        }
-                    } else {
-                        const double* base = p.clv + (size_t)row.src[c] * S * K * A;
-                        for (int e = lane; e < NT * 8 * KCOLS; e += 32) {
-                            const int n = e / KCOLS, j = e - n * KCOLS;
-                            const int64_t s = wsite0 + n;
-                            tileL[n * LDL + j] = (s < p.S && j < A) ? base[((size_t)s * K + k) * A + j] : 0.0;
-                        }
-                    }
-                }
-                __syncthreads();   // P staged (and, within the warp, its own child rows)
-
-                double acc1[MT][NT][2], acc2[MT][NT][2];
+            double acc0[MT][NT][2], acc1[MT][NT][2];
+            // DMMAs of one phase: acc = P[buf] . (this warp's child rows in buf)^T
+            auto run_phase = [&](int ph, double (&acc)[MT][NT][2]) {
+                const int buf = ph & 1;
+                cp_async_wait_all();
+                __syncthreads();      // phase ph's operands have landed; everybody has left phase ph-1
+                if (ph + 1 < n_phases) prefetch(ph + 1);
+                const double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
+                const double* myLr = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) acc1[mt][nt][0] = acc1[mt][nt][1] = acc2[mt][nt][0] = acc2[mt][nt][1] = 0.0;
-#pragma unroll 2
+                    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll 4
                 for (int ks = 0; ks < KS; ++ks) {
-                    double b1[NT], b2[NT];
+                    double bf[NT];
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        b1[nt] = myLa[(nt * 8 + fr) * LDL + ks * 4 + fc];
-                        b2[nt] = myLb[(nt * 8 + fr) * LDL + ks * 4 + fc];
-                    }
+                    for (int nt = 0; nt < NT; ++nt) bf[nt] = myLr[(nt * 8 + fr) * LDL + ks * 4 + fc];
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        const double a1 = P1[(mt * 8 + fr) * LDP + ks * 4 + fc];
-                        const double a2 = P2[(mt * 8 + fr) * LDP + ks * 4 + fc];
+                        const double af = Pd[(mt * 8 + fr) * LDP + ks * 4 + fc];
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {
-                            dmma(acc1[mt][nt], a1, b1[nt]);
-                            dmma(acc2[mt][nt], a2, b2[nt]);
-                        }
+                        for (int nt = 0; nt < NT; ++nt) dmma(acc[mt][nt], af, bf[nt]);
                     }
                 }
+            };
+
+            __syncthreads();          // the previous row is completely done with both buffer pairs
+            prefetch(0);
+            for (int k = 0; k < K; ++k) {
+                run_phase(2 * k, acc0);
+                run_phase(2 * k + 1, acc1);
+                double* myL = Lbuf + ((size_t)TS + (size_t)warp * WR) * LDL;   // child-1 rows (buffer 1) become the output rows
+                // both children of category k are done: multiply, find the maxima, write the block row out
                 __syncwarp();      // all lanes have read their child rows; they now become the output rows
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
@@ -148,17 +169,21 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
-                            const double o = acc1[mt][nt][q] * acc2[mt][nt][q];
+                            const double o = acc0[mt][nt][q] * acc1[mt][nt][q];
                             const int i = mt * 8 + fr, n = nt * 8 + 2 * fc + q;
-                            myLa[n * LDL + i] = o;
+                            myL[n * LDL + i] = o;
                             if (i < A) mx[nt][q] = fmax(mx[nt][q], o);
                         }
                 __syncwarp();
-                for (int e = lane; e < NT * 8 * A; e += 32) {   // coalesced: A contiguous doubles per pattern
+                for (int e = lane; e < WR * A; e += 32) {   // coalesced: A contiguous doubles per pattern
                     const int n = e / A, i = e - n * A;
                     const int64_t s = wsite0 + n;
-                    if (s < p.S) out[((size_t)s * K + k) * A + i] = myLa[n * LDL + i];
+                    if (s < p.S) out[((size_t)s * K + k) * A + i] = myL[n * LDL + i];
                 }
+                __syncwarp();
+                // the padding columns of these rows must read as zero again when they next hold a child row
+                if (MROWS > KCOLS || KCOLS > A)
+                    for (int e = lane; e < WR * (LDL - A); e += 32) myL[(e / (LDL - A)) * LDL + A + e % (LDL - A)] = 0.0;
                 __syncwarp();
             }
             // per-pattern maximum over states (lanes sharing fc) and categories (already folded into mx)
@@ -194,6 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         p.scale[(size_t)row.dst * S + s] = e;
                     }
             }
+            __threadfence_block();   // this row's block is visible to the cp.async reads of the next row
             __syncwarp();
         }
     }
@@ -219,7 +245,7 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     a.n_tiles = (c->S + TS - 1) / TS;
     a.A = c->A;
     a.K = c->K;
-    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double);
+    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 2 * TS;
     auto kern = mma_prune_kernel<MT, KS, NT, WARPS, LEVEL>;
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
