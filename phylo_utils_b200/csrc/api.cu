@@ -22,6 +22,7 @@ inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 struct Plan {
     size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab,
         pattern_lnl, cat_lnl, partial, result, total;
+    int root_block;
 };
 
 inline size_t code_pitch_for(int64_t S) { return ((size_t)S + 127) / 128 * 128; }
@@ -44,20 +45,21 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.weights = take((size_t)S * 8);
     // down partials [n_int blocks] immediately followed by up partials [n_nodes blocks] (if requested)
     const size_t n_nodes = 2 * (size_t)n_tips - 2;
-    const size_t n_blocks = n_int + (up ? n_nodes : 0);
+    const size_t n_blocks = n_int + (up ? n_nodes : 0) + 1;   // + the virtual-root block
     p.clv = take(store ? n_blocks * node_doubles * 8 : 0);
     p.scale = take(store ? n_blocks * (size_t)S * 4 : 0);
     p.up = p.clv + n_int * node_doubles * 8;
     p.up_scale = p.scale + n_int * (size_t)S * 4;
     p.up_rows = take(up ? 2 * max_rows * sizeof(OpRow) : 0);
-    p.root_clv = take(store ? node_doubles * 8 : 0);
-    p.root_scale = take(store ? (size_t)S * 4 : 0);
+    p.root_clv = p.clv + (n_blocks - 1) * node_doubles * 8;
+    p.root_scale = p.scale + (n_blocks - 1) * (size_t)S * 4;
+    p.root_block = (int)(n_blocks - 1);
     p.pmats = take((2 * max_rows + 2) * (size_t)K * A * A * 8);
     p.dmats = take((size_t)kMaxEdgeBatch * 3 * K * A * A * 8);
     p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32 : 0);
     p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
     p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
-    p.rows = take(max_rows * sizeof(OpRow));
+    p.rows = take((max_rows + 1) * sizeof(OpRow));   // + the root pseudo-row
     p.res_rows = take((max_rows + 1) * 16);
     // parking area of the lnL-only resident kernel (4-state models): 160 SMs x 16 warps x 15 blocks
     p.scratch_size = A == 4 ? (size_t)160 * 16 * 15 * ((size_t)K * 1024 + 128) : 0;
@@ -288,6 +290,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->d_up_rows = up ? (OpRow*)(w + p.up_rows) : nullptr;
     c->d_root_clv = store ? (double*)(w + p.root_clv) : nullptr;
     c->d_root_scale = store ? (int32_t*)(w + p.root_scale) : nullptr;
+    c->root_block = p.root_block;
     c->d_pmats = (double*)(w + p.pmats);
     c->d_dmats = (double*)(w + p.dmats);
     c->d_tiptab = n_states == 4 ? (double*)(w + p.tiptab) : nullptr;

@@ -15,6 +15,8 @@
 // thread rescales its K*A outputs in place after the tile has been written.
 //
 // Also here: the root / mixture / reduction kernel for arbitrary A, and the final deterministic sum.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace phb {
@@ -134,111 +136,48 @@ __global__ void generic_prune_kernel(const GenArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-struct GenRootArgs {
-    const double* pmats;  // [2][K][A][A]
-    const uint8_t* codes;
-    size_t pitch;
-    const double* lut;
-    const double* clv;
-    const int32_t* scale;
+// Root finishing: the virtual-root partial has been computed into the root block by the ordinary pruning
+// kernels (it is just one more `clv` row: tree_model.py:178-198); what is left of
+// compute_likelihood_at_edge (tree_model.py:200-217) is pi-dot per category (lnl_node), the mixture, the log and
+// the weighted sum.  One warp per pattern: lanes stride over the states (coalesced), five shuffles per sum.
+struct RootFinishArgs {
+    const double* root_clv;    // [S][K][A]
+    const int32_t* root_scale; // [S]
     const double* freqs;
     const double* catw;
     const double* weights;
-    int src[2], kind[2];
     int64_t S;
     int A, K;
     double* pattern_lnl;
-    double* cat_lnl;
-    double* root_clv;
-    int32_t* root_scale;
+    double* cat_lnl;           // [S][K] or null
     double* partial_sums;
 };
 
-// thread = pattern.  Two passes over the categories: the first finds the pattern maximum (for the
-// exponent), the second forms pi . root per category.  Work is recomputed rather than stored because
-// this kernel runs once per evaluation (1 of N-2 node updates) and A can be 61.
-__global__ void generic_root_kernel(const GenRootArgs p) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(128) root_finish_kernel(const RootFinishArgs p) {
+    __shared__ double s_red[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int A = p.A, K = p.K;
-    double* Pa = sm;               // [A][A] current category
-    double* Pb = Pa + A * A;
-    double* s_red = Pb + A * A;    // [blockDim/32]
-    const size_t S = (size_t)p.S;
     double acc = 0.0;
-    const int64_t n_iter = (p.S + blockDim.x - 1) / blockDim.x;
-    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
-        const int64_t s = it * blockDim.x + threadIdx.x;
-        const bool ok = s < p.S;
-        const size_t ss = ok ? (size_t)s : 0;
-        const double* va[2];
-        int e = 0;
-        for (int c = 0; c < 2; ++c) {
-            if (p.kind[c] == SRC_TIP) {
-                va[c] = p.lut + (size_t)p.codes[(size_t)p.src[c] * p.pitch + ss] * A;
-            } else {
-                va[c] = p.clv + ((size_t)p.src[c] * S + ss) * K * A;
-                e += p.scale[(size_t)p.src[c] * S + ss];
-            }
-        }
+    for (int64_t s = (int64_t)blockIdx.x * 4 + warp; s < p.S; s += (int64_t)gridDim.x * 4) {
+        const double* v = p.root_clv + (size_t)s * K * A;
+        const double shift = (double)p.root_scale[s] * kLn2;
         double mix = 0.0;
-        double m = 0.0;
-        for (int pass = 0; pass < 2; ++pass) {
-            int shift = 0;
-            double f2 = 1.0;
-            if (pass == 1) {
-                const int hi = __double2hiint(m);
-                if (hi < kScaleThresholdHi && hi >= 0x00100000) {
-                    shift = 1023 - (hi >> 20);
-                    f2 = pow2i(shift);
-                    e -= shift;
-                }
-                if (p.root_scale != nullptr && ok) p.root_scale[ss] = e;
-            }
-            for (int k = 0; k < K; ++k) {
-                __syncthreads();
-                for (int q = threadIdx.x; q < A * A; q += blockDim.x) {
-                    Pa[q] = p.pmats[(size_t)k * A * A + q];
-                    Pb[q] = p.pmats[(size_t)(K + k) * A * A + q];
-                }
-                __syncthreads();
-                const double* la = va[0] + (p.kind[0] == SRC_TIP ? 0 : (size_t)k * A);
-                const double* lb = va[1] + (p.kind[1] == SRC_TIP ? 0 : (size_t)k * A);
-                double f = 0.0;
-                for (int i = 0; i < A; ++i) {
-                    double x = 0.0, y = 0.0;
-                    for (int j = 0; j < A; ++j) {
-                        x = fma(Pa[i * A + j], la[j], x);
-                        y = fma(Pb[i * A + j], lb[j], y);
-                    }
-                    const double o = x * y;
-                    if (pass == 0) {
-                        m = fmax(m, o);
-                    } else {
-                        const double os = o * f2;
-                        if (p.root_clv != nullptr && ok) p.root_clv[(ss * K + k) * A + i] = os;
-                        f = fma(p.freqs[i], os, f);
-                    }
-                }
-                if (pass == 1) {
-                    if (p.cat_lnl != nullptr && ok) p.cat_lnl[ss * K + k] = f > 0 ? log(f) + (double)e * kLn2 : -INFINITY;
-                    if (f > 0) mix += p.catw[k] * f;
-                }
-            }
+        for (int k = 0; k < K; ++k) {
+            double f = 0.0;
+            for (int i = lane; i < A; i += 32) f = fma(p.freqs[i], v[k * A + i], f);
+            f = warp_sum(f);
+            if (p.cat_lnl != nullptr && lane == 0) p.cat_lnl[(size_t)s * K + k] = f > 0 ? log(f) + shift : -INFINITY;
+            if (f > 0) mix = fma(p.catw[k], f, mix);
         }
-        if (ok) {
-            const double lnl = mix > 0 ? log(mix) + (double)e * kLn2 : -INFINITY;
-            p.pattern_lnl[ss] = lnl;
-            acc += (p.weights ? p.weights[ss] : 1.0) * lnl;
+        if (lane == 0) {
+            const double lnl = mix > 0 ? log(mix) + shift : -INFINITY;
+            p.pattern_lnl[s] = lnl;
+            acc += (p.weights ? p.weights[s] : 1.0) * lnl;
         }
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    if (lane == 0) s_red[warp] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double tsum = 0;
-        for (int w = 0; w < (int)blockDim.x / 32; ++w) tsum += s_red[w];
-        p.partial_sums[blockIdx.x] = tsum;
-    }
+    if (threadIdx.x == 0) p.partial_sums[blockIdx.x] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
 }
 
 // out[o] = sum_i parts[o * n_parts + i], fixed summation order
@@ -344,43 +283,50 @@ int generic_run_rows(Ctx* c, const RowSet& rs, int mode) {
 }
 
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root) {
-    GenRootArgs p;
-    p.pmats = c->d_pmats + (size_t)(2 * c->max_rows()) * c->K * c->A * c->A;
-    p.codes = c->d_codes;
-    p.pitch = c->code_pitch;
-    p.lut = c->d_lut;
-    p.clv = c->d_clv;
-    p.scale = c->d_scale;
-    p.freqs = c->model_freqs();
-    p.catw = c->model_catw();
-    p.weights = c->d_weights;
+    (void)store_root;   // the root partial always lands in the root block
+    // the root as one more row: children a, b; P blocks 2*max_rows (+1) = P(0), P(length)
+    OpRow row{};
+    row.dst = c->root_block;
     const int nodes[2] = {a, b};
     for (int i = 0; i < 2; ++i) {
         if (c->node_tip[nodes[i]] >= 0) {
-            p.kind[i] = SRC_TIP;
-            p.src[i] = c->node_tip[nodes[i]];
+            row.kind[i] = SRC_TIP;
+            row.src[i] = c->node_tip[nodes[i]];
         } else {
-            p.kind[i] = SRC_GLOBAL;
-            p.src[i] = c->node_slot[nodes[i]];
+            row.kind[i] = SRC_GLOBAL;
+            row.src[i] = c->node_slot[nodes[i]];
         }
+        row.pidx[i] = 2 * c->max_rows() + i;
     }
+    if (row.kind[0] != SRC_TIP && row.kind[1] == SRC_TIP) {   // canonical order: tips first
+        std::swap(row.kind[0], row.kind[1]);
+        std::swap(row.src[0], row.src[1]);
+        std::swap(row.pidx[0], row.pidx[1]);
+    }
+    OpRow* d_row = c->d_rows + c->max_rows();
+    PHB_CUDA(c, cudaMemcpyAsync(d_row, &row, sizeof row, cudaMemcpyHostToDevice, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `row` lives on the stack
+    static const std::vector<int32_t> one_level = {0, 1};
+    const RowSet rs{d_row, 1, &one_level};
+    int st = run_rows(c, rs, PHB_MODE_LEVEL);
+    if (st) return st;
+
+    RootFinishArgs p;
+    p.root_clv = c->d_root_clv;
+    p.root_scale = c->d_root_scale;
+    p.freqs = c->model_freqs();
+    p.catw = c->model_catw();
+    p.weights = c->d_weights;
     p.S = c->S;
     p.A = c->A;
     p.K = c->K;
     p.pattern_lnl = c->d_pattern_lnl;
     p.cat_lnl = want_cat ? c->d_cat_lnl : nullptr;
-    p.root_clv = store_root ? c->d_root_clv : nullptr;
-    p.root_scale = store_root ? c->d_root_scale : nullptr;
     p.partial_sums = c->d_partial_sums;
-    const int threads = 128;
-    const int64_t n_iter = (c->S + threads - 1) / threads;
-    int64_t grid = (int64_t)c->sm_count * 4;
-    if (grid > n_iter) grid = n_iter;
-    if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+    int64_t grid = (c->S + 3) / 4;
+    if (grid > (int64_t)c->sm_count * 16) grid = (int64_t)c->sm_count * 16;
     if (grid < 1) grid = 1;
-    const size_t smem = (2 * (size_t)c->A * c->A + threads / 32) * sizeof(double);
-    PHB_CUDA(c, cudaFuncSetAttribute(generic_root_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    generic_root_kernel<<<(int)grid, threads, smem, c->stream>>>(p);
+    root_finish_kernel<<<(int)grid, 128, 0, c->stream>>>(p);
     c->launches++;
     PHB_CUDA(c, cudaGetLastError());
     return launch_final_reduce(c, c->d_partial_sums, (int)grid, 1, c->d_result);

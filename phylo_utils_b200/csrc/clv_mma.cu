@@ -64,7 +64,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // one P buffer and one child-row buffer, the P block and the child rows of phase ph+1 stream into the other
 // pair with cp.async (8-byte pieces: rows of 20 or 61 doubles are only 8-byte aligned).  Padding rows and
 // columns are zeroed once and never touched again.
-template <int MT, int KS, int NT, int WARPS, bool LEVEL>
+template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL>
 __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     double* Pbuf = sm;                               // [2][MROWS][LDP]
     double* Lbuf = Pbuf + 2 * MROWS * LDP;           // [2][TS][LDL]
     unsigned char* s_codes = reinterpret_cast<unsigned char*>(Lbuf + 2 * TS * LDL);   // [2 children][TS]
-    const int A = p.A, K = p.K;
+    constexpr int A = AA;   // compile-time: the staging loops divide by it
+    const int K = p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / column
     const size_t S = (size_t)p.S;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 }
                 __syncwarp();
                 // the padding columns of these rows must read as zero again when they next hold a child row
-                if (MROWS > KCOLS || KCOLS > A)
+                if (LDL > A)
                     for (int e = lane; e < WR * (LDL - A); e += 32) myL[(e / (LDL - A)) * LDL + A + e % (LDL - A)] = 0.0;
                 __syncwarp();
             }
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     }
 }
 
-template <int MT, int KS, int NT, int WARPS, bool LEVEL>
+template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL>
 int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
@@ -246,7 +247,7 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     a.A = c->A;
     a.K = c->K;
     const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 2 * TS;
-    auto kern = mma_prune_kernel<MT, KS, NT, WARPS, LEVEL>;
+    auto kern = mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL>;
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -261,19 +262,19 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     return PHB_OK;
 }
 
-template <int MT, int KS, int NT, int WARPS>
+template <int AA, int MT, int KS, int NT, int WARPS>
 int run_rows_mma(Ctx* c, const RowSet& rs, int mode) {
     if (rs.n_rows == 0) return PHB_OK;
     if (mode == PHB_MODE_LEVEL) {
         const std::vector<int32_t>& lv = *rs.levels;
         for (int l = 0; l + 1 < (int)lv.size(); ++l) {
             if (lv[l + 1] <= lv[l]) continue;
-            int st = launch_mma<MT, KS, NT, WARPS, true>(c, rs.d_rows, lv[l], lv[l + 1]);
+            int st = launch_mma<AA, MT, KS, NT, WARPS, true>(c, rs.d_rows, lv[l], lv[l + 1]);
             if (st) return st;
         }
         return PHB_OK;
     }
-    return launch_mma<MT, KS, NT, WARPS, false>(c, rs.d_rows, 0, rs.n_rows);
+    return launch_mma<AA, MT, KS, NT, WARPS, false>(c, rs.d_rows, 0, rs.n_rows);
 }
 
 }  // namespace
@@ -281,8 +282,8 @@ int run_rows_mma(Ctx* c, const RowSet& rs, int mode) {
 bool mma_supported(const Ctx* c) { return c->A == 20 || c->A == 61; }
 
 int mma_run_rows(Ctx* c, const RowSet& rs, int mode) {
-    if (c->A == 20) return run_rows_mma<3, 5, 4, 4>(c, rs, mode);    // 24 x 20 P, 128 patterns per CTA
-    if (c->A == 61) return run_rows_mma<8, 16, 1, 8>(c, rs, mode);   // 64 x 64 P, 64 patterns per CTA
+    if (c->A == 20) return run_rows_mma<20, 3, 5, 4, 4>(c, rs, mode);    // 24 x 20 P, 128 patterns per CTA
+    if (c->A == 61) return run_rows_mma<61, 8, 16, 1, 8>(c, rs, mode);   // 64 x 64 P, 64 patterns per CTA
     return c->fail(PHB_ERR_UNSUPPORTED, "DMMA kernels cover 20 and 61 states");
 }
 

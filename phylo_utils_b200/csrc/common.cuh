@@ -82,7 +82,8 @@ struct Ctx {
     OpRow* d_up_rows = nullptr;        // [2 * max_rows]
     std::vector<OpRow> up_rows;
     std::vector<int32_t> up_levels;
-    double* d_root_clv = nullptr;      // [S][K][A]
+    int root_block = 0;                // index of the virtual-root block in the shared block array
+    double* d_root_clv = nullptr;      // [S][K][A] = block root_block
     int32_t* d_root_scale = nullptr;   // [S]
     double* d_pmats = nullptr;         // [2*max_rows + 2][K][A][A]
     double* d_dmats = nullptr;         // derivative scratch [3][K][A][A] per edge chunk

@@ -54,8 +54,9 @@ def report(name, tm, n_taxa, n_pat, A, reps, derivs=False):
     b_node = 2 * K * A * 8 + 16
     flops_node = K * (4 * A * A + A)
     ms, lnl = timed(lambda: (tm.compute_partials(), tm.lnl())[1], reps)
+    prune_ms, _ = timed(lambda: tm.compute_partials(), reps)
     nodes = (n_taxa - 2) * n_pat
-    out = {"config": name, "taxa": n_taxa, "patterns": n_pat, "states": A, "lnl": lnl, "lnl_ms": ms,
+    out = {"config": name, "taxa": n_taxa, "patterns": n_pat, "states": A, "lnl": lnl, "lnl_ms": ms, "prune_ms": prune_ms,
            "site_node_updates_per_s": nodes / ms * 1e3, "algorithmic_GBs": nodes * b_node / ms / 1e6,
            "fp64_TFLOPs": nodes * flops_node / ms / 1e9, "mma_disabled": bool(os.environ.get("PHB_DISABLE_MMA"))}
     if derivs:
