@@ -56,7 +56,8 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.root_block = (int)(n_blocks - 1);
     p.pmats = take((2 * max_rows + 2) * (size_t)K * A * A * 8);
     p.dmats = take((size_t)kMaxEdgeBatch * 3 * K * A * A * 8);
-    p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32 : 0);
+    p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32
+                           : ((A == 20 || A == 61) ? (2 * max_rows + 2) * (size_t)K * 64 * A * 8 : 0));
     p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
     p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
     p.rows = take((max_rows + 1) * sizeof(OpRow));   // + the root pseudo-row
@@ -293,7 +294,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->root_block = p.root_block;
     c->d_pmats = (double*)(w + p.pmats);
     c->d_dmats = (double*)(w + p.dmats);
-    c->d_tiptab = n_states == 4 ? (double*)(w + p.tiptab) : nullptr;
+    c->d_tiptab = (n_states == 4 || n_states == 20 || n_states == 61) ? (double*)(w + p.tiptab) : nullptr;
     c->d_model = (double*)(w + p.model);
     c->d_lengths = (double*)(w + p.lengths);
     c->d_rows = (OpRow*)(w + p.rows);

@@ -21,6 +21,8 @@
 // loads are bank-conflict free.  Semantics (reference `clv`, numba_likelihood_engine.py:10-46, with the
 // per-pattern binary exponent of clv_dna.cu) and data layout are those of clv_generic.cu, which remains the
 // fallback for every other state count.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace phb {
@@ -31,6 +33,8 @@ struct MmaArgs {
     const OpRow* rows;
     int row_begin, row_end;
     const double* pmats;  // [pidx][K][A][A]
+    const double* tiptab; // [pidx][K][nc][A] = P . lut[code], or null
+    int nc;
     const uint8_t* codes;
     size_t pitch;
     const double* lut;    // [256][A]
@@ -95,15 +99,27 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
 
             // tip codes of this warp's patterns (same for every category)
             for (int c = 0; c < 2; ++c)
-                if (row.kind[c] == SRC_TIP && lane < WR) {
-                    const int64_t s = wsite0 + lane;
-                    s_codes[c * TS + warp * WR + lane] = s < p.S ? p.codes[(size_t)row.src[c] * p.pitch + s] : 0;
-                }
+                if (row.kind[c] == SRC_TIP)
+                    for (int n = lane; n < WR; n += 32) {
+                        const int64_t s = wsite0 + n;
+                        s_codes[c * TS + warp * WR + n] = s < p.S ? p.codes[(size_t)row.src[c] * p.pitch + s] : 0;
+                    }
             __syncwarp();
 
             auto prefetch = [&](int ph) {
                 const int k = ph >> 1, c = ph & 1, buf = ph & 1;
                 double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
+                if (row.kind[c] == SRC_TIP && p.tiptab != nullptr) {
+                    // a tip child needs no product at all: its contribution is row `code` of T = P . lut, staged
+                    // where the P block would go (row = code, n_codes <= MROWS rows)
+                    const double* q = p.tiptab + ((size_t)row.pidx[c] * K + k) * p.nc * A;
+                    for (int e = threadIdx.x; e < p.nc * A; e += WARPS * 32) {
+                        const int i = e / A, j = e - i * A;
+                        cp_async8(Pd + i * LDP + j, q + e);
+                    }
+                    cp_async_commit_all();
+                    return;
+                }
                 const double* q = p.pmats + ((size_t)row.pidx[c] * K + k) * A * A;
                 for (int e = threadIdx.x; e < A * A; e += WARPS * 32) {
                     const int i = e / A, j = e - i * A;
@@ -138,6 +154,18 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 if (ph + 1 < n_phases) prefetch(ph + 1);
                 const double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
                 const double* myLr = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
+                if (row.kind[ph & 1] == SRC_TIP && p.tiptab != nullptr) {
+                    // gather in fragment layout: acc[mt][nt][q] = T[code(pattern nt*8 + 2fc + q)][state mt*8 + fr]
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int code = s_codes[(ph & 1) * TS + warp * WR + nt * 8 + 2 * fc + q];
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) acc[mt][nt][q] = Pd[code * LDP + mt * 8 + fr];
+                        }
+                    return;
+                }
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -237,6 +265,9 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     a.row_begin = row_begin;
     a.row_end = row_end;
     a.pmats = c->d_pmats;
+    // tables are staged in the P buffer (MROWS rows): usable when every code has a row there
+    a.nc = tip_table_rows(c);
+    a.tiptab = (tip_tables_usable(c) && a.nc <= MROWS && getenv("PHB_DISABLE_TIPTAB") == nullptr) ? c->d_tiptab : nullptr;
     a.codes = c->d_codes;
     a.pitch = c->code_pitch;
     a.lut = c->d_lut;
@@ -282,8 +313,16 @@ int run_rows_mma(Ctx* c, const RowSet& rs, int mode) {
 bool mma_supported(const Ctx* c) { return c->A == 20 || c->A == 61; }
 
 int mma_run_rows(Ctx* c, const RowSet& rs, int mode) {
-    if (c->A == 20) return run_rows_mma<20, 3, 5, 4, 4>(c, rs, mode);    // 24 x 20 P, 128 patterns per CTA
-    if (c->A == 61) return run_rows_mma<61, 8, 16, 1, 8>(c, rs, mode);   // 64 x 64 P, 64 patterns per CTA
+    const char* env = getenv("PHB_MMA_VARIANT");   // tuning knob: alternative tile shapes
+    const int variant = env ? atoi(env) : 0;
+    if (c->A == 20) {
+        if (variant == 1) return run_rows_mma<20, 3, 5, 4, 8>(c, rs, mode);   // 256 patterns per CTA, 8 warps
+        return run_rows_mma<20, 3, 5, 4, 4>(c, rs, mode);                     // 128 patterns per CTA, 4 warps
+    }
+    if (c->A == 61) {
+        if (variant == 1) return run_rows_mma<61, 8, 16, 1, 8>(c, rs, mode);  // 64 patterns per CTA
+        return run_rows_mma<61, 8, 16, 2, 8>(c, rs, mode);                    // 128 patterns per CTA
+    }
     return c->fail(PHB_ERR_UNSUPPORTED, "DMMA kernels cover 20 and 61 states");
 }
 

@@ -158,7 +158,15 @@ constexpr int kTipTabCodes = 16;     // tip tables cover look-up tables of up to
 // pmatrix.cu
 int launch_build_pmatrices(Ctx* c, const double* d_lengths, int n_mats, double* d_out, int order, int chain_rule);
 int launch_tip_tables(Ctx* c, int first_mat, int n_mats);
-inline int tip_table_rows(const Ctx* c) { return c->n_codes <= 8 ? 8 : kTipTabCodes; }   // rows per category block
+// rows per category block of the tip tables: 8 or 16 for 4-state models, a multiple of 8 up to 64 otherwise
+inline int tip_table_rows(const Ctx* c) {
+    if (c->A == 4) return c->n_codes <= 8 ? 8 : kTipTabCodes;
+    return (c->n_codes + 7) / 8 * 8;
+}
+inline bool tip_tables_usable(const Ctx* c) {
+    if (c->d_tiptab == nullptr || !c->have_tips) return false;
+    return c->A == 4 ? c->n_codes <= kTipTabCodes : c->n_codes <= 64;
+}
 cudaError_t launch_pmatrix_raw(cudaStream_t stream, const double* evecs, const double* evals, const double* ivecs,
                                const double* rates, const double* d_lengths, double* d_out, int A, int K, int n_mats,
                                int order, int chain_rule);

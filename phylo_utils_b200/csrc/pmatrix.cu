@@ -76,8 +76,31 @@ __global__ void tip_table_kernel(const double* __restrict__ pmats, const double*
     }
 }
 
+// any state count: T[m][k][code][i], grid (n_mats, K)
+__global__ void tip_table_generic_kernel(const double* __restrict__ pmats, const double* __restrict__ lut, int n_codes,
+                                         int nc, int A, int K, int first_mat, double* __restrict__ out) {
+    const int m = first_mat + blockIdx.x, k = blockIdx.y;
+    const double* P = pmats + ((size_t)m * K + k) * A * A;
+    double* dst = out + ((size_t)m * K + k) * nc * A;
+    for (int idx = threadIdx.x; idx < nc * A; idx += blockDim.x) {
+        const int code = idx / A, i = idx - code * A;
+        double acc = 0.0;
+        if (code < n_codes)
+            for (int j = 0; j < A; ++j) acc = fma(P[i * A + j], lut[code * A + j], acc);
+        dst[idx] = acc;
+    }
+}
+
 int launch_tip_tables(Ctx* c, int first_mat, int n_mats) {
-    if (c->d_tiptab == nullptr || n_mats <= 0 || !c->have_tips || c->n_codes > kTipTabCodes) return PHB_OK;
+    if (n_mats <= 0 || !tip_tables_usable(c)) return PHB_OK;
+    if (c->A != 4) {
+        dim3 grid(n_mats, c->K);
+        tip_table_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->A,
+                                                              c->K, first_mat, c->d_tiptab);
+        c->launches++;
+        PHB_CUDA(c, cudaGetLastError());
+        return PHB_OK;
+    }
     tip_table_kernel<<<n_mats, 128, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->K, first_mat,
                                                     c->d_tiptab);
     c->launches++;
