@@ -146,6 +146,16 @@ int phb_lnl_resident(phb_ctx* ctx, int node_a, int node_b, double length, double
 int phb_lnl_from_host(phb_ctx* ctx, const uint8_t* codes, int n_chunks, int node_a, int node_b, double length,
                       double* total, double* pattern_lnl);
 
+/* phb_lnl_from_host with the tip codes packed two per byte: packed_codes[n_tips][(n_patterns + 1) / 2], pattern 2j in
+ * the low nibble of byte j, pattern 2j+1 in the high nibble (look-up tables of at most 16 rows, i.e. every
+ * nucleotide alphabet including the IUPAC ambiguity codes of alignment/charmaps.py:2-20).  Half the bytes cross
+ * PCIe; the kernel reads the nibbles directly.  Afterwards the device holds PACKED codes: phb_lnl_resident keeps
+ * working, everything that reads tips otherwise returns PHB_ERR_STATE until the next phb_set_tips. */
+int phb_lnl_from_host_packed(phb_ctx* ctx, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
+                             double length, double* total, double* pattern_lnl);
+/* host helper: codes[n_tips][n_patterns] (values < 16) -> out[n_tips][(n_patterns + 1) / 2] as described above */
+int phb_pack_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* out);
+
 /* ---- read-back for parity tests (TreeModel.partials / .scale / .root_partials attributes) --- */
 /* out[S][K][A]; tips are expanded from their codes */
 int phb_get_partials(phb_ctx* ctx, int node, double* out);

@@ -352,8 +352,9 @@ int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_co
                     "phb_set_tips: look-up table entries must be finite and non-negative");
     // host or device source, always copied into the pitched workspace buffer (padding stays zero)
     const size_t n_code_bytes = (size_t)c->n_tips * c->code_pitch;
-    if (c->code_pitch != (size_t)c->S && !c->have_tips)
+    if (c->code_pitch != (size_t)c->S && (!c->have_tips || c->codes_packed))
         PHB_CUDA(c, cudaMemsetAsync(c->d_codes_ws, 0, n_code_bytes, c->stream));
+    c->codes_packed = false;
     PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws, c->code_pitch, codes, (size_t)c->S, (size_t)c->S, (size_t)c->n_tips,
                                   codes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     c->d_codes = c->d_codes_ws;
@@ -546,6 +547,8 @@ int phb_compute_partials(phb_ctx* c, int mode) {
     PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS), PHB_ERR_STATE,
                 "phb_compute_partials: context was created without partial storage");
     PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_compute_partials: no tip data");
+    PHB_REQUIRE(c, !c->codes_packed, PHB_ERR_STATE,
+                "phb_compute_partials: the device holds packed codes (phb_lnl_from_host_packed); call phb_set_tips");
     PHB_REQUIRE(c, c->have_schedule, PHB_ERR_STATE, "phb_compute_partials: no schedule");
     PHB_REQUIRE(c, c->have_pmats, PHB_ERR_STATE, "phb_compute_partials: transition matrices not built");
     if (c->n_rows() == 0) {  // two-tip tree: nothing to prune
@@ -630,6 +633,8 @@ int phb_root_lnl(phb_ctx* c, int node_a, int node_b, double length, const double
     PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS), PHB_ERR_STATE,
                 "phb_root_lnl: context has no partial storage, use phb_lnl_resident");
     PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_root_lnl: no tip data");
+    PHB_REQUIRE(c, !c->codes_packed, PHB_ERR_STATE,
+                "phb_root_lnl: the device holds packed codes (phb_lnl_from_host_packed); call phb_set_tips");
     PHB_REQUIRE(c, c->have_partials || c->n_rows() == 0, PHB_ERR_STATE,
                 "phb_root_lnl: partials are stale, call phb_compute_partials first");
     st = prepare_root(c, node_a, node_b, length, root_pmats);
@@ -663,7 +668,47 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
     c->have_pmats = true;
     st = prepare_root(c, node_a, node_b, length, nullptr);
     if (st) return st;
-    st = dna_resident(c, node_a, node_b, false, true);
+    // default: two patterns per lane (clv_dna_pair.cu); PHB_RESIDENT_V1 selects the one-pattern-per-lane walk
+    if (getenv("PHB_RESIDENT_V1") == nullptr) {
+        st = dna_pair_lnl(c, node_a, node_b);
+    } else {
+        PHB_REQUIRE(c, !c->codes_packed, PHB_ERR_STATE, "phb_lnl_resident: packed codes need the pair kernel");
+        st = dna_resident(c, node_a, node_b, false, true);
+    }
+    if (st) return st;
+    PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (pattern_lnl)
+        PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PHB_OK;
+}
+
+static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_chunks, int node_a, int node_b,
+                         double length, double* total, double* pattern_lnl) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, codes != nullptr && total != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host: NULL argument");
+    PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
+                "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
+    PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
+    PHB_REQUIRE(c, !packed || c->n_codes <= 16, PHB_ERR_UNSUPPORTED, "phb_lnl_from_host_packed: more than 16 codes");
+    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
+    if (st) return st;
+    st = launch_tip_tables(c, 0, (int)c->lengths.size());
+    if (st) return st;
+    c->have_pmats = true;
+    st = prepare_root(c, node_a, node_b, length, nullptr);
+    if (st) return st;
+    c->have_partials = false;
+    c->have_up = false;
+    if (n_chunks <= 0) n_chunks = 16;
+    if (!packed && getenv("PHB_RESIDENT_V1") != nullptr) {
+        c->codes_packed = false;
+        st = dna_resident_from_host(c, codes, n_chunks, node_a, node_b);
+    } else {
+        st = dna_pair_from_host(c, codes, packed, n_chunks, node_a, node_b);
+    }
     if (st) return st;
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)
@@ -674,28 +719,32 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
 
 int phb_lnl_from_host(phb_ctx* c, const uint8_t* codes, int n_chunks, int node_a, int node_b, double length,
                       double* total, double* pattern_lnl) {
-    if (!c) return PHB_ERR_INVALID;
-    int st = activate(c);
-    if (st) return st;
-    PHB_REQUIRE(c, codes != nullptr && total != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host: NULL argument");
-    PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
-                "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
-    PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
-    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
-    if (st) return st;
-    st = launch_tip_tables(c, 0, (int)c->lengths.size());
-    if (st) return st;
-    c->have_pmats = true;
-    st = prepare_root(c, node_a, node_b, length, nullptr);
-    if (st) return st;
-    c->have_partials = false;
-    c->have_up = false;
-    st = dna_resident_from_host(c, codes, n_chunks > 0 ? n_chunks : 8, node_a, node_b);
-    if (st) return st;
-    PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
-    if (pattern_lnl)
-        PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
-    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return lnl_from_host(c, codes, false, n_chunks, node_a, node_b, length, total, pattern_lnl);
+}
+
+int phb_lnl_from_host_packed(phb_ctx* c, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
+                             double length, double* total, double* pattern_lnl) {
+    return lnl_from_host(c, packed_codes, true, n_chunks, node_a, node_b, length, total, pattern_lnl);
+}
+
+int phb_pack_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* out) {
+    if (codes == nullptr || out == nullptr || n_tips < 0 || n_patterns < 0) {
+        set_thread_error("phb_pack_codes: bad argument");
+        return PHB_ERR_INVALID;
+    }
+    const int64_t row = (n_patterns + 1) / 2;
+    for (int t = 0; t < n_tips; ++t) {
+        const uint8_t* src = codes + (size_t)t * n_patterns;
+        uint8_t* dst = out + (size_t)t * row;
+        for (int64_t j = 0; j < row; ++j) {
+            const unsigned lo = src[2 * j], hi = 2 * j + 1 < n_patterns ? src[2 * j + 1] : 0u;
+            if (lo > 15u || hi > 15u) {
+                set_thread_error("phb_pack_codes: a code does not fit in 4 bits");
+                return PHB_ERR_INVALID;
+            }
+            dst[j] = (uint8_t)(lo | (hi << 4));
+        }
+    }
     return PHB_OK;
 }
 
@@ -707,7 +756,7 @@ int phb_get_partials(phb_ctx* c, int node, double* out) {
     PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "phb_get_partials: node id out of range");
     const size_t S = (size_t)c->S, K = c->K, A = c->A;
     if (c->node_tip[node] >= 0) {
-        PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_get_partials: no tip data");
+        PHB_REQUIRE(c, c->have_tips && !c->codes_packed, PHB_ERR_STATE, "phb_get_partials: no (unpacked) tip data");
         std::vector<uint8_t> codes(S);
         std::vector<double> lut(256 * A);
         PHB_CUDA(c, cudaMemcpyAsync(codes.data(), c->d_codes + (size_t)c->node_tip[node] * c->code_pitch, S, cudaMemcpyDeviceToHost,

@@ -1,0 +1,525 @@
+// lnL-only operand-resident pruning for 4-state models, two patterns per lane.
+//
+// Same arithmetic as clv_dna.cu / clv_dna_resident.cu (reference `clv`, numba_likelihood_engine.py:10-46; root
+// step = tree_model.py:178-217 with lnl_node, numba_likelihood_engine.py:82-87), same parking plan
+// (resident_plan.cuh), different mapping:
+//
+//   * a WARP owns a tile of 64 patterns and walks ALL rows (+ the virtual-root pseudo-row) for it; every lane
+//     carries TWO adjacent patterns, so every broadcast read of a P row, every descriptor decode, every
+//     prefetch address and every branch is paid once per 64 pattern-node updates instead of once per 32;
+//   * the result of a row stays in registers when the next row consumes it (2/3 of the internal operands);
+//   * a result needed later is parked in a per-warp scratch stripe that lives in L2.  The stripe layout is
+//     private to the warp, so it is chosen for the hardware: 16-byte chunk c of lane l sits at
+//     (c * 32 + l) * 16 - the park is 4K coalesced 128-bit stores straight from registers (no staging tile,
+//     no __syncwarp), the fetch is 4K coalesced cp.async one row ahead, the consumer's LDS.128 is conflict
+//     free.  Every lane reads back exactly the chunks it wrote itself;
+//   * everything else a row needs - the two operands' P block (or the P.lut tip table of a tip operand), the
+//     tile's tip codes (64 bytes per tip operand, 32 when packed two per byte) and the 16-byte row descriptor
+//     (two rows ahead) - arrives by cp.async one row ahead in per-warp double buffers, so nothing a row reads
+//     has a load latency on its critical path and no register carries a pending load across the row loop
+//     (a first version that passed descriptors and codes through registers spent half its time stalled on
+//     them: profiles/r01k_pair_v1_1000x1M.txt);
+//   * there is ONE operand tile: the parked operand of row r+1 is fetched during row r, or right after row
+//     r's arithmetic when row r reads the tile itself (1 row in 9);
+//   * the last pseudo-row does the root combine, pi-dot, Gamma mixture, log and the weighted tile sum.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "resident_plan.cuh"
+
+namespace phb {
+
+namespace {
+
+// 16-byte row descriptor of this kernel
+struct __align__(16) PairRow {
+    uint32_t off_a;   // 16-byte units from PairArgs::opbase: operand a's tip table (tip) or P block (otherwise)
+    uint32_t off_b;
+    int32_t src_a;    // tip row of operand a (operand a is never a parked block: canonical order TIP <= PREV <= SLOT)
+    uint32_t packed;  // src_b [0:24) (tip row | scratch slot) | kind_a [24:26) | kind_b [26:28) | dst slot [28:32), 15 = none
+};
+
+struct PairArgs {
+    const PairRow* rows;
+    int n_steps;                  // rows walked per tile, including the root pseudo-row
+    const unsigned char* opbase;  // base the descriptors' operand offsets refer to
+    const uint8_t* codes;
+    size_t pitch;                 // bytes between tip rows of `codes`
+    unsigned char* scratch;
+    int n_slots;
+    const double* freqs;
+    const double* catw;
+    const double* weights;
+    double* pattern_lnl;
+    double* partial_sums;         // one per CTA
+    int64_t S;
+    int64_t tile_begin, tile_end; // 64-pattern tiles covered by this launch
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int K, int NC>
+struct PairLayout {
+    static constexpr int P_ROUNDS = (K * 128 + 511) / 512;        // warp-wide 512-byte copy rounds of a P block
+    static constexpr int T_ROUNDS = (K * NC * 32 + 511) / 512;    // ... of a tip table [k][code][4 doubles]
+    static constexpr int ROUNDS = P_ROUNDS > T_ROUNDS ? P_ROUNDS : T_ROUNDS;
+    static constexpr int OPER_BYTES = ROUNDS * 512;
+    static constexpr int CODES_OFF = 2 * OPER_BYTES;              // 64 bytes of tip codes per operand
+    static constexpr int STAGE_BYTES = 2 * OPER_BYTES + 128;
+    static constexpr int DESC_BYTES = 4 * 16;                     // descriptor ring: rows r .. r+2 in flight
+    static constexpr int CHUNKS = 2 * K * 2;                      // 16-byte chunks per lane in a parked block
+    static constexpr int BLOCK_BYTES = CHUNKS * 512;              // [pattern of the lane][k][half][lane]
+    static constexpr int SLOT_BYTES = BLOCK_BYTES + 256;          // + two exponents per lane
+    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + SLOT_BYTES;
+    // CTAs (= warps) per SM the register file is budgeted for.  A warp lives in one of the four SM
+    // sub-partitions with 16384 registers each: 12 CTAs = 3 warps per sub-partition = 168 registers.
+    static constexpr int MIN_CTAS = K <= 2 ? 16 : (K <= 4 ? 12 : 4);
+};
+
+// the two codes of a lane, as byte offsets of their tip-table rows
+template <int NC, bool PACKED>
+__device__ __forceinline__ void table_rows(const unsigned char* codes, int lane, int (&row)[2]) {
+    if (PACKED) {
+        const unsigned raw = codes[lane];
+        row[0] = (int)(raw & (NC - 1)) * 32;
+        row[1] = (int)((raw >> 4) & (NC - 1)) * 32;
+    } else {
+        const unsigned raw = *reinterpret_cast<const unsigned short*>(codes + 2 * lane);
+        row[0] = (int)(raw & (NC - 1)) * 32;
+        row[1] = (int)((raw >> 8) & (NC - 1)) * 32;
+    }
+}
+
+__device__ __forceinline__ void lds32(const unsigned char* p, double (&v)[4]) {
+    const double2 lo = *reinterpret_cast<const double2*>(p);
+    const double2 hi = *reinterpret_cast<const double2*>(p + 16);
+    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+}
+
+// prev[p][k] <- (Pa[k] . a[p][k]) * (Pb[k] . b[p][k]) for the lane's two patterns; pe <- cumulative exponents
+template <int K, int NC, bool PACKED, int KA, int KB>
+__device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
+                                            double (&prev)[2][K][4], int (&pe)[2]) {
+    using L = PairLayout<K, NC>;
+    static_assert(KA != KIND_SLOT, "operand a is a tip or the previous row");
+    int e[2] = {0, 0};
+    if (KA == KIND_PREV || KB == KIND_PREV) {
+        e[0] = pe[0];
+        e[1] = pe[1];
+    }
+    if (KB == KIND_SLOT) {
+        const int2 x = *reinterpret_cast<const int2*>(opin + L::BLOCK_BYTES + lane * 8);
+        e[0] += x.x;
+        e[1] += x.y;
+    }
+    int ra[2] = {0, 0}, rb[2] = {0, 0};
+    if (KA == KIND_TIP) table_rows<NC, PACKED>(st + L::CODES_OFF, lane, ra);
+    if (KB == KIND_TIP) table_rows<NC, PACKED>(st + L::CODES_OFF + 64, lane, rb);
+    int mh[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double x[2][4], y[2][4];
+        if (KA == KIND_TIP) {
+            // a tip operand contributes the row `code` of its staged table T[k] = P[k] . lut - no arithmetic
+#pragma unroll
+            for (int p = 0; p < 2; ++p) lds32(st + k * NC * 32 + ra[p], x[p]);
+        } else {
+            const double2* q = reinterpret_cast<const double2*>(st + k * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 r0 = q[2 * i], r1 = q[2 * i + 1];   // P row i: warp-wide broadcast
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+                    x[p][i] = fma(r1.y, prev[p][k][3], fma(r1.x, prev[p][k][2], fma(r0.y, prev[p][k][1], r0.x * prev[p][k][0])));
+            }
+        }
+        if (KB == KIND_TIP) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) lds32(st + L::OPER_BYTES + k * NC * 32 + rb[p], y[p]);
+        } else {
+            double b[2][4];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                if (KB == KIND_PREV) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) b[p][i] = prev[p][k][i];
+                } else {
+                    const unsigned char* src = opin + ((p * K + k) * 2) * 512 + lane * 16;
+                    const double2 lo = *reinterpret_cast<const double2*>(src);
+                    const double2 hi = *reinterpret_cast<const double2*>(src + 512);
+                    b[p][0] = lo.x; b[p][1] = lo.y; b[p][2] = hi.x; b[p][3] = hi.y;
+                }
+            }
+            const double2* q = reinterpret_cast<const double2*>(st + L::OPER_BYTES + k * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double2 r0 = q[2 * i], r1 = q[2 * i + 1];
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+                    y[p][i] = fma(r1.y, b[p][3], fma(r1.x, b[p][2], fma(r0.y, b[p][1], r0.x * b[p][0])));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double o = x[p][i] * y[p][i];
+                prev[p][k][i] = o;
+                mh[p] = max(mh[p], __double2hiint(o));   // partials are >= 0: the high word orders them
+            }
+    }
+    // 0 < max < 2^-128: multiply by the exact power of two that brings the maximum into [1, 2)
+    const bool small0 = mh[0] < kScaleThresholdHi && mh[0] >= 0x00100000;
+    const bool small1 = mh[1] < kScaleThresholdHi && mh[1] >= 0x00100000;
+    if (__any_sync(0xffffffffu, small0 || small1)) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            if (p == 0 ? small0 : small1) {
+                const int shift = 1023 - (mh[p] >> 20);
+                const double f = pow2i(shift);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) prev[p][k][i] *= f;
+                e[p] -= shift;
+            }
+        }
+    }
+    pe[0] = e[0];
+    pe[1] = e[1];
+}
+
+template <int K, int NC, bool PACKED>
+__global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kernel(const PairArgs p) {
+    using L = PairLayout<K, NC>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    PairRow* const s_desc = reinterpret_cast<PairRow*>(smem);
+    unsigned char* const s_stage = smem + L::DESC_BYTES;
+    unsigned char* const s_opin = s_stage + 2 * L::STAGE_BYTES;
+    const int wstride = gridDim.x, n_steps = p.n_steps, tile_end = (int)p.tile_end;
+    double acc = 0.0;
+    unsigned char* const my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * L::SLOT_BYTES;
+
+    // parked block `slot` -> the operand tile (the lane's own chunks, in the layout it wrote them)
+    auto fetch_slot = [&](int slot) {
+        const unsigned char* src = my_scratch + (size_t)slot * L::SLOT_BYTES;
+#pragma unroll
+        for (int j = 0; j < L::CHUNKS; ++j) cp_async16(s_opin + j * 512 + lane * 16, src + j * 512 + lane * 16);
+        cp_async8(s_opin + L::BLOCK_BYTES + lane * 8, src + L::BLOCK_BYTES + lane * 8);
+    };
+    // read-only inputs of row `d` at tile t -> stage buffer q: per operand its P block or tip table, and its codes
+    auto stage_row = [&](const PairRow d, int t, int q) {
+        unsigned char* st = s_stage + q * L::STAGE_BYTES;
+        const int kind_a = (d.packed >> 24) & 3, kind_b = (d.packed >> 26) & 3;
+        const unsigned char* ga = p.opbase + (size_t)d.off_a * 16 + lane * 16;
+        const unsigned char* gb = p.opbase + (size_t)d.off_b * 16 + lane * 16;
+#pragma unroll
+        for (int j = 0; j < L::ROUNDS; ++j)
+            if (j < L::P_ROUNDS || kind_a == KIND_TIP) cp_async16(st + j * 512 + lane * 16, ga + j * 512);
+#pragma unroll
+        for (int j = 0; j < L::ROUNDS; ++j)
+            if (j < L::P_ROUNDS || kind_b == KIND_TIP) cp_async16(st + L::OPER_BYTES + j * 512 + lane * 16, gb + j * 512);
+        // codes of the tile: 64 (32 when packed) bytes per tip operand; lanes 0..3 serve operand a, 4..7 operand b
+        constexpr int CL = PACKED ? 2 : 4;
+        const int which = lane >> 2, piece = lane & 3;
+        const bool tip = which == 0 ? kind_a == KIND_TIP : kind_b == KIND_TIP;
+        if (which < 2 && piece < CL && tip) {
+            const int tip_row = which == 0 ? d.src_a : (int)(d.packed & 0xffffff);
+            cp_async16(st + L::CODES_OFF + which * 64 + piece * 16,
+                       p.codes + (size_t)tip_row * p.pitch + (size_t)t * (CL * 16) + piece * 16);
+        }
+    };
+
+    int tile = (int)p.tile_begin + blockIdx.x;
+    if (tile < tile_end) {
+        // prologue: descriptors of rows 0 and 1, then the inputs of row 0
+        if (lane < 2) cp_async16(&s_desc[lane], &p.rows[lane < n_steps ? lane : 0]);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+        {
+            const PairRow d0 = s_desc[0];
+            stage_row(d0, tile, 0);
+            if (((d0.packed >> 26) & 3) == KIND_SLOT) fetch_slot(d0.packed & 0xffffff);   // never: row 0 has no parked operand
+        }
+        cp_async_commit();
+
+        double prev[2][K][4];
+        int pe[2] = {0, 0};
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) prev[q][k][i] = 0.0;
+
+        int row = 0, q = 0;
+        int row2 = n_steps > 2 ? 2 : 0;   // row index two steps ahead (descriptors do not depend on the tile)
+        while (true) {
+            int row_n = row + 1, tile_n = tile;
+            if (row_n == n_steps) {
+                row_n = 0;
+                tile_n += wstride;
+            }
+            const bool has_next = tile_n < tile_end;
+            cp_async_wait_all();   // everything issued one row ago has had a whole row to land
+            __syncwarp();
+            const uint32_t pk = s_desc[q & 3].packed;
+            const int kinds = (pk >> 24) & 15, dst_slot = pk >> 28;   // kind_a | kind_b << 2
+            const bool opin_busy = (kinds >> 2) == KIND_SLOT;         // this row still has to read the operand tile
+            bool fetch_late = false;
+            int slot_n = 0;
+            if (lane == 0) cp_async16(&s_desc[(q + 2) & 3], &p.rows[row2]);
+            if (has_next) {
+                const PairRow dn = s_desc[(q + 1) & 3];
+                stage_row(dn, tile_n, (q + 1) & 1);
+                if (((dn.packed >> 26) & 3) == KIND_SLOT) {
+                    slot_n = dn.packed & 0xffffff;
+                    if (opin_busy) fetch_late = true;
+                    else fetch_slot(slot_n);
+                }
+            }
+            cp_async_commit();
+
+            const unsigned char* st = s_stage + (q & 1) * L::STAGE_BYTES;
+            switch (kinds) {
+                case KIND_TIP | (KIND_TIP << 2):
+                    pair_update<K, NC, PACKED, KIND_TIP, KIND_TIP>(st, s_opin, lane, prev, pe);
+                    break;
+                case KIND_TIP | (KIND_PREV << 2):
+                    pair_update<K, NC, PACKED, KIND_TIP, KIND_PREV>(st, s_opin, lane, prev, pe);
+                    break;
+                case KIND_PREV | (KIND_SLOT << 2):
+                    pair_update<K, NC, PACKED, KIND_PREV, KIND_SLOT>(st, s_opin, lane, prev, pe);
+                    break;
+                case KIND_TIP | (KIND_SLOT << 2):
+                    pair_update<K, NC, PACKED, KIND_TIP, KIND_SLOT>(st, s_opin, lane, prev, pe);
+                    break;
+                default:   // not a row shape the host plan emits: do not touch memory
+                    break;
+            }
+            if (fetch_late) {   // the operand tile is free now (a lane only ever touches its own chunks of it)
+                fetch_slot(slot_n);
+                cp_async_commit();
+            }
+            if (row != n_steps - 1) {
+                if (dst_slot != 15) {
+                    // park: coalesced 128-bit stores straight from registers into the warp's own stripe
+                    unsigned char* dst = my_scratch + (size_t)dst_slot * L::SLOT_BYTES + lane * 16;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            *reinterpret_cast<double2*>(dst + ((h * K + k) * 2) * 512) = make_double2(prev[h][k][0], prev[h][k][1]);
+                            *reinterpret_cast<double2*>(dst + ((h * K + k) * 2 + 1) * 512) = make_double2(prev[h][k][2], prev[h][k][3]);
+                        }
+                    *reinterpret_cast<int2*>(my_scratch + (size_t)dst_slot * L::SLOT_BYTES + L::BLOCK_BYTES + lane * 8) =
+                        make_int2(pe[0], pe[1]);
+                }
+            } else {
+                // root pseudo-row: pi-dot, Gamma mixture, log, weighted sum (tree_model.py:200-217)
+                const int64_t s0 = (int64_t)tile * 64 + 2 * lane;
+                double lnl[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double mix = 0.0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        double f = p.freqs[0] * prev[h][k][0];
+                        f = fma(p.freqs[1], prev[h][k][1], f);
+                        f = fma(p.freqs[2], prev[h][k][2], f);
+                        f = fma(p.freqs[3], prev[h][k][3], f);
+                        if (f > 0) mix = fma(p.catw[k], f, mix);
+                    }
+                    lnl[h] = mix > 0 ? log(mix) + (double)pe[h] * kLn2 : -INFINITY;
+                }
+                if (s0 + 1 < p.S) {
+                    *reinterpret_cast<double2*>(p.pattern_lnl + s0) = make_double2(lnl[0], lnl[1]);
+                    if (p.weights) {
+                        const double2 w = *reinterpret_cast<const double2*>(p.weights + s0);
+                        acc += w.x * lnl[0];
+                        acc += w.y * lnl[1];
+                    } else {
+                        acc += lnl[0];
+                        acc += lnl[1];
+                    }
+                } else if (s0 < p.S) {
+                    p.pattern_lnl[s0] = lnl[0];
+                    acc += (p.weights ? p.weights[s0] : 1.0) * lnl[0];
+                }
+            }
+            if (!has_next) break;
+            row = row_n;
+            tile = tile_n;
+            if (++row2 == n_steps) row2 = 0;
+            ++q;
+        }
+        cp_async_wait_all();
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p.partial_sums[blockIdx.x] = acc;
+}
+
+template <int K, int NC, bool PACKED>
+int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
+                int max_grid, int* grid_out) {
+    using L = PairLayout<K, NC>;
+    PairArgs a;
+    a.rows = static_cast<const PairRow*>(c->d_res_rows);
+    a.n_steps = n_steps;
+    a.opbase = reinterpret_cast<const unsigned char*>(c->d_pmats);
+    a.codes = c->d_codes;
+    a.pitch = PACKED ? c->code_pitch / 2 : c->code_pitch;
+    a.scratch = c->d_scratch;
+    a.n_slots = n_slots;
+    a.freqs = c->model_freqs();
+    a.catw = c->model_catw();
+    a.weights = c->d_weights;
+    a.pattern_lnl = c->d_pattern_lnl;
+    a.partial_sums = partial_sums;
+    a.S = c->S;
+    a.tile_begin = tile_begin;
+    a.tile_end = tile_end;
+    auto kern = dna_pair_kernel<K, NC, PACKED>;
+    const size_t smem = L::WARP_BYTES;
+    if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
+    PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* f = getenv("PHB_PAIR_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(f)));
+    int64_t grid = std::min<int64_t>(tile_end - tile_begin, (int64_t)c->sm_count * per_sm);
+    grid = std::min<int64_t>(grid, max_grid);
+    // every resident warp needs its own scratch stripe
+    const int64_t cap = (int64_t)(c->scratch_bytes / ((size_t)n_slots * L::SLOT_BYTES));
+    if (cap < 1) return c->fail(PHB_ERR_NOMEM, "pair kernel: scratch area too small");
+    grid = std::max<int64_t>(1, std::min(grid, cap));
+    kern<<<(int)grid, 32, smem, c->stream>>>(a);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    c->resident_warps = per_sm;
+    *grid_out = (int)grid;
+    return PHB_OK;
+}
+
+int launch_pair_k(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
+                  int* grid_out) {
+    static_assert(kTipTabCodes == 16, "tip tables are staged with 8 or 16 rows per category");
+    const int key = c->K * 1000 + tip_table_rows(c) * 10 + (packed ? 1 : 0);
+    switch (key) {
+#define PHB_PAIR_CASE(K_, NC_)                                                                             \
+    case K_ * 1000 + NC_ * 10: return launch_pair<K_, NC_, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out); \
+    case K_ * 1000 + NC_ * 10 + 1: return launch_pair<K_, NC_, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out);
+        PHB_PAIR_CASE(1, 8)
+        PHB_PAIR_CASE(1, 16)
+        PHB_PAIR_CASE(2, 8)
+        PHB_PAIR_CASE(2, 16)
+        PHB_PAIR_CASE(4, 8)
+        PHB_PAIR_CASE(4, 16)
+        PHB_PAIR_CASE(8, 8)
+        PHB_PAIR_CASE(8, 16)
+#undef PHB_PAIR_CASE
+    }
+    return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel needs K in {1,2,4,8}");
+}
+
+// resident_plan rows -> this kernel's descriptors (operand offsets resolved on the host), uploaded
+int upload_pair_rows(Ctx* c, const ResPlan& plan) {
+    if (c->n_codes > kTipTabCodes)
+        return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: look-up tables of more than 16 rows are not covered");
+    const size_t tab_bytes = (size_t)c->K * tip_table_rows(c) * 32, p_bytes = (size_t)c->K * 128;
+    const size_t tab_base = reinterpret_cast<const unsigned char*>(c->d_tiptab) - reinterpret_cast<const unsigned char*>(c->d_pmats);
+    std::vector<PairRow> rows(plan.rows.size());
+    for (size_t r = 0; r < plan.rows.size(); ++r) {
+        const ResRow& s = plan.rows[r];
+        const int pidx_a = s.pidx_a, pidx_b = (int)(s.packed & 0xffffff);
+        const int kind_a = (s.packed >> 24) & 3, kind_b = (s.packed >> 26) & 3;
+        if (kind_a == KIND_SLOT) return c->fail(PHB_ERR_STATE, "pair kernel: plan is not in canonical operand order");
+        if (s.src_b < 0 || s.src_b >= (1 << 24)) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: too many tips");
+        const size_t oa = kind_a == KIND_TIP ? tab_base + pidx_a * tab_bytes : pidx_a * p_bytes;
+        const size_t ob = kind_b == KIND_TIP ? tab_base + pidx_b * tab_bytes : pidx_b * p_bytes;
+        PairRow d;
+        d.off_a = (uint32_t)(oa / 16);
+        d.off_b = (uint32_t)(ob / 16);
+        d.src_a = s.src_a;
+        d.packed = (uint32_t)s.src_b | (s.packed & 0xff000000u);
+        rows[r] = d;
+    }
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_res_rows, rows.data(), rows.size() * sizeof(PairRow), cudaMemcpyHostToDevice, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` is a stack object
+    return PHB_OK;
+}
+
+}  // namespace
+
+// One evaluation from the tip codes resident on the device: per-pattern lnL + their weighted sum in d_result[0]
+int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
+    ResPlan plan;
+    int st = plan_rows(c, root_a, root_b, true, false, &plan);
+    if (st) return st;
+    st = upload_pair_rows(c, plan);
+    if (st) return st;
+    int grid = 0;
+    const int64_t n_tiles = (c->S + 63) / 64;
+    st = launch_pair_k(c, c->codes_packed, (int)plan.rows.size(), plan.n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
+    if (st) return st;
+    c->resident_slots = plan.n_slots;
+    return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
+}
+
+// Whole evaluation starting from HOST tip codes: the pattern axis is cut into chunks; chunk i+1 is copied
+// host->device on a second stream while the kernel walks chunk i (patterns are independent, so a chunk can be
+// evaluated as soon as its codes have landed).  packed: two 4-bit codes per byte (even pattern in the low
+// nibble), rows of (S + 1) / 2 bytes - half the bytes over PCIe.  One synchronisation at the very end (caller).
+int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b) {
+    ResPlan plan;
+    int st = plan_rows(c, root_a, root_b, true, false, &plan);
+    if (st) return st;
+    st = upload_pair_rows(c, plan);
+    if (st) return st;
+    if (c->copy_stream == nullptr) {
+        PHB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; ++i) PHB_CUDA(c, cudaEventCreateWithFlags(&c->chunk_events[i], cudaEventDisableTiming));
+        PHB_CUDA(c, cudaEventCreateWithFlags(&c->start_event, cudaEventDisableTiming));
+    }
+    const int64_t n_tiles = (c->S + 63) / 64;
+    n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_chunks, kMaxChunks), n_tiles));
+    // the copy stream must not overtake work already queued on the compute stream (previous evaluation)
+    PHB_CUDA(c, cudaEventRecord(c->start_event, c->stream));
+    PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
+    const size_t host_row = packed ? ((size_t)c->S + 1) / 2 : (size_t)c->S;
+    const size_t dev_pitch = packed ? c->code_pitch / 2 : c->code_pitch;
+    const int per_tile = packed ? 32 : 64;   // bytes of one tile in a code row
+    c->codes_packed = packed;
+    c->d_codes = c->d_codes_ws;
+    int parts = 0;
+    for (int i = 0; i < n_chunks; ++i) {
+        const int64_t b = n_tiles * i / n_chunks, e = n_tiles * (i + 1) / n_chunks;
+        const size_t c0 = (size_t)b * per_tile, c1 = std::min<size_t>((size_t)e * per_tile, host_row);
+        PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws + c0, dev_pitch, codes_host + c0, host_row, c1 - c0, (size_t)c->n_tips,
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+        PHB_CUDA(c, cudaEventRecord(c->chunk_events[i], c->copy_stream));
+        PHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[i], 0));
+        int grid = 0;
+        st = launch_pair_k(c, packed, (int)plan.rows.size(), plan.n_slots, b, e, c->d_partial_sums + parts,
+                           kPartialCap / n_chunks, &grid);
+        if (st) return st;
+        parts += grid;
+    }
+    c->resident_slots = plan.n_slots;
+    return launch_final_reduce(c, c->d_partial_sums, parts, 1, c->d_result);
+}
+
+}  // namespace phb

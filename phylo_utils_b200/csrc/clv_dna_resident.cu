@@ -27,23 +27,14 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "resident_plan.cuh"
 
 namespace phb {
 
 namespace {
 
-constexpr int KIND_TIP = 0, KIND_PREV = 1, KIND_SLOT = 2;
 constexpr int kMaxWarps = 1;      // one warp per CTA: warps share nothing but the (tiny) look-up table
 constexpr int kMinCtas = 16;      // register budget: 65536 / (16 * 32) = 128 per thread
-constexpr int kScratchSlots = 15;
-
-// 16-byte row descriptor
-struct __align__(16) ResRow {
-    int32_t src_a;   // tip row | parked-block id (scratch slot, or producer row in STORE mode)
-    int32_t src_b;
-    int32_t pidx_a;  // P block of operand a
-    uint32_t packed; // pidx_b [0:24) | kind_a [24:26) | kind_b [26:28) | dst slot [28:32) (15 = not parked)
-};
 
 struct ResArgs {
     const ResRow* rows;     // [n_steps]
@@ -370,12 +361,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, kMinCtas) dna_resident_kernel(
     }
 }
 
-// ---- host side: parking plan + launch -------------------------------------------------------------------------
-struct ResPlan {
-    std::vector<ResRow> rows;
-    int n_slots = 0;
-};
+}  // namespace
 
+// ---- host side: parking plan + launch -------------------------------------------------------------------------
 // Walk the schedule like a register allocator: a result consumed by the very next row stays in
 // registers; anything else is parked.  In STORE mode the parking place is the node's own block of the
 // partials array (id = producer row); otherwise the lowest free scratch slot, recycled once consumed.
@@ -453,6 +441,8 @@ int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPla
     out->n_slots = std::max<int>((int)busy.size(), 1);
     return PHB_OK;
 }
+
+namespace {
 
 template <int K, int NC, bool STORE, bool ROOT>
 int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_end, double* partial_sums, int max_grid,

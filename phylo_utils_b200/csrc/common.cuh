@@ -71,6 +71,9 @@ struct Ctx {
     const uint8_t* d_codes = nullptr;
     uint8_t* d_codes_ws = nullptr;
     size_t code_pitch = 0;
+    // true after phb_lnl_from_host_packed: the buffer holds two 4-bit codes per byte (rows of code_pitch / 2
+    // bytes), which only the pair kernel reads; every other consumer asks for phb_set_tips first
+    bool codes_packed = false;
     double* d_lut = nullptr;           // [256][A]
     double* d_weights = nullptr;       // [S]
     double* d_clv = nullptr;           // [n_internal][S][K][A]
@@ -182,6 +185,9 @@ int dna_run_rows(Ctx* c, const RowSet& rs, int mode);
 int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root);   // clv_dna_resident.cu
 int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int root_a, int root_b);
+// clv_dna_pair.cu: lnL-only walk, two patterns per lane (the default lnL-only path)
+int dna_pair_lnl(Ctx* c, int root_a, int root_b);
+int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b);
 // clv_generic.cu (any A <= 64, any K <= 16)
 int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 // clv_mma.cu (A == 20 or 61, FP64 tensor cores)

@@ -187,16 +187,30 @@ class LikelihoodEngine(object):
                                             dptr(pattern) if want_pattern else None))
         return total.value, pattern
 
-    def lnl_from_host(self, codes, node_a, node_b, length, n_chunks=0, want_pattern=False):
-        """Evaluate starting from host tip codes (numpy uint8 (n_tips, n_patterns), ideally pinned); copy and compute overlap."""
+    @staticmethod
+    def pack_codes(codes):
+        """uint8 (n_tips, n_patterns) codes < 16 -> (n_tips, (n_patterns + 1) // 2) bytes, two patterns per byte
+        (even pattern in the low nibble): the input format of ``lnl_from_host(..., packed=True)``."""
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
-        if codes.shape != (self.n_tips, self.n_patterns):
+        if codes.ndim != 2:
             raise ValueError("codes must be (n_tips, n_patterns)")
+        out = np.empty((codes.shape[0], (codes.shape[1] + 1) // 2), dtype=np.uint8)
+        check(lib().phb_pack_codes(ctypes.c_void_p(codes.ctypes.data), codes.shape[0], codes.shape[1],
+                                   ctypes.c_void_p(out.ctypes.data)))
+        return out
+
+    def lnl_from_host(self, codes, node_a, node_b, length, n_chunks=0, want_pattern=False, packed=False):
+        """Evaluate starting from host tip codes (numpy uint8, ideally pinned); copy and compute overlap.
+        codes is (n_tips, n_patterns), or with packed=True the output of ``pack_codes``."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        want = (self.n_tips, (self.n_patterns + 1) // 2) if packed else (self.n_tips, self.n_patterns)
+        if codes.shape != want:
+            raise ValueError("codes must be {}".format(want))
         total = ctypes.c_double(0.0)
         pattern = np.empty(self.n_patterns) if want_pattern else None
-        self._ok(self._lib.phb_lnl_from_host(self._ctx, ctypes.c_void_p(codes.ctypes.data), int(n_chunks), int(node_a),
-                                             int(node_b), float(length), ctypes.byref(total),
-                                             dptr(pattern) if want_pattern else None))
+        fn = self._lib.phb_lnl_from_host_packed if packed else self._lib.phb_lnl_from_host
+        self._ok(fn(self._ctx, ctypes.c_void_p(codes.ctypes.data), int(n_chunks), int(node_a), int(node_b),
+                    float(length), ctypes.byref(total), dptr(pattern) if want_pattern else None))
         return total.value, pattern
 
     # ---- read-back --------------------------------------------------------------------------

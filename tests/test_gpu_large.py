@@ -196,3 +196,38 @@ def test_pipelined_evaluation_from_host_codes_matches_resident():
     # and the original alignment again, through the same path
     t3, p3 = tm.engine.lnl_from_host(codes, a, b, length, want_pattern=True)
     assert np.array_equal(p3, pattern) and t3 == total
+    # two codes per byte: same bits out, half the bytes in
+    packed = torch.from_numpy(phy.LikelihoodEngine.pack_codes(other)).pin_memory().numpy()
+    assert packed.shape == (other.shape[0], other.shape[1] // 2)
+    for chunks in (1, 5, 16):
+        t4, p4 = tm.engine.lnl_from_host(packed, a, b, length, n_chunks=chunks, want_pattern=True, packed=True)
+        assert np.array_equal(p4, p2)
+        assert_lnl_close(t4, t2)
+    # the device now holds packed codes: the resident evaluation keeps working, tip readers ask for set_tips
+    t5, p5 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
+    assert np.array_equal(p5, p2)
+    with pytest.raises(RuntimeError):
+        tm.engine.get_partials(tm.traversal.names[names[0]])
+
+
+@pytest.mark.parametrize("n_pat", [1, 2, 63, 64, 65, 127, 4097])
+def test_packed_codes_ragged_pattern_counts(n_pat):
+    tree, names, codes, lut = synthetic(33, n_pat, 4, seed=900 + n_pat)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    w = np.random.default_rng(3).integers(1, 4, size=n_pat)
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, siteweights=w)
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    a, b = tm.traversal.root_edge
+    length = tm.traversal.brlens[(a, b)]
+    tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+    want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights)
+    for packed in (False, True):
+        src = phy.LikelihoodEngine.pack_codes(codes) if packed else codes
+        t, p = tm.engine.lnl_from_host(src, a, b, length, want_pattern=True, packed=packed)
+        assert_lnl_close(p, want)
+        assert_lnl_close(t, float(np.dot(want, w)))
