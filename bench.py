@@ -289,6 +289,8 @@ def main():
     lut = dna_lut()
     codes_host = torch.from_numpy(make_codes(n_taxa, n_pat, args.seed, rank)).pin_memory()
     codes_np = codes_host.numpy()
+    # the e2e path ships the tip codes two per byte (4-bit state-set codes; packed once when the alignment is loaded)
+    packed_np = torch.from_numpy(phy.LikelihoodEngine.pack_codes(codes_np)).pin_memory().numpy()
     tip_nodes = np.asarray([trav.names[n] for n in names], dtype=np.int32)
 
     args.lnl_only = not args.store_partials
@@ -318,10 +320,12 @@ def main():
         eng.compute_partials(mode)
         return eng.root_lnl(a, b, root_len)[0]
 
-    def eval_e2e():
+    def eval_e2e(packed=True):
         eng.set_edge_lengths(lengths)
         if args.lnl_only:
             # pinned host codes -> device in chunks, overlapped with the pruning of the previous chunk
+            if packed:
+                return eng.lnl_from_host(packed_np, a, b, root_len, n_chunks=args.chunks, packed=True)[0]
             return eng.lnl_from_host(codes_np, a, b, root_len, n_chunks=args.chunks)[0]
         eng.set_tips(codes_np, lut, tip_nodes)          # pinned host -> device, N x S bytes
         eng.build_pmatrices()
@@ -384,7 +388,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = prune_bytes / (kernel_ms * 1e-3) / 1e9
     if args.lnl_only:
-        kernel_name = "dna_resident_kernel<K=4,STORE=0,ROOT=1> (operands on chip, no partials stored)"
+        kernel_name = "dna_pair_kernel<K=4,NC=8> (two patterns per lane, operands on chip, no partials stored)"
     else:
         kernel_name = {_lib.PHB_MODE_TILE: "dna_prune_kernel<K=4> (tile mode)",
                        _lib.PHB_MODE_LEVEL: "dna_prune_kernel<K=4> (level mode)",
@@ -434,12 +438,22 @@ def main():
             allreduce(eval_e2e())
         e_ms, e_lnl = timed(eval_e2e, args.steps)
         e_ms /= args.steps
+        code_bytes = packed_np.nbytes if args.lnl_only else n_taxa * n_pat
         e2e = {"value": world * 1e3 / e_ms, "unit": "lnL evals/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(n_taxa * n_pat + lengths.nbytes + 16), "d2h_bytes_per_step": 8,
-               "api": ("LikelihoodEngine.set_edge_lengths + lnl_from_host (C ABI phb_lnl_from_host: pinned host codes, "
-                       "{} chunks, copy overlapped with compute)".format(args.chunks) if args.lnl_only else
+               "h2d_bytes_per_step": int(code_bytes + lengths.nbytes + 16), "d2h_bytes_per_step": 8,
+               "api": ("LikelihoodEngine.set_edge_lengths + lnl_from_host(packed=True) (C ABI phb_lnl_from_host_packed: "
+                       "pinned host tip codes, two 4-bit codes per byte, {} chunks, copy overlapped with compute)".format(
+                           args.chunks) if args.lnl_only else
                        "LikelihoodEngine.set_tips(host codes) + set_edge_lengths + build_pmatrices + "
                        "compute_partials + root_lnl (C ABI, pinned host buffers)"), "lnl": e_lnl}
+        if args.lnl_only:
+            # the same call with one byte per code (phb_lnl_from_host), for the record
+            for _ in range(2):
+                allreduce(eval_e2e(False))
+            u_ms, u_lnl = timed(lambda: eval_e2e(False), args.steps)
+            u_ms /= args.steps
+            e2e["one_byte_codes"] = {"value": world * 1e3 / u_ms, "ms_per_step": u_ms,
+                                     "h2d_bytes_per_step": int(n_taxa * n_pat + lengths.nbytes + 16), "lnl": u_lnl}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
