@@ -75,6 +75,19 @@ int64_t phb_launch_count(const phb_ctx* ctx);
  * rates[ncat], weights[ncat] are outputs; mean rate is alpha/beta. */
 int phb_discrete_gamma(double alpha, double beta, int ncat, int use_median, double* rates, double* weights);
 
+/* ---- site-pattern compression (context-free) --------------------------------------------
+ * Device form of alignment_to_numpy's np.unique(axis=1, return_inverse, return_counts)
+ * (alignment/alignment.py:40-57) fused with the charmap look-up of seq_to_partials (:26-37).
+ * data[n_tips][n_sites]: state-set codes (byte_table == NULL), or raw characters that byte_table[256] maps to
+ * codes (255 = not in the charmap: PHB_ERR_INVALID, flat index of the first offender in *bad_index_out -
+ * the reference raises KeyError there).  Codes must be ranks of the charmap's 0/1 rows in lexicographic order
+ * (charmaps.CodeBook) for the pattern order to equal the reference's.
+ * Outputs (host, caller-allocated for the worst case n_patterns == n_sites): patterns_out[n_tips][n_patterns]
+ * (dense, row length = *n_patterns_out), weights_out[n_patterns] (siteweights), inverse_out[n_sites]. */
+int phb_compress_patterns(int device, const uint8_t* data, const uint8_t* byte_table, int n_tips, int64_t n_sites,
+                          uint8_t* patterns_out, int64_t* weights_out, int64_t* inverse_out, int64_t* n_patterns_out,
+                          int64_t* bad_index_out);
+
 /* ---- context --------------------------------------------------------------------------
  * Replaces the array allocation of TreeModel.initialise (phylo_utils/tree_model.py:101-132).
  * `workspace` is device memory owned by the caller (e.g. a torch uint8 tensor's data_ptr) of at

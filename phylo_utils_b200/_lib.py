@@ -30,6 +30,7 @@ SIGNATURES = {
     "phb_last_error": (c_char_p, [c_void_p]),
     "phb_launch_count": (c_int64, [c_void_p]),
     "phb_discrete_gamma": (c_int, [c_double, c_double, c_int, c_int, _dp, _dp]),
+    "phb_compress_patterns": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, _lp, _lp, _lp, _lp]),
     "phb_workspace_bytes": (c_size_t, [c_int, c_int64, c_int, c_int, c_uint]),
     "phb_create": (c_int, [c_int, c_int, c_int64, c_int, c_int, c_uint, c_void_p, c_size_t, c_void_p,
                            POINTER(c_void_p)]),

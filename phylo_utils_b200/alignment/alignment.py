@@ -143,14 +143,55 @@ def compress_codes(codes):
     return patterns, weights, inverse
 
 
-def alignment_to_codes(alignment, alphabet, compress=True):
+def compress_codes_gpu(data, byte_table=None, device=0):
+    """
+    ``compress_codes`` on the GPU (C ABI ``phb_compress_patterns``, csrc/compress.cu): radix sort of the columns,
+    run detection, weights, inverse index - bit-identical outputs.  ``data`` is uint8 ``(ntax, nsite)``: codes, or
+    raw characters when ``byte_table`` (256 uint8, 255 = unmapped) is given; an unmapped character raises KeyError
+    like the reference's charmap look-up.
+    """
+    import ctypes
+    from .._lib import lib, check
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    if data.ndim != 2 or data.shape[0] < 1:
+        raise ValueError("data must be (ntax, nsite) with at least one row")
+    ntax, nsite = data.shape
+    patterns = np.empty((ntax, nsite), dtype=np.uint8)
+    weights = np.empty(nsite, dtype=np.int64)
+    inverse = np.empty(nsite, dtype=np.int64)
+    npat, bad = ctypes.c_int64(0), ctypes.c_int64(-1)
+    table = None if byte_table is None else np.ascontiguousarray(byte_table, dtype=np.uint8)
+    if table is not None and table.shape != (256,):
+        raise ValueError("byte_table must have 256 entries")
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    status = lib().phb_compress_patterns(
+        int(device), ctypes.c_void_p(data.ctypes.data), None if table is None else ctypes.c_void_p(table.ctypes.data),
+        ntax, nsite, ctypes.c_void_p(patterns.ctypes.data), weights.ctypes.data_as(i64p), inverse.ctypes.data_as(i64p),
+        ctypes.byref(npat), ctypes.byref(bad))
+    if bad.value >= 0:
+        raise KeyError(chr(int(data.reshape(-1)[bad.value])))
+    check(status)
+    n = int(npat.value)
+    return np.ascontiguousarray(patterns.reshape(-1)[:ntax * n].reshape(ntax, n)), weights[:n].copy(), inverse
+
+
+def alignment_to_codes(alignment, alphabet, compress=True, device=None):
     """
     -> (codes ``(ntax, npat)`` uint8, lut ``(ncodes, A)`` float64, siteweights int64,
         inverse_index int64, names ``{label: row}``)
+
+    ``device`` = a CUDA device index runs the character look-up and the compression on that GPU
+    (``compress_codes_gpu``); None keeps them on the host.  Same outputs either way.
     """
     book = codebook_for(alphabet)
     records = list(alignment)
     names = {rec.name: i for i, rec in enumerate(records)}
+    if device is not None and compress and records and len(records[0].seq) > 0:
+        raw = [np.frombuffer(str(rec.seq).encode("latin-1"), dtype=np.uint8) for rec in records]
+        if len({len(r) for r in raw}) != 1:
+            raise ValueError("sequences have unequal lengths")
+        codes, weights, inverse = compress_codes_gpu(np.stack(raw), book.byte_table, device)
+        return codes, book.lut, weights, inverse, names
     rows = [book.encode(str(rec.seq)) for rec in records]
     if rows and len({len(r) for r in rows}) != 1:
         raise ValueError("sequences have unequal lengths")

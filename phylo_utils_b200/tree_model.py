@@ -68,9 +68,12 @@ class TreeModel(object):
     # ------------------------------------------------------------------------------------------
     # inputs (reference: tree_model.py:42-98)
     # ------------------------------------------------------------------------------------------
-    def set_alignment(self, alignment, alphabet, compress=True):
-        """``alignment``: iterable of records with ``.name`` and ``.seq`` (Biopython alignment or alignment.SeqRecord list)."""
-        codes, lut, sw, ii, names = alignment_to_codes(alignment, alphabet, compress)
+    def set_alignment(self, alignment, alphabet, compress=True, compress_on_gpu=True):
+        """``alignment``: iterable of records with ``.name`` and ``.seq`` (Biopython alignment or alignment.SeqRecord list).
+        Character look-up and site-pattern compression run on this model's GPU (csrc/compress.cu, bit-identical to the
+        reference's np.unique); ``compress_on_gpu=False`` keeps them on the host."""
+        codes, lut, sw, ii, names = alignment_to_codes(alignment, alphabet, compress,
+                                                       device=self.device if (compress and compress_on_gpu) else None)
         self.set_tip_codes(codes, lut, names, sw, ii)
 
     def set_tip_codes(self, codes, lut, names, siteweights=None, inverse_index=None):
