@@ -20,7 +20,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, flags,
         pattern_lnl, cat_lnl, partial, result, total;
     int root_block;
 };
@@ -65,6 +65,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     // parking area of the lnL-only resident kernel (4-state models): 160 SMs x 16 warps x 15 blocks
     p.scratch_size = A == 4 ? (size_t)160 * 16 * 15 * ((size_t)K * 1024 + 128) : 0;
     p.scratch = take(p.scratch_size);
+    p.flags = take((kMaxFlagChunks + 1) * sizeof(int));
     p.pattern_lnl = take((size_t)S * 8);
     p.cat_lnl = take((size_t)S * K * 8);
     p.partial = take((size_t)kPartialCap * 8);
@@ -301,6 +302,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->d_res_rows = (void*)(w + p.res_rows);
     c->d_scratch = p.scratch_size ? w + p.scratch : nullptr;
     c->scratch_bytes = p.scratch_size;
+    c->d_flags = (int*)(w + p.flags);
     c->d_pattern_lnl = (double*)(w + p.pattern_lnl);
     c->d_cat_lnl = (double*)(w + p.cat_lnl);
     c->d_partial_sums = (double*)(w + p.partial);
@@ -320,6 +322,7 @@ int phb_destroy(phb_ctx* c) {
         cudaEventDestroy(c->start_event);
         cudaStreamDestroy(c->copy_stream);
     }
+    if (c->h_epoch) cudaFreeHost(c->h_epoch);
     if (c->owns_ws && c->ws) cudaFree(c->ws);
     delete c;
     return PHB_OK;
@@ -710,10 +713,21 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
         st = dna_pair_from_host(c, codes, packed, n_chunks, node_a, node_b);
     }
     if (st) return st;
+    int late = 0;
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (c->pipelined_pending)
+        PHB_CUDA(c, cudaMemcpyAsync(&late, c->d_flags + kMaxFlagChunks, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)
         PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
     PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->pipelined_pending) {
+        c->pipelined_pending = false;
+        PHB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        if (late) {
+            cudaMemsetAsync(c->d_flags + kMaxFlagChunks, 0, sizeof(int), c->stream);
+            return c->fail(PHB_ERR_CUDA, "phb_lnl_from_host: a chunk of tip codes never arrived on the device");
+        }
+    }
     return PHB_OK;
 }
 

@@ -55,6 +55,11 @@ struct PairArgs {
     double* partial_sums;         // one per CTA
     int64_t S;
     int64_t tile_begin, tile_end; // 64-pattern tiles covered by this launch
+    // host->device pipelining (dna_pair_from_host): the codes of tile t are valid once flags[t / tiles_per_chunk] ==
+    // epoch - written by the copy engine right behind the chunk's bytes.  flags == nullptr: codes are resident.
+    const int* flags;
+    int epoch, chunk_shift;       // tiles per chunk = 1 << chunk_shift
+    int* error;                   // set to 1 if a chunk never arrived (bounded wait)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -177,6 +182,9 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
                 prev[p][k][i] = o;
                 mh[p] = max(mh[p], __double2hiint(o));   // partials are >= 0: the high word orders them
             }
+#ifdef PHB_PAIR_KFENCE
+        asm volatile("" ::: "memory");   // keep the categories' shared-memory reads from being hoisted over each other
+#endif
     }
     // 0 < max < 2^-128: multiply by the exact power of two that brings the maximum into [1, 2)
     const bool small0 = mh[0] < kScaleThresholdHi && mh[0] >= 0x00100000;
@@ -199,7 +207,21 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
     pe[1] = e[1];
 }
 
-template <int K, int NC, bool PACKED>
+// Block (politely, and not forever) until the copy engine has delivered the chunk that holds tile t.
+// Deliberately NOT inlined: it runs once per tile, and as a call its registers stay out of the row loop's allocation.
+__device__ __noinline__ void wait_for_chunk(const int* flags, int chunk_shift, int epoch, int* error, int t) {
+    const int* f = flags + (t >> chunk_shift);
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 23); ++spin) {   // ~10 s of 1 us naps: the copies were never issued - report, do not hang
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if (v == epoch) return;
+        __nanosleep(1000);
+    }
+    *error = 1;
+}
+
+template <int K, int NC, bool PACKED, bool PIPE>
 __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kernel(const PairArgs p) {
     using L = PairLayout<K, NC>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -208,7 +230,8 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
     unsigned char* const s_stage = smem + L::DESC_BYTES;
     unsigned char* const s_opin = s_stage + 2 * L::STAGE_BYTES;
     const int wstride = gridDim.x, n_steps = p.n_steps, tile_end = (int)p.tile_end;
-    double acc = 0.0;
+    double* const s_acc = reinterpret_cast<double*>(smem + L::WARP_BYTES);   // per-lane running sum of weight * lnL
+    s_acc[lane] = 0.0;
     unsigned char* const my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * L::SLOT_BYTES;
 
     // parked block `slot` -> the operand tile (the lane's own chunks, in the layout it wrote them)
@@ -250,6 +273,7 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
         __syncwarp();
         {
             const PairRow d0 = s_desc[0];
+            if (PIPE) wait_for_chunk(p.flags, p.chunk_shift, p.epoch, p.error, tile);
             stage_row(d0, tile, 0);
             if (((d0.packed >> 26) & 3) == KIND_SLOT) fetch_slot(d0.packed & 0xffffff);   // never: row 0 has no parked operand
         }
@@ -283,6 +307,7 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
             if (lane == 0) cp_async16(&s_desc[(q + 2) & 3], &p.rows[row2]);
             if (has_next) {
                 const PairRow dn = s_desc[(q + 1) & 3];
+                if (PIPE && row_n == 0) wait_for_chunk(p.flags, p.chunk_shift, p.epoch, p.error, tile_n);
                 stage_row(dn, tile_n, (q + 1) & 1);
                 if (((dn.packed >> 26) & 3) == KIND_SLOT) {
                     slot_n = dn.packed & 0xffffff;
@@ -344,6 +369,7 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
                     }
                     lnl[h] = mix > 0 ? log(mix) + (double)pe[h] * kLn2 : -INFINITY;
                 }
+                double acc = s_acc[lane];
                 if (s0 + 1 < p.S) {
                     *reinterpret_cast<double2*>(p.pattern_lnl + s0) = make_double2(lnl[0], lnl[1]);
                     if (p.weights) {
@@ -358,6 +384,7 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
                     p.pattern_lnl[s0] = lnl[0];
                     acc += (p.weights ? p.weights[s0] : 1.0) * lnl[0];
                 }
+                s_acc[lane] = acc;
             }
             if (!has_next) break;
             row = row_n;
@@ -367,13 +394,13 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
         }
         cp_async_wait_all();
     }
-    acc = warp_sum(acc);
-    if (lane == 0) p.partial_sums[blockIdx.x] = acc;
+    const double total = warp_sum(s_acc[lane]);
+    if (lane == 0) p.partial_sums[blockIdx.x] = total;
 }
 
-template <int K, int NC, bool PACKED>
+template <int K, int NC, bool PACKED, bool PIPE>
 int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
-                int max_grid, int* grid_out) {
+                int max_grid, int* grid_out, int chunk_shift) {
     using L = PairLayout<K, NC>;
     PairArgs a;
     a.rows = static_cast<const PairRow*>(c->d_res_rows);
@@ -391,8 +418,12 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.S = c->S;
     a.tile_begin = tile_begin;
     a.tile_end = tile_end;
-    auto kern = dna_pair_kernel<K, NC, PACKED>;
-    const size_t smem = L::WARP_BYTES;
+    a.flags = c->d_flags;
+    a.epoch = c->flag_epoch;
+    a.chunk_shift = chunk_shift;
+    a.error = c->d_flags + kMaxFlagChunks;
+    auto kern = dna_pair_kernel<K, NC, PACKED, PIPE>;
+    const size_t smem = L::WARP_BYTES + 256;   // + the per-lane running sums
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -415,13 +446,17 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
 }
 
 int launch_pair_k(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
-                  int* grid_out) {
+                  int* grid_out, int chunk_shift = -1) {
     static_assert(kTipTabCodes == 16, "tip tables are staged with 8 or 16 rows per category");
     const int key = c->K * 1000 + tip_table_rows(c) * 10 + (packed ? 1 : 0);
     switch (key) {
 #define PHB_PAIR_CASE(K_, NC_)                                                                             \
-    case K_ * 1000 + NC_ * 10: return launch_pair<K_, NC_, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out); \
-    case K_ * 1000 + NC_ * 10 + 1: return launch_pair<K_, NC_, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out);
+    case K_ * 1000 + NC_ * 10:                                                                                       \
+        return chunk_shift < 0 ? launch_pair<K_, NC_, false, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, 0)    \
+                               : launch_pair<K_, NC_, false, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift); \
+    case K_ * 1000 + NC_ * 10 + 1:                                                                                   \
+        return chunk_shift < 0 ? launch_pair<K_, NC_, true, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, 0)     \
+                               : launch_pair<K_, NC_, true, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift);
         PHB_PAIR_CASE(1, 8)
         PHB_PAIR_CASE(1, 16)
         PHB_PAIR_CASE(2, 8)
@@ -479,10 +514,13 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
     return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
 }
 
-// Whole evaluation starting from HOST tip codes: the pattern axis is cut into chunks; chunk i+1 is copied
-// host->device on a second stream while the kernel walks chunk i (patterns are independent, so a chunk can be
-// evaluated as soon as its codes have landed).  packed: two 4-bit codes per byte (even pattern in the low
-// nibble), rows of (S + 1) / 2 bytes - half the bytes over PCIe.  One synchronisation at the very end (caller).
+// Whole evaluation starting from HOST tip codes, in ONE launch.  The pattern axis is cut into chunks; the copy engine
+// moves chunk after chunk on a second stream and drops a 4-byte flag behind each one; the kernel - already running,
+// every SM busy - starts a tile as soon as the flag of its chunk shows this evaluation's epoch (patterns are
+// independent).  No per-chunk launches, no tail per chunk; the copy of chunk i+1 overlaps the pruning of chunk i.
+// packed: two 4-bit codes per byte (even pattern in the low nibble), rows of (S + 1) / 2 bytes - half the bytes over
+// PCIe.  Flags and data are written by memcpy from pinned memory only (copy engine): nothing here needs an SM while
+// the kernel occupies all of them.  One synchronisation at the very end (caller).
 int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b) {
     ResPlan plan;
     int st = plan_rows(c, root_a, root_b, true, false, &plan);
@@ -494,9 +532,19 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chu
         for (int i = 0; i < kMaxChunks; ++i) PHB_CUDA(c, cudaEventCreateWithFlags(&c->chunk_events[i], cudaEventDisableTiming));
         PHB_CUDA(c, cudaEventCreateWithFlags(&c->start_event, cudaEventDisableTiming));
     }
+    if (c->h_epoch == nullptr) {
+        PHB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_epoch), 64, cudaHostAllocDefault));
+        PHB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, (kMaxFlagChunks + 1) * sizeof(int), c->stream));
+    }
     const int64_t n_tiles = (c->S + 63) / 64;
-    n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_chunks, kMaxChunks), n_tiles));
-    // the copy stream must not overtake work already queued on the compute stream (previous evaluation)
+    n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_chunks, kMaxFlagChunks), n_tiles));
+    int chunk_shift = 0;   // chunks are a power of two of tiles: the kernel finds a tile's flag with a shift
+    while (((int64_t)1 << chunk_shift) * n_chunks < n_tiles) ++chunk_shift;
+    const int64_t tpc = (int64_t)1 << chunk_shift;
+    n_chunks = (int)((n_tiles + tpc - 1) / tpc);
+    c->flag_epoch = c->flag_epoch >= (1 << 30) ? 1 : c->flag_epoch + 1;
+    *c->h_epoch = c->flag_epoch;
+    // the copy stream must not overtake work already queued on the compute stream (previous evaluation, flag reset)
     PHB_CUDA(c, cudaEventRecord(c->start_event, c->stream));
     PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
     const size_t host_row = packed ? ((size_t)c->S + 1) / 2 : (size_t)c->S;
@@ -504,22 +552,20 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chu
     const int per_tile = packed ? 32 : 64;   // bytes of one tile in a code row
     c->codes_packed = packed;
     c->d_codes = c->d_codes_ws;
-    int parts = 0;
     for (int i = 0; i < n_chunks; ++i) {
-        const int64_t b = n_tiles * i / n_chunks, e = n_tiles * (i + 1) / n_chunks;
+        const int64_t b = tpc * i, e = std::min<int64_t>(tpc * (i + 1), n_tiles);
         const size_t c0 = (size_t)b * per_tile, c1 = std::min<size_t>((size_t)e * per_tile, host_row);
         PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws + c0, dev_pitch, codes_host + c0, host_row, c1 - c0, (size_t)c->n_tips,
                                       cudaMemcpyHostToDevice, c->copy_stream));
-        PHB_CUDA(c, cudaEventRecord(c->chunk_events[i], c->copy_stream));
-        PHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->chunk_events[i], 0));
-        int grid = 0;
-        st = launch_pair_k(c, packed, (int)plan.rows.size(), plan.n_slots, b, e, c->d_partial_sums + parts,
-                           kPartialCap / n_chunks, &grid);
-        if (st) return st;
-        parts += grid;
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_flags + i, c->h_epoch, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
     }
+    int grid = 0;
+    st = launch_pair_k(c, packed, (int)plan.rows.size(), plan.n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid,
+                       chunk_shift);
+    if (st) return st;
     c->resident_slots = plan.n_slots;
-    return launch_final_reduce(c, c->d_partial_sums, parts, 1, c->d_result);
+    c->pipelined_pending = true;
+    return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
 }
 
 }  // namespace phb

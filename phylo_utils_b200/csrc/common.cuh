@@ -107,6 +107,12 @@ struct Ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_events[32] = {};
     cudaEvent_t start_event = nullptr;
+    // single-launch pipelining (clv_dna_pair.cu): per-chunk arrival flags + error word on the device, the epoch the
+    // copy engine stamps them with (pinned host word), and whether an evaluation's error word is still unread
+    int* d_flags = nullptr;            // [kMaxFlagChunks + 1]
+    int* h_epoch = nullptr;
+    int flag_epoch = 0;
+    bool pipelined_pending = false;
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
     double* d_partial_sums = nullptr;  // [kPartialCap]
@@ -155,6 +161,7 @@ constexpr int kMaxReduceBlocks = 4096;
 constexpr int kPartialCap = 65536;   // doubles in the block-sum buffer
 constexpr int kMaxEdgeBatch = 64;
 constexpr int kMaxChunks = 32;
+constexpr int kMaxFlagChunks = 255;
 constexpr int kTipTabCodes = 16;     // tip tables cover look-up tables of up to 16 rows (IUPAC DNA has 15)
 
 // kernel families (each returns a phb_status) ---------------------------------------------------
