@@ -405,7 +405,7 @@ def main():
         roofline["note"] = ("operand-resident kernel: intermediate partials stay in registers / shared memory / L2, so the "
                             "kernel moves far fewer DRAM bytes than the algorithmic count (see `traffic` and "
                             "profiles/); frac > 1 is expected here (SURVEY.md 8(d): 'kernels that fuse levels on-chip "
-                            "may legitimately exceed 100 %'), the binding resources are instruction issue and the FP64 pipe")
+                            "may legitimately exceed 100 %'); what binds it is the shared-memory data pipe (78 % busy, profiles/r01l_pair_v2_1000x1M.txt), then the FP64 pipe")
 
     # the same evaluation while ALSO keeping every node's partials in HBM (what TreeModel.partials and the
     # derivative path need): reported next to the headline so that both costs are on record
