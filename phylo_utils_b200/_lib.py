@@ -11,7 +11,7 @@ import os
 from ctypes import c_int, c_int32, c_int64, c_size_t, c_uint, c_double, c_void_p, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphylo_b200.so")
+LIB_PATH = os.environ.get("PHB_LIBRARY") or os.path.join(_HERE, "libphylo_b200.so")   # PHB_LIBRARY: developer override (what-if builds)
 
 PHB_OK, PHB_ERR_INVALID, PHB_ERR_CUDA, PHB_ERR_NO_DEVICE, PHB_ERR_STATE, PHB_ERR_NOMEM, PHB_ERR_UNSUPPORTED = range(7)
 PHB_FLAG_UP_PARTIALS = 0x1

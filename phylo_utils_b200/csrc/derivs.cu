@@ -21,6 +21,7 @@
 //     dlnL = sum_s wt_s L'_s / L_s ,   d2lnL = sum_s wt_s [ L''_s / L_s - (L'_s / L_s)^2 ]
 // i.e. lnl_branch_derivs composed over the Gamma mixture.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -220,6 +221,241 @@ __global__ void __launch_bounds__(128) dna_edge_deriv_kernel(const DerivArgs p) 
     if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
 }
 
+// ---- 20 and 61 states: edge derivatives on the FP64 tensor cores ------------------------------------------------
+// With P_k(t) = V diag(exp(lambda r_k t)) V^-1 the three quantities of an edge share everything but a diagonal:
+//     f_k^(d) = sum_m  g_d(lambda_m r_k) exp(lambda_m r_k t) . x_km . y_km,
+//     x_k = V^-1 a_k,   y_k = V^T (pi * b_k)                       ("sum table" of the edge)
+// so an edge costs two dense (A x A) . (A x N) products per category - the same DMMA tile loop as the pruning
+// kernel (clv_mma.cu), with the two constant matrices staged ONCE per CTA - plus a 3A-term epilogue per pattern in
+// fragment layout.  Nothing is written but the block sums.  The generic kernel below needs 3 A^2 shared-memory
+// reads per pattern and category instead.
+struct MmaDerivArgs {
+    const double* m1;       // V^-1 [A][A] row-major
+    const double* m2;       // [A][A]: m2[m][i] = V[i][m] pi[i]
+    const double* coef;     // [edge][3][K][MROWS]: w_k g_d(lambda_m r_k) exp(lambda_m r_k t), zero for m >= A
+    const uint8_t* codes;
+    size_t pitch;
+    const double* lut;
+    const double* clv;
+    const int32_t* scale;
+    const double* weights;
+    int64_t S, n_tiles;
+    int K, n_parts;
+    int src_a[kMaxEdgeBatch], kind_a[kMaxEdgeBatch];
+    int src_b[kMaxEdgeBatch], kind_b[kMaxEdgeBatch];
+    double* partial_sums;   // [n_edges * 3][n_parts]
+};
+
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+constexpr int deriv_pad_pitch(int cols) {   // smallest pitch >= cols with pitch % 16 == 4: conflict-free 8 x 4 fragment loads
+    int p = cols;
+    while (p % 16 != 4) ++p;
+    return p;
+}
+__device__ __forceinline__ void deriv_cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// coef[e][d][k][m]; grid = n_edges, one thread per (d, k, m)
+__global__ void deriv_coef_kernel(const double* __restrict__ evals, const double* __restrict__ rates,
+                                  const double* __restrict__ catw, const double* __restrict__ lengths, int A, int K,
+                                  int mrows, int chain_rule, double* __restrict__ coef) {
+    const int e = blockIdx.x;
+    for (int idx = threadIdx.x; idx < 3 * K * mrows; idx += blockDim.x) {
+        const int m = idx % mrows, k = (idx / mrows) % K, d = idx / (mrows * K);
+        double v = 0.0;
+        if (m < A) {
+            const double lam = evals[m], r = rates[k];
+            const double base = chain_rule ? lam * r : lam;
+            const double g = d == 0 ? 1.0 : (d == 1 ? base : base * base);
+            v = catw[k] * g * exp(lam * (lengths[e] * r));
+        }
+        coef[(size_t)e * 3 * K * mrows + idx] = v;
+    }
+}
+
+// m2[m][i] = evecs[i][m] * freqs[i]
+__global__ void deriv_m2_kernel(const double* __restrict__ evecs, const double* __restrict__ freqs, int A,
+                                double* __restrict__ m2) {
+    for (int idx = threadIdx.x; idx < A * A; idx += blockDim.x) {
+        const int m = idx / A, i = idx - m * A;
+        m2[idx] = evecs[i * A + m] * freqs[i];
+    }
+}
+
+// grid = (n_parts, n_edges); a CTA walks pattern tiles of one edge, every warp owns NT * 8 patterns of the tile
+template <int AA, int MT, int KS, int NT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDerivArgs p) {
+    constexpr int A = AA, MROWS = MT * 8, KCOLS = KS * 4;
+    constexpr int LDP = deriv_pad_pitch(KCOLS), LDL = deriv_pad_pitch(KCOLS);
+    constexpr int TS = WARPS * NT * 8, WR = NT * 8;
+    extern __shared__ double sm[];
+    double* M1 = sm;                          // [MROWS][LDP]
+    double* M2 = M1 + MROWS * LDP;            // [MROWS][LDP]
+    double* La = M2 + MROWS * LDP;            // [TS][LDL]   rows of the operand below the edge
+    double* Lb = La + TS * LDL;               // [TS][LDL]   rows of the operand above the edge
+    double* coef = Lb + TS * LDL;             // [3][K][MROWS]
+    __shared__ double s_red[3][WARPS];
+    const int K = p.K, e = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fr = lane >> 2, fc = lane & 3;
+    const size_t S = (size_t)p.S;
+    for (int i = threadIdx.x; i < 2 * MROWS * LDP + 2 * TS * LDL; i += WARPS * 32) sm[i] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < A * A; i += WARPS * 32) {
+        const int r = i / A, c = i - r * A;
+        M1[r * LDP + c] = p.m1[i];
+        M2[r * LDP + c] = p.m2[i];
+    }
+    for (int i = threadIdx.x; i < 3 * K * MROWS; i += WARPS * 32) coef[i] = p.coef[(size_t)e * 3 * K * MROWS + i];
+    __syncthreads();
+    const int ka = p.kind_a[e], kb = p.kind_b[e];
+    const size_t sa = (size_t)p.src_a[e], sb = (size_t)p.src_b[e];
+    double* myA = La + (size_t)warp * WR * LDL;
+    double* myB = Lb + (size_t)warp * WR * LDL;
+    double tot[3] = {0.0, 0.0, 0.0};
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t wsite0 = tile * TS + (int64_t)warp * WR;
+        double t[3][NT][2];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) t[d][nt][0] = t[d][nt][1] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            __syncwarp();   // every lane is done with the rows of the previous category
+            for (int idx = lane; idx < WR * A; idx += 32) {
+                const int n = idx / A, j = idx - n * A;
+                const int64_t s = wsite0 + n;
+                if (s >= p.S) continue;
+                if (ka == SRC_TIP) {
+                    if (k == 0) myA[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[sa * p.pitch + s] * A + j);
+                } else {
+                    deriv_cp_async8(myA + n * LDL + j, p.clv + ((sa * S + s) * K + k) * A + j);
+                }
+                if (kb == SRC_TIP) {
+                    if (k == 0) myB[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[sb * p.pitch + s] * A + j);
+                } else {
+                    deriv_cp_async8(myB + n * LDL + j, p.clv + ((sb * S + s) * K + k) * A + j);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            double x[MT][NT][2], y[MT][NT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) x[mt][nt][0] = x[mt][nt][1] = y[mt][nt][0] = y[mt][nt][1] = 0.0;
+#pragma unroll 2
+            for (int ks = 0; ks < KS; ++ks) {
+                double fa[NT], fb[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    fa[nt] = myA[(nt * 8 + fr) * LDL + ks * 4 + fc];
+                    fb[nt] = myB[(nt * 8 + fr) * LDL + ks * 4 + fc];
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const double a1 = M1[(mt * 8 + fr) * LDP + ks * 4 + fc];
+                    const double a2 = M2[(mt * 8 + fr) * LDP + ks * 4 + fc];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        dmma884(x[mt][nt], a1, fa[nt]);
+                        dmma884(y[mt][nt], a2, fb[nt]);
+                    }
+                }
+            }
+            // fragment element (mt, nt, q) = eigen-component mt*8+fr of pattern nt*8 + 2fc + q
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const double c0 = coef[(0 * K + k) * MROWS + mt * 8 + fr];
+                const double c1 = coef[(1 * K + k) * MROWS + mt * 8 + fr];
+                const double c2 = coef[(2 * K + k) * MROWS + mt * 8 + fr];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const double xy = x[mt][nt][q] * y[mt][nt][q];
+                        t[0][nt][q] = fma(c0, xy, t[0][nt][q]);
+                        t[1][nt][q] = fma(c1, xy, t[1][nt][q]);
+                        t[2][nt][q] = fma(c2, xy, t[2][nt][q]);
+                    }
+            }
+        }
+        // sum over the eigen-components held by the lanes that share fc
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double v = t[d][nt][q];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    t[d][nt][q] = v;
+                }
+        if (fr == 0) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int64_t s = wsite0 + nt * 8 + 2 * fc + q;
+                    if (s >= p.S) continue;
+                    int ex = 0;
+                    if (ka != SRC_TIP) ex += p.scale[sa * S + s];
+                    if (kb != SRC_TIP) ex += p.scale[sb * S + s];
+                    const double w = p.weights ? p.weights[s] : 1.0;
+                    const double L = t[0][nt][q];
+                    const double g = t[1][nt][q] / L;
+                    tot[0] += w * (L > 0 ? log(L) + (double)ex * kLn2 : -INFINITY);
+                    tot[1] += w * g;
+                    tot[2] += w * (t[2][nt][q] / L - g * g);
+                }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double v = warp_sum(tot[d]);
+        if (lane == 0) s_red[d][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0;
+        for (int w = 0; w < WARPS; ++w) v += s_red[threadIdx.x][w];
+        p.partial_sums[((size_t)e * 3 + threadIdx.x) * p.n_parts + blockIdx.x] = v;
+    }
+}
+
+template <int AA, int MT, int KS, int NT, int WARPS>
+int launch_mma_derivs(Ctx* c, MmaDerivArgs& a, int n_edges) {
+    constexpr int MROWS = MT * 8, KCOLS = KS * 4;
+    constexpr int LDP = deriv_pad_pitch(KCOLS), LDL = deriv_pad_pitch(KCOLS);
+    constexpr int TS = WARPS * NT * 8;
+    a.n_tiles = (c->S + TS - 1) / TS;
+    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL + 3 * (size_t)c->K * MROWS) * sizeof(double);
+    auto kern = mma_edge_deriv_kernel<AA, MT, KS, NT, WARPS>;
+    if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "DMMA derivative kernel: does not fit in shared memory");
+    PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    // enough CTAs per edge to fill the chip across the whole batch, few enough for the block-sum buffer
+    int64_t parts = std::max<int64_t>(1, ((int64_t)c->sm_count * per_sm + n_edges - 1) / n_edges);
+    parts = std::min<int64_t>(parts, std::min<int64_t>(a.n_tiles, kPartialCap / (3 * n_edges)));
+    a.n_parts = (int)parts;
+    dim3 grid((unsigned)parts, (unsigned)n_edges);
+    kern<<<grid, WARPS * 32, smem, c->stream>>>(a);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    return PHB_OK;
+}
+
 void fill_operand(const Ctx* c, int node, int* src, int* kind) {
     if (c->node_tip[node] >= 0) {
         *kind = SRC_TIP;
@@ -322,6 +558,42 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
         }
         PHB_CUDA(c, cudaMemcpyAsync(d_len, lengths + start, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
         PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr) {
+            // sum-table form on the FP64 tensor cores; the matrix scratch area holds the coefficients and V^T diag(pi)
+            const int mrows = A == 20 ? 24 : 64;
+            MmaDerivArgs m;
+            std::copy(p.src_a, p.src_a + n, m.src_a);
+            std::copy(p.kind_a, p.kind_a + n, m.kind_a);
+            std::copy(p.src_b, p.src_b + n, m.src_b);
+            std::copy(p.kind_b, p.kind_b + n, m.kind_b);
+            double* d_coef = c->d_dmats;
+            double* d_m2 = c->d_dmats + (size_t)kMaxEdgeBatch * 3 * K * mrows;
+            deriv_coef_kernel<<<n, 256, 0, c->stream>>>(c->model_evals(), c->model_rates(), c->model_catw(), d_len, A, K, mrows,
+                                                        chain_rule, d_coef);
+            deriv_m2_kernel<<<1, 256, 0, c->stream>>>(c->model_evecs(), c->model_freqs(), A, d_m2);
+            c->launches += 2;
+            PHB_CUDA(c, cudaGetLastError());
+            m.m1 = c->model_ivecs();
+            m.m2 = d_m2;
+            m.coef = d_coef;
+            m.codes = c->d_codes;
+            m.pitch = c->code_pitch;
+            m.lut = c->d_lut;
+            m.clv = c->d_clv;
+            m.scale = c->d_scale;
+            m.weights = c->d_weights;
+            m.S = c->S;
+            m.K = K;
+            m.partial_sums = c->d_partial_sums;
+            int st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8>(c, m, n);
+            if (st) return st;
+            st = launch_final_reduce(c, c->d_partial_sums, m.n_parts, 3 * n, c->d_result);
+            if (st) return st;
+            PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, c->d_result, (size_t)3 * n * 8, cudaMemcpyDeviceToHost,
+                                        c->stream));
+            PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+            continue;
+        }
         for (int order = 0; order < 3; ++order) {
             int st = launch_build_pmatrices(c, d_len, n, c->d_dmats + (size_t)order * kMaxEdgeBatch * blk, order,
                                             chain_rule);
