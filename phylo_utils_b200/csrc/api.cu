@@ -20,7 +20,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, flags,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, flags, edges, dmats_doubles,
         pattern_lnl, cat_lnl, partial, result, total;
     int root_block;
 };
@@ -55,11 +55,18 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.root_scale = p.scale + (n_blocks - 1) * (size_t)S * 4;
     p.root_block = (int)(n_blocks - 1);
     p.pmats = take((2 * max_rows + 2) * (size_t)K * A * A * 8);
-    p.dmats = take((size_t)kMaxEdgeBatch * 3 * K * A * A * 8);
+    // derivative matrices for a whole launch of edges: every edge of the tree when that costs <= 16 MB, never fewer than 64
+    {
+        const size_t per_edge = 3 * (size_t)K * A * A, n_edges = 2 * (size_t)n_tips - 2;
+        const size_t want = std::max<size_t>(kMaxEdgeBatch, std::min<size_t>(n_edges, ((size_t)16 << 20) / (per_edge * 8)));
+        p.dmats_doubles = want * per_edge;
+        p.dmats = take(p.dmats_doubles * 8);
+        p.edges = take(n_edges * 16);
+    }
     p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32
                            : ((A == 20 || A == 61) ? (2 * max_rows + 2) * (size_t)K * 64 * A * 8 : 0));
     p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
-    p.lengths = take((2 * max_rows + 2 + kMaxEdgeBatch) * 8);
+    p.lengths = take((2 * max_rows + 2 + 2 * (size_t)n_tips) * 8);   // rows, root, + trial lengths of a derivative launch
     p.rows = take((max_rows + 1) * sizeof(OpRow));   // + the root pseudo-row
     p.res_rows = take((max_rows + 1) * 16);
     // parking area of the lnL-only resident kernel (4-state models): 160 SMs x 16 warps x 15 blocks
@@ -69,7 +76,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     p.pattern_lnl = take((size_t)S * 8);
     p.cat_lnl = take((size_t)S * K * 8);
     p.partial = take((size_t)kPartialCap * 8);
-    p.result = take((size_t)kMaxEdgeBatch * 4 * 8);
+    p.result = take(std::max<size_t>((size_t)kMaxEdgeBatch * 4, 6 * (size_t)n_tips) * 8);   // 3 sums per edge
     p.total = off;
     return p;
 }
@@ -295,6 +302,8 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->root_block = p.root_block;
     c->d_pmats = (double*)(w + p.pmats);
     c->d_dmats = (double*)(w + p.dmats);
+    c->dmats_doubles = p.dmats_doubles;
+    c->d_edges = (void*)(w + p.edges);
     c->d_tiptab = (n_states == 4 || n_states == 20 || n_states == 61) ? (double*)(w + p.tiptab) : nullptr;
     c->d_model = (double*)(w + p.model);
     c->d_lengths = (double*)(w + p.lengths);

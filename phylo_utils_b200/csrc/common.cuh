@@ -89,7 +89,9 @@ struct Ctx {
     double* d_root_clv = nullptr;      // [S][K][A] = block root_block
     int32_t* d_root_scale = nullptr;   // [S]
     double* d_pmats = nullptr;         // [2*max_rows + 2][K][A][A]
-    double* d_dmats = nullptr;         // derivative scratch [3][K][A][A] per edge chunk
+    double* d_dmats = nullptr;         // derivative scratch: [3][edges per launch][K][A][A], or the sum-table coefficients
+    size_t dmats_doubles = 0;
+    void* d_edges = nullptr;           // [n_nodes] edge operand descriptors of a derivative launch
     // 4-state models: T[m][k][code][:] = P[m][k] . lut[code] for every P block m, so that a tip operand is
     // a 32-byte table look-up instead of a matrix-vector product (codes padded to kTipTabCodes rows)
     double* d_tiptab = nullptr;

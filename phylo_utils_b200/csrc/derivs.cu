@@ -29,6 +29,11 @@ namespace phb {
 
 namespace {
 
+// the two operands of an edge: a = partial below it, b = partial above it (block index or tip row + SRC_* kind)
+struct EdgeDesc {
+    int32_t src_a, kind_a, src_b, kind_b;
+};
+
 struct DerivArgs {
     const double* mats;     // [3][batch_cap][K][A][A]
     const uint8_t* codes;
@@ -41,8 +46,7 @@ struct DerivArgs {
     const double* weights;
     int64_t S;
     int A, K, batch_cap, n_parts;
-    int src_a[kMaxEdgeBatch], kind_a[kMaxEdgeBatch];
-    int src_b[kMaxEdgeBatch], kind_b[kMaxEdgeBatch];
+    const EdgeDesc* edges;  // [n_edges] operands at the two ends of every edge of the batch
     double* partial_sums;   // [n_edges * 3][n_parts]
 };
 
@@ -55,6 +59,7 @@ __global__ void __launch_bounds__(kDerivThreads) edge_deriv_kernel(const DerivAr
     const int A = p.A, K = p.K, e = blockIdx.y;
     double* M = sm;                       // [3][A][A]
     __shared__ double s_red[3][kDerivThreads / 32];
+    const EdgeDesc ed = p.edges[e];
     const size_t S = (size_t)p.S;
     const int64_t span = (int64_t)kDerivThreads * kSitesPerThread;
     double tot[3] = {0.0, 0.0, 0.0};
@@ -69,17 +74,17 @@ __global__ void __launch_bounds__(kDerivThreads) edge_deriv_kernel(const DerivAr
             const int64_t s = base + (int64_t)q * kDerivThreads + threadIdx.x;
             const size_t ss = s < p.S ? (size_t)s : 0;
             ex[q] = 0;
-            if (p.kind_a[e] == SRC_TIP) {
-                va[q] = p.lut + (size_t)p.codes[(size_t)p.src_a[e] * p.pitch + ss] * A;
+            if (ed.kind_a == SRC_TIP) {
+                va[q] = p.lut + (size_t)p.codes[(size_t)ed.src_a * p.pitch + ss] * A;
             } else {
-                va[q] = p.clv + ((size_t)p.src_a[e] * S + ss) * K * A;
-                ex[q] += p.scale[(size_t)p.src_a[e] * S + ss];
+                va[q] = p.clv + ((size_t)ed.src_a * S + ss) * K * A;
+                ex[q] += p.scale[(size_t)ed.src_a * S + ss];
             }
-            if (p.kind_b[e] == SRC_TIP) {
-                vb[q] = p.lut + (size_t)p.codes[(size_t)p.src_b[e] * p.pitch + ss] * A;
+            if (ed.kind_b == SRC_TIP) {
+                vb[q] = p.lut + (size_t)p.codes[(size_t)ed.src_b * p.pitch + ss] * A;
             } else {
-                vb[q] = p.clv + ((size_t)p.src_b[e] * S + ss) * K * A;
-                ex[q] += p.scale[(size_t)p.src_b[e] * S + ss];
+                vb[q] = p.clv + ((size_t)ed.src_b * S + ss) * K * A;
+                ex[q] += p.scale[(size_t)ed.src_b * S + ss];
             }
         }
         for (int k = 0; k < K; ++k) {
@@ -92,8 +97,8 @@ __global__ void __launch_bounds__(kDerivThreads) edge_deriv_kernel(const DerivAr
             const double wk = p.catw[k];
 #pragma unroll
             for (int q = 0; q < kSitesPerThread; ++q) {
-                const double* a = va[q] + (p.kind_a[e] == SRC_TIP ? 0 : (size_t)k * A);
-                const double* b = vb[q] + (p.kind_b[e] == SRC_TIP ? 0 : (size_t)k * A);
+                const double* a = va[q] + (ed.kind_a == SRC_TIP ? 0 : (size_t)k * A);
+                const double* b = vb[q] + (ed.kind_b == SRC_TIP ? 0 : (size_t)k * A);
                 double f0 = 0.0, f1 = 0.0, f2 = 0.0;
                 for (int i = 0; i < A; ++i) {
                     double x0 = 0.0, x1 = 0.0, x2 = 0.0;
@@ -162,54 +167,66 @@ __global__ void __launch_bounds__(128) dna_edge_deriv_kernel(const DerivArgs p) 
     for (int i = 0; i < 4; ++i) pi[i] = p.freqs[i];
     const double wk = p.catw[k];
     const size_t S = (size_t)p.S;
-    const int ka = p.kind_a[e], kb = p.kind_b[e];
-    const size_t sa = (size_t)p.src_a[e], sb = (size_t)p.src_b[e];
+    const EdgeDesc ed = p.edges[e];
+    const int ka = ed.kind_a, kb = ed.kind_b;
+    const size_t sa = (size_t)ed.src_a, sb = (size_t)ed.src_b;
     double tot[3] = {0.0, 0.0, 0.0};
     const int64_t n_iter = (p.S + SPI - 1) / SPI;
-    for (int64_t it = blockIdx.x; it < n_iter; it += gridDim.x) {
-        const int64_t s = it * SPI + g;
-        const bool ok = s < p.S;
-        const size_t ss = ok ? (size_t)s : 0;
-        double a[4], b[4];
-        int ex = 0;
-        if (ka == SRC_TIP) {
-            const int code = p.codes[sa * p.pitch + ss];
+    constexpr int U = 1;   // pattern groups per trip (2 was measured: more registers, no gain - the kernel is FP64-issue bound)
+    for (int64_t it0 = blockIdx.x; it0 < n_iter; it0 += (int64_t)U * gridDim.x) {
+        double a[U][4], b[U][4];
+        int ex[U];
+        bool ok[U];
+        size_t ss[U];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = s_lut[code][i];
-        } else {
-            ld256(p.clv + ((sa * S + ss) * K + k) * 4, a);
-            ex += p.scale[sa * S + ss];
-        }
-        if (kb == SRC_TIP) {
-            const int code = p.codes[sb * p.pitch + ss];
+        for (int u = 0; u < U; ++u) {
+            const int64_t it = it0 + (int64_t)u * gridDim.x;
+            const int64_t s = it * SPI + g;
+            ok[u] = it < n_iter && s < p.S;
+            ss[u] = ok[u] ? (size_t)s : 0;
+            ex[u] = 0;
+            if (ka == SRC_TIP) {
+                const int code = p.codes[sa * p.pitch + ss[u]];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) b[i] = s_lut[code][i];
-        } else {
-            ld256(p.clv + ((sb * S + ss) * K + k) * 4, b);
-            ex += p.scale[sb * S + ss];
-        }
-        double f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                double x = M[d][4 * i] * a[0];
-                x = fma(M[d][4 * i + 1], a[1], x);
-                x = fma(M[d][4 * i + 2], a[2], x);
-                x = fma(M[d][4 * i + 3], a[3], x);
-                acc = fma(pi[i] * b[i], x, acc);
+                for (int i = 0; i < 4; ++i) a[u][i] = s_lut[code][i];
+            } else {
+                ld256(p.clv + ((sa * S + ss[u]) * K + k) * 4, a[u]);
+                ex[u] += p.scale[sa * S + ss[u]];
             }
-            f[d] = wk * acc;
+            if (kb == SRC_TIP) {
+                const int code = p.codes[sb * p.pitch + ss[u]];
 #pragma unroll
-            for (int o = K / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+                for (int i = 0; i < 4; ++i) b[u][i] = s_lut[code][i];
+            } else {
+                ld256(p.clv + ((sb * S + ss[u]) * K + k) * 4, b[u]);
+                ex[u] += p.scale[sb * S + ss[u]];
+            }
         }
-        if (ok && k == 0) {
-            const double w = p.weights ? p.weights[ss] : 1.0;
-            const double gq = f[1] / f[0];
-            tot[0] += w * (f[0] > 0 ? log(f[0]) + (double)ex * kLn2 : -INFINITY);
-            tot[1] += w * gq;
-            tot[2] += w * (f[2] / f[0] - gq * gq);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double f[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double x = M[d][4 * i] * a[u][0];
+                    x = fma(M[d][4 * i + 1], a[u][1], x);
+                    x = fma(M[d][4 * i + 2], a[u][2], x);
+                    x = fma(M[d][4 * i + 3], a[u][3], x);
+                    acc = fma(pi[i] * b[u][i], x, acc);
+                }
+                f[d] = wk * acc;
+#pragma unroll
+                for (int o = K / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+            }
+            if (ok[u] && k == 0) {
+                const double w = p.weights ? p.weights[ss[u]] : 1.0;
+                const double gq = f[1] / f[0];
+                tot[0] += w * (f[0] > 0 ? log(f[0]) + (double)ex[u] * kLn2 : -INFINITY);
+                tot[1] += w * gq;
+                tot[2] += w * (f[2] / f[0] - gq * gq);
+            }
         }
     }
 #pragma unroll
@@ -241,8 +258,7 @@ struct MmaDerivArgs {
     const double* weights;
     int64_t S, n_tiles;
     int K, n_parts;
-    int src_a[kMaxEdgeBatch], kind_a[kMaxEdgeBatch];
-    int src_b[kMaxEdgeBatch], kind_b[kMaxEdgeBatch];
+    const EdgeDesc* edges;
     double* partial_sums;   // [n_edges * 3][n_parts]
 };
 
@@ -314,8 +330,9 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
     }
     for (int i = threadIdx.x; i < 3 * K * MROWS; i += WARPS * 32) coef[i] = p.coef[(size_t)e * 3 * K * MROWS + i];
     __syncthreads();
-    const int ka = p.kind_a[e], kb = p.kind_b[e];
-    const size_t sa = (size_t)p.src_a[e], sb = (size_t)p.src_b[e];
+    const EdgeDesc ed = p.edges[e];
+    const int ka = ed.kind_a, kb = ed.kind_b;
+    const size_t sa = (size_t)ed.src_a, sb = (size_t)ed.src_b;
     double* myA = La + (size_t)warp * WR * LDL;
     double* myB = Lb + (size_t)warp * WR * LDL;
     double tot[3] = {0.0, 0.0, 0.0};
@@ -539,35 +556,42 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
                             double* out) {
     const int A = c->A, K = c->K;
     const size_t blk = (size_t)K * A * A;
+    const bool use_mma = mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr;
+    const int mrows = A == 20 ? 24 : 64;
+    // edges per launch: as many as the matrix scratch area (or, for the sum-table kernel, the coefficient table), the
+    // block-sum buffer and the grid's y dimension hold - all 2N-3 edges of a 4-state tree go out in one launch
+    int cap = use_mma ? (int)std::min<size_t>((c->dmats_doubles - (size_t)A * A) / (3 * (size_t)K * mrows), 1 << 20)
+                      : (int)std::min<size_t>(c->dmats_doubles / (3 * blk), 1 << 20);
+    cap = std::min(std::min(cap, c->n_nodes), std::min(kPartialCap / 3, 65535));
+    if (cap < 1) return c->fail(PHB_ERR_NOMEM, "edge derivatives: scratch area too small");
     double* d_len = c->d_lengths + 2 * (size_t)c->max_rows() + 2;
-    for (int start = 0; start < n_edges; start += kMaxEdgeBatch) {
-        const int n = std::min(kMaxEdgeBatch, n_edges - start);
-        DerivArgs p;
+    std::vector<EdgeDesc> edges;
+    for (int start = 0; start < n_edges; start += cap) {
+        const int n = std::min(cap, n_edges - start);
+        edges.assign(n, EdgeDesc{});
         for (int i = 0; i < n; ++i) {
             const int node = nodes[start + i];
             PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "edge derivatives: node id out of range");
             PHB_REQUIRE(c, lengths[start + i] >= 0, PHB_ERR_INVALID, "edge derivatives: negative branch length");
-            fill_operand(c, node, &p.src_a[i], &p.kind_a[i]);
+            fill_operand(c, node, &edges[i].src_a, &edges[i].kind_a);
             if (node == c->root_a || node == c->root_b) {
-                fill_operand(c, node == c->root_a ? c->root_b : c->root_a, &p.src_b[i], &p.kind_b[i]);
+                fill_operand(c, node == c->root_a ? c->root_b : c->root_a, &edges[i].src_b, &edges[i].kind_b);
             } else {
                 PHB_REQUIRE(c, c->node_parent[node] >= 0, PHB_ERR_INVALID, "edge derivatives: node has no edge above it");
-                p.src_b[i] = c->n_internal + node;
-                p.kind_b[i] = SRC_GLOBAL;
+                edges[i].src_b = c->n_internal + node;
+                edges[i].kind_b = SRC_GLOBAL;
             }
         }
         PHB_CUDA(c, cudaMemcpyAsync(d_len, lengths + start, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr) {
+        PHB_CUDA(c, cudaMemcpyAsync(c->d_edges, edges.data(), (size_t)n * sizeof(EdgeDesc), cudaMemcpyHostToDevice, c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `edges` is reused by the next batch
+        const EdgeDesc* d_edges = static_cast<const EdgeDesc*>(c->d_edges);
+        int n_parts = 0;
+        if (use_mma) {
             // sum-table form on the FP64 tensor cores; the matrix scratch area holds the coefficients and V^T diag(pi)
-            const int mrows = A == 20 ? 24 : 64;
             MmaDerivArgs m;
-            std::copy(p.src_a, p.src_a + n, m.src_a);
-            std::copy(p.kind_a, p.kind_a + n, m.kind_a);
-            std::copy(p.src_b, p.src_b + n, m.src_b);
-            std::copy(p.kind_b, p.kind_b + n, m.kind_b);
             double* d_coef = c->d_dmats;
-            double* d_m2 = c->d_dmats + (size_t)kMaxEdgeBatch * 3 * K * mrows;
+            double* d_m2 = c->d_dmats + (size_t)cap * 3 * K * mrows;
             deriv_coef_kernel<<<n, 256, 0, c->stream>>>(c->model_evals(), c->model_rates(), c->model_catw(), d_len, A, K, mrows,
                                                         chain_rule, d_coef);
             deriv_m2_kernel<<<1, 256, 0, c->stream>>>(c->model_evecs(), c->model_freqs(), A, d_m2);
@@ -584,58 +608,57 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             m.weights = c->d_weights;
             m.S = c->S;
             m.K = K;
+            m.edges = d_edges;
             m.partial_sums = c->d_partial_sums;
             int st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8>(c, m, n);
             if (st) return st;
-            st = launch_final_reduce(c, c->d_partial_sums, m.n_parts, 3 * n, c->d_result);
-            if (st) return st;
-            PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, c->d_result, (size_t)3 * n * 8, cudaMemcpyDeviceToHost,
-                                        c->stream));
-            PHB_CUDA(c, cudaStreamSynchronize(c->stream));
-            continue;
-        }
-        for (int order = 0; order < 3; ++order) {
-            int st = launch_build_pmatrices(c, d_len, n, c->d_dmats + (size_t)order * kMaxEdgeBatch * blk, order,
-                                            chain_rule);
-            if (st) return st;
-        }
-        p.mats = c->d_dmats;
-        p.codes = c->d_codes;
-        p.pitch = c->code_pitch;
-        p.lut = c->d_lut;
-        p.clv = c->d_clv;
-        p.scale = c->d_scale;
-        p.freqs = c->model_freqs();
-        p.catw = c->model_catw();
-        p.weights = c->d_weights;
-        p.S = c->S;
-        p.A = A;
-        p.K = K;
-        p.batch_cap = kMaxEdgeBatch;
-        const bool dna = dna_supported(c);
-        const int64_t span = dna ? 128 / K : (int64_t)kDerivThreads * kSitesPerThread;
-        int64_t parts = (c->S + span - 1) / span;
-        // enough CTAs per edge to fill the chip across the whole batch, few enough for the block-sum buffer
-        const int64_t cap = std::max<int64_t>(1, std::min<int64_t>(kPartialCap / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 8 / n)));
-        if (parts > cap) parts = cap;
-        p.n_parts = (int)parts;
-        p.partial_sums = c->d_partial_sums;
-        dim3 grid((unsigned)parts, (unsigned)n);
-        if (dna) {
-            switch (K) {
-                case 1: dna_edge_deriv_kernel<1><<<grid, 128, 0, c->stream>>>(p); break;
-                case 2: dna_edge_deriv_kernel<2><<<grid, 128, 0, c->stream>>>(p); break;
-                case 4: dna_edge_deriv_kernel<4><<<grid, 128, 0, c->stream>>>(p); break;
-                default: dna_edge_deriv_kernel<8><<<grid, 128, 0, c->stream>>>(p); break;
-            }
+            n_parts = m.n_parts;
         } else {
-            const size_t smem = 3 * (size_t)A * A * sizeof(double);
-            PHB_CUDA(c, cudaFuncSetAttribute(edge_deriv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            edge_deriv_kernel<<<grid, kDerivThreads, smem, c->stream>>>(p);
+            DerivArgs p;
+            for (int order = 0; order < 3; ++order) {
+                int st = launch_build_pmatrices(c, d_len, n, c->d_dmats + (size_t)order * cap * blk, order, chain_rule);
+                if (st) return st;
+            }
+            p.mats = c->d_dmats;
+            p.codes = c->d_codes;
+            p.pitch = c->code_pitch;
+            p.lut = c->d_lut;
+            p.clv = c->d_clv;
+            p.scale = c->d_scale;
+            p.freqs = c->model_freqs();
+            p.catw = c->model_catw();
+            p.weights = c->d_weights;
+            p.S = c->S;
+            p.A = A;
+            p.K = K;
+            p.batch_cap = cap;
+            p.edges = d_edges;
+            const bool dna = dna_supported(c);
+            const int64_t span = dna ? 128 / K : (int64_t)kDerivThreads * kSitesPerThread;
+            int64_t parts = (c->S + span - 1) / span;
+            // enough CTAs per edge to fill the chip across the whole batch, few enough for the block-sum buffer
+            const int64_t lim = std::max<int64_t>(1, std::min<int64_t>(kPartialCap / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 16 / n)));
+            if (parts > lim) parts = lim;
+            p.n_parts = (int)parts;
+            p.partial_sums = c->d_partial_sums;
+            dim3 grid((unsigned)parts, (unsigned)n);
+            if (dna) {
+                switch (K) {
+                    case 1: dna_edge_deriv_kernel<1><<<grid, 128, 0, c->stream>>>(p); break;
+                    case 2: dna_edge_deriv_kernel<2><<<grid, 128, 0, c->stream>>>(p); break;
+                    case 4: dna_edge_deriv_kernel<4><<<grid, 128, 0, c->stream>>>(p); break;
+                    default: dna_edge_deriv_kernel<8><<<grid, 128, 0, c->stream>>>(p); break;
+                }
+            } else {
+                const size_t smem = 3 * (size_t)A * A * sizeof(double);
+                PHB_CUDA(c, cudaFuncSetAttribute(edge_deriv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                edge_deriv_kernel<<<grid, kDerivThreads, smem, c->stream>>>(p);
+            }
+            c->launches++;
+            PHB_CUDA(c, cudaGetLastError());
+            n_parts = (int)parts;
         }
-        c->launches++;
-        PHB_CUDA(c, cudaGetLastError());
-        int st = launch_final_reduce(c, c->d_partial_sums, (int)parts, 3 * n, c->d_result);
+        int st = launch_final_reduce(c, c->d_partial_sums, n_parts, 3 * n, c->d_result);
         if (st) return st;
         PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, c->d_result, (size_t)3 * n * 8, cudaMemcpyDeviceToHost,
                                     c->stream));
