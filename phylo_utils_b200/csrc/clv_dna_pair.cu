@@ -73,36 +73,35 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int K, int NC>
+template <int K, int NC, int PPT>
 struct PairLayout {
     static constexpr int P_ROUNDS = (K * 128 + 511) / 512;        // warp-wide 512-byte copy rounds of a P block
     static constexpr int T_ROUNDS = (K * NC * 32 + 511) / 512;    // ... of a tip table [k][code][4 doubles]
     static constexpr int ROUNDS = P_ROUNDS > T_ROUNDS ? P_ROUNDS : T_ROUNDS;
     static constexpr int OPER_BYTES = ROUNDS * 512;
-    static constexpr int CODES_OFF = 2 * OPER_BYTES;              // 64 bytes of tip codes per operand
-    static constexpr int STAGE_BYTES = 2 * OPER_BYTES + 128;
+    static constexpr int TILE = 32 * PPT;                         // patterns per warp tile
+    static constexpr int CODES_OFF = 2 * OPER_BYTES;              // TILE bytes of tip codes per operand (half when packed)
+    static constexpr int STAGE_BYTES = 2 * OPER_BYTES + 2 * TILE;
     static constexpr int DESC_BYTES = 4 * 16;                     // descriptor ring: rows r .. r+2 in flight
-    static constexpr int CHUNKS = 2 * K * 2;                      // 16-byte chunks per lane in a parked block
+    static constexpr int CHUNKS = PPT * K * 2;                    // 16-byte chunks per lane in a parked block
     static constexpr int BLOCK_BYTES = CHUNKS * 512;              // [pattern of the lane][k][half][lane]
-    static constexpr int SLOT_BYTES = BLOCK_BYTES + 256;          // + two exponents per lane
+    static constexpr int SLOT_BYTES = BLOCK_BYTES + 128 * PPT;    // + PPT exponents per lane
     static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + SLOT_BYTES;
     // CTAs (= warps) per SM the register file is budgeted for.  A warp lives in one of the four SM
     // sub-partitions with 16384 registers each: 12 CTAs = 3 warps per sub-partition = 168 registers.
-    static constexpr int MIN_CTAS = K <= 2 ? 16 : (K <= 4 ? 12 : 4);
+    // Four patterns per lane (K <= 4) double the register footprint: 8 CTAs = 2 warps per sub-partition = 255 registers.
+    static constexpr int MIN_CTAS = PPT == 2 ? (K <= 2 ? 16 : (K <= 4 ? 12 : 4)) : (K <= 1 ? 16 : (K <= 2 ? 12 : 8));
 };
 
-// the two codes of a lane, as byte offsets of their tip-table rows
-template <int NC, bool PACKED>
-__device__ __forceinline__ void table_rows(const unsigned char* codes, int lane, int (&row)[2]) {
-    if (PACKED) {
-        const unsigned raw = codes[lane];
-        row[0] = (int)(raw & (NC - 1)) * 32;
-        row[1] = (int)((raw >> 4) & (NC - 1)) * 32;
-    } else {
-        const unsigned raw = *reinterpret_cast<const unsigned short*>(codes + 2 * lane);
-        row[0] = (int)(raw & (NC - 1)) * 32;
-        row[1] = (int)((raw >> 8) & (NC - 1)) * 32;
-    }
+// the PPT codes of a lane, as byte offsets of their tip-table rows
+template <int NC, int PPT, bool PACKED>
+__device__ __forceinline__ void table_rows(const unsigned char* codes, int lane, int (&row)[PPT]) {
+    unsigned raw;
+    if (PACKED) raw = PPT == 2 ? (unsigned)codes[lane] : (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane);
+    else raw = PPT == 2 ? (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane)
+                        : *reinterpret_cast<const unsigned*>(codes + 4 * lane);
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) row[p] = (int)((raw >> ((PACKED ? 4 : 8) * p)) & (NC - 1)) * 32;
 }
 
 __device__ __forceinline__ void lds32(const unsigned char* p, double (&v)[4]) {
@@ -111,50 +110,67 @@ __device__ __forceinline__ void lds32(const unsigned char* p, double (&v)[4]) {
     v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
 }
 
-// prev[p][k] <- (Pa[k] . a[p][k]) * (Pb[k] . b[p][k]) for the lane's two patterns; pe <- cumulative exponents
-template <int K, int NC, bool PACKED, int KA, int KB>
+// prev[p][k] <- (Pa[k] . a[p][k]) * (Pb[k] . b[p][k]) for the lane's PPT patterns; pe <- cumulative exponents
+template <int K, int NC, int PPT, bool PACKED, int KA, int KB>
 __device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
-                                            double (&prev)[2][K][4], int (&pe)[2]) {
-    using L = PairLayout<K, NC>;
+                                            double (&prev)[PPT][K][4], int (&pe)[PPT]) {
+    using L = PairLayout<K, NC, PPT>;
     static_assert(KA != KIND_SLOT, "operand a is a tip or the previous row");
-    int e[2] = {0, 0};
-    if (KA == KIND_PREV || KB == KIND_PREV) {
-        e[0] = pe[0];
-        e[1] = pe[1];
-    }
+    int e[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) e[p] = (KA == KIND_PREV || KB == KIND_PREV) ? pe[p] : 0;
     if (KB == KIND_SLOT) {
-        const int2 x = *reinterpret_cast<const int2*>(opin + L::BLOCK_BYTES + lane * 8);
-        e[0] += x.x;
-        e[1] += x.y;
+        const int* x = reinterpret_cast<const int*>(opin + L::BLOCK_BYTES + lane * (4 * PPT));
+        if (PPT == 2) {
+            const int2 v = *reinterpret_cast<const int2*>(x);
+            e[0] += v.x;
+            e[1] += v.y;
+        } else {
+            const int4 v = *reinterpret_cast<const int4*>(x);
+            e[0] += v.x;
+            e[1] += v.y;
+            e[PPT - 2] += v.z;
+            e[PPT - 1] += v.w;
+        }
     }
-    int ra[2] = {0, 0}, rb[2] = {0, 0};
-    if (KA == KIND_TIP) table_rows<NC, PACKED>(st + L::CODES_OFF, lane, ra);
-    if (KB == KIND_TIP) table_rows<NC, PACKED>(st + L::CODES_OFF + 64, lane, rb);
-    int mh[2] = {0, 0};
+    int ra[PPT], rb[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) ra[p] = rb[p] = 0;
+    if (KA == KIND_TIP) table_rows<NC, PPT, PACKED>(st + L::CODES_OFF, lane, ra);
+    if (KB == KIND_TIP) table_rows<NC, PPT, PACKED>(st + L::CODES_OFF + L::TILE, lane, rb);
+    int mh[PPT];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) mh[p] = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        double x[2][4], y[2][4];
+        double x[PPT][4];
         if (KA == KIND_TIP) {
             // a tip operand contributes the row `code` of its staged table T[k] = P[k] . lut - no arithmetic
 #pragma unroll
-            for (int p = 0; p < 2; ++p) lds32(st + k * NC * 32 + ra[p], x[p]);
+            for (int p = 0; p < PPT; ++p) lds32(st + k * NC * 32 + ra[p], x[p]);
         } else {
             const double2* q = reinterpret_cast<const double2*>(st + k * 128);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const double2 r0 = q[2 * i], r1 = q[2 * i + 1];   // P row i: warp-wide broadcast
 #pragma unroll
-                for (int p = 0; p < 2; ++p)
+                for (int p = 0; p < PPT; ++p)
                     x[p][i] = fma(r1.y, prev[p][k][3], fma(r1.x, prev[p][k][2], fma(r0.y, prev[p][k][1], r0.x * prev[p][k][0])));
             }
         }
+        // the second operand's contribution is folded into x as it is produced
         if (KB == KIND_TIP) {
 #pragma unroll
-            for (int p = 0; p < 2; ++p) lds32(st + L::OPER_BYTES + k * NC * 32 + rb[p], y[p]);
-        } else {
-            double b[2][4];
+            for (int p = 0; p < PPT; ++p) {
+                double y[4];
+                lds32(st + L::OPER_BYTES + k * NC * 32 + rb[p], y);
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
+                for (int i = 0; i < 4; ++i) x[p][i] *= y[i];
+            }
+        } else {
+            double b[PPT][4];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
                 if (KB == KIND_PREV) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) b[p][i] = prev[p][k][i];
@@ -170,29 +186,29 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
             for (int i = 0; i < 4; ++i) {
                 const double2 r0 = q[2 * i], r1 = q[2 * i + 1];
 #pragma unroll
-                for (int p = 0; p < 2; ++p)
-                    y[p][i] = fma(r1.y, b[p][3], fma(r1.x, b[p][2], fma(r0.y, b[p][1], r0.x * b[p][0])));
+                for (int p = 0; p < PPT; ++p)
+                    x[p][i] *= fma(r1.y, b[p][3], fma(r1.x, b[p][2], fma(r0.y, b[p][1], r0.x * b[p][0])));
             }
         }
 #pragma unroll
-        for (int p = 0; p < 2; ++p)
+        for (int p = 0; p < PPT; ++p)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double o = x[p][i] * y[p][i];
-                prev[p][k][i] = o;
-                mh[p] = max(mh[p], __double2hiint(o));   // partials are >= 0: the high word orders them
+                prev[p][k][i] = x[p][i];
+                mh[p] = max(mh[p], __double2hiint(x[p][i]));   // partials are >= 0: the high word orders them
             }
-#ifdef PHB_PAIR_KFENCE
-        asm volatile("" ::: "memory");   // keep the categories' shared-memory reads from being hoisted over each other
-#endif
     }
     // 0 < max < 2^-128: multiply by the exact power of two that brings the maximum into [1, 2)
-    const bool small0 = mh[0] < kScaleThresholdHi && mh[0] >= 0x00100000;
-    const bool small1 = mh[1] < kScaleThresholdHi && mh[1] >= 0x00100000;
-    if (__any_sync(0xffffffffu, small0 || small1)) {
+    bool small[PPT], any = false;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            if (p == 0 ? small0 : small1) {
+    for (int p = 0; p < PPT; ++p) {
+        small[p] = mh[p] < kScaleThresholdHi && mh[p] >= 0x00100000;
+        any = any || small[p];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            if (small[p]) {
                 const int shift = 1023 - (mh[p] >> 20);
                 const double f = pow2i(shift);
 #pragma unroll
@@ -203,8 +219,8 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
             }
         }
     }
-    pe[0] = e[0];
-    pe[1] = e[1];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) pe[p] = e[p];
 }
 
 // Block (politely, and not forever) until the copy engine has delivered the chunk that holds tile t.
@@ -221,9 +237,9 @@ __device__ __noinline__ void wait_for_chunk(const int* flags, int chunk_shift, i
     *error = 1;
 }
 
-template <int K, int NC, bool PACKED, bool PIPE>
-__global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kernel(const PairArgs p) {
-    using L = PairLayout<K, NC>;
+template <int K, int NC, int PPT, bool PACKED, bool PIPE>
+__global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair_kernel(const PairArgs p) {
+    using L = PairLayout<K, NC, PPT>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
     PairRow* const s_desc = reinterpret_cast<PairRow*>(smem);
@@ -239,7 +255,8 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
         const unsigned char* src = my_scratch + (size_t)slot * L::SLOT_BYTES;
 #pragma unroll
         for (int j = 0; j < L::CHUNKS; ++j) cp_async16(s_opin + j * 512 + lane * 16, src + j * 512 + lane * 16);
-        cp_async8(s_opin + L::BLOCK_BYTES + lane * 8, src + L::BLOCK_BYTES + lane * 8);
+        if (PPT == 2) cp_async8(s_opin + L::BLOCK_BYTES + lane * 8, src + L::BLOCK_BYTES + lane * 8);
+        else cp_async16(s_opin + L::BLOCK_BYTES + lane * 16, src + L::BLOCK_BYTES + lane * 16);
     };
     // read-only inputs of row `d` at tile t -> stage buffer q: per operand its P block or tip table, and its codes
     auto stage_row = [&](const PairRow d, int t, int q) {
@@ -253,13 +270,13 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
 #pragma unroll
         for (int j = 0; j < L::ROUNDS; ++j)
             if (j < L::P_ROUNDS || kind_b == KIND_TIP) cp_async16(st + L::OPER_BYTES + j * 512 + lane * 16, gb + j * 512);
-        // codes of the tile: 64 (32 when packed) bytes per tip operand; lanes 0..3 serve operand a, 4..7 operand b
-        constexpr int CL = PACKED ? 2 : 4;
-        const int which = lane >> 2, piece = lane & 3;
+        // codes of the tile: TILE (TILE / 2 when packed) bytes per tip operand; lanes 0..7 serve operand a, 8..15 operand b
+        constexpr int CL = (PACKED ? L::TILE / 2 : L::TILE) / 16;
+        const int which = lane >> 3, piece = lane & 7;
         const bool tip = which == 0 ? kind_a == KIND_TIP : kind_b == KIND_TIP;
         if (which < 2 && piece < CL && tip) {
             const int tip_row = which == 0 ? d.src_a : (int)(d.packed & 0xffffff);
-            cp_async16(st + L::CODES_OFF + which * 64 + piece * 16,
+            cp_async16(st + L::CODES_OFF + which * L::TILE + piece * 16,
                        p.codes + (size_t)tip_row * p.pitch + (size_t)t * (CL * 16) + piece * 16);
         }
     };
@@ -279,14 +296,16 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
         }
         cp_async_commit();
 
-        double prev[2][K][4];
-        int pe[2] = {0, 0};
+        double prev[PPT][K][4];
+        int pe[PPT];
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < PPT; ++q) {
+            pe[q] = 0;
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) prev[q][k][i] = 0.0;
+        }
 
         int row = 0, q = 0;
         int row2 = n_steps > 2 ? 2 : 0;   // row index two steps ahead (descriptors do not depend on the tile)
@@ -318,21 +337,16 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
             cp_async_commit();
 
             const unsigned char* st = s_stage + (q & 1) * L::STAGE_BYTES;
-            switch (kinds) {
-                case KIND_TIP | (KIND_TIP << 2):
-                    pair_update<K, NC, PACKED, KIND_TIP, KIND_TIP>(st, s_opin, lane, prev, pe);
-                    break;
-                case KIND_TIP | (KIND_PREV << 2):
-                    pair_update<K, NC, PACKED, KIND_TIP, KIND_PREV>(st, s_opin, lane, prev, pe);
-                    break;
-                case KIND_PREV | (KIND_SLOT << 2):
-                    pair_update<K, NC, PACKED, KIND_PREV, KIND_SLOT>(st, s_opin, lane, prev, pe);
-                    break;
-                case KIND_TIP | (KIND_SLOT << 2):
-                    pair_update<K, NC, PACKED, KIND_TIP, KIND_SLOT>(st, s_opin, lane, prev, pe);
-                    break;
-                default:   // not a row shape the host plan emits: do not touch memory
-                    break;
+            // four row shapes (canonical operand order); a short if-chain instead of a jump table: no table load and
+            // indirect branch on the row's critical path
+            const int kind_a = kinds & 3, kind_b = kinds >> 2;
+            if (kind_b == KIND_SLOT) {
+                if (kind_a == KIND_PREV) pair_update<K, NC, PPT, PACKED, KIND_PREV, KIND_SLOT>(st, s_opin, lane, prev, pe);
+                else pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_SLOT>(st, s_opin, lane, prev, pe);
+            } else if (kind_b == KIND_PREV) {
+                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_PREV>(st, s_opin, lane, prev, pe);
+            } else {
+                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_TIP>(st, s_opin, lane, prev, pe);
             }
             if (fetch_late) {   // the operand tile is free now (a lane only ever touches its own chunks of it)
                 fetch_slot(slot_n);
@@ -343,21 +357,22 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
                     // park: coalesced 128-bit stores straight from registers into the warp's own stripe
                     unsigned char* dst = my_scratch + (size_t)dst_slot * L::SLOT_BYTES + lane * 16;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < PPT; ++h)
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
                             *reinterpret_cast<double2*>(dst + ((h * K + k) * 2) * 512) = make_double2(prev[h][k][0], prev[h][k][1]);
                             *reinterpret_cast<double2*>(dst + ((h * K + k) * 2 + 1) * 512) = make_double2(prev[h][k][2], prev[h][k][3]);
                         }
-                    *reinterpret_cast<int2*>(my_scratch + (size_t)dst_slot * L::SLOT_BYTES + L::BLOCK_BYTES + lane * 8) =
-                        make_int2(pe[0], pe[1]);
+                    int* ex = reinterpret_cast<int*>(my_scratch + (size_t)dst_slot * L::SLOT_BYTES + L::BLOCK_BYTES + lane * (4 * PPT));
+                    if (PPT == 2) *reinterpret_cast<int2*>(ex) = make_int2(pe[0], pe[1]);
+                    else *reinterpret_cast<int4*>(ex) = make_int4(pe[0], pe[1], pe[PPT - 2], pe[PPT - 1]);
                 }
             } else {
                 // root pseudo-row: pi-dot, Gamma mixture, log, weighted sum (tree_model.py:200-217)
-                const int64_t s0 = (int64_t)tile * 64 + 2 * lane;
-                double lnl[2];
+                const int64_t s0 = (int64_t)tile * L::TILE + PPT * lane;
+                double lnl[PPT];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < PPT; ++h) {
                     double mix = 0.0;
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
@@ -370,19 +385,26 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
                     lnl[h] = mix > 0 ? log(mix) + (double)pe[h] * kLn2 : -INFINITY;
                 }
                 double acc = s_acc[lane];
-                if (s0 + 1 < p.S) {
-                    *reinterpret_cast<double2*>(p.pattern_lnl + s0) = make_double2(lnl[0], lnl[1]);
-                    if (p.weights) {
-                        const double2 w = *reinterpret_cast<const double2*>(p.weights + s0);
-                        acc += w.x * lnl[0];
-                        acc += w.y * lnl[1];
-                    } else {
-                        acc += lnl[0];
-                        acc += lnl[1];
+                if (s0 + PPT <= p.S) {
+#pragma unroll
+                    for (int h = 0; h < PPT; h += 2) {
+                        *reinterpret_cast<double2*>(p.pattern_lnl + s0 + h) = make_double2(lnl[h], lnl[h + 1]);
+                        if (p.weights) {
+                            const double2 w = *reinterpret_cast<const double2*>(p.weights + s0 + h);
+                            acc += w.x * lnl[h];
+                            acc += w.y * lnl[h + 1];
+                        } else {
+                            acc += lnl[h];
+                            acc += lnl[h + 1];
+                        }
                     }
-                } else if (s0 < p.S) {
-                    p.pattern_lnl[s0] = lnl[0];
-                    acc += (p.weights ? p.weights[s0] : 1.0) * lnl[0];
+                } else {
+#pragma unroll
+                    for (int h = 0; h < PPT; ++h)
+                        if (s0 + h < p.S) {
+                            p.pattern_lnl[s0 + h] = lnl[h];
+                            acc += (p.weights ? p.weights[s0 + h] : 1.0) * lnl[h];
+                        }
                 }
                 s_acc[lane] = acc;
             }
@@ -398,10 +420,10 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC>::MIN_CTAS) dna_pair_kern
     if (lane == 0) p.partial_sums[blockIdx.x] = total;
 }
 
-template <int K, int NC, bool PACKED, bool PIPE>
+template <int K, int NC, int PPT, bool PACKED, bool PIPE>
 int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
                 int max_grid, int* grid_out, int chunk_shift) {
-    using L = PairLayout<K, NC>;
+    using L = PairLayout<K, NC, PPT>;
     PairArgs a;
     a.rows = static_cast<const PairRow*>(c->d_res_rows);
     a.n_steps = n_steps;
@@ -422,7 +444,7 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.epoch = c->flag_epoch;
     a.chunk_shift = chunk_shift;
     a.error = c->d_flags + kMaxFlagChunks;
-    auto kern = dna_pair_kernel<K, NC, PACKED, PIPE>;
+    auto kern = dna_pair_kernel<K, NC, PPT, PACKED, PIPE>;
     const size_t smem = L::WARP_BYTES + 256;   // + the per-lane running sums
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -445,26 +467,42 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     return PHB_OK;
 }
 
+// patterns per lane: 2 everywhere; 4 is built for K = 4 and selected with PHB_PAIR_PPT=4 (tuning knob)
+int pair_ppt(const Ctx* c) {
+    const char* env = getenv("PHB_PAIR_PPT");
+    return (env != nullptr && atoi(env) == 4 && c->K == 4) ? 4 : 2;
+}
+
+template <int K, int NC, int PPT>
+int launch_pair_v(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
+                  int* grid_out, int chunk_shift) {
+    const int cs = chunk_shift < 0 ? 0 : chunk_shift;
+    if (packed) {
+        if (chunk_shift >= 0) return launch_pair<K, NC, PPT, true, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+        return launch_pair<K, NC, PPT, true, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+    }
+    if (chunk_shift >= 0) return launch_pair<K, NC, PPT, false, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+    return launch_pair<K, NC, PPT, false, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+}
+
 int launch_pair_k(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
                   int* grid_out, int chunk_shift = -1) {
     static_assert(kTipTabCodes == 16, "tip tables are staged with 8 or 16 rows per category");
-    const int key = c->K * 1000 + tip_table_rows(c) * 10 + (packed ? 1 : 0);
+    const int key = c->K * 1000 + tip_table_rows(c) * 10 + pair_ppt(c);
     switch (key) {
-#define PHB_PAIR_CASE(K_, NC_)                                                                             \
-    case K_ * 1000 + NC_ * 10:                                                                                       \
-        return chunk_shift < 0 ? launch_pair<K_, NC_, false, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, 0)    \
-                               : launch_pair<K_, NC_, false, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift); \
-    case K_ * 1000 + NC_ * 10 + 1:                                                                                   \
-        return chunk_shift < 0 ? launch_pair<K_, NC_, true, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, 0)     \
-                               : launch_pair<K_, NC_, true, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift);
-        PHB_PAIR_CASE(1, 8)
-        PHB_PAIR_CASE(1, 16)
-        PHB_PAIR_CASE(2, 8)
-        PHB_PAIR_CASE(2, 16)
-        PHB_PAIR_CASE(4, 8)
-        PHB_PAIR_CASE(4, 16)
-        PHB_PAIR_CASE(8, 8)
-        PHB_PAIR_CASE(8, 16)
+#define PHB_PAIR_CASE(K_, NC_, PPT_) \
+    case K_ * 1000 + NC_ * 10 + PPT_: \
+        return launch_pair_v<K_, NC_, PPT_>(c, packed, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift);
+        PHB_PAIR_CASE(1, 8, 2)
+        PHB_PAIR_CASE(1, 16, 2)
+        PHB_PAIR_CASE(2, 8, 2)
+        PHB_PAIR_CASE(2, 16, 2)
+        PHB_PAIR_CASE(4, 8, 2)
+        PHB_PAIR_CASE(4, 16, 2)
+        PHB_PAIR_CASE(8, 8, 2)
+        PHB_PAIR_CASE(8, 16, 2)
+        PHB_PAIR_CASE(4, 8, 4)
+        PHB_PAIR_CASE(4, 16, 4)
 #undef PHB_PAIR_CASE
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel needs K in {1,2,4,8}");
@@ -507,7 +545,8 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
     st = upload_pair_rows(c, plan);
     if (st) return st;
     int grid = 0;
-    const int64_t n_tiles = (c->S + 63) / 64;
+    const int tile = 32 * pair_ppt(c);
+    const int64_t n_tiles = (c->S + tile - 1) / tile;
     st = launch_pair_k(c, c->codes_packed, (int)plan.rows.size(), plan.n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
     if (st) return st;
     c->resident_slots = plan.n_slots;
@@ -536,7 +575,8 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chu
         PHB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_epoch), 64, cudaHostAllocDefault));
         PHB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, (kMaxFlagChunks + 1) * sizeof(int), c->stream));
     }
-    const int64_t n_tiles = (c->S + 63) / 64;
+    const int tile = 32 * pair_ppt(c);
+    const int64_t n_tiles = (c->S + tile - 1) / tile;
     n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_chunks, kMaxFlagChunks), n_tiles));
     int chunk_shift = 0;   // chunks are a power of two of tiles: the kernel finds a tile's flag with a shift
     while (((int64_t)1 << chunk_shift) * n_chunks < n_tiles) ++chunk_shift;
@@ -549,7 +589,7 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chu
     PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
     const size_t host_row = packed ? ((size_t)c->S + 1) / 2 : (size_t)c->S;
     const size_t dev_pitch = packed ? c->code_pitch / 2 : c->code_pitch;
-    const int per_tile = packed ? 32 : 64;   // bytes of one tile in a code row
+    const int per_tile = packed ? tile / 2 : tile;   // bytes of one tile in a code row
     c->codes_packed = packed;
     c->d_codes = c->d_codes_ws;
     for (int i = 0; i < n_chunks; ++i) {

@@ -231,3 +231,31 @@ def test_packed_codes_ragged_pattern_counts(n_pat):
         t, p = tm.engine.lnl_from_host(src, a, b, length, want_pattern=True, packed=packed)
         assert_lnl_close(p, want)
         assert_lnl_close(t, float(np.dot(want, w)))
+
+
+def test_four_patterns_per_lane_knob_gives_the_same_answer(monkeypatch):
+    """PHB_PAIR_PPT=4 selects the 128-pattern-tile flavour of the lnL-only kernel (tuning knob, K = 4 only)."""
+    tree, names, codes, lut = synthetic(150, 30011, 4, seed=4242)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    w = np.random.default_rng(8).integers(1, 4, size=codes.shape[1])
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, siteweights=w)
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    a, b = tm.traversal.root_edge
+    length = tm.traversal.brlens[(a, b)]
+    t2, p2 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
+    monkeypatch.setenv("PHB_PAIR_PPT", "4")
+    t4, p4 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
+    packed = phy.LikelihoodEngine.pack_codes(codes)
+    t4p, p4p = tm.engine.lnl_from_host(packed, a, b, length, n_chunks=7, want_pattern=True, packed=True)
+    monkeypatch.delenv("PHB_PAIR_PPT")
+    assert_lnl_close(p4, p2)
+    assert np.array_equal(p4p, p4)
+    assert_lnl_close(t4, t2)
+    tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+    want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights)
+    assert_lnl_close(p4, want)
