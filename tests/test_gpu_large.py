@@ -259,3 +259,35 @@ def test_four_patterns_per_lane_knob_gives_the_same_answer(monkeypatch):
     tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
     want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights)
     assert_lnl_close(p4, want)
+
+
+def test_headline_shape_full_size_properties():
+    """
+    BASELINE configs[1] at its full size - 1000 taxa x 1,000,000 patterns, GTR+G4 - through the lnL-only path the
+    benchmark times.  The alignment is a 500-pattern block repeated 2000 times, so (size-independent properties):
+    per-pattern lnL is bitwise periodic in the block, the total is 2000 x the block total, the block itself matches the
+    oracle to 1e-10, and the evaluation fed from packed host codes returns the same bits as the resident one.
+    """
+    n_taxa, block, reps = 1000, 500, 2000
+    tree, names, codes, lut = synthetic(n_taxa, block, 4, seed=2)
+    big = np.ascontiguousarray(np.tile(codes, (1, reps)))
+    assert big.shape == (1000, 1000000)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree)
+    tm.set_tip_codes(big, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    a, b = tm.traversal.root_edge
+    length = tm.traversal.brlens[(a, b)]
+    total, pattern = tm.engine.lnl_resident(a, b, length, want_pattern=True)
+    tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+    want = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights)
+    assert np.array_equal(pattern.reshape(reps, block), np.tile(pattern[:block], (reps, 1)))
+    assert_lnl_close(pattern[:block], want)
+    assert_lnl_close(total, reps * want.sum())
+    packed = phy.LikelihoodEngine.pack_codes(big)
+    t2, p2 = tm.engine.lnl_from_host(packed, a, b, length, n_chunks=32, want_pattern=True, packed=True)
+    assert np.array_equal(p2, pattern) and t2 == total
