@@ -91,6 +91,16 @@ bool shape_ok(int n_tips, int64_t S, int K, int A, std::string* why) {
 
 }  // namespace
 
+// operand-resident post-order pass with all blocks stored: two patterns per lane (clv_dna_pair.cu) where that kernel
+// covers the shape, the one-pattern-per-lane walk (clv_dna_resident.cu) otherwise or with PHB_RESIDENT_V1
+int resident_store(Ctx* c) {
+    if (getenv("PHB_RESIDENT_V1") == nullptr) {
+        const int st = dna_pair_store(c);
+        if (st != PHB_ERR_UNSUPPORTED) return st;
+    }
+    return dna_resident(c, -1, -1, true, false);
+}
+
 int run_rows(Ctx* c, const RowSet& rs, int mode) {
     if (dna_supported(c)) return dna_run_rows(c, rs, mode);
     if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr) return mma_run_rows(c, rs, mode);
@@ -573,7 +583,7 @@ int phb_compute_partials(phb_ctx* c, int mode) {
         } else if (dna_supported(c) && c->S >= 16384) {
             // operand-resident walk with streamed stores; needs a post-order schedule - if the caller's row order
             // is not one, fall back to the plain tile walk
-            st = dna_resident(c, -1, -1, true, false);
+            st = resident_store(c);
             if (st == PHB_OK) {
                 c->have_partials = true;
                 c->have_up = false;
@@ -590,7 +600,7 @@ int phb_compute_partials(phb_ctx* c, int mode) {
     if (mode == PHB_MODE_RESIDENT) {
         PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED,
                     "phb_compute_partials: resident mode covers 4-state models with K in {1,2,4,8}");
-        st = dna_resident(c, -1, -1, true, false);
+        st = resident_store(c);
         if (st) return st;
         c->have_partials = true;
         c->have_up = false;

@@ -93,9 +93,20 @@ struct PairLayout {
     static constexpr int MIN_CTAS = PPT == 2 ? (K <= 2 ? 16 : (K <= 4 ? 12 : 4)) : (K <= 1 ? 16 : (K <= 2 ? 12 : 8));
 };
 
+// Which patterns of its tile a lane owns, and how a parked operand tile is laid out in shared memory:
+//   LAYOUT_PRIVATE  lane l owns patterns PPT*l .. PPT*l + PPT-1; the operand tile is the warp's private chunk layout
+//   LAYOUT_ARRAY    lane l owns patterns l, l + 32, ...; the operand tile mirrors the caller-visible partials array
+//                   (pattern-major rows, padded to ROWB bytes so that 128-bit accesses are conflict-free)
+constexpr int LAYOUT_PRIVATE = 0, LAYOUT_ARRAY = 1;
+
 // the PPT codes of a lane, as byte offsets of their tip-table rows
-template <int NC, int PPT, bool PACKED>
+template <int NC, int PPT, bool PACKED, int LAYOUT>
 __device__ __forceinline__ void table_rows(const unsigned char* codes, int lane, int (&row)[PPT]) {
+    if (LAYOUT == LAYOUT_ARRAY) {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) row[p] = (int)(codes[lane + 32 * p] & (NC - 1)) * 32;
+        return;
+    }
     unsigned raw;
     if (PACKED) raw = PPT == 2 ? (unsigned)codes[lane] : (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane);
     else raw = PPT == 2 ? (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane)
@@ -111,15 +122,19 @@ __device__ __forceinline__ void lds32(const unsigned char* p, double (&v)[4]) {
 }
 
 // prev[p][k] <- (Pa[k] . a[p][k]) * (Pb[k] . b[p][k]) for the lane's PPT patterns; pe <- cumulative exponents
-template <int K, int NC, int PPT, bool PACKED, int KA, int KB>
+template <int K, int NC, int PPT, bool PACKED, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE>
 __device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
                                             double (&prev)[PPT][K][4], int (&pe)[PPT]) {
     using L = PairLayout<K, NC, PPT>;
+    constexpr int ROWB = K * 32 + 16;   // LAYOUT_ARRAY: one pattern's row of the operand tile
     static_assert(KA != KIND_SLOT, "operand a is a tip or the previous row");
     int e[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) e[p] = (KA == KIND_PREV || KB == KIND_PREV) ? pe[p] : 0;
-    if (KB == KIND_SLOT) {
+    if (KB == KIND_SLOT && LAYOUT == LAYOUT_ARRAY) {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) e[p] += *reinterpret_cast<const int*>(opin + (lane + 32 * p) * ROWB + K * 32);   // in the row's padding
+    } else if (KB == KIND_SLOT) {
         const int* x = reinterpret_cast<const int*>(opin + L::BLOCK_BYTES + lane * (4 * PPT));
         if (PPT == 2) {
             const int2 v = *reinterpret_cast<const int2*>(x);
@@ -136,8 +151,8 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
     int ra[PPT], rb[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) ra[p] = rb[p] = 0;
-    if (KA == KIND_TIP) table_rows<NC, PPT, PACKED>(st + L::CODES_OFF, lane, ra);
-    if (KB == KIND_TIP) table_rows<NC, PPT, PACKED>(st + L::CODES_OFF + L::TILE, lane, rb);
+    if (KA == KIND_TIP) table_rows<NC, PPT, PACKED, LAYOUT>(st + L::CODES_OFF, lane, ra);
+    if (KB == KIND_TIP) table_rows<NC, PPT, PACKED, LAYOUT>(st + L::CODES_OFF + L::TILE, lane, rb);
     int mh[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) mh[p] = 0;
@@ -174,6 +189,8 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
                 if (KB == KIND_PREV) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) b[p][i] = prev[p][k][i];
+                } else if (LAYOUT == LAYOUT_ARRAY) {
+                    lds32(opin + (lane + 32 * p) * ROWB + k * 32, b[p]);
                 } else {
                     const unsigned char* src = opin + ((p * K + k) * 2) * 512 + lane * 16;
                     const double2 lo = *reinterpret_cast<const double2*>(src);
@@ -420,6 +437,208 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
     if (lane == 0) p.partial_sums[blockIdx.x] = total;
 }
 
+// ---- the same walk with every node block written to the caller-visible partials array --------------------------
+// (PHB_MODE_RESIDENT: what TreeModel.partials, the pre-order pass and the derivative kernels read.)  Differences to
+// the lnL-only kernel: a parked operand is the producer row's block of the partials array [row][S][K][4] (+ its
+// exponents [row][S]), fetched one row ahead into a pattern-major operand tile; every row's result goes registers ->
+// padded staging tile -> coalesced streaming 128-bit stores; a lane owns patterns l and l + 32 of the tile so that
+// both tiles are conflict-free; there is no root step and no scratch.
+struct PairStoreArgs {
+    const PairRow* rows;
+    int n_steps;
+    const unsigned char* opbase;
+    const uint8_t* codes;
+    size_t pitch;
+    double* clv;       // [row][S][K][4]
+    int32_t* scale;    // [row][S]
+    int64_t S, n_tiles;
+};
+
+template <int K, int NC>
+__global__ void __launch_bounds__(32, 8) dna_pair_store_kernel(const PairStoreArgs p) {
+    constexpr int PPT = 2;
+    using L = PairLayout<K, NC, PPT>;
+    constexpr int ROWB = K * 32 + 16, TILE_BYTES = L::TILE * ROWB, OPIN_BYTES = TILE_BYTES;   // exponents sit in the row padding
+    constexpr int PIECES = K * 2;                        // 16-byte pieces per pattern
+    constexpr int ROUNDS = L::TILE * PIECES / 32;        // warp-wide copy rounds per block
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x;
+    PairRow* const s_desc = reinterpret_cast<PairRow*>(smem);
+    unsigned char* const s_stage = smem + L::DESC_BYTES;
+    unsigned char* const s_opin = s_stage + 2 * L::STAGE_BYTES;
+    unsigned char* const s_out = s_opin + OPIN_BYTES;
+    const int wstride = gridDim.x, n_steps = p.n_steps;
+    const int n_tiles = (int)p.n_tiles;
+    const size_t S = (size_t)p.S;
+
+    auto fetch_block = [&](int prod_row, int t) {
+        const size_t site0 = (size_t)t * L::TILE;
+        const int valid = (int)min((int64_t)L::TILE, p.S - (int64_t)site0);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.clv + ((size_t)prod_row * S + site0) * (K * 4));
+#pragma unroll
+        for (int j = 0; j < ROUNDS; ++j) {
+            const int c = lane + 32 * j;
+            if (c < valid * PIECES) cp_async16(s_opin + (c / PIECES) * ROWB + (c % PIECES) * 16, src + (size_t)c * 16);
+        }
+        const int32_t* ex = p.scale + (size_t)prod_row * S + site0;
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+            if (lane + 32 * q < valid)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(
+                                                                                s_opin + (lane + 32 * q) * ROWB + K * 32)),
+                             "l"(ex + lane + 32 * q)
+                             : "memory");
+    };
+    auto stage_row = [&](const PairRow d, int t, int q) {
+        unsigned char* st = s_stage + q * L::STAGE_BYTES;
+        const int kind_a = (d.packed >> 24) & 3, kind_b = (d.packed >> 26) & 3;
+        const unsigned char* ga = p.opbase + (size_t)d.off_a * 16 + lane * 16;
+        const unsigned char* gb = p.opbase + (size_t)d.off_b * 16 + lane * 16;
+#pragma unroll
+        for (int j = 0; j < L::ROUNDS; ++j)
+            if (j < L::P_ROUNDS || kind_a == KIND_TIP) cp_async16(st + j * 512 + lane * 16, ga + j * 512);
+#pragma unroll
+        for (int j = 0; j < L::ROUNDS; ++j)
+            if (j < L::P_ROUNDS || kind_b == KIND_TIP) cp_async16(st + L::OPER_BYTES + j * 512 + lane * 16, gb + j * 512);
+        constexpr int CL = L::TILE / 16;   // code rows are pitched and zero-padded: a whole tile can always be read
+        const int which = lane >> 3, piece = lane & 7;
+        const bool tip = which == 0 ? kind_a == KIND_TIP : kind_b == KIND_TIP;
+        if (which < 2 && piece < CL && tip) {
+            const int tip_row = which == 0 ? d.src_a : (int)(d.packed & 0xffffff);
+            cp_async16(st + L::CODES_OFF + which * L::TILE + piece * 16,
+                       p.codes + (size_t)tip_row * p.pitch + (size_t)t * L::TILE + piece * 16);
+        }
+    };
+
+    int tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    if (lane < 2) cp_async16(&s_desc[lane], &p.rows[lane < n_steps ? lane : 0]);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncwarp();
+    stage_row(s_desc[0], tile, 0);
+    cp_async_commit();
+
+    double prev[PPT][K][4];
+    int pe[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        pe[q] = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prev[q][k][i] = 0.0;
+    }
+    int row = 0, q = 0;
+    int row2 = n_steps > 2 ? 2 : 0;
+    while (true) {
+        int row_n = row + 1, tile_n = tile;
+        if (row_n == n_steps) {
+            row_n = 0;
+            tile_n += wstride;
+        }
+        const bool has_next = tile_n < n_tiles;
+        cp_async_wait_all();
+        __syncwarp();
+        const uint32_t pk = s_desc[q & 3].packed;
+        const int kinds = (pk >> 24) & 15;
+        const bool opin_busy = (kinds >> 2) == KIND_SLOT;
+        bool fetch_late = false;
+        int slot_n = 0;
+        if (lane == 0) cp_async16(&s_desc[(q + 2) & 3], &p.rows[row2]);
+        if (has_next) {
+            const PairRow dn = s_desc[(q + 1) & 3];
+            stage_row(dn, tile_n, (q + 1) & 1);
+            if (((dn.packed >> 26) & 3) == KIND_SLOT) {
+                slot_n = dn.packed & 0xffffff;       // producer row of the parked operand
+                if (opin_busy) fetch_late = true;
+                else fetch_block(slot_n, tile_n);
+            }
+        }
+        cp_async_commit();
+
+        const unsigned char* st = s_stage + (q & 1) * L::STAGE_BYTES;
+        const int kind_a = kinds & 3, kind_b = kinds >> 2;
+        if (kind_b == KIND_SLOT) {
+            if (kind_a == KIND_PREV) pair_update<K, NC, PPT, false, KIND_PREV, KIND_SLOT, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+            else pair_update<K, NC, PPT, false, KIND_TIP, KIND_SLOT, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+        } else if (kind_b == KIND_PREV) {
+            pair_update<K, NC, PPT, false, KIND_TIP, KIND_PREV, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+        } else {
+            pair_update<K, NC, PPT, false, KIND_TIP, KIND_TIP, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+        }
+        if (fetch_late) {   // each lane only ever touches its own rows of the operand tile
+            __syncwarp();
+            fetch_block(slot_n, tile_n);
+            cp_async_commit();
+        }
+        // store: registers -> padded staging tile -> coalesced streaming stores into the block of this row
+        {
+            const size_t site0 = (size_t)tile * L::TILE;
+            const int valid = (int)min((int64_t)L::TILE, p.S - (int64_t)site0);
+            unsigned char* dst = reinterpret_cast<unsigned char*>(p.clv + ((size_t)row * S + site0) * (K * 4));
+#pragma unroll
+            for (int h = 0; h < PPT; ++h) {   // 32 patterns at a time through a half-size staging tile
+                if (h) __syncwarp();
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    unsigned char* d = s_out + lane * ROWB + k * 32;
+                    *reinterpret_cast<double2*>(d) = make_double2(prev[h][k][0], prev[h][k][1]);
+                    *reinterpret_cast<double2*>(d + 16) = make_double2(prev[h][k][2], prev[h][k][3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < ROUNDS / PPT; ++j) {
+                    const int c = lane + 32 * j;
+                    if (c + h * 32 * PIECES < valid * PIECES) {
+                        const int4 v = *reinterpret_cast<const int4*>(s_out + (c / PIECES) * ROWB + (c % PIECES) * 16);
+                        __stcs(reinterpret_cast<int4*>(dst + (size_t)(c + h * 32 * PIECES) * 16), v);
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < PPT; ++h)
+                if (lane + 32 * h < valid) p.scale[(size_t)row * S + site0 + lane + 32 * h] = pe[h];
+        }
+        if (!has_next) break;
+        row = row_n;
+        tile = tile_n;
+        if (++row2 == n_steps) row2 = 0;
+        ++q;
+    }
+    cp_async_wait_all();
+}
+
+template <int K, int NC>
+int launch_pair_store(Ctx* c, int n_steps) {
+    using L = PairLayout<K, NC, 2>;
+    constexpr int ROWB = K * 32 + 16;
+    PairStoreArgs a;
+    a.rows = static_cast<const PairRow*>(c->d_res_rows);
+    a.n_steps = n_steps;
+    a.opbase = reinterpret_cast<const unsigned char*>(c->d_pmats);
+    a.codes = c->d_codes;
+    a.pitch = c->code_pitch;
+    a.clv = c->d_clv;
+    a.scale = c->d_scale;
+    a.S = c->S;
+    a.n_tiles = (c->S + L::TILE - 1) / L::TILE;
+    auto kern = dna_pair_store_kernel<K, NC>;
+    const size_t smem = L::DESC_BYTES + 2 * L::STAGE_BYTES + (size_t)L::TILE * ROWB + 32 * ROWB;   // operand tile + half-size staging tile
+    if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair store kernel: does not fit in shared memory");
+    PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 0;
+    PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(a.n_tiles, (int64_t)c->sm_count * per_sm));
+    kern<<<(int)grid, 32, smem, c->stream>>>(a);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    c->resident_warps = per_sm;
+    return PHB_OK;
+}
+
 template <int K, int NC, int PPT, bool PACKED, bool PIPE>
 int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
                 int max_grid, int* grid_out, int chunk_shift) {
@@ -536,6 +755,27 @@ int upload_pair_rows(Ctx* c, const ResPlan& plan) {
 }
 
 }  // namespace
+
+// Post-order pass with every node block stored (PHB_MODE_RESIDENT / PHB_MODE_AUTO of phb_compute_partials)
+int dna_pair_store(Ctx* c) {
+    if (c->K > 4) return PHB_ERR_UNSUPPORTED;   // K = 8 keeps the one-pattern-per-lane walk (register budget)
+    ResPlan plan;
+    int st = plan_rows(c, -1, -1, false, true, &plan);
+    if (st) return st;
+    if (plan.rows.empty()) return PHB_OK;
+    st = upload_pair_rows(c, plan);
+    if (st) return st;
+    const int n_steps = (int)plan.rows.size();
+    switch (c->K * 100 + tip_table_rows(c)) {
+        case 108: return launch_pair_store<1, 8>(c, n_steps);
+        case 116: return launch_pair_store<1, 16>(c, n_steps);
+        case 208: return launch_pair_store<2, 8>(c, n_steps);
+        case 216: return launch_pair_store<2, 16>(c, n_steps);
+        case 408: return launch_pair_store<4, 8>(c, n_steps);
+        case 416: return launch_pair_store<4, 16>(c, n_steps);
+    }
+    return PHB_ERR_UNSUPPORTED;
+}
 
 // One evaluation from the tip codes resident on the device: per-pattern lnL + their weighted sum in d_result[0]
 int dna_pair_lnl(Ctx* c, int root_a, int root_b) {

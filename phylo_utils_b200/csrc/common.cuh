@@ -196,6 +196,7 @@ int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root);   
 int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int root_a, int root_b);
 // clv_dna_pair.cu: lnL-only walk, two patterns per lane (the default lnL-only path)
 int dna_pair_lnl(Ctx* c, int root_a, int root_b);
+int dna_pair_store(Ctx* c);   // all partials stored; PHB_ERR_UNSUPPORTED (no message) when the shape is not covered
 int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b);
 // clv_generic.cu (any A <= 64, any K <= 16)
 int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
