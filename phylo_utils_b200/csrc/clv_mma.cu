@@ -132,11 +132,18 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         Ld[n * LDL + j] = __ldg(p.lut + (size_t)s_codes[c * TS + warp * WR + n] * A + j);
                     }
                 } else {
-                    const double* base = p.clv + (size_t)row.src[c] * S * K * A;
-                    for (int e = lane; e < WR * A; e += 32) {
-                        const int n = e / A, j = e - n * A;
-                        const int64_t s = wsite0 + n;
-                        if (s < p.S) cp_async8(Ld + n * LDL + j, base + ((size_t)s * K + k) * A + j);
+                    // rows of A doubles are 16-byte aligned when A is even (A = 20: ten 16-byte pieces per row)
+                    constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
+                    const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
+                    const unsigned char* g =
+                        reinterpret_cast<const unsigned char*>(p.clv + (((size_t)row.src[c] * S + wsite0) * K + k) * A);
+                    const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld);
+                    for (int e = lane; e < n_valid * PIECES; e += 32) {
+                        const int n = e / PIECES, piece = e - n * PIECES;
+                        const unsigned d = sdst + n * (LDL * 8) + piece * PB;
+                        const unsigned char* q = g + (size_t)n * (K * A * 8) + piece * PB;
+                        if (PB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
+                        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
                     }
                 }
                 cp_async_commit_all();

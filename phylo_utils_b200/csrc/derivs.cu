@@ -345,21 +345,31 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
             for (int nt = 0; nt < NT; ++nt) t[d][nt][0] = t[d][nt][1] = 0.0;
         for (int k = 0; k < K; ++k) {
             __syncwarp();   // every lane is done with the rows of the previous category
-            for (int idx = lane; idx < WR * A; idx += 32) {
-                const int n = idx / A, j = idx - n * A;
-                const int64_t s = wsite0 + n;
-                if (s >= p.S) continue;
-                if (ka == SRC_TIP) {
-                    if (k == 0) myA[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[sa * p.pitch + s] * A + j);
-                } else {
-                    deriv_cp_async8(myA + n * LDL + j, p.clv + ((sa * S + s) * K + k) * A + j);
+            // operand rows of this warp's patterns for category k.  Rows of A doubles are 16-byte aligned when A is
+            // even (A = 20: ten 16-byte pieces per row), 8-byte aligned otherwise (A = 61).
+            constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
+            const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
+            auto stage = [&](int kind, size_t src, double* mine) {
+                if (kind == SRC_TIP) {
+                    if (k == 0)
+                        for (int idx = lane; idx < n_valid * A; idx += 32) {
+                            const int n = idx / A, j = idx - n * A;
+                            mine[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[src * p.pitch + wsite0 + n] * A + j);
+                        }
+                    return;
                 }
-                if (kb == SRC_TIP) {
-                    if (k == 0) myB[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[sb * p.pitch + s] * A + j);
-                } else {
-                    deriv_cp_async8(myB + n * LDL + j, p.clv + ((sb * S + s) * K + k) * A + j);
+                const unsigned char* g = reinterpret_cast<const unsigned char*>(p.clv + ((src * S + wsite0) * K + k) * A);
+                const unsigned sdst = (unsigned)__cvta_generic_to_shared(mine);
+                for (int c = lane; c < n_valid * PIECES; c += 32) {
+                    const int n = c / PIECES, piece = c - n * PIECES;
+                    const unsigned d = sdst + n * (LDL * 8) + piece * PB;
+                    const unsigned char* q = g + (size_t)n * (K * A * 8) + piece * PB;
+                    if (PB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
                 }
-            }
+            };
+            stage(ka, sa, myA);
+            stage(kb, sb, myB);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
@@ -463,7 +473,8 @@ int launch_mma_derivs(Ctx* c, MmaDerivArgs& a, int n_edges) {
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     // enough CTAs per edge to fill the chip across the whole batch, few enough for the block-sum buffer
-    int64_t parts = std::max<int64_t>(1, ((int64_t)c->sm_count * per_sm + n_edges - 1) / n_edges);
+    // at least two CTAs per edge: with one, ~1000 edges are 3.4 waves of the chip and the last one runs a third full
+    int64_t parts = std::max<int64_t>(2, ((int64_t)c->sm_count * per_sm + n_edges - 1) / n_edges);
     parts = std::min<int64_t>(parts, std::min<int64_t>(a.n_tiles, kPartialCap / (3 * n_edges)));
     a.n_parts = (int)parts;
     dim3 grid((unsigned)parts, (unsigned)n_edges);

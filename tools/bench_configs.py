@@ -74,8 +74,37 @@ def report(name, tm, n_taxa, n_pat, A, reps, derivs=False):
 
 
 def main():
-    which = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg3", "cfg4", "cfg5"]
+    which = [a for a in sys.argv[1:] if a.startswith("cfg")] or ["cfg1", "cfg3", "cfg4", "cfg5"]
     reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
+    if "cfg1" in which:
+        # the reference's own test-sized case: 10 taxa x 1000 patterns, launch-latency bound.  Wall clock per
+        # evaluation through TreeModel (new branch lengths -> lnL on the host), 200 evaluations each way.
+        model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+        out = {"config": "cfg1 GTR+G4 10x1000"}
+        for label, kw in (("partials_stored", {}), ("lnl_only", {"store_partials": False})):
+            rng = np.random.default_rng(1)
+            tree = random_tree(10, 1)
+            names = [l.taxon.label for l in tree.leaf_node_iter()]
+            lut = np.vstack([np.eye(4)[::-1], np.ones((1, 4))])
+            codes = rng.integers(0, 5, size=(10, 1000)).astype(np.uint8)
+            tm = phy.TreeModel(**kw)
+            tm.set_tree(tree)
+            tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+            tm.set_rate_model(phy.rate_models.GammaRateModel(4, 0.5))
+            tm.set_substitution_model(model)
+            tm.initialise()
+
+            def one():
+                tm.compute_partials()      # new branch lengths (and, when partials are stored, P build + post-order pass)
+                return tm.lnl()
+            for _ in range(20):
+                lnl = one()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                lnl = one()
+            out[label + "_us_per_eval"] = (time.perf_counter() - t0) / 200 * 1e6
+            out["lnl"] = lnl
+        print(json.dumps(out), flush=True)
     if "cfg3" in which:
         tm = build(500, 100000, 20, phy.substitution_models.LG(), 3, up=True)
         report("cfg3 LG+G4 500x100k", tm, 500, 100000, 20, reps, derivs=True)
