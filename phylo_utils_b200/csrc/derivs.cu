@@ -172,61 +172,69 @@ __global__ void __launch_bounds__(128) dna_edge_deriv_kernel(const DerivArgs p) 
     const size_t sa = (size_t)ed.src_a, sb = (size_t)ed.src_b;
     double tot[3] = {0.0, 0.0, 0.0};
     const int64_t n_iter = (p.S + SPI - 1) / SPI;
-    constexpr int U = 1;   // pattern groups per trip (2 was measured: more registers, no gain - the kernel is FP64-issue bound)
-    for (int64_t it0 = blockIdx.x; it0 < n_iter; it0 += (int64_t)U * gridDim.x) {
-        double a[U][4], b[U][4];
-        int ex[U];
-        bool ok[U];
-        size_t ss[U];
+    // K consecutive pattern groups per trip.  After the width-K shuffles all K lanes of a group hold the same three
+    // sums; lane k keeps those of round k, so that the expensive tail (log, two divisions) then runs ONCE per trip
+    // with a different pattern in every lane instead of once per round in a quarter of the lanes.
+    for (int64_t it0 = (int64_t)blockIdx.x * K; it0 < n_iter; it0 += (int64_t)gridDim.x * K) {
+        double keep[3] = {1.0, 0.0, 0.0};
+        int keep_ex = 0;
+        size_t keep_s = 0;
+        bool keep_ok = false;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t it = it0 + (int64_t)u * gridDim.x;
+        for (int u = 0; u < K; ++u) {
+            const int64_t it = it0 + u;
             const int64_t s = it * SPI + g;
-            ok[u] = it < n_iter && s < p.S;
-            ss[u] = ok[u] ? (size_t)s : 0;
-            ex[u] = 0;
+            const bool ok = it < n_iter && s < p.S;
+            const size_t ss = ok ? (size_t)s : 0;
+            double a[4], b[4];
+            int ex = 0;
             if (ka == SRC_TIP) {
-                const int code = p.codes[sa * p.pitch + ss[u]];
+                const int code = p.codes[sa * p.pitch + ss];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[u][i] = s_lut[code][i];
+                for (int i = 0; i < 4; ++i) a[i] = s_lut[code][i];
             } else {
-                ld256(p.clv + ((sa * S + ss[u]) * K + k) * 4, a[u]);
-                ex[u] += p.scale[sa * S + ss[u]];
+                ld256(p.clv + ((sa * S + ss) * K + k) * 4, a);
+                ex += p.scale[sa * S + ss];
             }
             if (kb == SRC_TIP) {
-                const int code = p.codes[sb * p.pitch + ss[u]];
+                const int code = p.codes[sb * p.pitch + ss];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) b[u][i] = s_lut[code][i];
+                for (int i = 0; i < 4; ++i) b[i] = s_lut[code][i];
             } else {
-                ld256(p.clv + ((sb * S + ss[u]) * K + k) * 4, b[u]);
-                ex[u] += p.scale[sb * S + ss[u]];
+                ld256(p.clv + ((sb * S + ss) * K + k) * 4, b);
+                ex += p.scale[sb * S + ss];
             }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
             double f[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 double acc = 0.0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    double x = M[d][4 * i] * a[u][0];
-                    x = fma(M[d][4 * i + 1], a[u][1], x);
-                    x = fma(M[d][4 * i + 2], a[u][2], x);
-                    x = fma(M[d][4 * i + 3], a[u][3], x);
-                    acc = fma(pi[i] * b[u][i], x, acc);
+                    double x = M[d][4 * i] * a[0];
+                    x = fma(M[d][4 * i + 1], a[1], x);
+                    x = fma(M[d][4 * i + 2], a[2], x);
+                    x = fma(M[d][4 * i + 3], a[3], x);
+                    acc = fma(pi[i] * b[i], x, acc);
                 }
                 f[d] = wk * acc;
 #pragma unroll
                 for (int o = K / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
             }
-            if (ok[u] && k == 0) {
-                const double w = p.weights ? p.weights[ss[u]] : 1.0;
-                const double gq = f[1] / f[0];
-                tot[0] += w * (f[0] > 0 ? log(f[0]) + (double)ex[u] * kLn2 : -INFINITY);
-                tot[1] += w * gq;
-                tot[2] += w * (f[2] / f[0] - gq * gq);
+            if (u == k) {
+                keep[0] = f[0];
+                keep[1] = f[1];
+                keep[2] = f[2];
+                keep_ex = ex;
+                keep_s = ss;
+                keep_ok = ok;
             }
+        }
+        if (keep_ok) {
+            const double w = p.weights ? p.weights[keep_s] : 1.0;
+            const double gq = keep[1] / keep[0];
+            tot[0] += w * (keep[0] > 0 ? log(keep[0]) + (double)keep_ex * kLn2 : -INFINITY);
+            tot[1] += w * gq;
+            tot[2] += w * (keep[2] / keep[0] - gq * gq);
         }
     }
 #pragma unroll
