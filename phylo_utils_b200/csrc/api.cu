@@ -438,6 +438,7 @@ static int upload_mixture(phb_ctx* c, const double* freqs, const double* rates, 
         buf[A + k] = rates[k];
         buf[A + K + k] = cat_weights[k];
     }
+    c->h_freqs.assign(freqs, freqs + A);
     PHB_CUDA(c, cudaMemcpyAsync(c->model_freqs(), buf.data(), ((size_t)A + 2 * K) * sizeof(double),
                                 cudaMemcpyHostToDevice, c->stream));
     PHB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -462,6 +463,8 @@ int phb_set_model(phb_ctx* c, const double* evecs, const double* evals, const do
     PHB_CUDA(c, cudaStreamSynchronize(c->stream));
     st = upload_mixture(c, freqs, rates, cat_weights);
     if (st) return st;
+    c->h_evecs.assign(evecs, evecs + AA);
+    c->h_ivecs.assign(ivecs, ivecs + AA);
     c->have_model = true;
     c->have_pmats = false;
     c->have_partials = false;

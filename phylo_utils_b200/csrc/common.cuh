@@ -129,6 +129,7 @@ struct Ctx {
     std::vector<int32_t> rows_raw;     // PAR, CH1, CH2 as given
     std::vector<int32_t> level_offsets;
     std::vector<double> lengths;       // [n_rows][2]
+    std::vector<double> h_evecs, h_ivecs, h_freqs;   // host copies of the eigenvectors / frequencies (sum-table derivatives)
     bool have_tips = false, have_model = false, have_mixture = false, have_schedule = false;
     bool have_lengths = false, have_pmats = false, have_partials = false, have_up = false;
     bool have_root = false;

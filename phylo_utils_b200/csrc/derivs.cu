@@ -492,6 +492,123 @@ int launch_mma_derivs(Ctx* c, MmaDerivArgs& a, int n_edges) {
     return PHB_OK;
 }
 
+// ---- 4 states: the same sum-table form, scalar ------------------------------------------------------------------
+// lane = (pattern, category) as in clv_dna.cu.  V^-1 and V^T diag(pi) travel in the kernel parameters, so the
+// compiler feeds them to the FMAs straight from the constant bank: no registers, no loads.  A lane keeps only the
+// twelve coefficients of its own category (w_k g_d(lambda_m r_k) exp(lambda_m r_k t)).  48 FP64 operations per
+// (pattern, category) instead of 72, and a third of the registers of the matrix form above.
+struct DnaSumArgs {
+    double m1[16];          // V^-1, row-major
+    double m2[16];          // m2[m][i] = V[i][m] pi[i]
+    const double* coef;     // [edge][3][K][4]
+    const uint8_t* codes;
+    size_t pitch;
+    const double* lut;
+    const double* clv;
+    const int32_t* scale;
+    const double* weights;
+    const EdgeDesc* edges;
+    int64_t S;
+    int n_parts;
+    double* partial_sums;   // [n_edges * 3][n_parts]
+};
+
+template <int K>
+__global__ void __launch_bounds__(128, 4) dna_edge_sumtable_kernel(const __grid_constant__ DnaSumArgs p) {
+    constexpr int SPI = 128 / K;
+    __shared__ double s_lut[256][4];
+    __shared__ double s_red[3][4];
+    const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
+    for (int i = tid; i < 256 * 4; i += 128) (&s_lut[0][0])[i] = p.lut[i];
+    __syncthreads();
+    double cf[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) cf[d][m] = p.coef[(((size_t)e * 3 + d) * K + k) * 4 + m];
+    const size_t S = (size_t)p.S;
+    const EdgeDesc ed = p.edges[e];
+    const int ka = ed.kind_a, kb = ed.kind_b;
+    const size_t sa = (size_t)ed.src_a, sb = (size_t)ed.src_b;
+    double tot[3] = {0.0, 0.0, 0.0};
+    const int64_t n_iter = (p.S + SPI - 1) / SPI;
+    // K consecutive pattern groups per trip; lane k keeps the sums of round k, so that the tail (log, two divisions)
+    // runs once per trip with a different pattern in every lane
+    for (int64_t it0 = (int64_t)blockIdx.x * K; it0 < n_iter; it0 += (int64_t)gridDim.x * K) {
+        double keep[3] = {1.0, 0.0, 0.0};
+        int keep_ex = 0;
+        size_t keep_s = 0;
+        bool keep_ok = false;
+#pragma unroll
+        for (int u = 0; u < K; ++u) {
+            const int64_t it = it0 + u;
+            const int64_t s = it * SPI + g;
+            const bool ok = it < n_iter && s < p.S;
+            const size_t ss = ok ? (size_t)s : 0;
+            double a[4], b[4];
+            int ex = 0;
+            if (ka == SRC_TIP) {
+                const int code = p.codes[sa * p.pitch + ss];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = s_lut[code][i];
+            } else {
+                ld256(p.clv + ((sa * S + ss) * K + k) * 4, a);
+                ex += p.scale[sa * S + ss];
+            }
+            if (kb == SRC_TIP) {
+                const int code = p.codes[sb * p.pitch + ss];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = s_lut[code][i];
+            } else {
+                ld256(p.clv + ((sb * S + ss) * K + k) * 4, b);
+                ex += p.scale[sb * S + ss];
+            }
+            double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                double x = p.m1[4 * m] * a[0];
+                x = fma(p.m1[4 * m + 1], a[1], x);
+                x = fma(p.m1[4 * m + 2], a[2], x);
+                x = fma(p.m1[4 * m + 3], a[3], x);
+                double y = p.m2[4 * m] * b[0];
+                y = fma(p.m2[4 * m + 1], b[1], y);
+                y = fma(p.m2[4 * m + 2], b[2], y);
+                y = fma(p.m2[4 * m + 3], b[3], y);
+                const double xy = x * y;
+                f[0] = fma(cf[0][m], xy, f[0]);
+                f[1] = fma(cf[1][m], xy, f[1]);
+                f[2] = fma(cf[2][m], xy, f[2]);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int o = K / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+            if (u == k) {
+                keep[0] = f[0];
+                keep[1] = f[1];
+                keep[2] = f[2];
+                keep_ex = ex;
+                keep_s = ss;
+                keep_ok = ok;
+            }
+        }
+        if (keep_ok) {
+            const double w = p.weights ? p.weights[keep_s] : 1.0;
+            const double gq = keep[1] / keep[0];
+            tot[0] += w * (keep[0] > 0 ? log(keep[0]) + (double)keep_ex * kLn2 : -INFINITY);
+            tot[1] += w * gq;
+            tot[2] += w * (keep[2] / keep[0] - gq * gq);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double v = warp_sum(tot[d]);
+        if ((tid & 31) == 0) s_red[d][tid >> 5] = v;
+    }
+    __syncthreads();
+    if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
+}
+
 void fill_operand(const Ctx* c, int node, int* src, int* kind) {
     if (c->node_tip[node] >= 0) {
         *kind = SRC_TIP;
@@ -632,6 +749,44 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             int st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8>(c, m, n);
             if (st) return st;
             n_parts = m.n_parts;
+        } else if (dna_supported(c) && (int)c->h_evecs.size() == A * A && (int)c->h_freqs.size() == A &&
+                   getenv("PHB_DERIV_MATRIX_FORM") == nullptr) {
+            DnaSumArgs q;
+            for (int m = 0; m < 4; ++m)
+                for (int i = 0; i < 4; ++i) {
+                    q.m1[4 * m + i] = c->h_ivecs[4 * m + i];
+                    q.m2[4 * m + i] = c->h_evecs[4 * i + m] * c->h_freqs[i];
+                }
+            double* d_coef = c->d_dmats;
+            deriv_coef_kernel<<<n, 64, 0, c->stream>>>(c->model_evals(), c->model_rates(), c->model_catw(), d_len, A, K, 4,
+                                                       chain_rule, d_coef);
+            c->launches++;
+            PHB_CUDA(c, cudaGetLastError());
+            q.coef = d_coef;
+            q.codes = c->d_codes;
+            q.pitch = c->code_pitch;
+            q.lut = c->d_lut;
+            q.clv = c->d_clv;
+            q.scale = c->d_scale;
+            q.weights = c->d_weights;
+            q.edges = d_edges;
+            q.S = c->S;
+            const int64_t span = 128 / K;
+            int64_t parts = (c->S + span * K - 1) / (span * K);
+            const int64_t lim = std::max<int64_t>(1, std::min<int64_t>(kPartialCap / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 16 / n)));
+            if (parts > lim) parts = lim;
+            q.n_parts = (int)parts;
+            q.partial_sums = c->d_partial_sums;
+            dim3 grid((unsigned)parts, (unsigned)n);
+            switch (K) {
+                case 1: dna_edge_sumtable_kernel<1><<<grid, 128, 0, c->stream>>>(q); break;
+                case 2: dna_edge_sumtable_kernel<2><<<grid, 128, 0, c->stream>>>(q); break;
+                case 4: dna_edge_sumtable_kernel<4><<<grid, 128, 0, c->stream>>>(q); break;
+                default: dna_edge_sumtable_kernel<8><<<grid, 128, 0, c->stream>>>(q); break;
+            }
+            c->launches++;
+            PHB_CUDA(c, cudaGetLastError());
+            n_parts = (int)parts;
         } else {
             DerivArgs p;
             for (int order = 0; order < 3; ++order) {
