@@ -85,3 +85,35 @@ def test_bad_arguments_are_value_errors():
         LikelihoodEngine(1, 10, 4, 4)
     with pytest.raises(ValueError):
         LikelihoodEngine(4, 10, 4, 100)
+
+
+def test_pack_codes_is_host_only_and_exact():
+    """phb_pack_codes needs no GPU: even pattern in the low nibble, odd length padded with a zero nibble."""
+    import numpy as np
+    from phylo_utils_b200 import LikelihoodEngine
+    rng = np.random.default_rng(0)
+    for ntax, nsite in [(1, 1), (3, 2), (4, 7), (5, 64), (2, 1001)]:
+        codes = rng.integers(0, 16, size=(ntax, nsite)).astype(np.uint8)
+        packed = LikelihoodEngine.pack_codes(codes)
+        assert packed.shape == (ntax, (nsite + 1) // 2) and packed.dtype == np.uint8
+        padded = np.concatenate([codes, np.zeros((ntax, nsite % 2), dtype=np.uint8)], axis=1)
+        assert np.array_equal(packed, padded[:, 0::2] | (padded[:, 1::2] << 4))
+        assert np.array_equal(packed & 15, padded[:, 0::2]) and np.array_equal(packed >> 4, padded[:, 1::2])
+    with pytest.raises(ValueError):
+        LikelihoodEngine.pack_codes(np.full((2, 4), 16, dtype=np.uint8))      # does not fit in four bits
+    with pytest.raises(ValueError):
+        LikelihoodEngine.pack_codes(np.zeros(5, dtype=np.uint8))              # not (n_tips, n_patterns)
+
+
+def test_compression_and_context_entry_points_fail_loudly_without_a_gpu():
+    """No CPU fallback anywhere: without a device the calls return PHB_ERR_NO_DEVICE (RuntimeError), they do not compute."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from phylo_utils_b200.alignment.alignment import compress_codes_gpu
+    with pytest.raises(RuntimeError):
+        compress_codes_gpu(np.zeros((3, 10), dtype=np.uint8))
+    from phylo_utils_b200 import LikelihoodEngine
+    with pytest.raises(RuntimeError):
+        LikelihoodEngine(4, 10, 4, 4)
