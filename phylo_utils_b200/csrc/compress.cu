@@ -18,7 +18,10 @@
 // All integer work, bit-exact by construction; HBM/L2-bound on the 4-byte permutation (8 bytes per site and
 // pass) plus one random byte gather per site and taxon.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "common.cuh"
 
@@ -320,6 +323,26 @@ __global__ void gather_patterns_kernel(const uint8_t* __restrict__ codes, int64_
     for (int t = blockIdx.y; t < n_tips; t += gridDim.y) out[(size_t)t * n_pat + g] = codes[(size_t)t * S + site];
 }
 
+// PHB_COMPRESS_TIMING=1: print the wall time of each phase of phb_compress_patterns to stderr (profiling aid)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t stream;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit PhaseTimer(cudaStream_t s) : on(getenv("PHB_COMPRESS_TIMING") != nullptr), stream(s), t0(now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(stream);
+        const double t = now();
+        fprintf(stderr, "[phb_compress_patterns] %-28s %9.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
+
 inline int grid_for(int64_t n, int threads) { return (int)std::min<int64_t>((n + threads - 1) / threads, 1 << 30); }
 
 }  // namespace
@@ -363,7 +386,10 @@ extern "C" int phb_compress_patterns(int device, const uint8_t* data, const uint
     CZ_CUDA(d_counts.alloc((size_t)256 * n_blocks * 4));
     CZ_CUDA(d_small.alloc(1024));
     cudaStream_t stream = nullptr;
+    PhaseTimer timer(stream);
+    timer.mark("allocations");
     CZ_CUDA(cudaMemcpyAsync(d_codes.p, data, n_bytes, cudaMemcpyHostToDevice, stream));
+    timer.mark("host -> device");
     unsigned long long* d_bad = d_small.as<unsigned long long>();
     unsigned* d_max = reinterpret_cast<unsigned*>(d_small.as<uint8_t>() + 8);
     int32_t* d_total = reinterpret_cast<int32_t*>(d_small.as<uint8_t>() + 16);
@@ -383,6 +409,7 @@ extern "C" int phb_compress_patterns(int device, const uint8_t* data, const uint
     CZ_CUDA(cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost, stream));
     CZ_CUDA(cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, stream));
     CZ_CUDA(cudaStreamSynchronize(stream));
+    timer.mark("byte table, validation");
     if (h_bad != ~0ull) {
         if (bad_index_out) *bad_index_out = (int64_t)h_bad;
         set_thread_error("phb_compress_patterns: a character is not in the byte table");
@@ -407,6 +434,7 @@ extern "C" int phb_compress_patterns(int device, const uint8_t* data, const uint
         std::swap(perm_in, perm_out);
     }
     CZ_CUDA(cudaGetLastError());
+    timer.mark("radix sort passes");
     // runs of equal columns
     CZ_CUDA(d_flag.alloc((size_t)S * 4));
     CZ_CUDA(d_id.alloc((size_t)S * 4));
@@ -423,6 +451,7 @@ extern "C" int phb_compress_patterns(int device, const uint8_t* data, const uint
     int32_t n_pat = 0;
     CZ_CUDA(cudaMemcpyAsync(&n_pat, d_total, 4, cudaMemcpyDeviceToHost, stream));
     CZ_CUDA(cudaStreamSynchronize(stream));
+    timer.mark("runs, ids, inverse index");
     CZ_CUDA(d_weights.alloc((size_t)n_pat * 8));
     CZ_CUDA(d_patterns.alloc((size_t)n_tips * n_pat));
     weights_kernel<<<grid_for(n_pat, 256), 256, 0, stream>>>(d_start.as<int32_t>(), n_pat, S, d_weights.as<int64_t>());
@@ -430,10 +459,12 @@ extern "C" int phb_compress_patterns(int device, const uint8_t* data, const uint
     gather_patterns_kernel<<<ggrid, 256, 0, stream>>>(codes, S, perm_in, d_start.as<int32_t>(), n_pat, n_tips,
                                                      d_patterns.as<uint8_t>());
     CZ_CUDA(cudaGetLastError());
+    timer.mark("weights, pattern gather");
     CZ_CUDA(cudaMemcpyAsync(patterns_out, d_patterns.p, (size_t)n_tips * n_pat, cudaMemcpyDeviceToHost, stream));
     CZ_CUDA(cudaMemcpyAsync(weights_out, d_weights.p, (size_t)n_pat * 8, cudaMemcpyDeviceToHost, stream));
     CZ_CUDA(cudaMemcpyAsync(inverse_out, d_inverse.p, (size_t)S * 8, cudaMemcpyDeviceToHost, stream));
     CZ_CUDA(cudaStreamSynchronize(stream));
+    timer.mark("device -> host");
     *n_patterns_out = n_pat;
     return PHB_OK;
 }
