@@ -211,15 +211,24 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                             if (i < A) mx[nt][q] = fmax(mx[nt][q], o);
                         }
                 __syncwarp();
-                for (int e = lane; e < WR * A; e += 32) {   // coalesced: A contiguous doubles per pattern
-                    const int n = e / A, i = e - n * A;
-                    const int64_t s = wsite0 + n;
-                    if (s < p.S) out[((size_t)s * K + k) * A + i] = myL[n * LDL + i];
+                {
+                    // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  The padding
+                    // columns need no attention: states >= A come out of zero rows of P (or of the tip table) as
+                    // exact zeros, columns >= MROWS are never written.
+                    constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
+                    const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
+                    unsigned char* g = reinterpret_cast<unsigned char*>(out + ((size_t)wsite0 * K + k) * A);
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(myL);
+                    for (int e = lane; e < n_valid * PIECES; e += 32) {
+                        const int n = e / PIECES, piece = e - n * PIECES;
+                        if (PB == 16)
+                            *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
+                                *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
+                        else
+                            *reinterpret_cast<double*>(g + (size_t)n * (K * A * 8) + piece * 8) =
+                                *reinterpret_cast<const double*>(src + n * (LDL * 8) + piece * 8);
+                    }
                 }
-                __syncwarp();
-                // the padding columns of these rows must read as zero again when they next hold a child row
-                if (LDL > A)
-                    for (int e = lane; e < WR * (LDL - A); e += 32) myL[(e / (LDL - A)) * LDL + A + e % (LDL - A)] = 0.0;
                 __syncwarp();
             }
             // per-pattern maximum over states (lanes sharing fc) and categories (already folded into mx)
