@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 cp_async_commit_all();
             };
 
-            double mx[NT][2];
+            int mx[NT][2];   // high word of the per-pattern maximum (partials are >= 0: the high word orders them)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) mx[nt][0] = mx[nt][1] = 0.0;
+            for (int nt = 0; nt < NT; ++nt) mx[nt][0] = mx[nt][1] = 0;
             double acc0[MT][NT][2], acc1[MT][NT][2];
             // DMMAs of one phase: acc = P[buf] . (this warp's child rows in buf)^T
             auto run_phase = [&](int ph, double (&acc)[MT][NT][2]) {
@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 double* myL = Lbuf + ((size_t)TS + (size_t)warp * WR) * LDL;   // child-1 rows (buffer 1) become the output rows
                 // both children of category k are done: multiply, find the maxima, write the block row out
                 __syncwarp();      // all lanes have read their child rows; they now become the output rows
+                // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q; states >= A are exact zeros
+                double* corner = myL + (2 * fc) * LDL + fr;
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -206,9 +208,8 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
                             const double o = acc0[mt][nt][q] * acc1[mt][nt][q];
-                            const int i = mt * 8 + fr, n = nt * 8 + 2 * fc + q;
-                            myL[n * LDL + i] = o;
-                            if (i < A) mx[nt][q] = fmax(mx[nt][q], o);
+                            corner[(nt * 8 + q) * LDL + mt * 8] = o;
+                            mx[nt][q] = max(mx[nt][q], __double2hiint(o));
                         }
                 __syncwarp();
                 {
@@ -236,10 +237,10 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    double m = mx[nt][q];
-                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                    m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                    int m = mx[nt][q];
+                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
                     mx[nt][q] = m;
                 }
             // lanes 0..3 (fr == 0) finalise the patterns 2*fc + q of every n-tile
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         int e = 0;
                         if (row.kind[0] != SRC_TIP) e += p.scale[(size_t)row.src[0] * S + s];
                         if (row.kind[1] != SRC_TIP) e += p.scale[(size_t)row.src[1] * S + s];
-                        const int hi = __double2hiint(mx[nt][q]);
+                        const int hi = mx[nt][q];
                         if (hi < kScaleThresholdHi && hi >= 0x00100000) {
                             const int shift = 1023 - (hi >> 20);
                             const double f = pow2i(shift);
