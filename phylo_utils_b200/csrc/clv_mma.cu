@@ -72,7 +72,7 @@ template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL>
 __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
-    constexpr int LDL = pad_pitch(KCOLS > MROWS ? KCOLS : MROWS);
+    constexpr int LDL = pad_pitch(KCOLS);             // child / output rows hold A <= KCOLS states
     constexpr int TS = WARPS * NT * 8, WR = NT * 8;   // patterns per CTA / per warp
     extern __shared__ double sm[];
     double* Pbuf = sm;                               // [2][MROWS][LDP]
@@ -199,10 +199,12 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 double* myL = Lbuf + ((size_t)TS + (size_t)warp * WR) * LDL;   // child-1 rows (buffer 1) become the output rows
                 // both children of category k are done: multiply, find the maxima, write the block row out
                 __syncwarp();      // all lanes have read their child rows; they now become the output rows
-                // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q; states >= A are exact zeros
+                // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q.  Padding states (>= A) are
+                // neither stored nor allowed into the maximum: a tip-table gather reads past its row for them.
                 double* corner = myL + (2 * fc) * LDL + fr;
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                for (int mt = 0; mt < MT; ++mt) {
+                    if (mt * 8 + 8 > A && mt * 8 + fr >= A) continue;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -211,11 +213,11 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                             corner[(nt * 8 + q) * LDL + mt * 8] = o;
                             mx[nt][q] = max(mx[nt][q], __double2hiint(o));
                         }
+                }
                 __syncwarp();
                 {
-                    // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  The padding
-                    // columns need no attention: states >= A come out of zero rows of P (or of the tip table) as
-                    // exact zeros, columns >= MROWS are never written.
+                    // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  Columns >= A of
+                    // the rows are never written (they stay zero for their next life as a child row).
                     constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
                     const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
                     unsigned char* g = reinterpret_cast<unsigned char*>(out + ((size_t)wsite0 * K + k) * A);
@@ -275,7 +277,7 @@ template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL>
 int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
-    constexpr int LDL = pad_pitch(KCOLS > MROWS ? KCOLS : MROWS);
+    constexpr int LDL = pad_pitch(KCOLS);
     constexpr int TS = WARPS * NT * 8;
     MmaArgs a;
     a.rows = d_rows;
