@@ -590,6 +590,7 @@ int phb_compute_partials(phb_ctx* c, int mode) {
             if (st == PHB_OK) {
                 c->have_partials = true;
                 c->have_up = false;
+                c->resident_partials = true;
                 return PHB_OK;
             }
             if (st != PHB_ERR_UNSUPPORTED) return st;
@@ -607,6 +608,7 @@ int phb_compute_partials(phb_ctx* c, int mode) {
         if (st) return st;
         c->have_partials = true;
         c->have_up = false;
+        c->resident_partials = true;
         return PHB_OK;
     }
     PHB_REQUIRE(c, mode != PHB_MODE_LEVEL || !c->level_offsets.empty(), PHB_ERR_STATE,
@@ -616,6 +618,7 @@ int phb_compute_partials(phb_ctx* c, int mode) {
     if (st) return st;
     c->have_partials = true;
     c->have_up = false;
+    c->resident_partials = false;
     return PHB_OK;
 }
 

@@ -133,6 +133,7 @@ struct Ctx {
     bool have_tips = false, have_model = false, have_mixture = false, have_schedule = false;
     bool have_lengths = false, have_pmats = false, have_partials = false, have_up = false;
     bool have_root = false;
+    bool resident_partials = false;    // the last post-order pass was the operand-resident walk (the pre-order pass follows suit)
     int root_a = -1, root_b = -1;
     double root_len = 0;
 
@@ -199,6 +200,8 @@ int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int 
 int dna_pair_lnl(Ctx* c, int root_a, int root_b);
 int dna_pair_store(Ctx* c);   // all partials stored; PHB_ERR_UNSUPPORTED (no message) when the shape is not covered
 int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b);
+// up_dna_pair.cu: pre-order pass as one operand-resident walk; PHB_ERR_UNSUPPORTED (no message) when not covered
+int dna_up_walk(Ctx* c, int node_a, int node_b);
 // clv_generic.cu (any A <= 64, any K <= 16)
 int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 // clv_mma.cu (A == 20 or 61, FP64 tensor cores)

@@ -626,6 +626,11 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     c->up_rows.clear();
     c->up_levels.clear();
     if (n_rows == 0) return PHB_OK;
+    // 4-state models whose post-order pass was the operand-resident walk: one pre-order walk (up_dna_pair.cu)
+    if (c->resident_partials && getenv("PHB_UP_TWO_ROWS") == nullptr) {
+        const int st = dna_up_walk(c, node_a, node_b);
+        if (st != PHB_ERR_UNSUPPORTED) return st;
+    }
     const int root_p = 2 * c->max_rows() + 1;  // P(root length), built by prepare_root
     std::vector<int> depth(c->n_nodes, 0), level_of;
     auto rank = [](int kind) { return kind == SRC_TIP ? 0 : 2; };

@@ -29,9 +29,11 @@ def setup_case(name, mode):
     return tm, tr, ot, up, model, rate, sw
 
 
-@pytest.mark.parametrize("mode", ["level", "tile"])
+@pytest.mark.parametrize("mode", ["level", "tile", "resident"])
 @pytest.mark.parametrize("name", ["cfg1_gtr_g4", "ambig_hky_ig", "prot12_lg_g4", "ladder120_k80_g4"])
 def test_all_edges_match_the_composed_oracle(name, mode):
+    if mode == "resident" and name in ("ambig_hky_ig", "prot12_lg_g4"):
+        pytest.skip("the operand-resident walks cover 4-state models with 1, 2, 4 or 8 categories")
     tm, tr, ot, up, model, rate, sw = setup_case(name, mode)
     nodes = [n for n in range(2 * len(tr.names) - 2) if n != tr.root_edge[1]]
     if len(nodes) > 40:
@@ -104,6 +106,44 @@ def test_up_partials_larger_tree_vs_oracle_total():
     out = tm.edge_derivatives(nodes)
     assert np.all(np.abs(out[:, 0] - base) <= 1e-10 * abs(base))          # every edge reproduces the same lnL
     assert np.all(np.isfinite(out))
+
+
+@pytest.mark.parametrize("tree_fn,n_taxa,n_pat", [(random_tree, 150, 20001), (caterpillar_tree, 200, 4099), (random_tree, 3, 70),
+                                                  (random_tree, 4, 33)])
+@pytest.mark.parametrize("ppt", ["1", "2"])
+def test_pre_order_walk_matches_the_two_row_form(tree_fn, n_taxa, n_pat, ppt, monkeypatch):
+    """up_dna_pair.cu against the two-rows-per-parent pass on the same device partials: every edge's
+    (lnL, dlnL, d2lnL) agrees to rounding, ragged last tile and deep scaling (caterpillar) included."""
+    rng = np.random.default_rng(n_taxa)
+    tr_tree = tree_fn(n_taxa, 7)
+    names = [l.taxon.label for l in tr_tree.leaf_node_iter()]
+    lut = np.vstack([np.eye(4)[::-1], np.ones((1, 4))])
+    codes = rng.integers(0, 5, size=(n_taxa, n_pat)).astype(np.uint8)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    weights = rng.integers(1, 5, size=n_pat)
+    out = {}
+    for label, env in (("walk", None), ("two_rows", "1")):
+        monkeypatch.setenv("PHB_UP_PPT", ppt)
+        if env:
+            monkeypatch.setenv("PHB_UP_TWO_ROWS", env)
+        else:
+            monkeypatch.delenv("PHB_UP_TWO_ROWS", raising=False)
+        tm = phy.TreeModel(mode="resident", up_partials=True)
+        tm.set_tree(tr_tree)
+        tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, siteweights=weights)
+        tm.set_rate_model(rate)
+        tm.set_substitution_model(model)
+        tm.initialise()
+        tm.compute_up_partials()
+        a, b = tm.traversal.root_edge
+        nodes = np.asarray([n for n in range(2 * n_taxa - 2) if n != b])
+        out[label] = (tm.edge_derivatives(nodes), tm.lnl())
+    walk, base = out["walk"]
+    two, _ = out["two_rows"]
+    assert np.all(np.isfinite(walk))
+    assert np.all(np.abs(walk[:, 0] - base) <= 1e-10 * abs(base))          # pulley principle on every edge
+    assert np.allclose(walk, two, rtol=1e-9, atol=1e-7)
 
 
 def test_derivatives_need_the_up_pass():
