@@ -24,7 +24,7 @@ constexpr double kLn2 = 0.693147180559945309417232121458;
 // level-order kernels treat it as SRC_GLOBAL.  The host canonicalises every row so that
 // rank(kind[0]) <= rank(kind[1]) with TIP < PREV < GLOBAL (children commute), which leaves five
 // row shapes: TT, TP, TG, PG, GG.
-enum : int32_t { SRC_GLOBAL = 0, SRC_TIP = 1, SRC_PREV = 2 };
+enum : int32_t { SRC_GLOBAL = 0, SRC_TIP = 1, SRC_PREV = 2, SRC_SUMTABLE = 3 };   // SRC_SUMTABLE: derivative edges only
 struct __align__(16) OpRow {
     int32_t dst;      // internal slot written by this row
     int32_t src[2];   // tip row or internal slot of each child
@@ -133,6 +133,7 @@ struct Ctx {
     bool have_tips = false, have_model = false, have_mixture = false, have_schedule = false;
     bool have_lengths = false, have_pmats = false, have_partials = false, have_up = false;
     bool have_root = false;
+    bool up_sumtable = false;          // the up blocks hold per-edge sum tables (up_dna_pair.cu), not up partials
     bool resident_partials = false;    // the last post-order pass was the operand-resident walk (the pre-order pass follows suit)
     int root_a = -1, root_b = -1;
     double root_len = 0;

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) dna_edge_deriv_kernel(const DerivArgs p) 
     __shared__ double s_lut[256][4];
     __shared__ double s_red[3][4];
     const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
+    if (p.edges[e].kind_a == SRC_SUMTABLE) return;   // dna_edge_st_kernel's edge (the whole CTA leaves)
     for (int i = tid; i < 256 * 4; i += 128) (&s_lut[0][0])[i] = p.lut[i];
     __syncthreads();
     double M[3][16];
@@ -519,6 +520,7 @@ __global__ void __launch_bounds__(128, 4) dna_edge_sumtable_kernel(const __grid_
     __shared__ double s_lut[256][4];
     __shared__ double s_red[3][4];
     const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
+    if (p.edges[e].kind_a == SRC_SUMTABLE) return;   // dna_edge_st_kernel's edge (the whole CTA leaves)
     for (int i = tid; i < 256 * 4; i += 128) (&s_lut[0][0])[i] = p.lut[i];
     __syncthreads();
     double cf[3][4];
@@ -609,6 +611,85 @@ __global__ void __launch_bounds__(128, 4) dna_edge_sumtable_kernel(const __grid_
     if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
 }
 
+// Edges whose up block holds the sum table s_km = (V^-1 a_k)_m (V^T (pi * b_k))_m left by the pre-order walk
+// (up_dna_pair.cu): f_k^(d) = sum_m coef[d][k][m] s_km - ONE block read per edge, twelve FMAs per (pattern, category).
+// lane = (pattern, category); 2K pattern groups per trip with all loads issued up front; lane k keeps the mixture
+// sums of rounds k and k + K, so that the tail (log, two divisions) runs with a distinct pattern in every lane.
+struct DnaStArgs {
+    const double* coef;     // [edge][3][K][4]
+    const double* clv;
+    const int32_t* scale;
+    const double* weights;
+    const int32_t* blocks;  // the launch's EdgeDesc array as ints: [4 e] = block of the edge's sum table, [4 e + 1] = kind
+    int64_t S;
+    int n_parts;
+    double* partial_sums;   // [n_edges * 3][n_parts]
+};
+
+template <int K>
+__global__ void __launch_bounds__(128, 4) dna_edge_st_kernel(const DnaStArgs p) {
+    constexpr int SPI = 128 / K, R = 2 * K;
+    __shared__ double s_red[3][4];
+    const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
+    double cf[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) cf[d][m] = p.coef[(((size_t)e * 3 + d) * K + k) * 4 + m];
+    if (p.blocks[4 * e + 1] != SRC_SUMTABLE) return;   // EdgeDesc {src_a, kind_a, ...}: the root edge goes the general way
+    const size_t S = (size_t)p.S, blk = (size_t)p.blocks[4 * e];
+    const double* const base = p.clv + blk * S * (K * 4);
+    const int32_t* const sc = p.scale + blk * S;
+    double tot[3] = {0.0, 0.0, 0.0};
+    const int64_t n_iter = (p.S + SPI - 1) / SPI;
+    for (int64_t it0 = (int64_t)blockIdx.x * R; it0 < n_iter; it0 += (int64_t)gridDim.x * R) {
+        double xy[R][4];
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const int64_t s = (it0 + u) * SPI + g;
+            ld256_nc(base + ((size_t)(s < p.S ? s : p.S - 1) * K + k) * 4, xy[u]);
+        }
+        double keep[2][3];
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                f[0] = fma(cf[0][m], xy[u][m], f[0]);
+                f[1] = fma(cf[1][m], xy[u][m], f[1]);
+                f[2] = fma(cf[2][m], xy[u][m], f[2]);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int o = K / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+            if (u % K == k) {
+                keep[u / K][0] = f[0];
+                keep[u / K][1] = f[1];
+                keep[u / K][2] = f[2];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int64_t s = (it0 + j * K + k) * SPI + g;
+            if (s < p.S) {
+                const double w = p.weights ? p.weights[s] : 1.0;
+                const double gq = keep[j][1] / keep[j][0];
+                tot[0] += w * (keep[j][0] > 0 ? log(keep[j][0]) + (double)sc[s] * kLn2 : -INFINITY);
+                tot[1] += w * gq;
+                tot[2] += w * (keep[j][2] / keep[j][0] - gq * gq);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double v = warp_sum(tot[d]);
+        if ((tid & 31) == 0) s_red[d][tid >> 5] = v;
+    }
+    __syncthreads();
+    if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
+}
+
 void fill_operand(const Ctx* c, int node, int* src, int* kind) {
     if (c->node_tip[node] >= 0) {
         *kind = SRC_TIP;
@@ -625,6 +706,7 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     const int n_rows = c->n_rows();
     c->up_rows.clear();
     c->up_levels.clear();
+    c->up_sumtable = false;
     if (n_rows == 0) return PHB_OK;
     // 4-state models whose post-order pass was the operand-resident walk: one pre-order walk (up_dna_pair.cu)
     if (c->resident_partials && getenv("PHB_UP_TWO_ROWS") == nullptr) {
@@ -721,6 +803,10 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
                 PHB_REQUIRE(c, c->node_parent[node] >= 0, PHB_ERR_INVALID, "edge derivatives: node has no edge above it");
                 edges[i].src_b = c->n_internal + node;
                 edges[i].kind_b = SRC_GLOBAL;
+                if (c->up_sumtable) {   // the edge's up block holds its sum table
+                    edges[i].src_a = c->n_internal + node;
+                    edges[i].kind_a = SRC_SUMTABLE;
+                }
             }
         }
         PHB_CUDA(c, cudaMemcpyAsync(d_len, lengths + start, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
@@ -755,7 +841,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             if (st) return st;
             n_parts = m.n_parts;
         } else if (dna_supported(c) && (int)c->h_evecs.size() == A * A && (int)c->h_freqs.size() == A &&
-                   getenv("PHB_DERIV_MATRIX_FORM") == nullptr) {
+                   (c->up_sumtable || getenv("PHB_DERIV_MATRIX_FORM") == nullptr)) {
             DnaSumArgs q;
             for (int m = 0; m < 4; ++m)
                 for (int i = 0; i < 4; ++i) {
@@ -791,6 +877,27 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             }
             c->launches++;
             PHB_CUDA(c, cudaGetLastError());
+            if (c->up_sumtable) {
+                // every edge but the root edge has its sum table in its up block: those CTAs of the launch above left
+                // at once (SRC_SUMTABLE), this launch does their work from one block read per edge
+                DnaStArgs t;
+                t.coef = d_coef;
+                t.clv = c->d_clv;
+                t.scale = c->d_scale;
+                t.weights = c->d_weights;
+                t.blocks = reinterpret_cast<const int32_t*>(d_edges);   // EdgeDesc::src_a, stride 4 ints
+                t.S = c->S;
+                t.n_parts = (int)parts;
+                t.partial_sums = c->d_partial_sums;
+                switch (K) {
+                    case 1: dna_edge_st_kernel<1><<<grid, 128, 0, c->stream>>>(t); break;
+                    case 2: dna_edge_st_kernel<2><<<grid, 128, 0, c->stream>>>(t); break;
+                    case 4: dna_edge_st_kernel<4><<<grid, 128, 0, c->stream>>>(t); break;
+                    default: dna_edge_st_kernel<8><<<grid, 128, 0, c->stream>>>(t); break;
+                }
+                c->launches++;
+                PHB_CUDA(c, cudaGetLastError());
+            }
             n_parts = (int)parts;
         } else {
             DerivArgs p;

@@ -23,6 +23,14 @@
 //
 // HBM traffic per parent: two block writes, one block read per internal child, one re-read per two-internal-children
 // parent - against two writes and up to four reads for the two-row form.
+//
+// Sum-table form (ST, the default).  What the edge-derivative kernels need from up[c] is only, per category k,
+//     s_km = (V^-1 down[c]_k)_m * (V^T (pi * up[c]_k))_m          f_k^(d)(t) = sum_m g_d(lambda_m r_k) e^(lambda_m r_k t) s_km
+// (derivs.cu).  At the parent's step both up[c] (registers) and down[c] (the operand tile) are on chip for BOTH
+// children, so the walk writes s - one block per edge, the size of a partial - into the up block instead of up[c], and
+// every Newton iteration reads ONE block per edge instead of two.  An up[other] that is needed again is parked in the
+// warp's private scratch stripe (clv_dna_pair.cu's layout: coalesced 128-bit stores straight from registers; at most
+// log2(internal nodes) deep because the lighter child goes first).
 #include <algorithm>
 #include <cstdlib>
 
@@ -32,18 +40,19 @@ namespace phb {
 
 namespace {
 
-constexpr int UP_X_PREV = 0, UP_X_TIP = 1, UP_LOAD = 2;
+constexpr int UP_X_PREV = 0, UP_X_TIP = 1, UP_LOAD = 2, UP_LOAD_SLOT = 3;
 
 // 32-byte step descriptor
 struct __align__(16) UpStep {
     uint32_t off_x;   // 16-byte units from UpArgs::opbase: P block of the branch above par, or its tip table (UP_X_TIP)
     uint32_t off_o;   // the other child's P block / tip table
     uint32_t off_k;   // the kept child's
-    int32_t src_x;    // tip row of X (UP_X_TIP) | block to load into the registers (UP_LOAD)
+    int32_t src_x;    // tip row of X (UP_X_TIP) | block (UP_LOAD) or scratch slot (UP_LOAD_SLOT) to load into the registers
     int32_t src_o;    // tip row | down block of the other child
     int32_t src_k;
     int32_t dst_o;    // block that receives up[other]
     uint32_t packed;  // block of up[kept] [0:24) | mode [24:26) | other child is a tip [26] | kept child is a tip [27]
+                      // | scratch slot up[other] is parked in [28:32), 15 = none (ST only)
 };
 static_assert(sizeof(UpStep) == 32, "UpStep must stay 32 bytes");
 
@@ -56,6 +65,12 @@ struct UpArgs {
     double* clv;       // shared block array: down blocks, then up blocks  [block][S][K][4]
     int32_t* scale;    // [block][S]
     int64_t S, n_tiles;
+    // sum-table form
+    double m1[16];     // V^-1, row-major
+    double m2[16];     // m2[m][i] = V[i][m] pi[i]
+    const double* lut; // [256][4]
+    unsigned char* scratch;
+    int n_slots;
 };
 
 template <int K, int NC, int PPT>
@@ -67,7 +82,13 @@ struct UpLayout {
     static constexpr int CODES_OFF = 3 * L::OPER_BYTES;
     static constexpr int DESC_BYTES = 4 * 32;
     static constexpr int OUT_BYTES = 32 * ROWB;                         // staging tile: 32 patterns at a time
-    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + 4 * TILE_BYTES + OUT_BYTES;
+    static constexpr int XTAB_BYTES = NC * 32;                          // ST: V^-1 . lut[code]
+    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + 4 * TILE_BYTES + OUT_BYTES + XTAB_BYTES;
+    // a parked block in the warp's scratch stripe (the private chunk layout of clv_dna_pair.cu)
+    static constexpr int CHUNKS = PPT * K * 2;
+    static constexpr int BLOCK_BYTES = CHUNKS * 512;
+    static constexpr int SLOT_BYTES = BLOCK_BYTES + 128 * PPT;
+    static_assert(SLOT_BYTES <= TILE_BYTES, "a parked block is fetched into an operand tile");
 };
 
 // y[p] <- P[k] . v[p]: the four rows of P[k] are warp-wide broadcast reads
@@ -107,12 +128,14 @@ __device__ __forceinline__ void rescale(double (&v)[PPT][K][4], const int (&mh)[
     }
 }
 
-// d[p] <- what a child contributes in category k: a row of its staged P.lut table (tip), or P[k] . (its down partial)
-template <int K, int NC, int PPT, bool TIP>
-__device__ __forceinline__ void child_term(const unsigned char* oper, const unsigned char* tile, const int (&trow)[PPT],
-                                           int lane, int k, double (&d)[PPT][4]) {
+// d[p] <- what a child contributes in category k: a row of its staged P.lut table (tip), or P[k] . (its down partial).
+// `tip` is warp-uniform: a branch instead of a template parameter keeps the step loop's code small (the eight-way
+// instantiation cost 10 % of the issue slots in instruction-cache misses: profiles/r01t_up_walk_cfg5.txt)
+template <int K, int NC, int PPT>
+__device__ __forceinline__ void child_term(bool tip, const unsigned char* oper, const unsigned char* tile,
+                                           const int (&trow)[PPT], int lane, int k, double (&d)[PPT][4]) {
     constexpr int ROWB = K * 32 + 16;
-    if (TIP) {
+    if (tip) {
 #pragma unroll
         for (int p = 0; p < PPT; ++p) lds32(oper + k * NC * 32 + trow[p], d[p]);
     } else {
@@ -124,31 +147,34 @@ __device__ __forceinline__ void child_term(const unsigned char* oper, const unsi
 }
 
 // prev <- up[kept], oth <- up[other]; on entry prev / pe hold X and its exponents (unless X is a tip)
-template <int K, int NC, int PPT, bool XTIP, bool OTIP, bool KTIP>
-__device__ __forceinline__ void up_update(const unsigned char* st, const unsigned char* tile_o, const unsigned char* tile_k,
-                                          int lane, double (&prev)[PPT][K][4], int (&pe)[PPT], double (&oth)[PPT][K][4],
-                                          int (&oe)[PPT]) {
+template <int K, int NC, int PPT>
+__device__ __forceinline__ void up_update(bool x_tip, bool o_tip, bool k_tip, const unsigned char* st,
+                                          const unsigned char* tile_o, const unsigned char* tile_k, int lane,
+                                          double (&prev)[PPT][K][4], int (&pe)[PPT], double (&oth)[PPT][K][4],
+                                          int (&oe)[PPT], int (&ed_o)[PPT], int (&ed_k)[PPT]) {
     using U = UpLayout<K, NC, PPT>;
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = U::ROWB;
     int rx[PPT], ro[PPT], rk[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) rx[p] = ro[p] = rk[p] = 0;
-    if (XTIP) table_rows<NC, PPT, false, LAYOUT_ARRAY>(st + U::CODES_OFF, lane, rx);
-    if (OTIP) table_rows<NC, PPT, false, LAYOUT_ARRAY>(st + U::CODES_OFF + L::TILE, lane, ro);
-    if (KTIP) table_rows<NC, PPT, false, LAYOUT_ARRAY>(st + U::CODES_OFF + 2 * L::TILE, lane, rk);
+    if (x_tip) table_rows<NC, PPT, false, LAYOUT_ARRAY>(st + U::CODES_OFF, lane, rx);
+    if (o_tip) table_rows<NC, PPT, false, LAYOUT_ARRAY>(st + U::CODES_OFF + L::TILE, lane, ro);
+    if (k_tip) table_rows<NC, PPT, false, LAYOUT_ARRAY>(st + U::CODES_OFF + 2 * L::TILE, lane, rk);
     int mo[PPT], mk[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
-        const int ex = XTIP ? 0 : pe[p];
-        oe[p] = ex + (KTIP ? 0 : *reinterpret_cast<const int*>(tile_k + (lane + 32 * p) * ROWB + K * 32));
-        pe[p] = ex + (OTIP ? 0 : *reinterpret_cast<const int*>(tile_o + (lane + 32 * p) * ROWB + K * 32));
+        const int ex = x_tip ? 0 : pe[p];
+        ed_k[p] = k_tip ? 0 : *reinterpret_cast<const int*>(tile_k + (lane + 32 * p) * ROWB + K * 32);
+        ed_o[p] = o_tip ? 0 : *reinterpret_cast<const int*>(tile_o + (lane + 32 * p) * ROWB + K * 32);
+        oe[p] = ex + ed_k[p];
+        pe[p] = ex + ed_o[p];
         mo[p] = mk[p] = 0;
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         double u[PPT][4], d[PPT][4];
-        if (XTIP) {
+        if (x_tip) {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) lds32(st + k * NC * 32 + rx[p], u[p]);
         } else {
@@ -159,7 +185,7 @@ __device__ __forceinline__ void up_update(const unsigned char* st, const unsigne
                 for (int i = 0; i < 4; ++i) x[p][i] = prev[p][k][i];
             matvec<PPT>(st + k * 128, x, u);
         }
-        child_term<K, NC, PPT, KTIP>(st + 2 * L::OPER_BYTES, tile_k, rk, lane, k, d);
+        child_term<K, NC, PPT>(k_tip, st + 2 * L::OPER_BYTES, tile_k, rk, lane, k, d);
 #pragma unroll
         for (int p = 0; p < PPT; ++p)
 #pragma unroll
@@ -168,7 +194,7 @@ __device__ __forceinline__ void up_update(const unsigned char* st, const unsigne
                 oth[p][k][i] = r;
                 mo[p] = max(mo[p], __double2hiint(r));   // partials are >= 0: the high word orders them
             }
-        child_term<K, NC, PPT, OTIP>(st + L::OPER_BYTES, tile_o, ro, lane, k, d);
+        child_term<K, NC, PPT>(o_tip, st + L::OPER_BYTES, tile_o, ro, lane, k, d);
 #pragma unroll
         for (int p = 0; p < PPT; ++p)
 #pragma unroll
@@ -182,8 +208,8 @@ __device__ __forceinline__ void up_update(const unsigned char* st, const unsigne
     rescale<K, PPT>(prev, mk, pe);
 }
 
-template <int K, int NC, int PPT>
-__global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpArgs p) {
+template <int K, int NC, int PPT, bool ST>
+__global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __grid_constant__ UpArgs p) {
     using U = UpLayout<K, NC, PPT>;
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = U::ROWB;
@@ -195,9 +221,23 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpAr
     unsigned char* const s_stage = smem + U::DESC_BYTES;
     unsigned char* const s_tiles = s_stage + 2 * U::STAGE_BYTES;   // [buffer][o | k]
     unsigned char* const s_out = s_tiles + 4 * U::TILE_BYTES;
+    unsigned char* const s_xtab = s_out + U::OUT_BYTES;
     const int wstride = gridDim.x, n_steps = p.n_steps;
     const int n_tiles = (int)p.n_tiles;
     const size_t S = (size_t)p.S;
+    unsigned char* const my_scratch = ST ? p.scratch + (size_t)blockIdx.x * p.n_slots * U::SLOT_BYTES : nullptr;
+    if (ST) {   // what a tip contributes to the first factor of a sum table: V^-1 . lut[code]
+        if (lane < NC) {
+            double v[4], x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = p.lut[lane * 4 + i];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) x[m] = fma(p.m1[4 * m + 3], v[3], fma(p.m1[4 * m + 2], v[2], fma(p.m1[4 * m + 1], v[1], p.m1[4 * m] * v[0])));
+            *reinterpret_cast<double2*>(s_xtab + lane * 32) = make_double2(x[0], x[1]);
+            *reinterpret_cast<double2*>(s_xtab + lane * 32 + 16) = make_double2(x[2], x[3]);
+        }
+        __syncwarp();
+    }
 
     // block `blk` of tile t -> a pattern-major operand tile (exponents into the row padding)
     auto fetch_block = [&](int blk, int t, unsigned char* dst) {
@@ -225,6 +265,15 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpAr
         const int mode = (d.packed >> 24) & 3;
         if (mode == UP_LOAD) {
             fetch_block(d.src_x, t, tl);
+            return;
+        }
+        if (mode == UP_LOAD_SLOT) {   // the lane's own chunks of a parked block, in the layout it wrote them
+            const unsigned char* src = my_scratch + (size_t)d.src_x * U::SLOT_BYTES;
+#pragma unroll
+            for (int j = 0; j < U::CHUNKS; ++j) cp_async16(tl + j * 512 + lane * 16, src + j * 512 + lane * 16);
+            if (PPT == 2) cp_async8(tl + U::BLOCK_BYTES + lane * 8, src + U::BLOCK_BYTES + lane * 8);
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(tl + U::BLOCK_BYTES + lane * 4)),
+                              "l"(src + U::BLOCK_BYTES + lane * 4) : "memory");
             return;
         }
         const bool x_tip = mode == UP_X_TIP, o_tip = (d.packed >> 26) & 1, k_tip = (d.packed >> 27) & 1;
@@ -278,6 +327,44 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpAr
             if (lane + 32 * h < valid) p.scale[(size_t)blk * S + site0 + lane + 32 * h] = e[h];
     };
 
+    // v <- (V^-1 down[c]) * (V^T (pi * v)) per category, v = up[c]: the edge's sum table (derivs.cu)
+    auto sum_table = [&](double (&v)[PPT][K][4], bool tip, const unsigned char* tl, const unsigned char* codes) {
+#pragma unroll
+        for (int h = 0; h < PPT; ++h) {
+            double xt[4] = {0.0, 0.0, 0.0, 0.0};
+            if (tip) lds32(s_xtab + (int)(codes[lane + 32 * h] & (NC - 1)) * 32, xt);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double a[4] = {0.0, 0.0, 0.0, 0.0};
+                if (!tip) lds32(tl + (lane + 32 * h) * ROWB + k * 32, a);
+                double r[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    double x = fma(p.m1[4 * m + 3], a[3], fma(p.m1[4 * m + 2], a[2], fma(p.m1[4 * m + 1], a[1], p.m1[4 * m] * a[0])));
+                    if (tip) x = xt[m];
+                    const double y = fma(p.m2[4 * m + 3], v[h][k][3], fma(p.m2[4 * m + 2], v[h][k][2], fma(p.m2[4 * m + 1], v[h][k][1], p.m2[4 * m] * v[h][k][0])));
+                    r[m] = x * y;
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) v[h][k][m] = r[m];
+            }
+        }
+    };
+    // park: coalesced 128-bit stores straight from registers into the warp's own stripe
+    auto park_block = [&](const double (&v)[PPT][K][4], const int (&e)[PPT], int slot) {
+        unsigned char* dst = my_scratch + (size_t)slot * U::SLOT_BYTES + lane * 16;
+#pragma unroll
+        for (int h = 0; h < PPT; ++h)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                *reinterpret_cast<double2*>(dst + ((h * K + k) * 2) * 512) = make_double2(v[h][k][0], v[h][k][1]);
+                *reinterpret_cast<double2*>(dst + ((h * K + k) * 2 + 1) * 512) = make_double2(v[h][k][2], v[h][k][3]);
+            }
+        int* ex = reinterpret_cast<int*>(my_scratch + (size_t)slot * U::SLOT_BYTES + U::BLOCK_BYTES + lane * (4 * PPT));
+#pragma unroll
+        for (int h = 0; h < PPT; ++h) ex[h] = e[h];
+    };
+
     int tile = blockIdx.x;
     if (tile >= n_tiles) return;
     // prologue: descriptors of steps 0 and 1 (two 16-byte halves each), then the inputs of step 0
@@ -293,10 +380,10 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpAr
     cp_async_commit();
 
     double prev[PPT][K][4], oth[PPT][K][4];
-    int pe[PPT], oe[PPT];
+    int pe[PPT], oe[PPT], ed_o[PPT], ed_k[PPT];
 #pragma unroll
     for (int q = 0; q < PPT; ++q) {
-        pe[q] = oe[q] = 0;
+        pe[q] = oe[q] = ed_o[q] = ed_k[q] = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -335,21 +422,44 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpAr
                 for (int k = 0; k < K; ++k) lds32(r + k * 32, prev[h][k]);
                 pe[h] = *reinterpret_cast<const int*>(r + K * 32);
             }
+        } else if (mode == UP_LOAD_SLOT) {
+            // ... or from the warp's scratch stripe
+#pragma unroll
+            for (int h = 0; h < PPT; ++h) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const unsigned char* src = tile_o + ((h * K + k) * 2) * 512 + lane * 16;
+                    const double2 lo = *reinterpret_cast<const double2*>(src);
+                    const double2 hi = *reinterpret_cast<const double2*>(src + 512);
+                    prev[h][k][0] = lo.x; prev[h][k][1] = lo.y; prev[h][k][2] = hi.x; prev[h][k][3] = hi.y;
+                }
+                pe[h] = *reinterpret_cast<const int*>(tile_o + U::BLOCK_BYTES + lane * (4 * PPT) + 4 * h);
+            }
         } else {
             const int shape = (pk >> 26) & 3;   // other is a tip | kept is a tip << 1
-            if (mode == UP_X_TIP) {
-                if (shape == 0) up_update<K, NC, PPT, true, false, false>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
-                else if (shape == 1) up_update<K, NC, PPT, true, true, false>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
-                else if (shape == 2) up_update<K, NC, PPT, true, false, true>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
-                else up_update<K, NC, PPT, true, true, true>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
+            up_update<K, NC, PPT>(mode == UP_X_TIP, (shape & 1) != 0, (shape & 2) != 0, st, tile_o, tile_k, lane, prev, pe, oth, oe,
+                                  ed_o, ed_k);
+            if (!ST) {
+                store_block(oth, oe, dst_o, tile);
+                store_block(prev, pe, (int)(pk & 0xffffff), tile);
             } else {
-                if (shape == 0) up_update<K, NC, PPT, false, false, false>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
-                else if (shape == 1) up_update<K, NC, PPT, false, true, false>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
-                else if (shape == 2) up_update<K, NC, PPT, false, false, true>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
-                else up_update<K, NC, PPT, false, true, true>(st, tile_o, tile_k, lane, prev, pe, oth, oe);
+                const int park = pk >> 28;
+                if (park != 15) park_block(oth, oe, park);
+                sum_table(oth, (shape & 1) != 0, tile_o, st + U::CODES_OFF + L::TILE);
+#pragma unroll
+                for (int h = 0; h < PPT; ++h) oe[h] += ed_o[h];
+                store_block(oth, oe, dst_o, tile);
+#pragma unroll
+                for (int h = 0; h < PPT; ++h) {
+                    oe[h] = pe[h] + ed_k[h];
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) oth[h][k][i] = prev[h][k][i];
+                }
+                sum_table(oth, (shape & 2) != 0, tile_k, st + U::CODES_OFF + 2 * L::TILE);
+                store_block(oth, oe, (int)(pk & 0xffffff), tile);
             }
-            store_block(oth, oe, dst_o, tile);
-            store_block(prev, pe, (int)(pk & 0xffffff), tile);
         }
         if (!has_next) break;
         step = step_n;
@@ -360,11 +470,11 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const UpAr
     cp_async_wait_all();
 }
 
-template <int K, int NC, int PPT>
-int launch_up(Ctx* c, int n_steps) {
+template <int K, int NC, int PPT, bool ST>
+int launch_up(Ctx* c, int n_steps, int n_slots) {
     using U = UpLayout<K, NC, PPT>;
     using L = PairLayout<K, NC, PPT>;
-    UpArgs a;
+    UpArgs a{};
     a.steps = reinterpret_cast<const UpStep*>(c->d_up_rows);
     a.n_steps = n_steps;
     a.opbase = reinterpret_cast<const unsigned char*>(c->d_pmats);
@@ -374,7 +484,17 @@ int launch_up(Ctx* c, int n_steps) {
     a.scale = c->d_scale;
     a.S = c->S;
     a.n_tiles = (c->S + L::TILE - 1) / L::TILE;
-    auto kern = dna_up_kernel<K, NC, PPT>;
+    a.lut = c->d_lut;
+    a.scratch = c->d_scratch;
+    a.n_slots = n_slots;
+    if (ST) {
+        for (int m = 0; m < 4; ++m)
+            for (int i = 0; i < 4; ++i) {
+                a.m1[4 * m + i] = c->h_ivecs[4 * m + i];
+                a.m2[4 * m + i] = c->h_evecs[4 * i + m] * c->h_freqs[i];
+            }
+    }
+    auto kern = dna_up_kernel<K, NC, PPT, ST>;
     const size_t smem = U::WARP_BYTES;
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "up kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -382,11 +502,17 @@ int launch_up(Ctx* c, int n_steps) {
     int per_sm = 0;
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
     if (per_sm < 1) per_sm = 1;
-    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(a.n_tiles, (int64_t)c->sm_count * per_sm));
+    int64_t grid = std::max<int64_t>(1, std::min<int64_t>(a.n_tiles, (int64_t)c->sm_count * per_sm));
+    if (ST) {   // every resident warp needs its own scratch stripe
+        const int64_t cap = (int64_t)(c->scratch_bytes / ((size_t)n_slots * U::SLOT_BYTES));
+        if (c->d_scratch == nullptr || cap < 1) return c->fail(PHB_ERR_NOMEM, "up kernel: scratch area too small");
+        grid = std::min(grid, cap);
+    }
     kern<<<(int)grid, 32, smem, c->stream>>>(a);
     c->launches++;
     PHB_CUDA(c, cudaGetLastError());
     c->resident_warps = per_sm;
+    c->resident_slots = n_slots;
     return PHB_OK;
 }
 
@@ -410,17 +536,22 @@ int dna_up_walk(Ctx* c, int node_a, int node_b) {
     std::vector<int> weight(c->n_nodes, 0);
     for (int r = 0; r < n_rows; ++r)
         weight[c->rows_raw[3 * r]] = 1 + weight[c->rows_raw[3 * r + 1]] + weight[c->rows_raw[3 * r + 2]];
+    // sum-table form needs the host copy of the eigen-system and the scratch area; PHB_UP_PLAIN keeps plain up partials
+    const bool st_form = getenv("PHB_UP_PLAIN") == nullptr && c->d_scratch != nullptr && (int)c->h_evecs.size() == 16 &&
+                         (int)c->h_ivecs.size() == 16 && (int)c->h_freqs.size() == 4;
     std::vector<UpStep> steps;
     steps.reserve(2 * (size_t)n_rows);
     struct Pending {
         int par;
         bool x_in_regs;
+        int slot;   // scratch slot X is parked in (sum-table form), -1: X comes from the block array
     };
     std::vector<Pending> stack;
+    int depth = 0, n_slots = 1;
     // the two ends of the root edge, each seeing the other end's down partial through P(root length)
     for (int pass = 1; pass >= 0; --pass) {
         const int par = pass == 0 ? node_a : node_b;
-        if (!is_tip(par)) stack.push_back({par, false});
+        if (!is_tip(par)) stack.push_back({par, false, -1});
     }
     while (!stack.empty()) {
         const Pending cur = stack.back();
@@ -447,8 +578,14 @@ int dna_up_walk(Ctx* c, int node_a, int node_b) {
         }
         if (mode == UP_X_PREV && !cur.x_in_regs) {
             UpStep ld{};
-            ld.src_x = at_root ? c->node_slot[above] : c->n_internal + par;
-            ld.packed = (uint32_t)UP_LOAD << 24;
+            if (cur.slot >= 0) {
+                ld.src_x = cur.slot;
+                ld.packed = (uint32_t)UP_LOAD_SLOT << 24;
+                depth = cur.slot;   // LIFO: everything parked after it has been consumed
+            } else {
+                ld.src_x = at_root ? c->node_slot[above] : c->n_internal + par;
+                ld.packed = (uint32_t)UP_LOAD << 24;
+            }
             steps.push_back(ld);
         }
         const int ch[2] = {c->rows_raw[3 * r + 1], c->rows_raw[3 * r + 2]};
@@ -466,21 +603,32 @@ int dna_up_walk(Ctx* c, int node_a, int node_b) {
         s.dst_o = c->n_internal + other;
         const int dst_k = c->n_internal + kept;
         if (dst_k >= (1 << 24)) return c->fail(PHB_ERR_UNSUPPORTED, "up kernel: too many nodes");
-        s.packed = (uint32_t)dst_k | ((uint32_t)mode << 24) | ((uint32_t)is_tip(other) << 26) | ((uint32_t)is_tip(kept) << 27);
+        int park = 15;
+        if (st_form && !is_tip(other)) {
+            park = depth++;
+            n_slots = std::max(n_slots, depth);
+            if (park >= 15) return PHB_ERR_UNSUPPORTED;   // deeper than 2^15 internal nodes allow; the two-row form takes over
+        }
+        s.packed = (uint32_t)dst_k | ((uint32_t)mode << 24) | ((uint32_t)is_tip(other) << 26) | ((uint32_t)is_tip(kept) << 27) |
+                   ((uint32_t)park << 28);
         steps.push_back(s);
         // LIFO: the kept child is popped first and finds its X in the registers
-        if (!is_tip(other)) stack.push_back({other, false});
-        if (!is_tip(kept)) stack.push_back({kept, true});
+        if (!is_tip(other)) stack.push_back({other, false, st_form ? park : -1});
+        if (!is_tip(kept)) stack.push_back({kept, true, -1});
     }
     if (steps.size() > 2 * (size_t)c->max_rows()) return c->fail(PHB_ERR_STATE, "up kernel: step table overflow");
     PHB_CUDA(c, cudaMemcpyAsync(c->d_up_rows, steps.data(), steps.size() * sizeof(UpStep), cudaMemcpyHostToDevice, c->stream));
     PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `steps` is a stack object
     const int n_steps = (int)steps.size();
+    // one pattern per lane: smaller tiles, 6-7 warps per SM instead of 4 (measured faster at every size tried;
+    // PHB_UP_PPT=2 selects two patterns per lane)
     const char* env = getenv("PHB_UP_PPT");
-    const int ppt = env != nullptr && atoi(env) == 1 ? 1 : 2;
+    const int ppt = K == 4 && !(env != nullptr && atoi(env) == 2) ? 1 : 2;
+    c->up_sumtable = st_form;
     switch (K * 1000 + tip_table_rows(c) * 10 + ppt) {
 #define PHB_UP_CASE(K_, NC_, PPT_) \
-    case K_ * 1000 + NC_ * 10 + PPT_: return launch_up<K_, NC_, PPT_>(c, n_steps);
+    case K_ * 1000 + NC_ * 10 + PPT_: \
+        return st_form ? launch_up<K_, NC_, PPT_, true>(c, n_steps, n_slots) : launch_up<K_, NC_, PPT_, false>(c, n_steps, n_slots);
         PHB_UP_CASE(1, 8, 2)
         PHB_UP_CASE(1, 16, 2)
         PHB_UP_CASE(2, 8, 2)

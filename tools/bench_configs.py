@@ -121,5 +121,17 @@ def main():
         report("cfg5 GTR+G4 2000x62.5k (1/8 shard)", tm, 2000, 62500, 4, reps, derivs=True)
 
 
+def custom():
+    """--shape N,S: a 4-state GTR+G4 problem of that size with the derivative passes (tuning aid)."""
+    n, s = (int(v) for v in sys.argv[sys.argv.index("--shape") + 1].split(","))
+    reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    tm = build(n, s, 4, model, 5, up=True)
+    report("custom GTR+G4 {}x{}".format(n, s), tm, n, s, 4, reps, derivs=True)
+
+
 if __name__ == "__main__":
+    if "--shape" in sys.argv:
+        custom()
+        sys.exit(0)
     main()
