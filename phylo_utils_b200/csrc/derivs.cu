@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(128) dna_edge_deriv_kernel(const DerivArgs p) 
     __shared__ double s_lut[256][4];
     __shared__ double s_red[3][4];
     const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
-    if (p.edges[e].kind_a == SRC_SUMTABLE) return;   // dna_edge_st_kernel's edge (the whole CTA leaves)
     for (int i = tid; i < 256 * 4; i += 128) (&s_lut[0][0])[i] = p.lut[i];
     __syncthreads();
     double M[3][16];
@@ -512,6 +511,8 @@ struct DnaSumArgs {
     int64_t S;
     int n_parts;
     double* partial_sums;   // [n_edges * 3][n_parts]
+    int n_list;             // > 0: grid.y walks list[] (the few edges of a sum-table pass that have no table: the root edge)
+    int list[4];
 };
 
 template <int K>
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(128, 4) dna_edge_sumtable_kernel(const __grid_
     constexpr int SPI = 128 / K;
     __shared__ double s_lut[256][4];
     __shared__ double s_red[3][4];
-    const int tid = threadIdx.x, g = tid / K, k = tid % K, e = blockIdx.y;
+    const int tid = threadIdx.x, g = tid / K, k = tid % K, e = p.n_list > 0 ? p.list[blockIdx.y] : blockIdx.y;
     if (p.edges[e].kind_a == SRC_SUMTABLE) return;   // dna_edge_st_kernel's edge (the whole CTA leaves)
     for (int i = tid; i < 256 * 4; i += 128) (&s_lut[0][0])[i] = p.lut[i];
     __syncthreads();
@@ -608,7 +609,8 @@ __global__ void __launch_bounds__(128, 4) dna_edge_sumtable_kernel(const __grid_
         if ((tid & 31) == 0) s_red[d][tid >> 5] = v;
     }
     __syncthreads();
-    if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
+    const size_t orow = p.n_list > 0 ? blockIdx.y : e;   // listed edges have their own block sums, indexed by list position
+    if (tid < 3) p.partial_sums[(orow * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
 }
 
 // Edges whose up block holds the sum table s_km = (V^-1 a_k)_m (V^T (pi * b_k))_m left by the pre-order walk
@@ -814,6 +816,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
         PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `edges` is reused by the next batch
         const EdgeDesc* d_edges = static_cast<const EdgeDesc*>(c->d_edges);
         int n_parts = 0;
+        int n_list_done = 0, list_done[4] = {0, 0, 0, 0}, list_parts_done = 0;   // edges reduced from their own block sums
         if (use_mma) {
             // sum-table form on the FP64 tensor cores; the matrix scratch area holds the coefficients and V^T diag(pi)
             MmaDerivArgs m;
@@ -862,22 +865,41 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             q.weights = c->d_weights;
             q.edges = d_edges;
             q.S = c->S;
+            // edges of a sum-table pass without a table (the root edge): up to four go out as a list, with their own
+            // (much finer) split of the pattern axis and their own block sums at the end of the buffer
+            constexpr int kListParts = 512, kListArea = 4 * 3 * kListParts;
+            q.n_list = 0;
+            int n_plain = 0;
+            for (int i = 0; i < n; ++i)
+                if (edges[i].kind_a != SRC_SUMTABLE) {
+                    if (n_plain < 4) q.list[n_plain] = i;
+                    ++n_plain;
+                }
+            if (c->up_sumtable && n_plain <= 4) q.n_list = n_plain;
             const int64_t span = 128 / K;
             int64_t parts = (c->S + span * K - 1) / (span * K);
-            const int64_t lim = std::max<int64_t>(1, std::min<int64_t>(kPartialCap / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 16 / n)));
+            const int64_t lim = std::max<int64_t>(1, std::min<int64_t>((kPartialCap - kListArea) / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 16 / n)));
+            const int list_parts = (int)std::min<int64_t>(kListParts, parts);
             if (parts > lim) parts = lim;
-            q.n_parts = (int)parts;
-            q.partial_sums = c->d_partial_sums;
+            double* const list_sums = c->d_partial_sums + (kPartialCap - kListArea);
+            q.n_parts = q.n_list > 0 ? list_parts : (int)parts;
+            q.partial_sums = q.n_list > 0 ? list_sums : c->d_partial_sums;
             dim3 grid((unsigned)parts, (unsigned)n);
-            switch (K) {
-                case 1: dna_edge_sumtable_kernel<1><<<grid, 128, 0, c->stream>>>(q); break;
-                case 2: dna_edge_sumtable_kernel<2><<<grid, 128, 0, c->stream>>>(q); break;
-                case 4: dna_edge_sumtable_kernel<4><<<grid, 128, 0, c->stream>>>(q); break;
-                default: dna_edge_sumtable_kernel<8><<<grid, 128, 0, c->stream>>>(q); break;
+            const dim3 grid_plain((unsigned)q.n_parts, (unsigned)(q.n_list > 0 ? q.n_list : n));
+            if (n_plain > 0) {
+                switch (K) {
+                    case 1: dna_edge_sumtable_kernel<1><<<grid_plain, 128, 0, c->stream>>>(q); break;
+                    case 2: dna_edge_sumtable_kernel<2><<<grid_plain, 128, 0, c->stream>>>(q); break;
+                    case 4: dna_edge_sumtable_kernel<4><<<grid_plain, 128, 0, c->stream>>>(q); break;
+                    default: dna_edge_sumtable_kernel<8><<<grid_plain, 128, 0, c->stream>>>(q); break;
+                }
+                c->launches++;
+                PHB_CUDA(c, cudaGetLastError());
             }
-            c->launches++;
-            PHB_CUDA(c, cudaGetLastError());
-            if (c->up_sumtable) {
+            n_list_done = q.n_list;
+            for (int j = 0; j < q.n_list; ++j) list_done[j] = q.list[j];
+            list_parts_done = list_parts;
+            if (c->up_sumtable && n_plain < n) {
                 // every edge but the root edge has its sum table in its up block: those CTAs of the launch above left
                 // at once (SRC_SUMTABLE), this launch does their work from one block read per edge
                 DnaStArgs t;
@@ -946,6 +968,11 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
         }
         int st = launch_final_reduce(c, c->d_partial_sums, n_parts, 3 * n, c->d_result);
         if (st) return st;
+        for (int j = 0; j < n_list_done; ++j) {   // overwrites what the launch above left in the listed edges' slots
+            st = launch_final_reduce(c, c->d_partial_sums + (kPartialCap - 4 * 3 * 512) + (size_t)j * 3 * list_parts_done,
+                                     list_parts_done, 3, c->d_result + 3 * (size_t)list_done[j]);
+            if (st) return st;
+        }
         PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, c->d_result, (size_t)3 * n * 8, cudaMemcpyDeviceToHost,
                                     c->stream));
         PHB_CUDA(c, cudaStreamSynchronize(c->stream));

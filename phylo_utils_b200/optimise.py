@@ -27,28 +27,15 @@ def edge_nodes(traversal):
     return np.asarray([n for n in range(n_nodes) if n != b], dtype=np.int32)
 
 
-def _edge_key(tm, node):
-    a, b = tm.traversal.root_edge
-    if node == a or node == b:
-        return tm.traversal.brlens.canonical_key((a, b))
-    return tm.traversal.brlens.canonical_key((int(node), int(tm._parent_of[int(node)])))
+def _get_lengths(br, keys):
+    get = dict.__getitem__
+    return np.fromiter((get(br, k) for k in keys), dtype=np.double, count=len(keys))
 
 
-def _parents(tm):
-    par = {}
-    for p, c1, c2 in tm.traversal.postorder_traversal:
-        par[int(c1)] = int(p)
-        par[int(c2)] = int(p)
-    return par
-
-
-def _get_lengths(tm, nodes):
-    return np.asarray([tm.traversal.brlens[_edge_key(tm, n)] for n in nodes], dtype=np.double)
-
-
-def _set_lengths(tm, nodes, lengths):
-    for n, t in zip(nodes, lengths):
-        tm.traversal.brlens[_edge_key(tm, n)] = float(t)
+def _set_lengths(br, keys, lengths):
+    put = dict.__setitem__
+    for k, t in zip(keys, np.asarray(lengths, dtype=np.double).tolist()):
+        put(br, k, t)
 
 
 def newton_step(t, d1, d2, lo=MIN_BRANCH_LENGTH, hi=MAX_BRANCH_LENGTH):
@@ -68,9 +55,10 @@ def optimise_branch_lengths(tm, max_sweeps=20, inner_iterations=3, tol=1e-4, ver
     ``up_partials=True`` and initialised).  Returns a dict with the lnL trace.
     """
     local = getattr(tm, "local", tm)
-    local._parent_of = _parents(local)
     nodes = edge_nodes(tm.traversal)
-    lengths = _get_lengths(local, nodes)
+    br = local.traversal.brlens
+    keys = local.edge_keys(nodes)        # dictionary keys resolved once: the sweeps run next to millisecond kernels
+    lengths = _get_lengths(br, keys)
     lnl = tm.lnl()
     trace = [lnl]
     derivative_launches = 0
@@ -84,7 +72,7 @@ def optimise_branch_lengths(tm, max_sweeps=20, inner_iterations=3, tol=1e-4, ver
         step = trial - lengths
         alpha, accepted = 1.0, False
         while alpha > 1e-3:
-            _set_lengths(local, nodes, lengths + alpha * step)
+            _set_lengths(br, keys, lengths + alpha * step)
             tm.compute_partials()
             new_lnl = tm.lnl()
             if new_lnl >= lnl:
@@ -92,7 +80,7 @@ def optimise_branch_lengths(tm, max_sweeps=20, inner_iterations=3, tol=1e-4, ver
                 break
             alpha *= 0.5
         if not accepted:
-            _set_lengths(local, nodes, lengths)
+            _set_lengths(br, keys, lengths)
             tm.compute_partials()
             break
         gain = new_lnl - lnl

@@ -231,12 +231,18 @@ class TreeModel(object):
             self.engine.set_mixture(m.freqs, r.rates, r.weights)
 
     def _row_lengths(self):
+        """(n_rows, 2) branch lengths in schedule order.  The dictionary keys of the rows' edges are resolved once
+        per schedule: this runs on every evaluation, next to kernels that take a few milliseconds."""
         br = self.traversal.brlens
-        out = np.empty((len(self._rows), 2))
-        for i, (par, c1, c2) in enumerate(self._rows):
-            out[i, 0] = br[(int(par), int(c1))]
-            out[i, 1] = br[(int(par), int(c2))]
-        return out
+        cache = getattr(self, "_row_keys", None)
+        if cache is None or cache[0] is not self._rows or cache[1] is not br:
+            keys = []
+            for par, c1, c2 in self._rows:
+                keys.append(br.canonical_key((int(par), int(c1))))
+                keys.append(br.canonical_key((int(par), int(c2))))
+            cache = self._row_keys = (self._rows, br, keys)
+        get = dict.__getitem__
+        return np.fromiter((get(br, k) for k in cache[2]), dtype=np.double, count=len(cache[2])).reshape(-1, 2)
 
     # ------------------------------------------------------------------------------------------
     # the hot path
@@ -348,14 +354,32 @@ class TreeModel(object):
         """
         nodes = np.asarray(nodes, dtype=np.int32)
         if lengths is None:
-            lengths = np.asarray([self.branch_length_above(int(n)) for n in nodes])
+            lengths = self.lengths_above(nodes)
         return self.engine.edge_derivatives(nodes, lengths, chain_rule)
 
-    def branch_length_above(self, node):
-        """Length of the edge above ``node`` (the root edge for either root child)."""
+    def edge_keys(self, nodes):
+        """``brlens`` key of the edge above each node (the root edge for either root child)."""
         a, b = self.traversal.root_edge
-        if node == a or node == b:
-            return self.traversal.brlens[(a, b)]
+        br = self.traversal.brlens
+        parents = self._parents()
+        keys = []
+        for n in nodes:
+            n = int(n)
+            if n == a or n == b:
+                keys.append(br.canonical_key((a, b)))
+            elif n in parents:
+                keys.append(br.canonical_key((n, parents[n])))
+            else:
+                raise ValueError("node {} has no edge above it".format(n))
+        return keys
+
+    def lengths_above(self, nodes):
+        br = self.traversal.brlens
+        get = dict.__getitem__
+        keys = self.edge_keys(nodes)
+        return np.fromiter((get(br, k) for k in keys), dtype=np.double, count=len(keys))
+
+    def _parents(self):
         parents = getattr(self, "_parent_map", None)
         if parents is None or getattr(self, "_parent_map_for", None) is not self.traversal:
             parents = {}
@@ -363,6 +387,14 @@ class TreeModel(object):
                 parents[int(c1)] = int(par)
                 parents[int(c2)] = int(par)
             self._parent_map, self._parent_map_for = parents, self.traversal
+        return parents
+
+    def branch_length_above(self, node):
+        """Length of the edge above ``node`` (the root edge for either root child)."""
+        a, b = self.traversal.root_edge
+        if node == a or node == b:
+            return self.traversal.brlens[(a, b)]
+        parents = self._parents()
         if int(node) not in parents:
             raise ValueError("node {} has no edge above it".format(node))
         return self.traversal.brlens[(int(node), parents[int(node)])]

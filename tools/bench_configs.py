@@ -62,7 +62,8 @@ def report(name, tm, n_taxa, n_pat, A, reps, derivs=False):
     if derivs:
         up_ms, _ = timed(lambda: tm.compute_up_partials(), reps)
         all_nodes = np.arange(2 * n_taxa - 2)
-        d_ms, d = timed(lambda: tm.edge_derivatives(all_nodes), max(1, reps // 2))
+        all_lengths = tm.lengths_above(all_nodes)        # resolved once, as the Newton driver does
+        d_ms, d = timed(lambda: tm.edge_derivatives(all_nodes, all_lengths), max(1, reps // 2))
         out.update(up_pass_ms=up_ms, all_edge_derivatives_ms=d_ms, n_edges=int(len(all_nodes)),
                    sweep_ms=ms + up_ms + d_ms, max_abs_dlnl=float(np.abs(d[:, 1]).max()))
         if "--newton" in sys.argv:
