@@ -19,7 +19,8 @@
 //   * the children's down blocks arrive by cp.async one step ahead into double-buffered pattern-major tiles (rows
 //     padded by 16 bytes - conflict-free 128-bit reads, and the pad holds the row's exponent); tip children contribute
 //     rows of the staged P.lut tables, no arithmetic;
-//   * both outputs leave through a padded staging tile as coalesced streaming 128-bit stores.
+//   * both outputs leave as coalesced streaming 128-bit stores, staged through the (by then dead) operand tile of the
+//     child they belong to.
 //
 // HBM traffic per parent: two block writes, one block read per internal child, one re-read per two-internal-children
 // parent - against two writes and up to four reads for the two-row form.
@@ -81,9 +82,10 @@ struct UpLayout {
     static constexpr int STAGE_BYTES = 3 * L::OPER_BYTES + 3 * L::TILE; // x, o, k operand blocks + their codes
     static constexpr int CODES_OFF = 3 * L::OPER_BYTES;
     static constexpr int DESC_BYTES = 4 * 32;
-    static constexpr int OUT_BYTES = 32 * ROWB;                         // staging tile: 32 patterns at a time
     static constexpr int XTAB_BYTES = NC * 32;                          // ST: V^-1 . lut[code]
-    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + 4 * TILE_BYTES + OUT_BYTES + XTAB_BYTES;
+    // (no staging tile of its own: an output leaves through the operand tile of the child it belongs to, which is
+    // dead by then)
+    static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + 4 * TILE_BYTES + XTAB_BYTES;
     // a parked block in the warp's scratch stripe (the private chunk layout of clv_dna_pair.cu)
     static constexpr int CHUNKS = PPT * K * 2;
     static constexpr int BLOCK_BYTES = CHUNKS * 512;
@@ -209,7 +211,7 @@ __device__ __forceinline__ void up_update(bool x_tip, bool o_tip, bool k_tip, co
 }
 
 template <int K, int NC, int PPT, bool ST>
-__global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __grid_constant__ UpArgs p) {
+__global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __grid_constant__ UpArgs p) {
     using U = UpLayout<K, NC, PPT>;
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = U::ROWB;
@@ -220,8 +222,7 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __gr
     UpStep* const s_desc = reinterpret_cast<UpStep*>(smem);
     unsigned char* const s_stage = smem + U::DESC_BYTES;
     unsigned char* const s_tiles = s_stage + 2 * U::STAGE_BYTES;   // [buffer][o | k]
-    unsigned char* const s_out = s_tiles + 4 * U::TILE_BYTES;
-    unsigned char* const s_xtab = s_out + U::OUT_BYTES;
+    unsigned char* const s_xtab = s_tiles + 4 * U::TILE_BYTES;
     const int wstride = gridDim.x, n_steps = p.n_steps;
     const int n_tiles = (int)p.n_tiles;
     const size_t S = (size_t)p.S;
@@ -298,8 +299,8 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __gr
         if (!o_tip) fetch_block(d.src_o, t, tl);
         if (!k_tip) fetch_block(d.src_k, t, tl + U::TILE_BYTES);
     };
-    // registers -> padded staging tile -> coalesced streaming stores into block `blk`
-    auto store_block = [&](const double (&v)[PPT][K][4], const int (&e)[PPT], int blk, int t) {
+    // registers -> padded staging tile (a dead operand tile) -> coalesced streaming stores into block `blk`
+    auto store_block = [&](const double (&v)[PPT][K][4], const int (&e)[PPT], int blk, int t, unsigned char* s_out) {
         const size_t site0 = (size_t)t * L::TILE;
         const int valid = (int)min((int64_t)L::TILE, p.S - (int64_t)site0);
         unsigned char* dst = reinterpret_cast<unsigned char*>(p.clv + ((size_t)blk * S + site0) * (K * 4));
@@ -410,8 +411,8 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __gr
         cp_async_commit();
 
         const unsigned char* st = s_stage + (q & 1) * U::STAGE_BYTES;
-        const unsigned char* tile_o = s_tiles + (q & 1) * 2 * U::TILE_BYTES;
-        const unsigned char* tile_k = tile_o + U::TILE_BYTES;
+        unsigned char* const tile_o = s_tiles + (q & 1) * 2 * U::TILE_BYTES;
+        unsigned char* const tile_k = tile_o + U::TILE_BYTES;
         const int mode = (pk >> 24) & 3;
         if (mode == UP_LOAD) {
             // X of the next step comes back from the block array
@@ -440,15 +441,15 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __gr
             up_update<K, NC, PPT>(mode == UP_X_TIP, (shape & 1) != 0, (shape & 2) != 0, st, tile_o, tile_k, lane, prev, pe, oth, oe,
                                   ed_o, ed_k);
             if (!ST) {
-                store_block(oth, oe, dst_o, tile);
-                store_block(prev, pe, (int)(pk & 0xffffff), tile);
+                store_block(oth, oe, dst_o, tile, tile_o);
+                store_block(prev, pe, (int)(pk & 0xffffff), tile, tile_k);
             } else {
                 const int park = pk >> 28;
                 if (park != 15) park_block(oth, oe, park);
                 sum_table(oth, (shape & 1) != 0, tile_o, st + U::CODES_OFF + L::TILE);
 #pragma unroll
                 for (int h = 0; h < PPT; ++h) oe[h] += ed_o[h];
-                store_block(oth, oe, dst_o, tile);
+                store_block(oth, oe, dst_o, tile, tile_o);
 #pragma unroll
                 for (int h = 0; h < PPT; ++h) {
                     oe[h] = pe[h] + ed_k[h];
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 6 : 4) dna_up_kernel(const __gr
                         for (int i = 0; i < 4; ++i) oth[h][k][i] = prev[h][k][i];
                 }
                 sum_table(oth, (shape & 2) != 0, tile_k, st + U::CODES_OFF + 2 * L::TILE);
-                store_block(oth, oe, (int)(pk & 0xffffff), tile);
+                store_block(oth, oe, (int)(pk & 0xffffff), tile, tile_k);
             }
         }
         if (!has_next) break;
@@ -508,6 +509,10 @@ int launch_up(Ctx* c, int n_steps, int n_slots) {
         if (c->d_scratch == nullptr || cap < 1) return c->fail(PHB_ERR_NOMEM, "up kernel: scratch area too small");
         grid = std::min(grid, cap);
     }
+    // a tile is one long job (the whole tree): every warp gets the same number of them - the launch takes
+    // ceil(tiles / warps) rounds either way, and fewer co-resident warps finish a round sooner
+    const int64_t rounds = (a.n_tiles + grid - 1) / grid;
+    grid = (a.n_tiles + rounds - 1) / rounds;
     kern<<<(int)grid, 32, smem, c->stream>>>(a);
     c->launches++;
     PHB_CUDA(c, cudaGetLastError());
