@@ -133,6 +133,7 @@ struct Ctx {
     bool have_tips = false, have_model = false, have_mixture = false, have_schedule = false;
     bool have_lengths = false, have_pmats = false, have_partials = false, have_up = false;
     bool have_root = false;
+    std::vector<char> st_ready;        // per node: its up block already holds the edge's sum table (DMMA derivative path)
     bool up_sumtable = false;          // the up blocks hold per-edge sum tables (up_dna_pair.cu), not up partials
     bool resident_partials = false;    // the last post-order pass was the operand-resident walk (the pre-order pass follows suit)
     int root_a = -1, root_b = -1;

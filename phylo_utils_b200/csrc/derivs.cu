@@ -268,6 +268,14 @@ struct MmaDerivArgs {
     int K, n_parts;
     const EdgeDesc* edges;
     double* partial_sums;   // [n_edges * 3][n_parts]
+    // sum-table write-out: an edge whose upper operand is an up block (block index >= st_first_block) gets its table
+    // s_km = x_m y_m written over that block (and the summed exponents over its scalers); < 0: off
+    int st_first_block;
+    double* clv_rw;
+    int32_t* scale_rw;
+    // ... and the root edge (both of whose operands are down partials) into the otherwise unused up block of the root
+    // child that owns it: up to two positions of the launch, -1 = none
+    int st_extra_edge[2], st_extra_block[2];
 };
 
 __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
@@ -326,6 +334,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
     double* coef = Lb + TS * LDL;             // [3][K][MROWS]
     __shared__ double s_red[3][WARPS];
     const int K = p.K, e = blockIdx.y;
+    if (p.edges[e].kind_a == SRC_SUMTABLE) return;   // edge_st_kernel's edge (the whole CTA leaves)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fr = lane >> 2, fc = lane & 3;
     const size_t S = (size_t)p.S;
@@ -341,6 +350,13 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
     const EdgeDesc ed = p.edges[e];
     const int ka = ed.kind_a, kb = ed.kind_b;
     const size_t sa = (size_t)ed.src_a, sb = (size_t)ed.src_b;
+    // the upper operand is this edge's up block: leave the sum table there for the next iterations (edge_st_kernel)
+    bool write_st = p.st_first_block >= 0 && kb == SRC_GLOBAL && ed.src_b >= p.st_first_block;
+    size_t st_blk = sb;
+    if (p.st_first_block >= 0 && (e == p.st_extra_edge[0] || e == p.st_extra_edge[1])) {
+        write_st = true;
+        st_blk = (size_t)(e == p.st_extra_edge[0] ? p.st_extra_block[0] : p.st_extra_block[1]);
+    }
     double* myA = La + (size_t)warp * WR * LDL;
     double* myB = Lb + (size_t)warp * WR * LDL;
     double tot[3] = {0.0, 0.0, 0.0};
@@ -419,6 +435,12 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
                         t[0][nt][q] = fma(c0, xy, t[0][nt][q]);
                         t[1][nt][q] = fma(c1, xy, t[1][nt][q]);
                         t[2][nt][q] = fma(c2, xy, t[2][nt][q]);
+                        if (write_st) {
+                            // eight lanes (fr) write eight consecutive components of one pattern: 64-byte runs.  The
+                            // block's rows of this category have all been staged (cp.async waited above).
+                            const int64_t st_s = wsite0 + nt * 8 + 2 * fc + q;
+                            if (mt * 8 + fr < A && st_s < p.S) p.clv_rw[((st_blk * S + (size_t)st_s) * K + k) * A + mt * 8 + fr] = xy;
+                        }
                     }
             }
         }
@@ -445,6 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
                     int ex = 0;
                     if (ka != SRC_TIP) ex += p.scale[sa * S + s];
                     if (kb != SRC_TIP) ex += p.scale[sb * S + s];
+                    if (write_st) p.scale_rw[st_blk * S + s] = ex;   // the table's exponent: both ends'
                     const double w = p.weights ? p.weights[s] : 1.0;
                     const double L = t[0][nt][q];
                     const double g = t[1][nt][q] / L;
@@ -490,6 +513,100 @@ int launch_mma_derivs(Ctx* c, MmaDerivArgs& a, int n_edges) {
     c->launches++;
     PHB_CUDA(c, cudaGetLastError());
     return PHB_OK;
+}
+
+// Any state count, edges that already have their sum table (written by mma_edge_deriv_kernel on the first derivative
+// pass after a pre-order pass): f^(d) = sum over j = (k, m) of coef[d][j] s[j] - three dot products of length K A over
+// ONE contiguous row per pattern, no matrix product.  LP lanes share a pattern (row pieces of 16 bytes, coalesced),
+// coefficients live in registers; every lane keeps the sums of one of 32 consecutive patterns, so the log / division
+// tail runs once per 32 patterns with a distinct pattern in every lane.
+struct StArgs {
+    const double* coef;     // [edge][3][K][mrows]
+    const double* clv;
+    const int32_t* scale;
+    const double* weights;
+    const int32_t* edges;   // EdgeDesc array as ints: [4 e] = block of the table, [4 e + 1] = kind
+    int64_t S;
+    int K, A, mrows, n_parts;
+    double* partial_sums;   // [n_edges * 3][n_parts]
+};
+
+template <int LP, int CPL>
+__global__ void __launch_bounds__(128) edge_st_kernel(const StArgs p) {
+    constexpr int PPW = 32 / LP;   // patterns per warp and sub-iteration
+    __shared__ double s_red[3][4];
+    const int e = blockIdx.y;
+    if (p.edges[4 * e + 1] != SRC_SUMTABLE) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane / LP, l = lane % LP;
+    const int row_doubles = p.K * p.A, row_chunks = row_doubles / 2;   // K A is even for every shape that gets here
+    double cf[3][CPL][2];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * (l + LP * i) + h;
+            const bool ok = j < row_doubles;
+            const int k = ok ? j / p.A : 0, m = ok ? j - k * p.A : 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) cf[d][i][h] = ok ? p.coef[(((size_t)e * 3 + d) * p.K + k) * p.mrows + m] : 0.0;
+        }
+    const size_t S = (size_t)p.S, blk = (size_t)p.edges[4 * e];
+    const double* const base = p.clv + blk * S * row_doubles;
+    const int32_t* const sc = p.scale + blk * S;
+    double tot[3] = {0.0, 0.0, 0.0};
+    // a warp takes 32 consecutive patterns per trip
+    const int64_t n_trips = (p.S + 31) / 32;
+    for (int64_t trip = (int64_t)blockIdx.x * 4 + warp; trip < n_trips; trip += (int64_t)gridDim.x * 4) {
+        double keep[3] = {1.0, 0.0, 0.0};
+        constexpr int UB = 4;   // sub-iterations whose loads are issued together
+#pragma unroll 1
+        for (int u0 = 0; u0 < LP; u0 += UB) {
+            double2 v[UB][CPL];
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const int64_t s = trip * 32 + (u0 + b) * PPW + g;
+                const double2* row = reinterpret_cast<const double2*>(base + (size_t)(s < p.S ? s : p.S - 1) * row_doubles);
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) {
+                    const int c = l + LP * i;
+                    v[b][i] = c < row_chunks ? __ldg(row + c) : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                for (int i = 0; i < CPL; ++i)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) f[d] = fma(cf[d][i][1], v[b][i].y, fma(cf[d][i][0], v[b][i].x, f[d]));
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int o = LP / 2; o > 0; o >>= 1) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+                // lane u of group g keeps pattern u * PPW + g of the trip
+                if (l == u0 + b) {
+                    keep[0] = f[0];
+                    keep[1] = f[1];
+                    keep[2] = f[2];
+                }
+            }
+        }
+        const int64_t s = trip * 32 + l * PPW + g;
+        if (s < p.S) {
+            const double w = p.weights ? p.weights[s] : 1.0;
+            const double gq = keep[1] / keep[0];
+            tot[0] += w * (keep[0] > 0 ? log(keep[0]) + (double)sc[s] * kLn2 : -INFINITY);
+            tot[1] += w * gq;
+            tot[2] += w * (keep[2] / keep[0] - gq * gq);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const double v = warp_sum(tot[d]);
+        if (lane == 0) s_red[d][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 3) p.partial_sums[((size_t)e * 3 + tid) * p.n_parts + blockIdx.x] = s_red[tid][0] + s_red[tid][1] + s_red[tid][2] + s_red[tid][3];
 }
 
 // ---- 4 states: the same sum-table form, scalar ------------------------------------------------------------------
@@ -709,6 +826,7 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     c->up_rows.clear();
     c->up_levels.clear();
     c->up_sumtable = false;
+    c->st_ready.assign(c->n_nodes, 0);
     if (n_rows == 0) return PHB_OK;
     // 4-state models whose post-order pass was the operand-resident walk: one pre-order walk (up_dna_pair.cu)
     if (c->resident_partials && getenv("PHB_UP_TWO_ROWS") == nullptr) {
@@ -801,12 +919,16 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             fill_operand(c, node, &edges[i].src_a, &edges[i].kind_a);
             if (node == c->root_a || node == c->root_b) {
                 fill_operand(c, node == c->root_a ? c->root_b : c->root_a, &edges[i].src_b, &edges[i].kind_b);
+                if (use_mma && (int)c->st_ready.size() == c->n_nodes && c->st_ready[node]) {
+                    edges[i].src_a = c->n_internal + node;   // the root edge's table sits in this root child's up block
+                    edges[i].kind_a = SRC_SUMTABLE;
+                }
             } else {
                 PHB_REQUIRE(c, c->node_parent[node] >= 0, PHB_ERR_INVALID, "edge derivatives: node has no edge above it");
                 edges[i].src_b = c->n_internal + node;
                 edges[i].kind_b = SRC_GLOBAL;
-                if (c->up_sumtable) {   // the edge's up block holds its sum table
-                    edges[i].src_a = c->n_internal + node;
+                if (c->up_sumtable || (use_mma && (int)c->st_ready.size() == c->n_nodes && c->st_ready[node])) {
+                    edges[i].src_a = c->n_internal + node;   // the edge's up block holds its sum table
                     edges[i].kind_a = SRC_SUMTABLE;
                 }
             }
@@ -840,8 +962,74 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             m.K = K;
             m.edges = d_edges;
             m.partial_sums = c->d_partial_sums;
-            int st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8>(c, m, n);
-            if (st) return st;
+            // First derivative pass after a pre-order pass: the kernel leaves each edge's sum table in its up block;
+            // later passes read that one block per edge (edge_st_kernel).  Needs 16-byte rows (K A even), a row that
+            // fits the register-resident coefficient layouts, and every node at most once per launch.
+            const int row_chunks = K * A / 2;
+            bool st_ok = getenv("PHB_DERIV_NO_ST") == nullptr && (K * A) % 2 == 0 && row_chunks <= 256 &&
+                         (int)c->st_ready.size() == c->n_nodes;
+            int n_table = 0, n_fresh = 0;
+            if (st_ok) {
+                std::vector<char> seen(c->n_nodes, 0);
+                for (int i = 0; i < n && st_ok; ++i) {
+                    const int node = nodes[start + i];
+                    if (seen[node]) st_ok = false;
+                    seen[node] = 1;
+                }
+            }
+            for (int i = 0; i < n; ++i) {
+                if (edges[i].kind_a == SRC_SUMTABLE) ++n_table;
+                else ++n_fresh;
+            }
+            m.st_first_block = st_ok ? c->n_internal : -1;
+            m.clv_rw = c->d_clv;
+            m.scale_rw = c->d_scale;
+            m.st_extra_edge[0] = m.st_extra_edge[1] = -1;
+            m.st_extra_block[0] = m.st_extra_block[1] = 0;
+            if (st_ok)
+                for (int i = 0, x = 0; i < n; ++i) {
+                    const int node = nodes[start + i];
+                    if ((node == c->root_a || node == c->root_b) && edges[i].kind_a != SRC_SUMTABLE && x < 2) {
+                        m.st_extra_edge[x] = i;
+                        m.st_extra_block[x] = c->n_internal + node;
+                        ++x;
+                    }
+                }
+            int st = PHB_OK;
+            if (n_fresh > 0) {
+                st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8>(c, m, n);
+                if (st) return st;
+            } else {
+                // block sums are laid out for this many parts either way
+                int64_t parts = std::max<int64_t>(2, ((int64_t)c->sm_count * 4 + n - 1) / n);
+                m.n_parts = (int)std::min<int64_t>(parts, std::min<int64_t>((c->S + 127) / 128, kPartialCap / (3 * n)));
+            }
+            if (n_table > 0) {
+                StArgs t;
+                t.coef = d_coef;
+                t.clv = c->d_clv;
+                t.scale = c->d_scale;
+                t.weights = c->d_weights;
+                t.edges = reinterpret_cast<const int32_t*>(d_edges);
+                t.S = c->S;
+                t.K = K;
+                t.A = A;
+                t.mrows = mrows;
+                t.n_parts = m.n_parts;
+                t.partial_sums = c->d_partial_sums;
+                dim3 grid((unsigned)m.n_parts, (unsigned)n);
+                if (row_chunks <= 40) edge_st_kernel<8, 5><<<grid, 128, 0, c->stream>>>(t);
+                else if (row_chunks <= 128) edge_st_kernel<32, 4><<<grid, 128, 0, c->stream>>>(t);
+                else edge_st_kernel<32, 8><<<grid, 128, 0, c->stream>>>(t);
+                c->launches++;
+                PHB_CUDA(c, cudaGetLastError());
+            }
+            if (st_ok)
+                for (int i = 0; i < n; ++i)
+                    if (edges[i].kind_a != SRC_SUMTABLE &&
+                        ((edges[i].kind_b == SRC_GLOBAL && edges[i].src_b >= c->n_internal) || i == m.st_extra_edge[0] ||
+                         i == m.st_extra_edge[1]))
+                        c->st_ready[nodes[start + i]] = 1;
             n_parts = m.n_parts;
         } else if (dna_supported(c) && (int)c->h_evecs.size() == A * A && (int)c->h_freqs.size() == A &&
                    (c->up_sumtable || getenv("PHB_DERIV_MATRIX_FORM") == nullptr)) {

@@ -85,6 +85,35 @@ def test_trial_lengths_and_reference_convention_flag():
             assert np.allclose(got, want, rtol=1e-8, atol=1e-8)
 
 
+@pytest.mark.parametrize("name,mode", [("prot12_lg_g4", "tile"), ("prot12_lg_g4", "level"), ("cfg1_gtr_g4", "resident"),
+                                       ("ladder120_k80_g4", "resident")])
+def test_repeated_passes_read_the_sum_tables(name, mode):
+    """Newton iterations evaluate the same edges again at new trial lengths: from the second pass on the kernels read
+    the per-edge sum tables the first pass (20 / 61 states) or the pre-order walk (4 states) left in the up blocks."""
+    tm, tr, ot, up, model, rate, sw = setup_case(name, mode)
+    nodes = [n for n in range(2 * len(tr.names) - 2) if n != tr.root_edge[1]]
+    if len(nodes) > 40:
+        nodes = nodes[::9] + list(tr.root_edge[:1])
+    lengths = np.array([tm.branch_length_above(n) for n in nodes])
+    first = tm.edge_derivatives(nodes, lengths)
+    again = tm.edge_derivatives(nodes, lengths)
+    assert np.allclose(first, again, rtol=1e-12, atol=1e-9)
+    for scale in (0.5, 3.0):
+        got = tm.edge_derivatives(nodes, lengths * scale)
+        for (node, t), row in zip(zip(nodes, lengths * scale), got):
+            want = oracle_edge_derivatives(tr, ot, up, model, rate, node, t, sw)
+            assert abs(row[0] - want[0]) <= 1e-10 * abs(want[0]), (node, row, want)
+            assert abs(row[1] - want[1]) <= 1e-8 * max(1.0, abs(want[1])), (node, row, want)
+            assert abs(row[2] - want[2]) <= 1e-8 * max(1.0, abs(want[2])), (node, row, want)
+    # a subset, with a node listed twice (no table is written by such a launch, existing ones are still read)
+    sub = [nodes[0], nodes[1], nodes[0]]
+    got = tm.edge_derivatives(sub, lengths[[0, 1, 0]])
+    assert np.allclose(got, first[[0, 1, 0]], rtol=1e-12, atol=1e-9)
+    # a new pre-order pass starts over
+    tm.compute_up_partials()
+    assert np.allclose(tm.edge_derivatives(nodes, lengths), first, rtol=1e-12, atol=1e-9)
+
+
 def test_up_partials_larger_tree_vs_oracle_total():
     rng = np.random.default_rng(12)
     n_taxa, n_pat = 80, 20000
