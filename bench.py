@@ -108,7 +108,45 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index, self.rows, self._stop, self._thread = index, [], threading.Event(), None
 
+    def _nvml_handle(self):
+        """NVML handle of CUDA device ``index`` (by UUID: CUDA_VISIBLE_DEVICES may renumber), or None."""
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except TypeError:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return None
+
     def _run(self):
+        nv = self._nvml_handle()
+        if nv is not None:
+            # in-process NVML queries: a sample every 10 ms instead of one nvidia-smi process every few hundred
+            pynvml, h = nv
+            bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+            try:
+                smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                while not self._stop.is_set():
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    try:
+                        watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    except Exception:
+                        watts = 0.0
+                    self.rows.append([str(sm), str(smax), str(watts)] + ["Active" if mask & b else "Not Active" for b, _ in bits])
+                    self._stop.wait(0.01)
+                return
+            except Exception:
+                pass                                   # fall through to nvidia-smi
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
@@ -143,7 +181,7 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_min_mhz": float(min(sm)) if sm else None}
 
 
 def measured_peak():

@@ -29,8 +29,20 @@ namespace phb {
 
 namespace {
 
+// A row as the kernel runs it: up to three operands, up to two outputs.
+//   n_ops == 2: dst[0] = op0 * op1                        (a pruning row, what an OpRow says)
+//   n_ops == 3: dst[0] = op0 * op1,  dst[1] = op0 * op2    (a pre-order parent step: op0 = what sits above the parent,
+//               op1 / op2 = its children; three products where two separate rows take four, X staged once)
+struct MmaRow {
+    int32_t src[3], kind[3], pidx[3];
+    int32_t dst[2];
+    int32_t n_ops;
+};
+static_assert(sizeof(MmaRow) == 48, "MmaRow must stay 48 bytes");
+
 struct MmaArgs {
     const OpRow* rows;
+    const MmaRow* frows;  // non-null: the launch runs these rows instead of `rows`
     int row_begin, row_end;
     const double* pmats;  // [pidx][K][A][A]
     const double* tiptab; // [pidx][K][nc][A] = P . lut[code], or null
@@ -68,7 +80,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // one P buffer and one child-row buffer, the P block and the child rows of phase ph+1 stream into the other
 // pair with cp.async (8-byte pieces: rows of 20 or 61 doubles are only 8-byte aligned).  Padding rows and
 // columns are zeroed once and never touched again.
-template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL>
+template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL, bool FUSED>
 __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
@@ -77,7 +89,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     extern __shared__ double sm[];
     double* Pbuf = sm;                               // [2][MROWS][LDP]
     double* Lbuf = Pbuf + 2 * MROWS * LDP;           // [2][TS][LDL]
-    unsigned char* s_codes = reinterpret_cast<unsigned char*>(Lbuf + 2 * TS * LDL);   // [2 children][TS]
+    unsigned char* s_codes = reinterpret_cast<unsigned char*>(Lbuf + 2 * TS * LDL);   // [3 operands][TS]
     constexpr int A = AA;   // compile-time: the staging loops divide by it
     const int K = p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,26 +105,44 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
         const int r1 = LEVEL ? r0 + 1 : p.row_end;
         const int64_t wsite0 = tile * TS + (int64_t)warp * WR;   // first pattern of this warp
         for (int r = r0; r < r1; ++r) {
-            const OpRow row = p.rows[r];
-            double* out = p.clv + (size_t)row.dst * S * K * A;
-            const int n_phases = 2 * K;
+            MmaRow row;
+            if (FUSED) {
+                row = p.frows[r];
+            } else {
+                const OpRow o = p.rows[r];
+                for (int c = 0; c < 2; ++c) {
+                    row.src[c] = o.src[c];
+                    row.kind[c] = o.kind[c];
+                    row.pidx[c] = o.pidx[c];
+                }
+                row.src[2] = row.pidx[2] = 0;
+                row.kind[2] = SRC_TIP;
+                row.dst[0] = row.dst[1] = o.dst;
+                row.n_ops = 2;
+            }
+            const int n_ops = FUSED ? 3 : 2, n_phases = n_ops * K;   // compile-time per instantiation: a pruning row costs what it did
+            // selects instead of indexed reads: the row stays in registers
+            auto src_of = [&](int c) { return c == 0 ? row.src[0] : (c == 1 ? row.src[1] : row.src[2]); };
+            auto kind_of = [&](int c) { return c == 0 ? row.kind[0] : (c == 1 ? row.kind[1] : row.kind[2]); };
+            auto pidx_of = [&](int c) { return c == 0 ? row.pidx[0] : (c == 1 ? row.pidx[1] : row.pidx[2]); };
 
             // tip codes of this warp's patterns (same for every category)
-            for (int c = 0; c < 2; ++c)
-                if (row.kind[c] == SRC_TIP)
+            for (int c = 0; c < n_ops; ++c)
+                if (kind_of(c) == SRC_TIP)
                     for (int n = lane; n < WR; n += 32) {
                         const int64_t s = wsite0 + n;
-                        s_codes[c * TS + warp * WR + n] = s < p.S ? p.codes[(size_t)row.src[c] * p.pitch + s] : 0;
+                        s_codes[c * TS + warp * WR + n] = s < p.S ? p.codes[(size_t)src_of(c) * p.pitch + s] : 0;
                     }
             __syncwarp();
 
-            auto prefetch = [&](int ph) {
-                const int k = ph >> 1, c = ph & 1, buf = ph & 1;
+            // phase ph = (category k, operand c), in the order (k, 0), (k, 1) [, (k, 2)]; buffers alternate with ph
+            auto prefetch = [&](int ph, int k, int c) {
+                const int buf = ph & 1;
                 double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
-                if (row.kind[c] == SRC_TIP && p.tiptab != nullptr) {
+                if (kind_of(c) == SRC_TIP && p.tiptab != nullptr) {
                     // a tip child needs no product at all: its contribution is row `code` of T = P . lut, staged
                     // where the P block would go (row = code, n_codes <= MROWS rows)
-                    const double* q = p.tiptab + ((size_t)row.pidx[c] * K + k) * p.nc * A;
+                    const double* q = p.tiptab + ((size_t)pidx_of(c) * K + k) * p.nc * A;
                     for (int e = threadIdx.x; e < p.nc * A; e += WARPS * 32) {
                         const int i = e / A, j = e - i * A;
                         cp_async8(Pd + i * LDP + j, q + e);
@@ -120,13 +150,13 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     cp_async_commit_all();
                     return;
                 }
-                const double* q = p.pmats + ((size_t)row.pidx[c] * K + k) * A * A;
+                const double* q = p.pmats + ((size_t)pidx_of(c) * K + k) * A * A;
                 for (int e = threadIdx.x; e < A * A; e += WARPS * 32) {
                     const int i = e / A, j = e - i * A;
                     cp_async8(Pd + i * LDP + j, q + e);
                 }
                 double* Ld = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
-                if (row.kind[c] == SRC_TIP) {
+                if (kind_of(c) == SRC_TIP) {
                     for (int e = lane; e < WR * A; e += 32) {
                         const int n = e / A, j = e - n * A;
                         Ld[n * LDL + j] = __ldg(p.lut + (size_t)s_codes[c * TS + warp * WR + n] * A + j);
@@ -136,7 +166,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
                     const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
                     const unsigned char* g =
-                        reinterpret_cast<const unsigned char*>(p.clv + (((size_t)row.src[c] * S + wsite0) * K + k) * A);
+                        reinterpret_cast<const unsigned char*>(p.clv + (((size_t)src_of(c) * S + wsite0) * K + k) * A);
                     const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld);
                     for (int e = lane; e < n_valid * PIECES; e += 32) {
                         const int n = e / PIECES, piece = e - n * PIECES;
@@ -149,25 +179,28 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 cp_async_commit_all();
             };
 
-            int mx[NT][2];   // high word of the per-pattern maximum (partials are >= 0: the high word orders them)
+            int mx[2][NT][2];   // per output: high word of the per-pattern maximum (partials are >= 0: the high word orders them)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) mx[nt][0] = mx[nt][1] = 0;
+            for (int nt = 0; nt < NT; ++nt) mx[0][nt][0] = mx[0][nt][1] = mx[1][nt][0] = mx[1][nt][1] = 0;
             double acc0[MT][NT][2], acc1[MT][NT][2];
             // DMMAs of one phase: acc = P[buf] . (this warp's child rows in buf)^T
-            auto run_phase = [&](int ph, double (&acc)[MT][NT][2]) {
+            auto run_phase = [&](int ph, int k, int c, double (&acc)[MT][NT][2]) {
                 const int buf = ph & 1;
                 cp_async_wait_all();
                 __syncthreads();      // phase ph's operands have landed; everybody has left phase ph-1
-                if (ph + 1 < n_phases) prefetch(ph + 1);
+                if (ph + 1 < n_phases) {
+                    const int cn = c + 1 == n_ops ? 0 : c + 1;
+                    prefetch(ph + 1, cn == 0 ? k + 1 : k, cn);
+                }
                 const double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
                 const double* myLr = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
-                if (row.kind[ph & 1] == SRC_TIP && p.tiptab != nullptr) {
+                if (kind_of(c) == SRC_TIP && p.tiptab != nullptr) {
                     // gather in fragment layout: acc[mt][nt][q] = T[code(pattern nt*8 + 2fc + q)][state mt*8 + fr]
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
-                            const int code = s_codes[(ph & 1) * TS + warp * WR + nt * 8 + 2 * fc + q];
+                            const int code = s_codes[c * TS + warp * WR + nt * 8 + 2 * fc + q];
 #pragma unroll
                             for (int mt = 0; mt < MT; ++mt) acc[mt][nt][q] = Pd[code * LDP + mt * 8 + fr];
                         }
@@ -192,80 +225,91 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
             };
 
             __syncthreads();          // the previous row is completely done with both buffer pairs
-            prefetch(0);
+            prefetch(0, 0, 0);
+            int ph = 0;
             for (int k = 0; k < K; ++k) {
-                run_phase(2 * k, acc0);
-                run_phase(2 * k + 1, acc1);
-                double* myL = Lbuf + ((size_t)TS + (size_t)warp * WR) * LDL;   // child-1 rows (buffer 1) become the output rows
-                // both children of category k are done: multiply, find the maxima, write the block row out
-                __syncwarp();      // all lanes have read their child rows; they now become the output rows
-                // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q.  Padding states (>= A) are
-                // neither stored nor allowed into the maximum: a tip-table gather reads past its row for them.
-                double* corner = myL + (2 * fc) * LDL + fr;
+                run_phase(ph, k, 0, acc0);
+                ++ph;
+                for (int j = 1; j < n_ops; ++j, ++ph) {
+                    run_phase(ph, k, j, acc1);
+                    // operand j of category k is done: output j-1 = acc0 * acc1.  It leaves through this warp's rows of
+                    // the L buffer the phase just read (the next copy into that buffer is issued behind a barrier)
+                    double* out = p.clv + (size_t)(j == 1 ? row.dst[0] : row.dst[1]) * S * K * A;
+                    double* myL = Lbuf + ((size_t)(ph & 1) * TS + (size_t)warp * WR) * LDL;
+                    __syncwarp();      // all lanes have read their operand rows; they now become the output rows
+                    // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q.  Padding states (>= A) are
+                    // neither stored nor allowed into the maximum: a tip-table gather reads past its row for them.
+                    double* corner = myL + (2 * fc) * LDL + fr;
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    if (mt * 8 + 8 > A && mt * 8 + fr >= A) continue;
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (mt * 8 + 8 > A && mt * 8 + fr >= A) continue;
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
+                        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const double o = acc0[mt][nt][q] * acc1[mt][nt][q];
-                            corner[(nt * 8 + q) * LDL + mt * 8] = o;
-                            mx[nt][q] = max(mx[nt][q], __double2hiint(o));
-                        }
-                }
-                __syncwarp();
-                {
-                    // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  Columns >= A of
-                    // the rows are never written (they stay zero for their next life as a child row).
-                    constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
-                    const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
-                    unsigned char* g = reinterpret_cast<unsigned char*>(out + ((size_t)wsite0 * K + k) * A);
-                    const unsigned char* src = reinterpret_cast<const unsigned char*>(myL);
-                    for (int e = lane; e < n_valid * PIECES; e += 32) {
-                        const int n = e / PIECES, piece = e - n * PIECES;
-                        if (PB == 16)
-                            *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
-                                *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
-                        else
-                            *reinterpret_cast<double*>(g + (size_t)n * (K * A * 8) + piece * 8) =
-                                *reinterpret_cast<const double*>(src + n * (LDL * 8) + piece * 8);
+                            for (int q = 0; q < 2; ++q) {
+                                const double o = acc0[mt][nt][q] * acc1[mt][nt][q];
+                                corner[(nt * 8 + q) * LDL + mt * 8] = o;
+                                if (j == 1) mx[0][nt][q] = max(mx[0][nt][q], __double2hiint(o));
+                                else mx[1][nt][q] = max(mx[1][nt][q], __double2hiint(o));
+                            }
                     }
+                    __syncwarp();
+                    {
+                        // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  Columns >= A of
+                        // the rows are never written (they stay zero for their next life as an operand row).
+                        constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
+                        const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
+                        unsigned char* g = reinterpret_cast<unsigned char*>(out + ((size_t)wsite0 * K + k) * A);
+                        const unsigned char* src = reinterpret_cast<const unsigned char*>(myL);
+                        for (int e = lane; e < n_valid * PIECES; e += 32) {
+                            const int n = e / PIECES, piece = e - n * PIECES;
+                            if (PB == 16)
+                                *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
+                                    *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
+                            else
+                                *reinterpret_cast<double*>(g + (size_t)n * (K * A * 8) + piece * 8) =
+                                    *reinterpret_cast<const double*>(src + n * (LDL * 8) + piece * 8);
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             // per-pattern maximum over states (lanes sharing fc) and categories (already folded into mx)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    int m = mx[nt][q];
-                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
-                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
-                    m = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
-                    mx[nt][q] = m;
-                }
-            // lanes 0..3 (fr == 0) finalise the patterns 2*fc + q of every n-tile
-            if (fr == 0) {
+            for (int j = 0; j + 1 < n_ops; ++j) {
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
-                        const int64_t s = wsite0 + nt * 8 + 2 * fc + q;
-                        if (s >= p.S) continue;
-                        int e = 0;
-                        if (row.kind[0] != SRC_TIP) e += p.scale[(size_t)row.src[0] * S + s];
-                        if (row.kind[1] != SRC_TIP) e += p.scale[(size_t)row.src[1] * S + s];
-                        const int hi = mx[nt][q];
-                        if (hi < kScaleThresholdHi && hi >= 0x00100000) {
-                            const int shift = 1023 - (hi >> 20);
-                            const double f = pow2i(shift);
-                            double* mine = out + (size_t)s * K * A;
-                            for (int z = 0; z < K * A; ++z) mine[z] *= f;
-                            e -= shift;
-                        }
-                        p.scale[(size_t)row.dst * S + s] = e;
+                        int m = j == 0 ? mx[0][nt][q] : mx[1][nt][q];
+                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                        m = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+                        if (j == 0) mx[0][nt][q] = m;
+                        else mx[1][nt][q] = m;
                     }
+                // lanes 0..3 (fr == 0) finalise the patterns 2*fc + q of every n-tile
+                if (fr == 0) {
+                    double* out = p.clv + (size_t)(j == 0 ? row.dst[0] : row.dst[1]) * S * K * A;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int64_t s = wsite0 + nt * 8 + 2 * fc + q;
+                            if (s >= p.S) continue;
+                            int e = 0;
+                            if (row.kind[0] != SRC_TIP) e += p.scale[(size_t)row.src[0] * S + s];
+                            if (kind_of(j + 1) != SRC_TIP) e += p.scale[(size_t)src_of(j + 1) * S + s];
+                            const int hi = j == 0 ? mx[0][nt][q] : mx[1][nt][q];
+                            if (hi < kScaleThresholdHi && hi >= 0x00100000) {
+                                const int shift = 1023 - (hi >> 20);
+                                const double f = pow2i(shift);
+                                double* mine = out + (size_t)s * K * A;
+                                for (int z = 0; z < K * A; ++z) mine[z] *= f;
+                                e -= shift;
+                            }
+                            p.scale[(size_t)(j == 0 ? row.dst[0] : row.dst[1]) * S + s] = e;
+                        }
+                }
             }
             __threadfence_block();   // this row's block is visible to the cp.async reads of the next row
             __syncwarp();
@@ -274,13 +318,14 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
 }
 
 template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL>
-int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
+int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, const MmaRow* d_frows = nullptr) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
     constexpr int LDL = pad_pitch(KCOLS);
     constexpr int TS = WARPS * NT * 8;
     MmaArgs a;
     a.rows = d_rows;
+    a.frows = d_frows;
     a.row_begin = row_begin;
     a.row_end = row_end;
     a.pmats = c->d_pmats;
@@ -296,8 +341,8 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
     a.n_tiles = (c->S + TS - 1) / TS;
     a.A = c->A;
     a.K = c->K;
-    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 2 * TS;
-    auto kern = mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL>;
+    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 3 * TS;
+    auto kern = d_frows != nullptr ? mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, true> : mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, false>;
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -313,36 +358,66 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end) {
 }
 
 template <int AA, int MT, int KS, int NT, int WARPS>
-int run_rows_mma(Ctx* c, const RowSet& rs, int mode) {
+int run_rows_mma(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frows = nullptr) {
     if (rs.n_rows == 0) return PHB_OK;
     if (mode == PHB_MODE_LEVEL) {
         const std::vector<int32_t>& lv = *rs.levels;
         for (int l = 0; l + 1 < (int)lv.size(); ++l) {
             if (lv[l + 1] <= lv[l]) continue;
-            int st = launch_mma<AA, MT, KS, NT, WARPS, true>(c, rs.d_rows, lv[l], lv[l + 1]);
+            int st = launch_mma<AA, MT, KS, NT, WARPS, true>(c, rs.d_rows, lv[l], lv[l + 1], d_frows);
             if (st) return st;
         }
         return PHB_OK;
     }
-    return launch_mma<AA, MT, KS, NT, WARPS, false>(c, rs.d_rows, 0, rs.n_rows);
+    return launch_mma<AA, MT, KS, NT, WARPS, false>(c, rs.d_rows, 0, rs.n_rows, d_frows);
 }
 
 }  // namespace
 
 bool mma_supported(const Ctx* c) { return c->A == 20 || c->A == 61; }
 
-int mma_run_rows(Ctx* c, const RowSet& rs, int mode) {
+static int mma_dispatch(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frows) {
     const char* env = getenv("PHB_MMA_VARIANT");   // tuning knob: alternative tile shapes
     const int variant = env ? atoi(env) : 0;
     if (c->A == 20) {
-        if (variant == 1) return run_rows_mma<20, 3, 5, 4, 8>(c, rs, mode);   // 256 patterns per CTA, 8 warps
-        return run_rows_mma<20, 3, 5, 4, 4>(c, rs, mode);                     // 128 patterns per CTA, 4 warps
+        if (variant == 1) return run_rows_mma<20, 3, 5, 4, 8>(c, rs, mode, d_frows);   // 256 patterns per CTA, 8 warps
+        return run_rows_mma<20, 3, 5, 4, 4>(c, rs, mode, d_frows);                     // 128 patterns per CTA, 4 warps
     }
     if (c->A == 61) {
-        if (variant == 1) return run_rows_mma<61, 8, 16, 1, 8>(c, rs, mode);  // 64 patterns per CTA
-        return run_rows_mma<61, 8, 16, 2, 8>(c, rs, mode);                    // 128 patterns per CTA
+        if (variant == 1) return run_rows_mma<61, 8, 16, 1, 8>(c, rs, mode, d_frows);  // 64 patterns per CTA
+        return run_rows_mma<61, 8, 16, 2, 8>(c, rs, mode, d_frows);                    // 128 patterns per CTA
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "DMMA kernels cover 20 and 61 states");
+}
+
+int mma_run_rows(Ctx* c, const RowSet& rs, int mode) { return mma_dispatch(c, rs, mode, nullptr); }
+
+// Pre-order pass as one three-operand row per parent.  parents[i] = {X src, X kind, X pidx, child0 .., child1 .., up block
+// of child0, up block of child1} in execution order (levels: offsets of independent groups, or empty for one launch that
+// walks the rows in order); the row table is staged in the context's up-row buffer.
+int mma_run_parent_rows(Ctx* c, const std::vector<int32_t>& parents, const std::vector<int32_t>& levels) {
+    const int n = (int)(parents.size() / 11);
+    if (n == 0) return PHB_OK;
+    if ((size_t)n * sizeof(MmaRow) > 2 * (size_t)c->max_rows() * sizeof(OpRow))
+        return c->fail(PHB_ERR_STATE, "pre-order pass: row table overflow");
+    std::vector<MmaRow> rows(n);
+    for (int i = 0; i < n; ++i) {
+        const int32_t* q = &parents[(size_t)i * 11];
+        MmaRow r;
+        // op0 = X, op1 = child 1 (so that dst[0] = up[child 0]), op2 = child 0 (dst[1] = up[child 1])
+        r.src[0] = q[0]; r.kind[0] = q[1]; r.pidx[0] = q[2];
+        r.src[1] = q[6]; r.kind[1] = q[7]; r.pidx[1] = q[8];
+        r.src[2] = q[3]; r.kind[2] = q[4]; r.pidx[2] = q[5];
+        r.dst[0] = q[9];
+        r.dst[1] = q[10];
+        r.n_ops = 3;
+        rows[i] = r;
+    }
+    MmaRow* d_frows = reinterpret_cast<MmaRow*>(c->d_up_rows);
+    PHB_CUDA(c, cudaMemcpyAsync(d_frows, rows.data(), rows.size() * sizeof(MmaRow), cudaMemcpyHostToDevice, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `rows` is a stack object
+    const RowSet rs{nullptr, n, &levels};
+    return mma_dispatch(c, rs, levels.empty() ? PHB_MODE_TILE : PHB_MODE_LEVEL, d_frows);
 }
 
 }  // namespace phb

@@ -209,6 +209,7 @@ int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 // clv_mma.cu (A == 20 or 61, FP64 tensor cores)
 bool mma_supported(const Ctx* c);
 int mma_run_rows(Ctx* c, const RowSet& rs, int mode);
+int mma_run_parent_rows(Ctx* c, const std::vector<int32_t>& parents, const std::vector<int32_t>& levels);   // pre-order pass
 // picks the kernel family for this context's shape
 int run_rows(Ctx* c, const RowSet& rs, int mode);
 int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);

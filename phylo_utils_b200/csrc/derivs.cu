@@ -836,6 +836,54 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     const int root_p = 2 * c->max_rows() + 1;  // P(root length), built by prepare_root
     std::vector<int> depth(c->n_nodes, 0), level_of;
     auto rank = [](int kind) { return kind == SRC_TIP ? 0 : 2; };
+    // 20 / 61 states: one three-operand row per parent on the FP64 tensor cores (clv_mma.cu) - P.X once for both
+    // children, three products instead of four
+    if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr && getenv("PHB_UP_TWO_ROWS") == nullptr) {
+        std::vector<int32_t> parents, plevel;
+        for (int r = n_rows - 1; r >= 0; --r) {
+            const int par = c->rows_raw[3 * r];
+            int x_src, x_kind, x_pidx;
+            if (par == node_a || par == node_b) {
+                fill_operand(c, par == node_a ? node_b : node_a, &x_src, &x_kind);
+                x_pidx = root_p;
+                depth[par] = 0;
+            } else {
+                const int q = c->node_parent[par];
+                PHB_REQUIRE(c, q >= 0, PHB_ERR_STATE, "up partials: the given root edge does not match the schedule");
+                const int rq = c->node_row[q];
+                x_src = c->n_internal + par;
+                x_kind = SRC_GLOBAL;
+                x_pidx = 2 * rq + (c->rows_raw[3 * rq + 1] == par ? 0 : 1);
+                depth[par] = depth[q] + 1;
+            }
+            parents.insert(parents.end(), {x_src, x_kind, x_pidx});
+            for (int i = 0; i < 2; ++i) {
+                int src, kind;
+                fill_operand(c, c->rows_raw[3 * r + 1 + i], &src, &kind);
+                parents.insert(parents.end(), {src, kind, 2 * r + i});
+            }
+            parents.push_back(c->n_internal + c->rows_raw[3 * r + 1]);
+            parents.push_back(c->n_internal + c->rows_raw[3 * r + 2]);
+            plevel.push_back(depth[par]);
+        }
+        std::vector<int32_t> levels;
+        if (!c->level_offsets.empty()) {   // level mode: parents grouped by depth (a parent's X is its parent's output)
+            const int n = (int)plevel.size();
+            std::vector<int> order(n);
+            for (int i = 0; i < n; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return plevel[x] < plevel[y]; });
+            std::vector<int32_t> sorted(parents.size());
+            const int n_levels = plevel[order.back()] + 1;
+            levels.assign(n_levels + 1, 0);
+            for (int i = 0; i < n; ++i) {
+                std::copy(parents.begin() + (size_t)order[i] * 11, parents.begin() + (size_t)order[i] * 11 + 11, sorted.begin() + (size_t)i * 11);
+                levels[plevel[order[i]] + 1]++;
+            }
+            for (int l = 0; l < n_levels; ++l) levels[l + 1] += levels[l];
+            parents.swap(sorted);
+        }
+        return mma_run_parent_rows(c, parents, levels);
+    }
     for (int r = n_rows - 1; r >= 0; --r) {
         const int par = c->rows_raw[3 * r];
         const int ch[2] = {c->rows_raw[3 * r + 1], c->rows_raw[3 * r + 2]};
