@@ -272,11 +272,11 @@ def run_reference_arm(args):
               "patterns; oracle port of the reference engine (the reference is Python+numba and cannot travel), "
               "OpenMP over {} threads").format(args.taxa, args.cpu_patterns, args.patterns, threads)
     line = {
-        "impl": "reference", "metric": "lnL evals/s (GTR+G4, {} taxa x {} patterns)".format(args.taxa, args.patterns),
+        "impl": "reference", "metric": "lnL evals/s (GTR+G4, {} taxa x {} patterns per GPU)".format(args.taxa, args.patterns),
         "value": value, "unit": "lnL evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, max(1, args.gpus)),   # the other arm's config, key for key
         "cpu_baseline": {"value": value, "unit": "lnL evals/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "lnL evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "sample_lnl": lnl,

@@ -137,27 +137,29 @@ def test_up_partials_larger_tree_vs_oracle_total():
     assert np.all(np.isfinite(out))
 
 
-@pytest.mark.parametrize("tree_fn,n_taxa,n_pat", [(random_tree, 150, 20001), (caterpillar_tree, 200, 4099), (random_tree, 3, 70),
-                                                  (random_tree, 4, 33)])
-@pytest.mark.parametrize("ppt", ["1", "2"])
-def test_pre_order_walk_matches_the_two_row_form(tree_fn, n_taxa, n_pat, ppt, monkeypatch):
-    """up_dna_pair.cu against the two-rows-per-parent pass on the same device partials: every edge's
-    (lnL, dlnL, d2lnL) agrees to rounding, ragged last tile and deep scaling (caterpillar) included."""
+def _walk_vs_two_rows(tree_fn, n_taxa, n_pat, ppt, monkeypatch, n_cat=4, iupac=False):
     rng = np.random.default_rng(n_taxa)
     tr_tree = tree_fn(n_taxa, 7)
     names = [l.taxon.label for l in tr_tree.leaf_node_iter()]
-    lut = np.vstack([np.eye(4)[::-1], np.ones((1, 4))])
-    codes = rng.integers(0, 5, size=(n_taxa, n_pat)).astype(np.uint8)
+    if iupac:
+        # all 15 non-empty state sets: look-up tables of more than 8 rows take the 16-row tip tables
+        lut = np.array([[(c >> (3 - i)) & 1 for i in range(4)] for c in range(1, 16)], dtype=float)
+        codes = rng.integers(0, 15, size=(n_taxa, n_pat)).astype(np.uint8)
+    else:
+        lut = np.vstack([np.eye(4)[::-1], np.ones((1, 4))])
+        codes = rng.integers(0, 5, size=(n_taxa, n_pat)).astype(np.uint8)
     model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
-    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    rate = phy.rate_models.GammaRateModel(n_cat, 0.5) if n_cat > 1 else phy.rate_models.UniformRateModel()
     weights = rng.integers(1, 5, size=n_pat)
     out = {}
-    for label, env in (("walk", None), ("two_rows", "1")):
+    for label, env in (("walk", None), ("plain_walk", "plain"), ("two_rows", "1")):
         monkeypatch.setenv("PHB_UP_PPT", ppt)
-        if env:
-            monkeypatch.setenv("PHB_UP_TWO_ROWS", env)
-        else:
-            monkeypatch.delenv("PHB_UP_TWO_ROWS", raising=False)
+        monkeypatch.delenv("PHB_UP_TWO_ROWS", raising=False)
+        monkeypatch.delenv("PHB_UP_PLAIN", raising=False)
+        if env == "1":
+            monkeypatch.setenv("PHB_UP_TWO_ROWS", "1")
+        elif env == "plain":
+            monkeypatch.setenv("PHB_UP_PLAIN", "1")       # the walk storing up partials instead of sum tables
         tm = phy.TreeModel(mode="resident", up_partials=True)
         tm.set_tree(tr_tree)
         tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, siteweights=weights)
@@ -167,12 +169,30 @@ def test_pre_order_walk_matches_the_two_row_form(tree_fn, n_taxa, n_pat, ppt, mo
         tm.compute_up_partials()
         a, b = tm.traversal.root_edge
         nodes = np.asarray([n for n in range(2 * n_taxa - 2) if n != b])
-        out[label] = (tm.edge_derivatives(nodes), tm.lnl())
-    walk, base = out["walk"]
-    two, _ = out["two_rows"]
+        first = tm.edge_derivatives(nodes)
+        second = tm.edge_derivatives(nodes, tm.lengths_above(nodes) * 1.7)
+        out[label] = (first, second, tm.lnl())
+    walk, walk2, base = out["walk"]
     assert np.all(np.isfinite(walk))
     assert np.all(np.abs(walk[:, 0] - base) <= 1e-10 * abs(base))          # pulley principle on every edge
-    assert np.allclose(walk, two, rtol=1e-9, atol=1e-7)
+    for other in ("plain_walk", "two_rows"):
+        assert np.allclose(walk, out[other][0], rtol=1e-9, atol=1e-7), other
+        assert np.allclose(walk2, out[other][1], rtol=1e-9, atol=1e-7), other
+
+
+@pytest.mark.parametrize("tree_fn,n_taxa,n_pat", [(random_tree, 150, 20001), (caterpillar_tree, 200, 4099), (random_tree, 3, 70),
+                                                  (random_tree, 4, 33)])
+@pytest.mark.parametrize("ppt", ["1", "2"])
+def test_pre_order_walk_matches_the_two_row_form(tree_fn, n_taxa, n_pat, ppt, monkeypatch):
+    """up_dna_pair.cu (sum-table form and plain form) against the two-rows-per-parent pass on the same device partials:
+    every edge's (lnL, dlnL, d2lnL) agrees to rounding at the current and at other trial lengths, ragged last tile and
+    deep scaling (caterpillar) included."""
+    _walk_vs_two_rows(tree_fn, n_taxa, n_pat, ppt, monkeypatch)
+
+
+@pytest.mark.parametrize("n_cat,iupac", [(1, False), (2, False), (2, True), (4, True)])
+def test_pre_order_walk_other_category_counts_and_iupac_codes(n_cat, iupac, monkeypatch):
+    _walk_vs_two_rows(random_tree, 60, 5003, "1", monkeypatch, n_cat=n_cat, iupac=iupac)
 
 
 def test_derivatives_need_the_up_pass():
