@@ -14,7 +14,7 @@ from .likelihood import numba_likelihood_engine, cuda_likelihood_engine   # noqa
 from . import substitution_models       # noqa: E402
 from . import rate_models               # noqa: E402
 from . import tree_model                # noqa: E402
-from . import traversal, tree, utils, gamma, alignment   # noqa: E402
+from . import traversal, tree, utils, gamma, alignment, optimise   # noqa: E402
 from .alignment.alignment import seq_to_partials          # noqa: E402
 from .tree_model import TreeModel       # noqa: E402
 from .engine import LikelihoodEngine    # noqa: E402
