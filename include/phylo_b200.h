@@ -182,7 +182,10 @@ int phb_get_root_partials(phb_ctx* ctx, double* out_partials, double* out_scaler
  * ("up" partial), the operand lnl_branch_derivs needs at the far end of each edge; device-side
  * equivalent of walking Traversal.optimising_traversal (utils.py:137-188) without re-rooting in place.
  * (node_a, node_b, length) is the root edge the down partials were computed for
- * (Traversal.root_edge).  Needs PHB_FLAG_UP_PARTIALS and a reversible model. */
+ * (Traversal.root_edge).  Needs PHB_FLAG_UP_PARTIALS and a reversible model.
+ * What the pass leaves in the "up" storage is private to the library and only consumed by
+ * phb_edge_derivatives: up partials, or - where a kernel can form it on the way - the per-edge sum table
+ * s_km = (V^-1 down)_m (V^T (pi * up))_m from which every later derivative pass reads one block per edge. */
 int phb_compute_up_partials(phb_ctx* ctx, int node_a, int node_b, double length);
 /* For each listed node (edge above it; for a root child: the root edge), at the given trial length:
  * out[i] = { lnL, d lnL / dt, d2 lnL / dt2 } summed over patterns with their weights, Gamma mixture
