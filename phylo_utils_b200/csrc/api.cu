@@ -180,6 +180,7 @@ int resolve_schedule(Ctx* c) {
     c->have_schedule = true;
     c->have_partials = false;
     c->have_up = false;
+    c->sched_gen++;
     return PHB_OK;
 }
 
@@ -399,6 +400,7 @@ int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_co
     c->have_tips = true;
     c->have_partials = false;
     c->have_up = false;
+    c->sched_gen++;   // the tip-table geometry the cached plans refer to may have changed
     if (remap && !c->rows_raw.empty()) return resolve_schedule(c);
     return PHB_OK;
 }
@@ -637,15 +639,51 @@ static int prepare_root(phb_ctx* c, int node_a, int node_b, double length, const
     } else {
         PHB_REQUIRE(c, c->have_model, PHB_ERR_STATE, "root edge: no eigen-system set and no matrices given");
         PHB_REQUIRE(c, length >= 0 && std::isfinite(length), PHB_ERR_INVALID, "root edge: bad length");
-        const double two[2] = {0.0, length};  // P(0) on a's side, P(length) on b's: tree_model.py:189-190
+        c->h_root_two[0] = 0.0;      // P(0) on a's side, P(length) on b's: tree_model.py:189-190
+        c->h_root_two[1] = length;
         double* d_len = c->d_lengths + 2 * (size_t)c->max_rows();
-        PHB_CUDA(c, cudaMemcpyAsync(d_len, two, sizeof two, cudaMemcpyHostToDevice, c->stream));
-        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        // pageable source: staged before the call returns - no synchronisation needed for a member array
+        PHB_CUDA(c, cudaMemcpyAsync(d_len, c->h_root_two, sizeof c->h_root_two, cudaMemcpyHostToDevice, c->stream));
         st = launch_build_pmatrices(c, d_len, 2, d_root_p, 0, 0);
         if (st) return st;
     }
     st = launch_tip_tables(c, 2 * c->max_rows(), 2);
     if (st) return st;
+    c->root_a = node_a;
+    c->root_b = node_b;
+    c->root_len = length;
+    return PHB_OK;
+}
+
+// Every matrix an lnL-only evaluation needs - the rows' 2 n_rows and the root edge's two - in ONE pmatrix launch and ONE
+// tip-table launch: the root lengths sit right behind the row lengths.  (At the reference's own test size, 10 taxa x
+// 1000 patterns, an evaluation is launch-latency: two launches, a copy and a synchronisation fewer.)
+static int build_eval_pmats(phb_ctx* c, int node_a, int node_b, double length) {
+    const size_t n = c->lengths.size();
+    if (n != 2 * (size_t)c->max_rows()) {   // two-tip tree, or a partial schedule: the two-step way
+        int st = launch_build_pmatrices(c, c->d_lengths, (int)n, c->d_pmats, 0, 0);
+        if (st) return st;
+        st = launch_tip_tables(c, 0, (int)n);
+        if (st) return st;
+        c->have_pmats = true;
+        return prepare_root(c, node_a, node_b, length, nullptr);
+    }
+    int st = node_operand_ok(c, node_a);
+    if (st) return st;
+    st = node_operand_ok(c, node_b);
+    if (st) return st;
+    PHB_REQUIRE(c, node_a != node_b, PHB_ERR_INVALID, "root edge: both ends are the same node");
+    PHB_REQUIRE(c, c->have_mixture, PHB_ERR_STATE, "root edge: frequencies / mixture not set");
+    PHB_REQUIRE(c, length >= 0 && std::isfinite(length), PHB_ERR_INVALID, "root edge: bad length");
+    c->h_root_two[0] = 0.0;      // P(0) on a's side, P(length) on b's: tree_model.py:189-190
+    c->h_root_two[1] = length;
+    // pageable source: the copy is staged before the call returns, the member array only has to outlive the call
+    PHB_CUDA(c, cudaMemcpyAsync(c->d_lengths + n, c->h_root_two, sizeof c->h_root_two, cudaMemcpyHostToDevice, c->stream));
+    st = launch_build_pmatrices(c, c->d_lengths, (int)n + 2, c->d_pmats, 0, 0);
+    if (st) return st;
+    st = launch_tip_tables(c, 0, (int)n + 2);
+    if (st) return st;
+    c->have_pmats = true;
     c->root_a = node_a;
     c->root_b = node_b;
     c->root_len = length;
@@ -689,12 +727,7 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
     PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
                 "phb_lnl_resident: tips, schedule, model and edge lengths must be set");
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_resident: only 4-state models with K in {1,2,4,8}");
-    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
-    if (st) return st;
-    st = launch_tip_tables(c, 0, (int)c->lengths.size());
-    if (st) return st;
-    c->have_pmats = true;
-    st = prepare_root(c, node_a, node_b, length, nullptr);
+    st = build_eval_pmats(c, node_a, node_b, length);
     if (st) return st;
     // default: two patterns per lane (clv_dna_pair.cu); PHB_RESIDENT_V1 selects the one-pattern-per-lane walk
     if (getenv("PHB_RESIDENT_V1") == nullptr) {
@@ -721,12 +754,7 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
                 "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
     PHB_REQUIRE(c, !packed || c->n_codes <= 16, PHB_ERR_UNSUPPORTED, "phb_lnl_from_host_packed: more than 16 codes");
-    st = launch_build_pmatrices(c, c->d_lengths, (int)c->lengths.size(), c->d_pmats, 0, 0);
-    if (st) return st;
-    st = launch_tip_tables(c, 0, (int)c->lengths.size());
-    if (st) return st;
-    c->have_pmats = true;
-    st = prepare_root(c, node_a, node_b, length, nullptr);
+    st = build_eval_pmats(c, node_a, node_b, length);
     if (st) return st;
     c->have_partials = false;
     c->have_up = false;

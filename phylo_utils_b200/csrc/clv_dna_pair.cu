@@ -695,18 +695,42 @@ int upload_pair_rows(Ctx* c, const ResPlan& plan) {
     return PHB_OK;
 }
 
+// plan + upload unless d_res_rows already holds exactly this plan (kind 1: lnL-only walk with the root step on edge
+// (root_a, root_b); kind 2: every block stored, no root step)
+int cached_pair_plan(Ctx* c, int kind, int root_a, int root_b, int* n_steps, int* n_slots) {
+    auto& rc = c->res_cache;
+    if (rc.kind == kind && rc.root_a == root_a && rc.root_b == root_b && rc.gen == c->sched_gen) {
+        *n_steps = rc.n_steps;
+        *n_slots = rc.n_slots;
+        return PHB_OK;
+    }
+    rc.kind = 0;
+    ResPlan plan;
+    int st = kind == 2 ? plan_rows(c, -1, -1, false, true, &plan) : plan_rows(c, root_a, root_b, true, false, &plan);
+    if (st) return st;
+    *n_steps = (int)plan.rows.size();
+    *n_slots = plan.n_slots;
+    if (plan.rows.empty()) return PHB_OK;
+    st = upload_pair_rows(c, plan);
+    if (st) return st;
+    rc.kind = kind;
+    rc.root_a = root_a;
+    rc.root_b = root_b;
+    rc.gen = c->sched_gen;
+    rc.n_steps = *n_steps;
+    rc.n_slots = *n_slots;
+    return PHB_OK;
+}
+
 }  // namespace
 
 // Post-order pass with every node block stored (PHB_MODE_RESIDENT / PHB_MODE_AUTO of phb_compute_partials)
 int dna_pair_store(Ctx* c) {
     if (c->K > 4) return PHB_ERR_UNSUPPORTED;   // K = 8 keeps the one-pattern-per-lane walk (register budget)
-    ResPlan plan;
-    int st = plan_rows(c, -1, -1, false, true, &plan);
+    int n_steps = 0, n_slots = 0;
+    int st = cached_pair_plan(c, 2, -1, -1, &n_steps, &n_slots);
     if (st) return st;
-    if (plan.rows.empty()) return PHB_OK;
-    st = upload_pair_rows(c, plan);
-    if (st) return st;
-    const int n_steps = (int)plan.rows.size();
+    if (n_steps == 0) return PHB_OK;
     switch (c->K * 100 + tip_table_rows(c)) {
         case 108: return launch_pair_store<1, 8>(c, n_steps);
         case 116: return launch_pair_store<1, 16>(c, n_steps);
@@ -720,17 +744,15 @@ int dna_pair_store(Ctx* c) {
 
 // One evaluation from the tip codes resident on the device: per-pattern lnL + their weighted sum in d_result[0]
 int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
-    ResPlan plan;
-    int st = plan_rows(c, root_a, root_b, true, false, &plan);
-    if (st) return st;
-    st = upload_pair_rows(c, plan);
+    int n_steps = 0, n_slots = 0;
+    int st = cached_pair_plan(c, 1, root_a, root_b, &n_steps, &n_slots);
     if (st) return st;
     int grid = 0;
     const int tile = 32 * pair_ppt(c);
     const int64_t n_tiles = (c->S + tile - 1) / tile;
-    st = launch_pair_k(c, c->codes_packed, (int)plan.rows.size(), plan.n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
+    st = launch_pair_k(c, c->codes_packed, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
     if (st) return st;
-    c->resident_slots = plan.n_slots;
+    c->resident_slots = n_slots;
     return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
 }
 
@@ -742,10 +764,8 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
 // PCIe.  Flags and data are written by memcpy from pinned memory only (copy engine): nothing here needs an SM while
 // the kernel occupies all of them.  One synchronisation at the very end (caller).
 int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b) {
-    ResPlan plan;
-    int st = plan_rows(c, root_a, root_b, true, false, &plan);
-    if (st) return st;
-    st = upload_pair_rows(c, plan);
+    int n_steps = 0, n_slots = 0;
+    int st = cached_pair_plan(c, 1, root_a, root_b, &n_steps, &n_slots);
     if (st) return st;
     if (c->copy_stream == nullptr) {
         PHB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -781,10 +801,9 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chu
         PHB_CUDA(c, cudaMemcpyAsync(c->d_flags + i, c->h_epoch, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
     }
     int grid = 0;
-    st = launch_pair_k(c, packed, (int)plan.rows.size(), plan.n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid,
-                       chunk_shift);
+    st = launch_pair_k(c, packed, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid, chunk_shift);
     if (st) return st;
-    c->resident_slots = plan.n_slots;
+    c->resident_slots = n_slots;
     c->pipelined_pending = true;
     return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
 }

@@ -536,6 +536,7 @@ int launch_resident_k(Ctx* c, const ResPlan& plan, int64_t b, int64_t e, double*
 }  // namespace
 
 int upload_plan(Ctx* c, const ResPlan& plan) {
+    c->res_cache.kind = 0;   // the descriptor buffer no longer holds a pair-kernel plan
     PHB_CUDA(c, cudaMemcpyAsync(c->d_res_rows, plan.rows.data(), plan.rows.size() * sizeof(ResRow),
                                 cudaMemcpyHostToDevice, c->stream));
     PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // plan.rows is a stack object

@@ -99,6 +99,16 @@ struct Ctx {
     double* d_lengths = nullptr;       // [2*max_rows + 2]
     OpRow* d_rows = nullptr;           // [max_rows]
     void* d_res_rows = nullptr;        // [max_rows + 1] 16-byte descriptors of the resident kernel
+    // what d_res_rows currently holds: a plan is a function of the schedule, the tip layout and the root edge only, so
+    // repeated evaluations (new branch lengths, same tree) skip planning and upload
+    int64_t sched_gen = 0;             // bumped whenever the schedule or the tip layout changes
+    struct {
+        int kind = 0;                  // 0 = nothing cached, 1 = pair lnL-only plan, 2 = pair store plan
+        int root_a = -1, root_b = -1;
+        int64_t gen = -1;
+        int n_steps = 0, n_slots = 0;
+    } res_cache;
+    double h_root_two[2] = {0.0, 0.0}; // P(0), P(root length): source of the asynchronous copy behind the row lengths
     int resident_u = 0;                // 0 = choose, else forced patterns-per-warp multiplier (tuning / tests)
     int resident_slots = 0;            // parked blocks the last resident launch needed
     int resident_warps = 0;            // warps per SM of the last resident launch
