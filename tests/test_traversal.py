@@ -116,3 +116,31 @@ def test_root_edge_length_is_the_sum_of_the_two_root_branches():
 def test_traversal_needs_a_binary_root():
     with pytest.raises(ValueError):
         Traversal(parse_newick("(a:1,b:1,c:1);"))
+
+
+def test_edge_keys_and_vectorised_length_gathers_match_the_dictionary():
+    """Host logic of the Newton driver: the brlens keys of the edges above a list of nodes are resolved once
+    (TreeModel.edge_keys) and lengths move through them; both must agree with the plain dictionary look-ups."""
+    import phylo_utils_b200 as phy
+    from phylo_utils_b200.optimise import edge_nodes, newton_step, _get_lengths, _set_lengths
+    tm = phy.TreeModel()
+    tm.set_tree(random_tree(37, 3))
+    tr = tm.traversal
+    nodes = edge_nodes(tr)
+    a, b = tr.root_edge
+    assert b not in nodes and a in nodes and len(nodes) == 2 * 37 - 3
+    keys = tm.edge_keys(nodes)
+    assert len(set(keys)) == len(keys) == len(tr.brlens)            # one key per edge of the unrooted tree, all covered
+    want = np.array([tm.branch_length_above(int(n)) for n in nodes])
+    assert np.array_equal(tm.lengths_above(nodes), want)
+    assert np.array_equal(_get_lengths(tr.brlens, keys), want)
+    _set_lengths(tr.brlens, keys, want * 2.0)
+    assert np.array_equal(tm.lengths_above(nodes), want * 2.0)
+    assert tm.branch_length_above(b) == tm.branch_length_above(a)  # either root child means the root edge
+    with pytest.raises(ValueError):
+        tm.edge_keys([2 * 37])                                      # no such node
+    # safeguarded Newton step: concave -> Newton, convex -> doubling / halving, always inside the bounds
+    t = np.array([0.1, 0.1, 0.1, 1e-6, 19.0])
+    out = newton_step(t, np.array([1.0, 1.0, -1.0, -5.0, 3.0]), np.array([-20.0, 5.0, 5.0, -1.0, 1.0]))
+    assert np.allclose(out[:3], [0.15, 0.2, 0.05])
+    assert out[3] >= 1.0 / 2 ** 16 and out[4] <= 20.0
