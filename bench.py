@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--store-partials", action="store_true",
                     help="headline path keeps every node's partials in HBM (TreeModel.partials / derivatives); "
                          "default is the pure lnL evaluation with the operand-resident kernel")
-    ap.add_argument("--chunks", type=int, default=16, help="host->device pipeline depth of the e2e path")
+    ap.add_argument("--chunks", type=int, default=64, help="host->device pipeline depth of the e2e path (16: 68.6, 32: 68.6, 64: 69.9, 128: 69.5 evals/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stored", action="store_true", help="skip the extra 'partials stored' measurements")

@@ -758,7 +758,7 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
     if (st) return st;
     c->have_partials = false;
     c->have_up = false;
-    if (n_chunks <= 0) n_chunks = 16;
+    if (n_chunks <= 0) n_chunks = 64;   // measured at 1000 x 1M: 16 -> 68.6, 64 -> 69.9 evaluations/s
     if (!packed && getenv("PHB_RESIDENT_V1") != nullptr) {
         c->codes_packed = false;
         st = dna_resident_from_host(c, codes, n_chunks, node_a, node_b);
