@@ -18,6 +18,9 @@ KEYS = [
     "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed_pipe_fp64.sum",
+    # FP64 tensor cores (DMMA): the pipe-utilisation figures of the 20- / 61-state kernels
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -30,8 +33,9 @@ def main(path):
         name = rec[hdr.index("Kernel Name")]
         print("kernel:", name)
         for k in KEYS:
-            if k in hdr:
-                i = hdr.index(k)
+            match = [h for h in hdr if h == k or h.endswith("." + k)]
+            if match:
+                i = hdr.index(match[0])
                 print("  {:70s} {:>18s} {}".format(k, rec[i], units[i]))
         stalls = []
         for i, h in enumerate(hdr):
