@@ -90,6 +90,9 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     double* Pbuf = sm;                               // [2][MROWS][LDP]
     double* Lbuf = Pbuf + 2 * MROWS * LDP;           // [2][TS][LDL]
     unsigned char* s_codes = reinterpret_cast<unsigned char*>(Lbuf + 2 * TS * LDL);   // [3 operands][TS]
+    int* s_exp = reinterpret_cast<int*>(s_codes + 4 * TS);   // [3 operands][TS] exponents of the operands' patterns
+    int* s_shift = s_exp + 3 * TS;                           // [TS] binary shift a pattern of the output is rescaled by
+    static_assert(WR <= 32, "one pattern per lane in the per-pattern bookkeeping");
     constexpr int A = AA;   // compile-time: the staging loops divide by it
     const int K = p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,6 +100,22 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     const size_t S = (size_t)p.S;
     for (int e = threadIdx.x; e < 2 * MROWS * LDP + 2 * TS * LDL; e += WARPS * 32) sm[e] = 0.0;
     __syncthreads();
+
+    // a P block or tip table -> the staging buffer: rows of A doubles, contiguous in shared memory too when LDP == A
+    // (20 states: one 16-byte copy per two doubles instead of two 8-byte ones)
+    auto stage_matrix = [&](double* Pd, const double* q, int n_rows) {
+        if (LDP == A && A % 2 == 0) {
+            for (int e = threadIdx.x; e < n_rows * A / 2; e += WARPS * 32) {
+                const unsigned d = (unsigned)__cvta_generic_to_shared(Pd + 2 * e);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q + 2 * e) : "memory");
+            }
+        } else {
+            for (int e = threadIdx.x; e < n_rows * A; e += WARPS * 32) {
+                const int i = e / A, j = e - i * A;
+                cp_async8(Pd + i * LDP + j, q + e);
+            }
+        }
+    };
 
     const int64_t items = LEVEL ? (int64_t)(p.row_end - p.row_begin) * p.n_tiles : p.n_tiles;
     for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
@@ -126,14 +145,27 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
             auto kind_of = [&](int c) { return c == 0 ? row.kind[0] : (c == 1 ? row.kind[1] : row.kind[2]); };
             auto pidx_of = [&](int c) { return c == 0 ? row.pidx[0] : (c == 1 ? row.pidx[1] : row.pidx[2]); };
 
-            // tip codes of this warp's patterns (same for every category)
-            for (int c = 0; c < n_ops; ++c)
-                if (kind_of(c) == SRC_TIP)
-                    for (int n = lane; n < WR; n += 32) {
-                        const int64_t s = wsite0 + n;
-                        s_codes[c * TS + warp * WR + n] = s < p.S ? p.codes[(size_t)src_of(c) * p.pitch + s] : 0;
-                    }
-            __syncwarp();
+            // tip codes and exponents of this warp's patterns (one per lane), same for every category.  The loads are
+            // issued here and parked in shared memory once the first operand copies are under way: one latency, not two.
+            const bool lane_ok = lane < WR && wsite0 + lane < p.S;
+            int code_reg[3] = {0, 0, 0}, exp_reg[3] = {0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (c < n_ops && lane_ok) {
+                    if (kind_of(c) == SRC_TIP) code_reg[c] = p.codes[(size_t)src_of(c) * p.pitch + wsite0 + lane];
+                    else exp_reg[c] = p.scale[(size_t)src_of(c) * S + wsite0 + lane];
+                }
+            auto park_codes = [&]() {
+                if (lane < WR) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (c < n_ops) {
+                            s_codes[c * TS + warp * WR + lane] = (unsigned char)code_reg[c];
+                            s_exp[c * TS + warp * WR + lane] = exp_reg[c];
+                        }
+                }
+                __syncwarp();
+            };
 
             // phase ph = (category k, operand c), in the order (k, 0), (k, 1) [, (k, 2)]; buffers alternate with ph
             auto prefetch = [&](int ph, int k, int c) {
@@ -142,19 +174,11 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 if (kind_of(c) == SRC_TIP && p.tiptab != nullptr) {
                     // a tip child needs no product at all: its contribution is row `code` of T = P . lut, staged
                     // where the P block would go (row = code, n_codes <= MROWS rows)
-                    const double* q = p.tiptab + ((size_t)pidx_of(c) * K + k) * p.nc * A;
-                    for (int e = threadIdx.x; e < p.nc * A; e += WARPS * 32) {
-                        const int i = e / A, j = e - i * A;
-                        cp_async8(Pd + i * LDP + j, q + e);
-                    }
+                    stage_matrix(Pd, p.tiptab + ((size_t)pidx_of(c) * K + k) * p.nc * A, p.nc);
                     cp_async_commit_all();
                     return;
                 }
-                const double* q = p.pmats + ((size_t)pidx_of(c) * K + k) * A * A;
-                for (int e = threadIdx.x; e < A * A; e += WARPS * 32) {
-                    const int i = e / A, j = e - i * A;
-                    cp_async8(Pd + i * LDP + j, q + e);
-                }
+                stage_matrix(Pd, p.pmats + ((size_t)pidx_of(c) * K + k) * A * A, A);
                 double* Ld = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
                 if (kind_of(c) == SRC_TIP) {
                     for (int e = lane; e < WR * A; e += 32) {
@@ -225,7 +249,9 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
             };
 
             __syncthreads();          // the previous row is completely done with both buffer pairs
+            if (p.tiptab == nullptr) park_codes();   // without tip tables the first copy gathers look-up rows by code
             prefetch(0, 0, 0);
+            if (p.tiptab != nullptr) park_codes();
             int ph = 0;
             for (int k = 0; k < K; ++k) {
                 run_phase(ph, k, 0, acc0);
@@ -287,29 +313,33 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         if (j == 0) mx[0][nt][q] = m;
                         else mx[1][nt][q] = m;
                     }
-                // lanes 0..3 (fr == 0) finalise the patterns 2*fc + q of every n-tile
+                // lanes 0..3 (fr == 0) hold the maxima of the patterns 2*fc + q of every n-tile: the shift of each pattern
                 if (fr == 0) {
-                    double* out = p.clv + (size_t)(j == 0 ? row.dst[0] : row.dst[1]) * S * K * A;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int q = 0; q < 2; ++q) {
-                            const int64_t s = wsite0 + nt * 8 + 2 * fc + q;
-                            if (s >= p.S) continue;
-                            int e = 0;
-                            if (row.kind[0] != SRC_TIP) e += p.scale[(size_t)row.src[0] * S + s];
-                            if (kind_of(j + 1) != SRC_TIP) e += p.scale[(size_t)src_of(j + 1) * S + s];
                             const int hi = j == 0 ? mx[0][nt][q] : mx[1][nt][q];
-                            if (hi < kScaleThresholdHi && hi >= 0x00100000) {
-                                const int shift = 1023 - (hi >> 20);
-                                const double f = pow2i(shift);
-                                double* mine = out + (size_t)s * K * A;
-                                for (int z = 0; z < K * A; ++z) mine[z] *= f;
-                                e -= shift;
-                            }
-                            p.scale[(size_t)(j == 0 ? row.dst[0] : row.dst[1]) * S + s] = e;
+                            s_shift[warp * WR + nt * 8 + 2 * fc + q] = (hi < kScaleThresholdHi && hi >= 0x00100000) ? 1023 - (hi >> 20) : 0;
                         }
                 }
+                __syncwarp();
+                // one pattern per lane: exponent of the output, and - rarely - the rescaling of a block row that is
+                // already in global memory, all 32 lanes on one pattern's K A doubles at a time (coalesced)
+                const int my_shift = lane_ok ? s_shift[warp * WR + lane] : 0;
+                const int dst_blk = j == 0 ? row.dst[0] : row.dst[1];
+                if (lane_ok)
+                    p.scale[(size_t)dst_blk * S + wsite0 + lane] =
+                        s_exp[warp * WR + lane] + s_exp[(j + 1) * TS + warp * WR + lane] - my_shift;
+                unsigned todo = __ballot_sync(0xffffffffu, my_shift != 0);
+                while (todo) {
+                    const int pi = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double f = pow2i(__shfl_sync(0xffffffffu, my_shift, pi));
+                    double* mine = p.clv + ((size_t)dst_blk * S + wsite0 + pi) * K * A;
+                    for (int z = lane; z < K * A; z += 32) mine[z] *= f;
+                }
+                __syncwarp();
             }
             __threadfence_block();   // this row's block is visible to the cp.async reads of the next row
             __syncwarp();
@@ -341,7 +371,7 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, const Mm
     a.n_tiles = (c->S + TS - 1) / TS;
     a.A = c->A;
     a.K = c->K;
-    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 3 * TS;
+    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 4 * TS + 4 * TS * sizeof(int);
     auto kern = d_frows != nullptr ? mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, true> : mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, false>;
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
