@@ -123,22 +123,30 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
         const int r0 = LEVEL ? p.row_begin + (int)(it / p.n_tiles) : p.row_begin;
         const int r1 = LEVEL ? r0 + 1 : p.row_end;
         const int64_t wsite0 = tile * TS + (int64_t)warp * WR;   // first pattern of this warp
-        for (int r = r0; r < r1; ++r) {
-            MmaRow row;
+        // the descriptor of row r + 1 is fetched while row r runs: its latency, and that of the codes / exponents that
+        // depend on it, no longer sit in front of every row
+        auto load_row = [&](int r) {
+            MmaRow d;
             if (FUSED) {
-                row = p.frows[r];
+                d = p.frows[r];
             } else {
                 const OpRow o = p.rows[r];
                 for (int c = 0; c < 2; ++c) {
-                    row.src[c] = o.src[c];
-                    row.kind[c] = o.kind[c];
-                    row.pidx[c] = o.pidx[c];
+                    d.src[c] = o.src[c];
+                    d.kind[c] = o.kind[c];
+                    d.pidx[c] = o.pidx[c];
                 }
-                row.src[2] = row.pidx[2] = 0;
-                row.kind[2] = SRC_TIP;
-                row.dst[0] = row.dst[1] = o.dst;
-                row.n_ops = 2;
+                d.src[2] = d.pidx[2] = 0;
+                d.kind[2] = SRC_TIP;
+                d.dst[0] = d.dst[1] = o.dst;
+                d.n_ops = 2;
             }
+            return d;
+        };
+        MmaRow next_row = load_row(r0);
+        for (int r = r0; r < r1; ++r) {
+            const MmaRow row = next_row;
+            if (r + 1 < r1) next_row = load_row(r + 1);
             const int n_ops = FUSED ? 3 : 2, n_phases = n_ops * K;   // compile-time per instantiation: a pruning row costs what it did
             // selects instead of indexed reads: the row stays in registers
             auto src_of = [&](int c) { return c == 0 ? row.src[0] : (c == 1 ? row.src[1] : row.src[2]); };
@@ -337,7 +345,14 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     todo &= todo - 1;
                     const double f = pow2i(__shfl_sync(0xffffffffu, my_shift, pi));
                     double* mine = p.clv + ((size_t)dst_blk * S + wsite0 + pi) * K * A;
-                    for (int z = lane; z < K * A; z += 32) mine[z] *= f;
+                    for (int z0 = lane; z0 < K * A; z0 += 128) {   // four loads in flight per lane, then the stores
+                        double v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = z0 + 32 * u < K * A ? mine[z0 + 32 * u] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (z0 + 32 * u < K * A) mine[z0 + 32 * u] = v[u] * f;
+                    }
                 }
                 __syncwarp();
             }
