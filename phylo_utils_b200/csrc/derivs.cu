@@ -320,25 +320,27 @@ __global__ void deriv_m2_kernel(const double* __restrict__ evecs, const double* 
     }
 }
 
-// grid = (n_parts, n_edges); a CTA walks pattern tiles of one edge, every warp owns NT * 8 patterns of the tile
-template <int AA, int MT, int KS, int NT, int WARPS>
+// grid = (n_parts, n_edges); a CTA walks pattern tiles of one edge, every warp owns NT * 8 patterns of the tile.
+// DB: the operand rows of step (tile, category) + 1 stream into a second pair of row buffers while the products of the
+// current step run (20 states; at 61 states one pair already fills the SM's shared memory).
+template <int AA, int MT, int KS, int NT, int WARPS, bool DB>
 __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDerivArgs p) {
     constexpr int A = AA, MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = deriv_pad_pitch(KCOLS), LDL = deriv_pad_pitch(KCOLS);
-    constexpr int TS = WARPS * NT * 8, WR = NT * 8;
+    constexpr int TS = WARPS * NT * 8, WR = NT * 8, NBUF = DB ? 2 : 1;
     extern __shared__ double sm[];
     double* M1 = sm;                          // [MROWS][LDP]
     double* M2 = M1 + MROWS * LDP;            // [MROWS][LDP]
-    double* La = M2 + MROWS * LDP;            // [TS][LDL]   rows of the operand below the edge
-    double* Lb = La + TS * LDL;               // [TS][LDL]   rows of the operand above the edge
-    double* coef = Lb + TS * LDL;             // [3][K][MROWS]
+    double* La = M2 + MROWS * LDP;            // [NBUF][TS][LDL]   rows of the operand below the edge
+    double* Lb = La + NBUF * TS * LDL;        // [NBUF][TS][LDL]   rows of the operand above the edge
+    double* coef = Lb + NBUF * TS * LDL;      // [3][K][MROWS]
     __shared__ double s_red[3][WARPS];
     const int K = p.K, e = blockIdx.y;
     if (p.edges[e].kind_a == SRC_SUMTABLE) return;   // edge_st_kernel's edge (the whole CTA leaves)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fr = lane >> 2, fc = lane & 3;
     const size_t S = (size_t)p.S;
-    for (int i = threadIdx.x; i < 2 * MROWS * LDP + 2 * TS * LDL; i += WARPS * 32) sm[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * MROWS * LDP + 2 * NBUF * TS * LDL; i += WARPS * 32) sm[i] = 0.0;
     __syncthreads();
     for (int i = threadIdx.x; i < A * A; i += WARPS * 32) {
         const int r = i / A, c = i - r * A;
@@ -357,126 +359,163 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
         write_st = true;
         st_blk = (size_t)(e == p.st_extra_edge[0] ? p.st_extra_block[0] : p.st_extra_block[1]);
     }
-    double* myA = La + (size_t)warp * WR * LDL;
-    double* myB = Lb + (size_t)warp * WR * LDL;
-    double tot[3] = {0.0, 0.0, 0.0};
-    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    // operand rows of this warp's patterns for one (tile, category) -> row buffer `buf`.  Rows of A doubles are 16-byte
+    // aligned when A is even (A = 20: ten 16-byte pieces per row), 8-byte aligned otherwise (A = 61).  Tip rows do not
+    // depend on the category: written when a tile meets a buffer for the first time.
+    constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
+    auto stage = [&](int64_t tile, int k, int buf) {
         const int64_t wsite0 = tile * TS + (int64_t)warp * WR;
-        double t[3][NT][2];
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) t[d][nt][0] = t[d][nt][1] = 0.0;
-        for (int k = 0; k < K; ++k) {
-            __syncwarp();   // every lane is done with the rows of the previous category
-            // operand rows of this warp's patterns for category k.  Rows of A doubles are 16-byte aligned when A is
-            // even (A = 20: ten 16-byte pieces per row), 8-byte aligned otherwise (A = 61).
-            constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
-            const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
-            auto stage = [&](int kind, size_t src, double* mine) {
-                if (kind == SRC_TIP) {
-                    if (k == 0)
-                        for (int idx = lane; idx < n_valid * A; idx += 32) {
-                            const int n = idx / A, j = idx - n * A;
-                            mine[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[src * p.pitch + wsite0 + n] * A + j);
-                        }
-                    return;
-                }
-                const unsigned char* g = reinterpret_cast<const unsigned char*>(p.clv + ((src * S + wsite0) * K + k) * A);
-                const unsigned sdst = (unsigned)__cvta_generic_to_shared(mine);
-                for (int c = lane; c < n_valid * PIECES; c += 32) {
-                    const int n = c / PIECES, piece = c - n * PIECES;
-                    const unsigned d = sdst + n * (LDL * 8) + piece * PB;
-                    const unsigned char* q = g + (size_t)n * (K * A * 8) + piece * PB;
-                    if (PB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
-                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
-                }
-            };
-            stage(ka, sa, myA);
-            stage(kb, sb, myB);
+        const int n_valid = (int)max((int64_t)0, min((int64_t)WR, p.S - wsite0));
+        auto one = [&](int kind, size_t src, double* mine) {
+            if (kind == SRC_TIP) {
+                if (k < NBUF)
+                    for (int idx = lane; idx < n_valid * A; idx += 32) {
+                        const int n = idx / A, j = idx - n * A;
+                        mine[n * LDL + j] = __ldg(p.lut + (size_t)p.codes[src * p.pitch + wsite0 + n] * A + j);
+                    }
+                return;
+            }
+            const unsigned char* g = reinterpret_cast<const unsigned char*>(p.clv + ((src * S + wsite0) * K + k) * A);
+            const unsigned sdst = (unsigned)__cvta_generic_to_shared(mine);
+            for (int c = lane; c < n_valid * PIECES; c += 32) {
+                const int n = c / PIECES, piece = c - n * PIECES;
+                const unsigned d = sdst + n * (LDL * 8) + piece * PB;
+                const unsigned char* q = g + (size_t)n * (K * A * 8) + piece * PB;
+                if (PB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
+                else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
+            }
+        };
+        one(ka, sa, La + ((size_t)buf * TS + (size_t)warp * WR) * LDL);
+        one(kb, sb, Lb + ((size_t)buf * TS + (size_t)warp * WR) * LDL);
+    };
+    // the pattern whose tail (log, two divisions) this lane runs: all 32 lanes busy instead of four
+    const int my_nt = fr >> 1, my_q = fr & 1;
+    const int my_pi = my_nt * 8 + 2 * fc + my_q;
+    double tot[3] = {0.0, 0.0, 0.0};
+    double t[3][NT][2];
+    int my_ex = 0;
+    int64_t tile = blockIdx.x;
+    int k = 0, buf = 0;
+    if (DB && tile < p.n_tiles) {
+        stage(tile, 0, 0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    while (tile < p.n_tiles) {
+        const int64_t wsite0 = tile * TS + (int64_t)warp * WR;
+        int64_t tile_n = tile;
+        int k_n = k + 1;
+        if (k_n == K) {
+            k_n = 0;
+            tile_n += gridDim.x;
+        }
+        __syncwarp();   // every lane is done with the rows of the previous step
+        if (DB) {
+            if (tile_n < p.n_tiles) stage(tile_n, k_n, buf ^ 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the copies just issued has landed
+        } else {
+            stage(tile, k, 0);
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            double x[MT][NT][2], y[MT][NT][2];
+        }
+        __syncwarp();
+        if (k == 0) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+            for (int d = 0; d < 3; ++d)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) x[mt][nt][0] = x[mt][nt][1] = y[mt][nt][0] = y[mt][nt][1] = 0.0;
-#pragma unroll 2
-            for (int ks = 0; ks < KS; ++ks) {
-                double fa[NT], fb[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    fa[nt] = myA[(nt * 8 + fr) * LDL + ks * 4 + fc];
-                    fb[nt] = myB[(nt * 8 + fr) * LDL + ks * 4 + fc];
-                }
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const double a1 = M1[(mt * 8 + fr) * LDP + ks * 4 + fc];
-                    const double a2 = M2[(mt * 8 + fr) * LDP + ks * 4 + fc];
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        dmma884(x[mt][nt], a1, fa[nt]);
-                        dmma884(y[mt][nt], a2, fb[nt]);
-                    }
-                }
+                for (int nt = 0; nt < NT; ++nt) t[d][nt][0] = t[d][nt][1] = 0.0;
+            // exponents of this lane's tail pattern: asked for now, needed K products later
+            my_ex = 0;
+            if (my_nt < NT && wsite0 + my_pi < p.S) {
+                if (ka != SRC_TIP) my_ex += p.scale[sa * S + wsite0 + my_pi];
+                if (kb != SRC_TIP) my_ex += p.scale[sb * S + wsite0 + my_pi];
             }
-            // fragment element (mt, nt, q) = eigen-component mt*8+fr of pattern nt*8 + 2fc + q
+        }
+        const double* myA = La + ((size_t)(DB ? buf : 0) * TS + (size_t)warp * WR) * LDL;
+        const double* myB = Lb + ((size_t)(DB ? buf : 0) * TS + (size_t)warp * WR) * LDL;
+        double x[MT][NT][2], y[MT][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) x[mt][nt][0] = x[mt][nt][1] = y[mt][nt][0] = y[mt][nt][1] = 0.0;
+#pragma unroll 2
+        for (int ks = 0; ks < KS; ++ks) {
+            double fa[NT], fb[NT];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                fa[nt] = myA[(nt * 8 + fr) * LDL + ks * 4 + fc];
+                fb[nt] = myB[(nt * 8 + fr) * LDL + ks * 4 + fc];
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const double c0 = coef[(0 * K + k) * MROWS + mt * 8 + fr];
-                const double c1 = coef[(1 * K + k) * MROWS + mt * 8 + fr];
-                const double c2 = coef[(2 * K + k) * MROWS + mt * 8 + fr];
+                const double a1 = M1[(mt * 8 + fr) * LDP + ks * 4 + fc];
+                const double a2 = M2[(mt * 8 + fr) * LDP + ks * 4 + fc];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const double xy = x[mt][nt][q] * y[mt][nt][q];
-                        t[0][nt][q] = fma(c0, xy, t[0][nt][q]);
-                        t[1][nt][q] = fma(c1, xy, t[1][nt][q]);
-                        t[2][nt][q] = fma(c2, xy, t[2][nt][q]);
-                        if (write_st) {
-                            // eight lanes (fr) write eight consecutive components of one pattern: 64-byte runs.  The
-                            // block's rows of this category have all been staged (cp.async waited above).
-                            const int64_t st_s = wsite0 + nt * 8 + 2 * fc + q;
-                            if (mt * 8 + fr < A && st_s < p.S) p.clv_rw[((st_blk * S + (size_t)st_s) * K + k) * A + mt * 8 + fr] = xy;
-                        }
-                    }
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma884(x[mt][nt], a1, fa[nt]);
+                    dmma884(y[mt][nt], a2, fb[nt]);
+                }
             }
         }
-        // sum over the eigen-components held by the lanes that share fc
+        // fragment element (mt, nt, q) = eigen-component mt*8+fr of pattern nt*8 + 2fc + q
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    double v = t[d][nt][q];
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    t[d][nt][q] = v;
-                }
-        if (fr == 0) {
+        for (int mt = 0; mt < MT; ++mt) {
+            const double c0 = coef[(0 * K + k) * MROWS + mt * 8 + fr];
+            const double c1 = coef[(1 * K + k) * MROWS + mt * 8 + fr];
+            const double c2 = coef[(2 * K + k) * MROWS + mt * 8 + fr];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    const int64_t s = wsite0 + nt * 8 + 2 * fc + q;
-                    if (s >= p.S) continue;
-                    int ex = 0;
-                    if (ka != SRC_TIP) ex += p.scale[sa * S + s];
-                    if (kb != SRC_TIP) ex += p.scale[sb * S + s];
-                    if (write_st) p.scale_rw[st_blk * S + s] = ex;   // the table's exponent: both ends'
-                    const double w = p.weights ? p.weights[s] : 1.0;
-                    const double L = t[0][nt][q];
-                    const double g = t[1][nt][q] / L;
-                    tot[0] += w * (L > 0 ? log(L) + (double)ex * kLn2 : -INFINITY);
-                    tot[1] += w * g;
-                    tot[2] += w * (t[2][nt][q] / L - g * g);
+                    const double xy = x[mt][nt][q] * y[mt][nt][q];
+                    t[0][nt][q] = fma(c0, xy, t[0][nt][q]);
+                    t[1][nt][q] = fma(c1, xy, t[1][nt][q]);
+                    t[2][nt][q] = fma(c2, xy, t[2][nt][q]);
+                    if (write_st) {
+                        // eight lanes (fr) write eight consecutive components of one pattern: 64-byte runs.  The
+                        // block's rows of this category have all been staged (cp.async waited above).
+                        const int64_t st_s = wsite0 + nt * 8 + 2 * fc + q;
+                        if (mt * 8 + fr < A && st_s < p.S) p.clv_rw[((st_blk * S + (size_t)st_s) * K + k) * A + mt * 8 + fr] = xy;
+                    }
                 }
         }
+        if (k == K - 1) {
+            // sum over the eigen-components held by the lanes that share fc; afterwards all eight of them hold the sums
+            // of the eight patterns (nt, q) of that fc, and lane fr takes pattern (fr >> 1, fr & 1)
+            double L = 1.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double v[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        v[d] = t[d][nt][q];
+                        v[d] += __shfl_xor_sync(0xffffffffu, v[d], 4);
+                        v[d] += __shfl_xor_sync(0xffffffffu, v[d], 8);
+                        v[d] += __shfl_xor_sync(0xffffffffu, v[d], 16);
+                    }
+                    if (fr == nt * 2 + q) {
+                        L = v[0];
+                        t1 = v[1];
+                        t2 = v[2];
+                    }
+                }
+            const int64_t s = wsite0 + my_pi;
+            if (my_nt < NT && s < p.S) {
+                if (write_st) p.scale_rw[st_blk * S + s] = my_ex;   // the table's exponent: both ends'
+                const double w = p.weights ? p.weights[s] : 1.0;
+                const double g = t1 / L;
+                tot[0] += w * (L > 0 ? log(L) + (double)my_ex * kLn2 : -INFINITY);
+                tot[1] += w * g;
+                tot[2] += w * (t2 / L - g * g);
+            }
+        }
+        tile = tile_n;
+        k = k_n;
+        buf ^= 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const double v = warp_sum(tot[d]);
@@ -490,14 +529,14 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
     }
 }
 
-template <int AA, int MT, int KS, int NT, int WARPS>
+template <int AA, int MT, int KS, int NT, int WARPS, bool DB>
 int launch_mma_derivs(Ctx* c, MmaDerivArgs& a, int n_edges) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = deriv_pad_pitch(KCOLS), LDL = deriv_pad_pitch(KCOLS);
     constexpr int TS = WARPS * NT * 8;
     a.n_tiles = (c->S + TS - 1) / TS;
-    const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL + 3 * (size_t)c->K * MROWS) * sizeof(double);
-    auto kern = mma_edge_deriv_kernel<AA, MT, KS, NT, WARPS>;
+    const size_t smem = (2 * (size_t)MROWS * LDP + (DB ? 4 : 2) * (size_t)TS * LDL + 3 * (size_t)c->K * MROWS) * sizeof(double);
+    auto kern = mma_edge_deriv_kernel<AA, MT, KS, NT, WARPS, DB>;
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "DMMA derivative kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -1045,7 +1084,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
                 }
             int st = PHB_OK;
             if (n_fresh > 0) {
-                st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8>(c, m, n);
+                st = A == 20 ? launch_mma_derivs<20, 3, 5, 4, 4, true>(c, m, n) : launch_mma_derivs<61, 8, 16, 2, 8, false>(c, m, n);
                 if (st) return st;
             } else {
                 // block sums are laid out for this many parts either way
