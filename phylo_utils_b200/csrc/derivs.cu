@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
     const int my_pi = my_nt * 8 + 2 * fc + my_q;
     double tot[3] = {0.0, 0.0, 0.0};
     double t[3][NT][2];
+    double* st_ptr[NT][2];   // where component fr of this lane's patterns goes in the edge's sum table
     int my_ex = 0;
     int64_t tile = blockIdx.x;
     int k = 0, buf = 0;
@@ -424,6 +425,13 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
             for (int d = 0; d < 3; ++d)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) t[d][nt][0] = t[d][nt][1] = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int64_t st_s = wsite0 + nt * 8 + 2 * fc + q;
+                    st_ptr[nt][q] = (write_st && st_s < p.S) ? p.clv_rw + (st_blk * S + (size_t)st_s) * K * A + fr : nullptr;
+                }
             // exponents of this lane's tail pattern: asked for now, needed K products later
             my_ex = 0;
             if (my_nt < NT && wsite0 + my_pi < p.S) {
@@ -471,12 +479,11 @@ __global__ void __launch_bounds__(WARPS * 32) mma_edge_deriv_kernel(const MmaDer
                     t[0][nt][q] = fma(c0, xy, t[0][nt][q]);
                     t[1][nt][q] = fma(c1, xy, t[1][nt][q]);
                     t[2][nt][q] = fma(c2, xy, t[2][nt][q]);
-                    if (write_st) {
-                        // eight lanes (fr) write eight consecutive components of one pattern: 64-byte runs.  The
-                        // block's rows of this category have all been staged (cp.async waited above).
-                        const int64_t st_s = wsite0 + nt * 8 + 2 * fc + q;
-                        if (mt * 8 + fr < A && st_s < p.S) p.clv_rw[((st_blk * S + (size_t)st_s) * K + k) * A + mt * 8 + fr] = xy;
-                    }
+                    // eight lanes (fr) write eight consecutive components of one pattern: 64-byte runs.  The block's
+                    // rows of this category have all been staged (cp.async waited above).  One pointer per pattern,
+                    // set up once per tile (null: nothing to write) - the address arithmetic of 24 scattered stores
+                    // per category was a third of the kernel's instructions.
+                    if (st_ptr[nt][q] != nullptr && (mt * 8 + 8 <= A || mt * 8 + fr < A)) st_ptr[nt][q][k * A + mt * 8] = xy;
                 }
         }
         if (k == K - 1) {
