@@ -340,18 +340,44 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     p.scale[(size_t)dst_blk * S + wsite0 + lane] =
                         s_exp[warp * WR + lane] + s_exp[(j + 1) * TS + warp * WR + lane] - my_shift;
                 unsigned todo = __ballot_sync(0xffffffffu, my_shift != 0);
-                while (todo) {
-                    const int pi = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const double f = pow2i(__shfl_sync(0xffffffffu, my_shift, pi));
-                    double* mine = p.clv + ((size_t)dst_blk * S + wsite0 + pi) * K * A;
-                    for (int z0 = lane; z0 < K * A; z0 += 128) {   // four loads in flight per lane, then the stores
-                        double v[4];
+                if (K * A <= 96) {
+                    // up to four patterns at a time, all of their loads (three per lane and pattern) before the first
+                    // store: the latency of the read-modify-write is paid once per four patterns
+                    while (todo) {
+                        double* mine[4];
+                        double f[4], v[4][3];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) v[u] = z0 + 32 * u < K * A ? mine[z0 + 32 * u] : 0.0;
+                        for (int u = 0; u < 4; ++u) {
+                            const int pi = todo ? __ffs(todo) - 1 : -1;
+                            if (todo) todo &= todo - 1;
+                            mine[u] = pi >= 0 ? p.clv + ((size_t)dst_blk * S + wsite0 + pi) * K * A : nullptr;
+                            f[u] = pi >= 0 ? pow2i(__shfl_sync(0xffffffffu, my_shift, pi)) : 1.0;
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            if (z0 + 32 * u < K * A) mine[z0 + 32 * u] = v[u] * f;
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+                                v[u][i] = (mine[u] != nullptr && lane + 32 * i < K * A) ? mine[u][lane + 32 * i] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i)
+                                if (mine[u] != nullptr && lane + 32 * i < K * A) mine[u][lane + 32 * i] = v[u][i] * f[u];
+                    }
+                } else {
+                    while (todo) {
+                        const int pi = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const double f = pow2i(__shfl_sync(0xffffffffu, my_shift, pi));
+                        double* mine = p.clv + ((size_t)dst_blk * S + wsite0 + pi) * K * A;
+                        for (int z0 = lane; z0 < K * A; z0 += 128) {   // four loads in flight per lane, then the stores
+                            double v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[u] = z0 + 32 * u < K * A ? mine[z0 + 32 * u] : 0.0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (z0 + 32 * u < K * A) mine[z0 + 32 * u] = v[u] * f;
+                        }
                     }
                 }
                 __syncwarp();
