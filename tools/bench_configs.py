@@ -8,6 +8,7 @@ Timings of the non-headline BASELINE configs (parity-test shapes, not bench.py l
     python tools/bench_configs.py [cfg3] [cfg4] [cfg5] [--reps 3]
 Prints one JSON line per config with CUDA-event timings and algorithmic rates (SURVEY.md 8(d) figures).
 """
+import gc
 import json
 import os
 import sys
@@ -22,6 +23,9 @@ from phylo_utils_b200.tree import random_tree  # noqa: E402
 
 
 def timed(fn, reps):
+    # contexts of earlier configs may still be waiting for the cycle collector: their cudaFree must not land in a
+    # timed region (it did: 10.5 vs 32-58 ms for the same derivative pass depending on what had run before)
+    gc.collect()
     fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -63,7 +67,7 @@ def report(name, tm, n_taxa, n_pat, A, reps, derivs=False):
         up_ms, _ = timed(lambda: tm.compute_up_partials(), reps)
         all_nodes = np.arange(2 * n_taxa - 2)
         all_lengths = tm.lengths_above(all_nodes)        # resolved once, as the Newton driver does
-        d_ms, d = timed(lambda: tm.edge_derivatives(all_nodes, all_lengths), max(1, reps // 2))
+        d_ms, d = timed(lambda: tm.edge_derivatives(all_nodes, all_lengths), reps)
         out.update(up_pass_ms=up_ms, all_edge_derivatives_ms=d_ms, n_edges=int(len(all_nodes)),
                    sweep_ms=ms + up_ms + d_ms, max_abs_dlnl=float(np.abs(d[:, 1]).max()))
         if "--newton" in sys.argv:
