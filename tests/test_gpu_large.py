@@ -291,3 +291,47 @@ def test_headline_shape_full_size_properties():
     packed = phy.LikelihoodEngine.pack_codes(big)
     t2, p2 = tm.engine.lnl_from_host(packed, a, b, length, n_chunks=32, want_pattern=True, packed=True)
     assert np.array_equal(p2, pattern) and t2 == total
+
+
+@pytest.mark.parametrize("shape", ["cfg5_shard", "cfg3"])
+def test_derivative_configs_full_size_properties(shape):
+    """
+    BASELINE configs 5 (one GPU's shard: 2000 taxa x 62,500 patterns, GTR+G4) and 3 (500 taxa x 100,000 patterns, LG+G4)
+    at full size through the derivative path - post-order pass, pre-order pass, all edges in one launch.  The alignment
+    is a small block repeated, so (size-independent properties): the total is reps x the block total, which the oracle
+    gives to 1e-10; EVERY edge reproduces that total (pulley principle); derivatives at other trial lengths agree between
+    the first pass and the passes that read the per-edge sum tables; a Newton sweep does not lower lnL.
+    """
+    from phylo_utils_b200.optimise import edge_nodes, optimise_branch_lengths
+    if shape == "cfg5_shard":
+        n_taxa, block, reps, n_states = 2000, 250, 250, 4
+        model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    else:
+        n_taxa, block, reps, n_states = 500, 200, 500, 20
+        model = phy.substitution_models.LG()
+    tree, names, codes, lut = synthetic(n_taxa, block, n_states, seed=5)
+    big = np.ascontiguousarray(np.tile(codes, (1, reps)))
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(up_partials=True)
+    tm.set_tree(tree)
+    tm.set_tip_codes(big, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+    want = reps * oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights).sum()
+    total = tm.lnl()
+    assert_lnl_close(total, want)
+    tm.compute_up_partials()
+    nodes = edge_nodes(tm.traversal)
+    lengths = tm.lengths_above(nodes)
+    first = tm.edge_derivatives(nodes, lengths)
+    assert np.all(np.isfinite(first))
+    assert np.all(np.abs(first[:, 0] - want) <= 1e-10 * abs(want))
+    again = tm.edge_derivatives(nodes, lengths)                      # from the sum tables
+    assert np.allclose(first, again, rtol=1e-12, atol=1e-6)
+    other = tm.edge_derivatives(nodes, lengths * 1.5)
+    tm.compute_up_partials()
+    assert np.allclose(tm.edge_derivatives(nodes, lengths * 1.5), other, rtol=1e-12, atol=1e-6)   # first pass again
+    res = optimise_branch_lengths(tm, max_sweeps=1, inner_iterations=2, tol=0.0)
+    assert res["lnl"] >= total
