@@ -190,7 +190,7 @@ def test_pre_order_walk_matches_the_two_row_form(tree_fn, n_taxa, n_pat, ppt, mo
     _walk_vs_two_rows(tree_fn, n_taxa, n_pat, ppt, monkeypatch)
 
 
-@pytest.mark.parametrize("n_cat,iupac", [(1, False), (2, False), (2, True), (4, True)])
+@pytest.mark.parametrize("n_cat,iupac", [(1, False), (2, False), (2, True), (4, True), (8, False)])   # 8: the walk declines, two rows per parent take over
 def test_pre_order_walk_other_category_counts_and_iupac_codes(n_cat, iupac, monkeypatch):
     _walk_vs_two_rows(random_tree, 60, 5003, "1", monkeypatch, n_cat=n_cat, iupac=iupac)
 
