@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import phylo_utils_b200 as phy
-from phylo_utils_b200.tree import random_tree, caterpillar_tree
+from phylo_utils_b200.tree import random_tree, caterpillar_tree, balanced_tree
 from helpers import (problem, records, tree, tip_partials, oracle_up_partials, oracle_edge_derivatives, assert_lnl_close)
 from oracle import oracle
 
@@ -181,7 +181,7 @@ def _walk_vs_two_rows(tree_fn, n_taxa, n_pat, ppt, monkeypatch, n_cat=4, iupac=F
 
 
 @pytest.mark.parametrize("tree_fn,n_taxa,n_pat", [(random_tree, 150, 20001), (caterpillar_tree, 200, 4099), (random_tree, 3, 70),
-                                                  (random_tree, 4, 33)])
+                                                  (random_tree, 4, 33), (balanced_tree, 512, 1500)])   # balanced: deepest parking
 @pytest.mark.parametrize("ppt", ["1", "2"])
 def test_pre_order_walk_matches_the_two_row_form(tree_fn, n_taxa, n_pat, ppt, monkeypatch):
     """up_dna_pair.cu (sum-table form and plain form) against the two-rows-per-parent pass on the same device partials:
