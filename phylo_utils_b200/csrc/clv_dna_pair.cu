@@ -396,7 +396,7 @@ struct PairStoreArgs {
 };
 
 template <int K, int NC>
-__global__ void __launch_bounds__(32, 8) dna_pair_store_kernel(const PairStoreArgs p) {
+__global__ void __launch_bounds__(32, 11) dna_pair_store_kernel(const PairStoreArgs p) {
     constexpr int PPT = 2;
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = K * 32 + 16, TILE_BYTES = L::TILE * ROWB, OPIN_BYTES = TILE_BYTES;   // exponents sit in the row padding
