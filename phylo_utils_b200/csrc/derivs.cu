@@ -20,6 +20,14 @@
 //     lnL  = sum_s wt_s [ log L_s + (e_a + e_b) ln 2 ]
 //     dlnL = sum_s wt_s L'_s / L_s ,   d2lnL = sum_s wt_s [ L''_s / L_s - (L'_s / L_s)^2 ]
 // i.e. lnl_branch_derivs composed over the Gamma mixture.
+//
+// Sum tables.  With P(t) = V e^(Lambda t) V^-1:  f_k^(d)(t) = sum_m g_d(lambda_m r_k) e^(lambda_m r_k t) s_km  with
+//     s_km = (V^-1 a_k)_m (V^T (pi * b_k))_m
+// which does not depend on t.  It is formed once per pre-order pass and kept in the edge's up block (whose up partial
+// nothing else reads): by the pre-order walk itself for 4 states (up_dna_pair.cu), by the first derivative pass for
+// 20 / 61 states (mma_edge_deriv_kernel's write-out).  Every further Newton iteration is a streaming dot product over
+// ONE block per edge (dna_edge_st_kernel / edge_st_kernel) at HBM speed.  Ctx::up_sumtable / Ctx::st_ready record which
+// edges have their table; a new pre-order pass starts over.
 #include <algorithm>
 #include <cstdlib>
 
