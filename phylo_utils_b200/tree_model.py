@@ -286,15 +286,15 @@ class TreeModel(object):
         self.engine.root_lnl(node_a, node_b, length, root_pmats=self._root_pmats(length))
         return self.engine.get_root_partials()
 
-    def _pattern_lnl(self, node_a, node_b):
+    def _pattern_lnl(self, node_a, node_b, want_pattern=True):
         length = self._edge_length(node_a, node_b)
         if not self.store_partials:
             if not getattr(self.substitution_model, "has_real_eigensystem", True):
                 raise ValueError("store_partials=False needs a model with a real eigen-system")
-            return self.engine.lnl_resident(node_a, node_b, length, want_pattern=True)
+            return self.engine.lnl_resident(node_a, node_b, length, want_pattern=want_pattern)
         rp = self._root_pmats(length)
         if not self.ascbias:
-            total, pattern, _ = self.engine.root_lnl(node_a, node_b, length, want_pattern=True, root_pmats=rp)
+            total, pattern, _ = self.engine.root_lnl(node_a, node_b, length, want_pattern=want_pattern, root_pmats=rp)
             return total, pattern
         # Lewis correction exactly as the reference composes it (tree_model.py:209-216): subtract
         # log(1 - sum over dummy patterns and categories of exp(lnl)) from every per-category value
@@ -315,7 +315,7 @@ class TreeModel(object):
         """Total log-likelihood = sum_p siteweights_p * lnl_p (what bin/phy.py:146 prints), reduced on the device."""
         if node_a is None:
             node_a, node_b = self.traversal.root_edge
-        total, _ = self._pattern_lnl(node_a, node_b)
+        total, _ = self._pattern_lnl(node_a, node_b, want_pattern=False)   # the per-pattern vector stays on the device
         return total
 
     # ------------------------------------------------------------------------------------------
