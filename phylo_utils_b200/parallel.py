@@ -115,6 +115,18 @@ class ShardedTreeModel(object):
         w = None if siteweights is None else np.asarray(siteweights)[lo:hi]
         self.local.set_tip_codes(np.ascontiguousarray(codes[:, lo:hi]), lut, names, w)
 
+    def set_local_tip_codes(self, codes, lut, names, n_patterns, siteweights=None):
+        """This rank's shard only: ``codes`` (ntax, hi - lo) are patterns [lo, hi) = ``shard_bounds(n_patterns, rank,
+        world)`` of an alignment of ``n_patterns`` patterns that no rank needs to hold in full (synthetic or
+        pre-sharded data).  Per-site output (``compute_likelihood_at_edge``) is then in pattern order."""
+        self.n_patterns = int(n_patterns)
+        self.sizes = [hi - lo for lo, hi in shard_slices(self.n_patterns, self.world)]
+        self.lo, self.hi = shard_bounds(self.n_patterns, self.rank, self.world)
+        if codes.shape[1] != self.hi - self.lo:
+            raise ValueError("rank {} owns {} patterns, got {}".format(self.rank, self.hi - self.lo, codes.shape[1]))
+        self.inverse_index = np.arange(self.n_patterns)
+        self.local.set_tip_codes(codes, lut, names, siteweights)
+
     def set_alignment(self, alignment, alphabet, compress=True):
         from .alignment.alignment import alignment_to_codes
         codes, lut, sw, ii, names = alignment_to_codes(alignment, alphabet, compress)

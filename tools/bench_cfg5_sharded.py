@@ -20,7 +20,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import phylo_utils_b200 as phy  # noqa: E402
-from phylo_utils_b200.parallel import ShardedTreeModel, shard_bounds, shard_slices  # noqa: E402
+from phylo_utils_b200.parallel import ShardedTreeModel, shard_bounds  # noqa: E402
 from phylo_utils_b200.tree import random_tree  # noqa: E402
 from phylo_utils_b200.optimise import optimise_branch_lengths, edge_nodes  # noqa: E402
 
@@ -50,12 +50,7 @@ def main():
     codes[rng.random(codes.shape) < 0.01] = 4
     tm = ShardedTreeModel(device=local_rank, up_partials=True)
     tm.set_tree(tree)
-    # what set_tip_codes would have sliced out of the full alignment
-    tm.n_patterns = args.patterns
-    tm.sizes = [b - a for a, b in shard_slices(args.patterns, world)]
-    tm.lo, tm.hi = lo, hi
-    tm.inverse_index = None
-    tm.local.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    tm.set_local_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, args.patterns)
     tm.set_rate_model(phy.rate_models.GammaRateModel(4, 0.5))
     tm.set_substitution_model(phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4]))
     tm.initialise()
