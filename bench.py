@@ -1,31 +1,34 @@
 #!/usr/bin/env python
 """
-Headline benchmark: full-tree lnL evaluations per second, GTR+Gamma4 nucleotide model,
-1,000 taxa x 1,000,000 site patterns per GPU (BASELINE.json configs[1]).
+Headline benchmark (BASELINE.json configs[1]): full-tree lnL evaluations per second, GTR+Gamma4 nucleotide
+model, ONE alignment of 1,000 taxa x 1,000,000 site patterns, at 1/2/4/8 B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one evaluation: branch lengths -> all transition matrices (one kernel) -> post-order
-pruning over all N-2 internal nodes -> root combine, Gamma mixture, log, weighted reduction -> scalar lnL
-on the host.
+One "step" = one evaluation of the whole alignment through the product's own multi-GPU object,
+``phylo_utils_b200.parallel.ShardedTreeModel`` (the reference-shaped TreeModel API on every rank):
 
-  value   evaluations/s with the tip codes already resident in HBM (CUDA events, max over ranks)
-  e2e     the same evaluation through the public TreeModel/engine API starting from HOST buffers:
-          every step copies the tip codes (N x S bytes, pinned) and the branch lengths to the device and reads
-          the lnL back
-  roofline  for the dominant kernel (the pruning kernel), timed on its own with CUDA events
-  cpu_baseline  the CPU oracle (C restatement of the reference engine, OpenMP over all host cores) on a
-          bounded pattern sample of the same tree, extrapolated linearly in the pattern count
+    tm.compute_partials()   new branch lengths -> device
+    tm.lnl()                all transition matrices (one kernel) -> post-order pruning over all N-2 internal nodes ->
+                            root combine, Gamma mixture, log, weighted reduction -> device all-reduce -> scalar on the host
 
-Multi-GPU: site patterns are independent, so each rank owns its own block of 1M patterns of one alignment
-(weak scaling); the only exchange is an NCCL all-reduce of the scalar lnL.  value = total patterns evaluated
-per second / 1e6 = "1M-pattern evaluations per second", summed over ranks.
-
---impl reference times the reference's CPU algorithm (the oracle port - the reference itself is Python +
-numba and cannot travel to the GPU box) with all host threads on a bounded sample of the same workload.
+  scaling   STRONG: the same 1M-pattern alignment is split into N contiguous pattern shards (rank r owns
+            shard_bounds(1M, r, N)); the columns are generated in fixed blocks so the alignment - and hence lnL - is
+            the same for every N.  `weak` (1M patterns PER GPU, what round 1 reported) is kept as an extra record.
+  value     evaluations/s with the tip codes resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       the same evaluation starting from pinned HOST codes every step: ShardedTreeModel.lnl_from_host_codes
+            (C ABI phb_lnl_from_host_packed_async: two 4-bit codes per byte, copy pipelined with the pruning)
+  roofline  the dominant kernel timed alone.  The lnL-only walk keeps every intermediate on chip: it is bound by the
+            fp64 / shared-memory pipes, NOT by HBM, and is reported as such (bound "fp64", denominator = the DFMA
+            rate measured in this run); its algorithmic-byte rate is given for the record and labelled as what it
+            is.  The walks that keep all partials in HBM carry the HBM rooflines (`with_stored_partials`).
+  configs   bounded sub-records for BASELINE configs 1, 3, 4, 5 (N = 1; cfg5 as named at N = 8)
+  cpu_baseline / --impl reference   the reference's CPU algorithm (oracle port, OpenMP on all host cores) on a
+            bounded pattern sample of the same workload; only the pattern-proportional part is extrapolated
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -43,6 +46,7 @@ GTR_RATES = [6., 5., 4., 3., 2., 1.]
 GTR_FREQS = [0.1, 0.2, 0.3, 0.4]
 ALPHA = 0.5
 NCAT = 4
+CODE_BLOCK = 125000          # the alignment's columns are generated in blocks of this many patterns
 
 
 def parse_args():
@@ -52,38 +56,34 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--taxa", type=int, default=1000)
-    ap.add_argument("--patterns", type=int, default=1000000, help="site patterns per GPU")
+    ap.add_argument("--patterns", type=int, default=1000000, help="site patterns of the WHOLE alignment (split over the GPUs)")
     ap.add_argument("--cpu-patterns", type=int, default=20000, help="pattern sample for the CPU baseline")
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--mode", choices=["auto", "tile", "level", "resident"], default="auto",
-                    help="how the rows are walked when per-node partials are stored (--store-partials)")
-    ap.add_argument("--store-partials", action="store_true",
-                    help="headline path keeps every node's partials in HBM (TreeModel.partials / derivatives); "
-                         "default is the pure lnL evaluation with the operand-resident kernel")
-    ap.add_argument("--chunks", type=int, default=64, help="host->device pipeline depth of the e2e path (16: 68.6, 32: 68.6, 64: 69.9, 128: 69.5 evals/s)")
+    ap.add_argument("--chunks", type=int, default=64, help="host->device pipeline depth of the e2e path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-stored", action="store_true", help="skip the extra 'partials stored' measurements")
+    ap.add_argument("--no-stored", action="store_true", help="skip the 'partials stored' measurements (HBM rooflines)")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling record (N > 1)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1/3/4/5 sub-records")
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------------------------------
-# synthetic workload: seeded random topology, branch lengths U(0.01, 0.3), iid uniform
-# states with 1 % fully ambiguous codes; at these sizes every column is a distinct pattern
+# synthetic workload: seeded random-join topology, branch lengths U(0.01, 0.3), iid uniform
+# states with 1 % fully ambiguous codes; at these sizes every column is a distinct pattern.
+# Pure numpy: the reference arm builds the SAME problem without importing phylo_utils_b200.
 # --------------------------------------------------------------------------------------------------
-def make_tree(n_taxa, seed):
-    import phylo_utils_b200 as phy
-    tree = phy.tree.random_tree(n_taxa, seed)
-    names = [lf.taxon.label for lf in tree.leaf_node_iter()]
-    return tree, names
-
-
-def make_codes(n_taxa, n_pat, seed, rank=0):
-    rng = np.random.default_rng([seed, rank])
-    codes = rng.integers(0, 4, size=(n_taxa, n_pat), dtype=np.uint8)
-    gaps = rng.random((n_taxa, n_pat), dtype=np.float32) < 0.01
-    codes[gaps] = 4
-    return codes
+def make_codes(n_taxa, lo, hi, seed):
+    """Columns [lo, hi) of the global alignment; block b of CODE_BLOCK columns comes from rng([seed, b])."""
+    out = np.empty((n_taxa, hi - lo), dtype=np.uint8)
+    for b in range(lo // CODE_BLOCK, (hi + CODE_BLOCK - 1) // CODE_BLOCK):
+        rng = np.random.default_rng([seed, b])
+        blk = rng.integers(0, 4, size=(n_taxa, CODE_BLOCK), dtype=np.uint8)
+        blk[rng.random((n_taxa, CODE_BLOCK), dtype=np.float32) < 0.01] = 4
+        b0 = b * CODE_BLOCK
+        s, e = max(lo, b0), min(hi, b0 + CODE_BLOCK)
+        out[:, s - lo:e - lo] = blk[:, s - b0:e - b0]
+    return out
 
 
 def dna_lut():
@@ -91,11 +91,75 @@ def dna_lut():
     return np.vstack([np.eye(4)[::-1], np.ones((1, 4))])
 
 
+def workload_tree(n_taxa, seed):
+    """
+    The bench tree as plain tables - the same random draws, in the same order, as phylo_utils_b200.tree.random_tree
+    (join two uniformly chosen live subtrees until one is left; lengths U(0.01, 0.3) in pre-order), so that both
+    bench arms evaluate one and the same tree.  Returns (rows, lengths, root_edge, root_length, leaf_order):
+    rows (N-2, 3) = PAR, CH1, CH2 in post-order without the root, lengths (N-2, 2), the root edge (a, b) with the
+    sum of the two root branches (what deroot() leaves, reference utils.py:114-118), and the tip node ids in the
+    pre-order in which the alignment rows are assigned.  Tip i of the join order is node i.
+    """
+    rng = np.random.default_rng(seed)
+    live = list(range(n_taxa))
+    children, nxt = {}, n_taxa
+    while len(live) > 1:
+        i, j = rng.choice(len(live), size=2, replace=False)
+        children[nxt] = (live[i], live[j])
+        for k in sorted((int(i), int(j)), reverse=True):
+            live.pop(k)
+        live.append(nxt)
+        nxt += 1
+    root = live[0]
+    length, leaves, stack = {}, [], [root]
+    while stack:                                     # pre-order, first child first
+        nd = stack.pop()
+        if nd != root:
+            length[nd] = float(rng.uniform(0.01, 0.3))
+        if nd in children:
+            stack.extend(reversed(children[nd]))
+        else:
+            leaves.append(nd)
+    rows, lens, stack = [], [], [(root, 0)]
+    while stack:                                     # post-order
+        nd, i = stack.pop()
+        kids = children.get(nd, ())
+        if i < len(kids):
+            stack.append((nd, i + 1))
+            stack.append((kids[i], 0))
+        elif kids and nd != root:
+            rows.append((nd, kids[0], kids[1]))
+            lens.append((length[kids[0]], length[kids[1]]))
+    a, b = children[root]
+    return np.asarray(rows, dtype=np.int64), np.asarray(lens), (a, b), length[a] + length[b], leaves
+
+
+def gtr_eigen(rates6, freqs):
+    """Reversible Q scaled to one substitution per site and its symmetric eigen-decomposition (textbook; the reference
+    does the same in substitution_models/utils.py:45-98)."""
+    pi = np.asarray(freqs, dtype=np.double)
+    r = np.zeros((4, 4))
+    r[np.triu_indices(4, 1)] = rates6
+    r = r + r.T
+    q = r * pi[None, :]
+    np.fill_diagonal(q, 0.0)
+    np.fill_diagonal(q, -q.sum(1))
+    q /= -(pi * np.diag(q)).sum()
+    sq = np.sqrt(pi)
+    lam, u = np.linalg.eigh(q * sq[:, None] / sq[None, :])
+    return u / sq[:, None], lam, u.T * sq[None, :]
+
+
 def algorithmic_bytes(n_taxa, n_pat, K=NCAT, A=4):
     """S * [(N-2) * (2*K*A*8 + 16) + N + 16]; the pruning kernel's share excludes the root's 16."""
     b_node = 2 * K * A * 8 + 16
     prune = n_pat * ((n_taxa - 2) * b_node + n_taxa)
     return prune, prune + n_pat * 16
+
+
+def algorithmic_flops(n_taxa, n_pat, K=NCAT, A=4):
+    """F_node = K * (2 * 2 A^2 + A) fp64 flop per site-node update (272 at A = 4, K = 4)."""
+    return float(n_taxa - 2) * n_pat * K * (4 * A * A + A)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -192,106 +256,125 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary, or None."""
+def ncu_record(key):
+    """Per-launch figures of a kernel from the committed `ncu --set full` summaries (profiles/roofline_traffic.json)."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return json.load(fh).get(workload)
+            return json.load(fh).get(key)
     return None
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference engine
+# CPU arm: the oracle port of the reference engine.  Nothing in here imports phylo_utils_b200.
 # --------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_eval_factory(n_taxa, n_pat, seed):
-    import phylo_utils_b200 as phy
+    """
+    One reference-style evaluation on a sample of the workload's patterns, split into the two parts that scale
+    differently: `p_matrices()` = the 2(N-2) + 2 Model.p calls of TreeModel.compute_partials (tree_model.py:166-169;
+    independent of the pattern count) and `prune(pm)` = the clv loop + compute_likelihood_at_edge (proportional to it).
+    """
     from oracle import oracle
-    tree, names = make_tree(n_taxa, seed)
-    clone = phy.utils.deepcopy_tree(tree)
-    trav = phy.traversal.Traversal(clone)
-    codes = make_codes(n_taxa, n_pat, seed)
+    rows, lengths, (a, b), root_len, leaves = workload_tree(n_taxa, seed)
+    codes = make_codes(n_taxa, 0, n_pat, seed)
     lut = dna_lut()
-    model = phy.substitution_models.GTR(GTR_RATES, GTR_FREQS)
-    rate = phy.rate_models.GammaRateModel(NCAT, ALPHA)
-    rows = np.asarray(trav.postorder_traversal, dtype=np.int64)
-    tips = {trav.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
-    ot = oracle.OracleTree(2 * n_taxa - 2, tips, NCAT)         # TreeModel.initialise (not timed, as in BASELINE.md 4.3)
-    a, b = trav.root_edge
+    evecs, evals, ivecs = gtr_eigen(GTR_RATES, GTR_FREQS)
+    rates = oracle.ref_discrete_gamma(ALPHA, NCAT) if oracle.have_ref_gamma() else oracle.discrete_gamma_scipy(ALPHA, NCAT)
+    weights = np.full(NCAT, 1.0 / NCAT)
+    freqs = np.asarray(GTR_FREQS)
+    threads = host_threads()        # explicit: torchrun exports OMP_NUM_THREADS=1, which would serialise the arm
 
-    def one_eval():
-        # TreeModel.compute_partials + compute_likelihood_at_edge, including the 2(N-2) model.p calls
+    def model_p(t):                 # Model.p(t, rates): abstract.py:49-59
+        return np.stack([(evecs * np.exp(evals * (t * r))).dot(ivecs) for r in rates])
+
+    tips = {node: np.ascontiguousarray(lut[codes[i]]) for i, node in enumerate(leaves)}
+    ot = oracle.OracleTree(2 * n_taxa - 1, tips, NCAT, n_threads=threads)   # TreeModel.initialise (not timed, BASELINE.md 4.3)
+
+    def p_matrices():
         pm = np.empty((len(rows), 2, NCAT, 4, 4))
-        for i, (par, c1, c2) in enumerate(rows):
-            pm[i, 0] = model.p(trav.brlens[(int(par), int(c1))], rate.rates)
-            pm[i, 1] = model.p(trav.brlens[(int(par), int(c2))], rate.rates)
-        ot.compute_partials(rows, pm)
-        length = trav.brlens[(a, b)]
-        root_pm = np.stack([model.p(0, rate.rates), model.p(length, rate.rates)])
-        return float(ot.likelihood_at_edge(a, b, root_pm, model.freqs, rate.weights).sum())
+        for i in range(len(rows)):
+            pm[i, 0] = model_p(lengths[i, 0])
+            pm[i, 1] = model_p(lengths[i, 1])
+        return pm, np.stack([model_p(0.0), model_p(root_len)])
 
-    return one_eval, oracle.max_threads()
+    def prune(pms):
+        pm, root_pm = pms
+        ot.compute_partials(rows, pm)
+        return float(ot.likelihood_at_edge(a, b, root_pm, freqs, weights).sum())
+
+    return p_matrices, prune, threads
+
+
+def time_cpu(args, steps, warmup):
+    p_matrices, prune, threads = cpu_eval_factory(args.taxa, args.cpu_patterns, args.seed)
+    for _ in range(max(warmup, 1)):
+        pms = p_matrices()
+        prune(pms)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pms = p_matrices()
+    t_p = (time.perf_counter() - t0) / steps
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lnl = prune(pms)
+    t_prune = (time.perf_counter() - t0) / steps
+    # only the pattern-proportional part is extrapolated; the P-matrix build does not depend on the pattern count
+    per_eval = t_p + t_prune * (args.patterns / float(args.cpu_patterns))
+    sample = ("{} taxa x {} of {} patterns (the first columns of the same alignment), {} timed evaluations: P-matrix build "
+              "{:.4f} s (counted once) + pruning {:.4f} s (x {:.0f}, patterns are independent); oracle/pruning_oracle.c "
+              "(C restatement of the reference's numba engine), OpenMP over {} threads").format(
+                  args.taxa, args.cpu_patterns, args.patterns, steps, t_p, t_prune, args.patterns / float(args.cpu_patterns), threads)
+    return {"value": 1.0 / per_eval, "unit": "lnL evals/s", "cores": threads, "kind": "port", "sample": sample,
+            "sample_lnl": lnl, "sample_seconds": t_p + t_prune,
+            "site_node_updates_per_s": (args.taxa - 2) * args.cpu_patterns / t_prune}
 
 
 def run_cpu_baseline(args, budget_s=12.0):
-    one_eval, threads = cpu_eval_factory(args.taxa, args.cpu_patterns, args.seed)
-    one_eval()                                   # warm-up (page faults, thread pool)
+    p_matrices, prune, _ = cpu_eval_factory(args.taxa, min(args.cpu_patterns, 2000), args.seed)
     t0 = time.perf_counter()
-    one_eval()
-    t1 = time.perf_counter() - t0
-    reps = int(min(50, max(1, budget_s / max(t1, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        one_eval()
-    per_eval = (time.perf_counter() - t0) / reps
-    scale = args.cpu_patterns / float(args.patterns)
-    return {
-        "value": scale / per_eval, "unit": "lnL evals/s", "cores": threads, "kind": "port",
-        "sample": "{} taxa x {} of {} patterns, {} evals of {:.3f} s each, extrapolated linearly in patterns "
-                  "(patterns are independent); oracle/pruning_oracle.c, OpenMP".format(
-                      args.taxa, args.cpu_patterns, args.patterns, reps, per_eval),
-        "site_node_updates_per_s": (args.taxa - 2) * args.cpu_patterns / per_eval,
-    }
+    prune(p_matrices())
+    probe = (time.perf_counter() - t0) * args.cpu_patterns / float(min(args.cpu_patterns, 2000))
+    return time_cpu(args, steps=int(min(20, max(2, budget_s / max(probe, 1e-3)))), warmup=1)
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference's CPU algorithm (oracle port; the reference itself is Python + numba + dendropy/Biopython and its
+    sources cannot travel to the GPU box) on the box's host cores.  Rank 0 alone works; other ranks exit."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    one_eval, threads = cpu_eval_factory(args.taxa, args.cpu_patterns, args.seed)
-    for _ in range(max(args.warmup, 1)):
-        one_eval()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lnl = one_eval()
-    elapsed = time.perf_counter() - t0
-    per_eval = elapsed / args.steps
-    scale = args.cpu_patterns / float(args.patterns)
-    value = scale / per_eval
-    sample = ("each step = one evaluation of {} taxa x {} patterns (of {}), value extrapolated linearly in "
-              "patterns; oracle port of the reference engine (the reference is Python+numba and cannot travel), "
-              "OpenMP over {} threads").format(args.taxa, args.cpu_patterns, args.patterns, threads)
+    cpu = time_cpu(args, steps=args.steps, warmup=args.warmup)
     line = {
-        "impl": "reference", "metric": "lnL evals/s (GTR+G4, {} taxa x {} patterns per GPU)".format(args.taxa, args.patterns),
-        "value": value, "unit": "lnL evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_eval * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "impl": "reference", "metric": metric_name(args), "value": cpu["value"], "unit": "lnL evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cpu["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, max(1, args.gpus)),   # the other arm's config, key for key
-        "cpu_baseline": {"value": value, "unit": "lnL evals/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "lnL evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "sample_lnl": lnl,
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "lnL evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "sample_lnl": cpu["sample_lnl"],
     }
     print(json.dumps(line), flush=True)
 
 
+def metric_name(args):
+    return "lnL evals/s (GTR+G4, {} taxa x {} site patterns)".format(args.taxa, args.patterns)
+
+
 def workload_config(args, world):
     return {
-        "workload": "GTR+G4 nucleotide full-tree lnL, {} taxa x {} site patterns per GPU (BASELINE configs[1])".format(
-            args.taxa, args.patterns),
-        "taxa": args.taxa, "patterns_per_gpu": args.patterns, "global_patterns": args.patterns * world,
+        "workload": "GTR+G4 nucleotide full-tree lnL, ONE alignment of {} taxa x {} site patterns (BASELINE configs[1]), "
+                    "split into {} pattern shard(s)".format(args.taxa, args.patterns, world),
+        "taxa": args.taxa, "global_patterns": args.patterns, "patterns_per_gpu": args.patterns // world,
         "categories": NCAT, "states": 4, "tree": "random joins, seed {}".format(args.seed),
-        "parallelism": "pattern shards x{}".format(world),
-        "l2": "inputs (>=128 MB per node block, 128 GB per evaluation) far exceed the 126 MB L2; no flush needed",
+        "parallelism": "pattern shards x{} (ShardedTreeModel, device all-reduce of the scalar)".format(world),
+        "l2": "every evaluation re-reads its shard's tip codes ({} MB per GPU) and, in the stored-partials walks, streams "
+              ">= 16 GB of node blocks: far beyond the 126 MB L2, no flush needed".format(args.taxa * (args.patterns // world) // 1000000),
     }
 
 
@@ -306,6 +389,8 @@ def main():
     import torch.distributed as dist
     import phylo_utils_b200 as phy
     from phylo_utils_b200 import _lib
+    from phylo_utils_b200.engine import fp64_peak
+    from phylo_utils_b200.parallel import ShardedTreeModel, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -319,200 +404,262 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n_taxa, n_pat = args.taxa, args.patterns
-    tree, names = make_tree(n_taxa, args.seed)
-    clone = phy.utils.deepcopy_tree(tree)
-    trav = phy.traversal.Traversal(clone)
+    tree = phy.tree.random_tree(n_taxa, args.seed)
+    names = {lf.taxon.label: i for i, lf in enumerate(tree.leaf_node_iter())}
     model = phy.substitution_models.GTR(GTR_RATES, GTR_FREQS)
     rate = phy.rate_models.GammaRateModel(NCAT, ALPHA)
     lut = dna_lut()
-    codes_host = torch.from_numpy(make_codes(n_taxa, n_pat, args.seed, rank)).pin_memory()
-    codes_np = codes_host.numpy()
-    # the e2e path ships the tip codes two per byte (4-bit state-set codes; packed once when the alignment is loaded)
-    packed_np = torch.from_numpy(phy.LikelihoodEngine.pack_codes(codes_np)).pin_memory().numpy()
-    tip_nodes = np.asarray([trav.names[n] for n in names], dtype=np.int32)
-
-    args.lnl_only = not args.store_partials
-    mode = {"auto": _lib.PHB_MODE_RESIDENT if n_pat >= 16384 else _lib.PHB_MODE_LEVEL, "tile": _lib.PHB_MODE_TILE,
-            "level": _lib.PHB_MODE_LEVEL, "resident": _lib.PHB_MODE_RESIDENT}[args.mode]
-    eng = phy.LikelihoodEngine(n_taxa, n_pat, NCAT, 4, device=local_rank, store_partials=not args.lnl_only)
-    if mode == _lib.PHB_MODE_LEVEL:
-        rows, offsets = trav.level_order()
-        eng.set_schedule(rows, offsets)
-    else:
-        rows = trav.locality_order()
-        eng.set_schedule(rows)
-    e = model.eigen
-    eng.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), model.freqs, rate.rates, rate.weights)
-    lengths = np.asarray([[trav.brlens[(int(p), int(c1))], trav.brlens[(int(p), int(c2))]] for p, c1, c2 in rows])
-    a, b = trav.root_edge
-    root_len = trav.brlens[(a, b)]
-
-    codes_dev = codes_host.to(dev, non_blocking=False)
-    eng.set_tips(codes_dev, lut, tip_nodes)
-
-    def eval_resident():
-        eng.set_edge_lengths(lengths)
-        if args.lnl_only:
-            return eng.lnl_resident(a, b, root_len)[0]
-        eng.build_pmatrices()
-        eng.compute_partials(mode)
-        return eng.root_lnl(a, b, root_len)[0]
-
-    def eval_e2e(packed=True):
-        eng.set_edge_lengths(lengths)
-        if args.lnl_only:
-            # pinned host codes -> device in chunks, overlapped with the pruning of the previous chunk
-            if packed:
-                return eng.lnl_from_host(packed_np, a, b, root_len, n_chunks=args.chunks, packed=True)[0]
-            return eng.lnl_from_host(codes_np, a, b, root_len, n_chunks=args.chunks)[0]
-        eng.set_tips(codes_np, lut, tip_nodes)          # pinned host -> device, N x S bytes
-        eng.build_pmatrices()
-        eng.compute_partials(mode)
-        return eng.root_lnl(a, b, root_len)[0]
-
-    def allreduce(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t)
-        return float(t.item())
+    lo, hi = shard_bounds(n_pat, rank, world)
+    n_local = hi - lo
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def timed(fn, steps):
+        """K calls of fn between barriers, CUDA events on the stream the engine launches on; ms = max over ranks."""
         barrier()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         out = None
         for _ in range(steps):
-            out = allreduce(fn())
+            out = fn()
         stop.record()
         barrier()
-        ms = start.elapsed_time(stop)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, out
+        return max_over_ranks(start.elapsed_time(stop)), out
 
-    for _ in range(max(args.warmup, 3)):
-        lnl = allreduce(eval_resident())
-    launches0 = eng.launch_count
+    def sharded_model(codes, n_global, **kw):
+        tm = ShardedTreeModel(device=local_rank, **kw)
+        tm.set_tree(tree)
+        tm.set_local_tip_codes(codes, lut, names, n_global)
+        tm.set_rate_model(rate)
+        tm.set_substitution_model(model)
+        tm.initialise()
+        return tm
+
+    # ---- the headline: strong scaling of the one alignment, lnL-only walk ---------------------------------------
+    codes_host = torch.from_numpy(make_codes(n_taxa, lo, hi, args.seed)).pin_memory()
+    tm = sharded_model(codes_host.numpy(), n_pat, store_partials=False)
+    eng = tm.local.engine
+    root_a, root_b = tm.traversal.root_edge
+
+    def evaluate():
+        tm.compute_partials()          # branch lengths -> device (an lnL-only model stores no partials)
+        return tm.lnl()                # P build + walk + reduction + device all-reduce + 8 bytes to the host
+
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        lnl = evaluate()
+    launches0, coll0 = eng.launch_count, tm.collectives
     with ClockSampler(local_rank) as clocks:
-        ms, lnl = timed(eval_resident, args.steps)
+        ms, lnl = timed(evaluate, args.steps)
     launches = eng.launch_count - launches0
+    collectives = tm.collectives - coll0
     ms_per_step = ms / args.steps
-    value = world * 1e3 / ms_per_step          # every rank evaluates its own block of `patterns` patterns per step
+    value = 1e3 / ms_per_step
 
-    # dominant kernel alone (pruning), CUDA events on the launching stream
-    eng.set_edge_lengths(lengths)
-    if not args.lnl_only:
-        eng.build_pmatrices()
+    # ---- dominant kernel alone (P build + walk + block-sum reduction enqueued back to back, no host round trips) --
+    root_len = tm.traversal.brlens[(root_a, root_b)]
     torch.cuda.synchronize(dev)
-    k_start, k_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k_start.record()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
     for _ in range(args.steps):
-        if args.lnl_only:
-            eng.lnl_resident(a, b, root_len)        # P build (tiny) + the resident kernel + reduction
-        else:
-            eng.compute_partials(mode)
-    k_stop.record()
+        eng.lnl_resident_async(root_a, root_b, root_len)
+    k1.record()
     torch.cuda.synchronize(dev)
-    kernel_ms = k_start.elapsed_time(k_stop) / args.steps
-    prune_bytes, eval_bytes = algorithmic_bytes(n_taxa, n_pat)
-    peak, peak_src = measured_peak()
-    achieved = prune_bytes / (kernel_ms * 1e-3) / 1e9
-    if args.lnl_only:
-        kernel_name = "dna_pair_kernel<K=4,NC=8> (two patterns per lane, operands on chip, no partials stored)"
-    else:
-        kernel_name = {_lib.PHB_MODE_TILE: "dna_prune_kernel<K=4> (tile mode)",
-                       _lib.PHB_MODE_LEVEL: "dna_prune_kernel<K=4> (level mode)",
-                       _lib.PHB_MODE_RESIDENT: "dna_resident_kernel<K=4,STORE=1> (operands on chip, blocks streamed out)"}[mode]
-    workload_key = "{}_{}x{}".format("lnl_only" if args.lnl_only else args.mode, n_taxa, n_pat)
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(workload_key), "kernel": kernel_name,
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": prune_bytes, "peak_source": peak_src,
-                "share_of_step": kernel_ms / ms_per_step}
-    if args.lnl_only or mode == _lib.PHB_MODE_RESIDENT:
-        # 64 fp64 FMA/clk/SM on B200: (N-2) * S * K * (2*16 + 4) FMA-pipe instructions-worth of work
-        fma_ops = (n_taxa - 2) * n_pat * NCAT * 36.0
-        roofline["fp64_pipe_frac_at_max_clock"] = fma_ops / (kernel_ms * 1e-3) / (64.0 * 148 * 1.965e9)
-        roofline["note"] = ("operand-resident kernel: intermediate partials stay in registers / shared memory / L2, so the "
-                            "kernel moves far fewer DRAM bytes than the algorithmic count (see `traffic` and "
-                            "profiles/); frac > 1 is expected here (SURVEY.md 8(d): 'kernels that fuse levels on-chip "
-                            "may legitimately exceed 100 %'); what binds it is the shared-memory data pipe (78 % busy, profiles/r01l_pair_v2_1000x1M.txt), then the FP64 pipe")
+    kernel_ms = max_over_ranks(k0.elapsed_time(k1) / args.steps)
+    peak_hbm, peak_src = measured_peak()
+    dfma_peak = fp64_peak(local_rank)
+    prune_bytes, _ = algorithmic_bytes(n_taxa, n_local)
+    flops = algorithmic_flops(n_taxa, n_local)
+    ncu = ncu_record("dna_pair_kernel_lnl_only_1000x1M") or {}
+    achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tf / dfma_peak,
+        "traffic": ncu.get("dram_bytes_per_launch"),
+        "kernel": "dna_pair_kernel<K=4,NC=8,PPT=2> (two patterns per lane, whole post-order walk + root + reduction in one "
+                  "launch, operands on chip, no partials stored)",
+        "kernel_ms": kernel_ms, "patterns_per_launch": n_local, "share_of_step": kernel_ms / ms_per_step,
+        "algorithmic_flops_per_launch": flops,
+        "flops_per_unit": "272 fp64 flop per site-node update (SURVEY.md 8(d): K (4 A^2 + A)), x (N-2) x patterns of the shard",
+        "peak_source": "measured in this run: phb_op_fp64_peak (8 independent DFMA chains per thread on every SM); "
+                       "nominal 64 FMA/clk/SM x 148 x 1.965 GHz = 37.2",
+        "limiter": "shared-memory (LSU) data pipe, then the fp64 pipe; DRAM is idle (see `ncu`)",
+        "ncu": ncu or None,
+        "hbm_algorithmic": {
+            "bytes_per_launch": prune_bytes, "gbs": prune_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak_hbm,
+            "ratio_to_hbm_peak": prune_bytes / (kernel_ms * 1e-3) / 1e9 / peak_hbm, "peak_source": peak_src,
+            "note": "NOT a roofline fraction: SURVEY.md 8(d)'s algorithmic bytes (272 B per site-node update) assume every "
+                    "node block is written to and read from HBM; this kernel keeps them in registers / shared memory / L2 "
+                    "and moves ~1.5 % of that through DRAM (`traffic`).  The HBM rooflines are in `with_stored_partials`."},
+    }
 
-    # the same evaluation while ALSO keeping every node's partials in HBM (what TreeModel.partials and the
-    # derivative path need): reported next to the headline so that both costs are on record
-    stored = None
-    if args.lnl_only and world == 1 and not args.no_stored:
-        eng2 = phy.LikelihoodEngine(n_taxa, n_pat, NCAT, 4, device=local_rank)
-        eng2.set_schedule(rows)
-        eng2.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), model.freqs, rate.rates, rate.weights)
-        eng2.set_tips(codes_dev, lut, tip_nodes)
-        stored = {}
-        for label, m2 in (("resident_store", _lib.PHB_MODE_RESIDENT), ("tile", _lib.PHB_MODE_TILE)):
-            def eval_stored():
-                eng2.set_edge_lengths(lengths)
-                eng2.build_pmatrices()
-                eng2.compute_partials(m2)
-                return eng2.root_lnl(a, b, root_len)[0]
-            for _ in range(2):
-                eval_stored()
-            s_ms, s_lnl = timed(eval_stored, max(2, args.steps // 2))
-            s_ms /= max(2, args.steps // 2)
-            stored[label] = {"evals_per_s": 1e3 / s_ms, "ms_per_step": s_ms, "lnl": s_lnl,
-                             "algorithmic_gbs": eval_bytes / (s_ms * 1e-3) / 1e9,
-                             "frac_of_hbm_peak": eval_bytes / (s_ms * 1e-3) / 1e9 / peak}
-        eng2.close()
-        del eng2
-
+    # ---- e2e: the same evaluation from pinned HOST codes every step (TreeModel-level API) ---------------------------
     e2e = None
     if not args.no_e2e:
+        packed = torch.from_numpy(phy.LikelihoodEngine.pack_codes(codes_host.numpy())).pin_memory().numpy()
+
+        def evaluate_e2e():
+            tm.compute_partials()
+            return tm.lnl_from_host_codes(packed, n_chunks=args.chunks)
         for _ in range(2):
-            allreduce(eval_e2e())
-        e_ms, e_lnl = timed(eval_e2e, args.steps)
+            evaluate_e2e()
+        e_ms, e_lnl = timed(evaluate_e2e, args.steps)
         e_ms /= args.steps
-        code_bytes = packed_np.nbytes if args.lnl_only else n_taxa * n_pat
-        e2e = {"value": world * 1e3 / e_ms, "unit": "lnL evals/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(code_bytes + lengths.nbytes + 16), "d2h_bytes_per_step": 8,
-               "api": ("LikelihoodEngine.set_edge_lengths + lnl_from_host(packed=True) (C ABI phb_lnl_from_host_packed: "
-                       "pinned host tip codes, two 4-bit codes per byte, {} chunks, copy overlapped with compute)".format(
-                           args.chunks) if args.lnl_only else
-                       "LikelihoodEngine.set_tips(host codes) + set_edge_lengths + build_pmatrices + "
-                       "compute_partials + root_lnl (C ABI, pinned host buffers)"), "lnl": e_lnl}
-        if args.lnl_only:
-            # the same call with one byte per code (phb_lnl_from_host), for the record
-            for _ in range(2):
-                allreduce(eval_e2e(False))
-            u_ms, u_lnl = timed(lambda: eval_e2e(False), args.steps)
-            u_ms /= args.steps
-            e2e["one_byte_codes"] = {"value": world * 1e3 / u_ms, "ms_per_step": u_ms,
-                                     "h2d_bytes_per_step": int(n_taxa * n_pat + lengths.nbytes + 16), "lnl": u_lnl}
+        e2e = {"value": 1e3 / e_ms, "unit": "lnL evals/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(packed.nbytes + (2 * (n_taxa - 2)) * 8 + 16), "d2h_bytes_per_step": 8,
+               "bytes_are": "per GPU (its shard's packed codes + the branch lengths); x{} over the box".format(world),
+               "api": "ShardedTreeModel.compute_partials() + lnl_from_host_codes(packed) -> TreeModel.lnl_from_host_codes -> C ABI "
+                      "phb_set_edge_lengths + phb_lnl_from_host_packed_async (pinned host tip codes, two 4-bit codes per byte, "
+                      "{} chunks, copy pipelined with the pruning), device all-reduce, phb_result_fetch".format(args.chunks),
+               "lnl": e_lnl}
+        del packed
+
+    # ---- parity inside the run ------------------------------------------------------------------------------------
+    # (a) the sharded product path against the reference-generated golden case cfg1 (10 taxa x 1000 patterns, numba
+    #     reference output committed under tests/golden/): total lnL over NCCL, per-edge derivative sums over NCCL
+    parity = sharded_golden_check(phy, ShardedTreeModel, local_rank)
+
+    # ---- weak scaling, for continuity with round 1 (1M patterns PER GPU) -----------------------------------------------
+    weak = None
+    if world > 1 and not args.no_weak:
+        del tm, eng
+        gc.collect()
+        w_codes = make_codes(n_taxa, rank * n_pat, (rank + 1) * n_pat, args.seed)
+        tmw = sharded_model(w_codes, n_pat * world, store_partials=False)
+
+        def evaluate_weak():
+            tmw.compute_partials()
+            return tmw.lnl()
+        for _ in range(warmup):
+            evaluate_weak()
+        w_ms, w_lnl = timed(evaluate_weak, args.steps)
+        w_ms /= args.steps
+        weak = {"scaling": "weak", "patterns_per_gpu": n_pat, "global_patterns": n_pat * world, "ms_per_step": w_ms,
+                "value_1M_pattern_evals_per_s": world * 1e3 / w_ms, "lnl": w_lnl}
+        del tmw, w_codes
+        gc.collect()
+    else:
+        del tm, eng
+        gc.collect()
+
+    # ---- the walks that keep every node block in HBM (TreeModel.partials, the derivative path): HBM rooflines -------------
+    stored = None
+    if world == 1 and not args.no_stored:
+        stored = stored_partials_records(phy, _lib, args, tree, names, model, rate, lut, codes_host, timed, peak_hbm, peak_src, dev)
+    del codes_host
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, bounded ------------------------------------------------------------------------------
+    configs = None
+    if not args.no_configs and world in (1, 8):
+        from tools import bench_configs
+        configs = bench_configs.sub_records(world, rank, local_rank, peak_hbm, fp64_peak(local_rank, tensor=True), dfma_peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_baseline(args)
+        # the GPU path on exactly the CPU sample: per-evaluation parity of the two arms inside the run
+        tm_s = phy.TreeModel(device=local_rank, store_partials=False)
+        tm_s.set_tree(tree)
+        tm_s.set_tip_codes(make_codes(n_taxa, 0, args.cpu_patterns, args.seed), lut, names)
+        tm_s.set_rate_model(rate)
+        tm_s.set_substitution_model(model)
+        tm_s.initialise()
+        gpu_sample = tm_s.lnl()
+        cpu["gpu_lnl_on_the_same_sample"] = gpu_sample
+        cpu["rel_diff"] = abs(gpu_sample - cpu["sample_lnl"]) / abs(cpu["sample_lnl"])
+        del tm_s
 
     if rank == 0:
         line = {
-            "metric": "lnL evals/s (GTR+G4, {} taxa x {} patterns per GPU)".format(n_taxa, n_pat),
-            "value": value, "unit": "lnL evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "metric": metric_name(args), "value": value, "unit": "lnL evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "path": "lnL only (no per-node partials stored)" if args.lnl_only else "partials stored ({})".format(args.mode),
-            "with_stored_partials": stored,
+            "collectives_in_timed_region": int(collectives),
+            "path": "ShardedTreeModel(store_partials=False): lnL-only operand-resident walk per shard, device all-reduce",
+            "with_stored_partials": stored, "weak_scaling": weak, "configs": configs, "sharded_parity": parity,
             "clocks": clocks.summary(), "lnl": lnl,
-            "site_node_updates_per_s": world * (n_taxa - 2) * n_pat * 1e3 / ms_per_step,
-            "eval_algorithmic_gbytes": eval_bytes / 1e9,
+            "site_node_updates_per_s": (n_taxa - 2) * n_pat * 1e3 / ms_per_step,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_golden_check(phy, ShardedTreeModel, local_rank):
+    """cfg1 golden case (output of the unmodified reference, tests/golden/cfg1_gtr_g4.npz) through ShardedTreeModel at
+    this run's world size: total lnL, per-site lnL (all-gather) and the pulley property of the all-reduced derivative sums."""
+    path = os.path.join(ROOT, "tests", "golden", "cfg1_gtr_g4.npz")
+    if not os.path.exists(path):
+        return None
+    from phylo_utils_b200.alignment.alignment import SeqRecord
+    with np.load(path) as z:
+        g = {k: z[k] for k in z.files}
+    records = [SeqRecord(str(n), bytes(row).decode("ascii")) for n, row in zip(g["names"], g["seqs"])]
+    tm = ShardedTreeModel(device=local_rank, up_partials=True)
+    tm.set_tree(phy.tree.parse_newick(str(g["newick"])))
+    tm.set_alignment(records, int(g["alphabet"]))
+    tm.set_rate_model(phy.rate_models.GammaRateModel(NCAT, ALPHA))
+    tm.set_substitution_model(phy.substitution_models.GTR(GTR_RATES, GTR_FREQS))
+    tm.initialise()
+    want = float(g["total_lnl"])
+    total = tm.lnl()
+    site = tm.compute_likelihood_at_edge(*tm.traversal.root_edge)
+    tm.compute_up_partials()
+    d = tm.edge_derivatives(phy.optimise.edge_nodes(tm.traversal))
+    return {"case": "tests/golden/cfg1_gtr_g4.npz (numba reference output), sharded x{}".format(tm.world),
+            "total_rel_err": abs(total - want) / abs(want),
+            "site_max_rel_err": float(np.max(np.abs(site - g["site_lnl"]) / np.abs(g["site_lnl"]))),
+            "pulley_max_rel_err": float(np.max(np.abs(d[:, 0] - want)) / abs(want)),
+            "collectives": tm.collectives,
+            "ok": bool(abs(total - want) <= 1e-10 * abs(want) and np.allclose(site, g["site_lnl"], rtol=1e-10, atol=0)
+                       and np.max(np.abs(d[:, 0] - want)) <= 1e-10 * abs(want))}
+
+
+def stored_partials_records(phy, _lib, args, tree, names, model, rate, lut, codes_host, timed, peak_hbm, peak_src, dev):
+    """Same evaluation with every node block kept in HBM (133 GB at 1000 x 1M): the operand-resident store walk and the
+    streaming tile walk, each with its HBM roofline (algorithmic bytes = SURVEY.md 8(d), all of them really moved)."""
+    import torch
+    n_taxa, n_pat = args.taxa, args.patterns
+    _, eval_bytes = algorithmic_bytes(n_taxa, n_pat)
+    out = {}
+    for label, mode, key in (("resident_store", "resident", "dna_pair_store_kernel_1000x1M"),
+                             ("tile", "tile", "dna_prune_kernel_tile_1000x1M")):
+        tm = phy.TreeModel(device=dev.index, mode=mode)
+        tm.set_tree(tree)
+        tm.set_tip_codes(codes_host.numpy(), lut, names)
+        tm.set_rate_model(rate)
+        tm.set_substitution_model(model)
+        tm.initialise()
+
+        def evaluate():
+            tm.compute_partials()
+            return tm.lnl()
+        evaluate()
+        steps = max(2, args.steps // 4)
+        s_ms, s_lnl = timed(evaluate, steps)
+        s_ms /= steps
+        ncu = ncu_record(key) or {}
+        gbs = eval_bytes / (s_ms * 1e-3) / 1e9
+        out[label] = {"evals_per_s": 1e3 / s_ms, "ms_per_step": s_ms, "lnl": s_lnl,
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                                   "traffic": ncu.get("dram_bytes_per_launch"), "algorithmic_bytes_per_step": eval_bytes,
+                                   "peak_source": peak_src, "timed": "whole step (P build + walk + root kernel), CUDA events"}}
+        del tm
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -195,6 +195,25 @@ int phb_compute_up_partials(phb_ctx* ctx, int node_a, int node_b, double length)
 int phb_edge_derivatives(phb_ctx* ctx, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
                          double* out);
 
+/* ---- stream-ordered forms (multi-GPU drivers) ------------------------------------------------
+ * The reference is one process and sums per-site lnL on the host (bin/phy.py:146).  With the site patterns sharded
+ * over several GPUs the only exchange is the sum of the per-shard scalars, and it must not cost a
+ * host round trip per GPU: these calls do the same work as phb_lnl_resident / phb_root_lnl /
+ * phb_lnl_from_host_packed / phb_edge_derivatives but only ENQUEUE it on the context's stream and leave the sums in
+ * the context's device result buffer - lnL at [0], or { lnL, d1, d2 } of edge i at [3 i .. 3 i + 2] - so that a
+ * collective (ncclAllReduce on the same stream, or torch.distributed on a tensor view of the buffer) can follow
+ * directly.  phb_result_fetch copies the first n doubles back and synchronises; it (or phb_sync) also completes a
+ * host-fed evaluation (reports a chunk of tip codes that never arrived). */
+int phb_lnl_resident_async(phb_ctx* ctx, int node_a, int node_b, double length);
+int phb_root_lnl_async(phb_ctx* ctx, int node_a, int node_b, double length);
+int phb_lnl_from_host_packed_async(phb_ctx* ctx, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
+                                   double length);
+int phb_edge_derivatives_async(phb_ctx* ctx, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule);
+/* device address and capacity (in doubles) of the result buffer; it lies inside the caller's workspace when one
+ * was given to phb_create */
+int phb_device_result(phb_ctx* ctx, void** device_ptr, int64_t* capacity_doubles);
+int phb_result_fetch(phb_ctx* ctx, int n, double* out);
+
 /* ---- stand-alone operators (host arrays in, host arrays out; reference-exact semantics) ------ */
 /* clv gufunc (numba_likelihood_engine.py:10-46): per-(site,category) natural-log scalers, rescale by the
  * category maximum when 0 < max < 2^-128.  p1,p2 [K][A][A]; clv1,clv2,out [S][K][A]; scalers [S][K]. */
@@ -212,6 +231,11 @@ int phb_op_lnl_branch(int device, int64_t S, int A, int n_derivs, const double* 
  * V diag(lambda^order exp(lambda t_i)) V^-1 */
 int phb_op_pmatrices(int device, int A, int n, const double* evecs, const double* evals, const double* ivecs,
                      const double* times, int order, double* out);
+
+/* Measured fp64 throughput of the device in TFLOP/s: kind 0 = vector pipe (independent DFMA chains on every SM),
+ * kind 1 = fp64 tensor pipe (DMMA m8n8k4 chains).  Measurement aid: the denominators of the compute-bound rooflines
+ * bench.py reports (no counterpart in the reference). */
+int phb_op_fp64_peak(int device, int kind, double* tflops);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -169,6 +169,15 @@ def reference_compress(one_hot):
     return patterns, counts, np.asarray(inverse).reshape(-1)
 
 
+def discrete_gamma_scipy(alpha, ncat):
+    """The reference's scipy formulation of Yang's mean-rate categories (gamma.py:4-18); agrees with the C code
+    to ~1e-8 relative.  Used by bench.py's CPU arm only when oracle/_ref is absent."""
+    from scipy.special import gammaincinv, gammainc
+    cuts = gammaincinv(alpha, np.arange(1, ncat) / float(ncat)) / alpha          # quantiles of Gamma(alpha, rate alpha)
+    upper = np.concatenate([[0.0], gammainc(alpha + 1.0, cuts * alpha), [1.0]])
+    return np.diff(upper) * ncat
+
+
 # ---- the reference's own C discrete gamma, compiled untouched -----------------------------------------
 def have_ref_gamma():
     return os.path.exists(_REF_GAMMA)

@@ -56,10 +56,17 @@ SIGNATURES = {
     "phb_get_root_partials": (c_int, [c_void_p, _dp, _dp]),
     "phb_compute_up_partials": (c_int, [c_void_p, c_int, c_int, c_double]),
     "phb_edge_derivatives": (c_int, [c_void_p, c_int, _ip, _dp, c_int, _dp]),
+    "phb_lnl_resident_async": (c_int, [c_void_p, c_int, c_int, c_double]),
+    "phb_root_lnl_async": (c_int, [c_void_p, c_int, c_int, c_double]),
+    "phb_lnl_from_host_packed_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double]),
+    "phb_edge_derivatives_async": (c_int, [c_void_p, c_int, _ip, _dp, c_int]),
+    "phb_device_result": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
+    "phb_result_fetch": (c_int, [c_void_p, c_int, _dp]),
     "phb_op_clv": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "phb_op_lnl_node": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp]),
     "phb_op_lnl_branch": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "phb_op_pmatrices": (c_int, [c_int, c_int, c_int, _dp, _dp, _dp, _dp, c_int, _dp]),
+    "phb_op_fp64_peak": (c_int, [c_int, c_int, _dp]),
 }
 
 _lib = None

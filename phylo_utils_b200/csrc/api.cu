@@ -12,6 +12,32 @@ namespace phb {
 
 static thread_local std::string g_thread_error;
 void set_thread_error(const std::string& msg) { g_thread_error = msg; }
+
+const Tuning& tuning() {
+    static const Tuning t = [] {
+        Tuning v;
+        auto flag = [](const char* name) { return getenv(name) != nullptr; };
+        auto num = [](const char* name) { const char* s = getenv(name); return s ? atoi(s) : 0; };
+        v.resident_v1 = flag("PHB_RESIDENT_V1");
+        v.disable_mma = flag("PHB_DISABLE_MMA");
+        v.disable_tiptab = flag("PHB_DISABLE_TIPTAB");
+        v.up_two_rows = flag("PHB_UP_TWO_ROWS");
+        v.up_plain = flag("PHB_UP_PLAIN");
+        v.deriv_no_st = flag("PHB_DERIV_NO_ST");
+        v.deriv_matrix_form = flag("PHB_DERIV_MATRIX_FORM");
+        v.compress_timing = flag("PHB_COMPRESS_TIMING");
+        v.pair_ctas = num("PHB_PAIR_CTAS");
+        v.pair_ppt = num("PHB_PAIR_PPT");
+        v.pair_grid = num("PHB_PAIR_GRID");
+        v.up_ppt = num("PHB_UP_PPT");
+        v.up_warps = num("PHB_UP_WARPS");
+        v.resident_warps = num("PHB_RESIDENT_WARPS");
+        v.tile_want = num("PHB_TILE_WANT");
+        v.mma_variant = num("PHB_MMA_VARIANT");
+        return v;
+    }();
+    return t;
+}
 const char* thread_error() { return g_thread_error.c_str(); }
 
 namespace {
@@ -94,7 +120,7 @@ bool shape_ok(int n_tips, int64_t S, int K, int A, std::string* why) {
 // operand-resident post-order pass with all blocks stored: two patterns per lane (clv_dna_pair.cu) where that kernel
 // covers the shape, the one-pattern-per-lane walk (clv_dna_resident.cu) otherwise or with PHB_RESIDENT_V1
 int resident_store(Ctx* c) {
-    if (getenv("PHB_RESIDENT_V1") == nullptr) {
+    if (!tuning().resident_v1) {
         const int st = dna_pair_store(c);
         if (st != PHB_ERR_UNSUPPORTED) return st;
     }
@@ -103,7 +129,7 @@ int resident_store(Ctx* c) {
 
 int run_rows(Ctx* c, const RowSet& rs, int mode) {
     if (dna_supported(c)) return dna_run_rows(c, rs, mode);
-    if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr) return mma_run_rows(c, rs, mode);
+    if (mma_supported(c) && !tuning().disable_mma) return mma_run_rows(c, rs, mode);
     return generic_run_rows(c, rs, mode);
 }
 
@@ -327,6 +353,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->d_cat_lnl = (double*)(w + p.cat_lnl);
     c->d_partial_sums = (double*)(w + p.partial);
     c->d_result = (double*)(w + p.result);
+    c->result_doubles = std::max<size_t>((size_t)kMaxEdgeBatch * 4, 6 * (size_t)n_tips);
     c->node_tip.assign(c->n_nodes, -1);
     *out = c;
     return PHB_OK;
@@ -348,12 +375,29 @@ int phb_destroy(phb_ctx* c) {
     return PHB_OK;
 }
 
+// Wait for the context's stream; if a host-fed evaluation (phb_lnl_from_host*) is in flight, also retire its copy
+// stream and report a chunk of tip codes that never arrived.
+static int finish_stream(phb_ctx* c) {
+    int late = 0;
+    if (c->pipelined_pending)
+        PHB_CUDA(c, cudaMemcpyAsync(&late, c->d_flags + kMaxFlagChunks, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->pipelined_pending) {
+        c->pipelined_pending = false;
+        PHB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        if (late) {
+            cudaMemsetAsync(c->d_flags + kMaxFlagChunks, 0, sizeof(int), c->stream);
+            return c->fail(PHB_ERR_CUDA, "phb_lnl_from_host: a chunk of tip codes never arrived on the device");
+        }
+    }
+    return PHB_OK;
+}
+
 int phb_sync(phb_ctx* c) {
     if (!c) return PHB_ERR_INVALID;
     int st = activate(c);
     if (st) return st;
-    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
-    return PHB_OK;
+    return finish_stream(c);
 }
 
 int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_codes, const double* lut,
@@ -398,6 +442,7 @@ int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_co
     c->node_tip.swap(node_tip);
     c->n_codes = n_codes;
     c->have_tips = true;
+    c->have_pmats = false;   // the P.lut tip tables depend on the look-up table and on n_codes: rebuild with the matrices
     c->have_partials = false;
     c->have_up = false;
     c->sched_gen++;   // the tip-table geometry the cached plans refer to may have changed
@@ -690,12 +735,10 @@ static int build_eval_pmats(phb_ctx* c, int node_a, int node_b, double length) {
     return PHB_OK;
 }
 
-int phb_root_lnl(phb_ctx* c, int node_a, int node_b, double length, const double* root_pmats, double* total,
-                 double* pattern_lnl, double* cat_lnl) {
-    if (!c) return PHB_ERR_INVALID;
+// enqueue only: root combine + mixture + log + weighted sum on the context's stream, total -> d_result[0]
+static int root_lnl_enqueue(phb_ctx* c, int node_a, int node_b, double length, const double* root_pmats, bool want_cat) {
     int st = activate(c);
     if (st) return st;
-    PHB_REQUIRE(c, total != nullptr, PHB_ERR_INVALID, "phb_root_lnl: total is NULL");
     PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS), PHB_ERR_STATE,
                 "phb_root_lnl: context has no partial storage, use phb_lnl_resident");
     PHB_REQUIRE(c, c->have_tips, PHB_ERR_STATE, "phb_root_lnl: no tip data");
@@ -705,11 +748,19 @@ int phb_root_lnl(phb_ctx* c, int node_a, int node_b, double length, const double
                 "phb_root_lnl: partials are stale, call phb_compute_partials first");
     st = prepare_root(c, node_a, node_b, length, root_pmats);
     if (st) return st;
-    const bool want_cat = cat_lnl != nullptr;
     st = dna_supported(c) ? dna_root(c, node_a, node_b, want_cat, true)
                           : generic_root(c, node_a, node_b, want_cat, true);
     if (st) return st;
     c->have_root = true;
+    return PHB_OK;
+}
+
+int phb_root_lnl(phb_ctx* c, int node_a, int node_b, double length, const double* root_pmats, double* total,
+                 double* pattern_lnl, double* cat_lnl) {
+    if (!c) return PHB_ERR_INVALID;
+    PHB_REQUIRE(c, total != nullptr, PHB_ERR_INVALID, "phb_root_lnl: total is NULL");
+    int st = root_lnl_enqueue(c, node_a, node_b, length, root_pmats, cat_lnl != nullptr);
+    if (st) return st;
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)
         PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -719,23 +770,28 @@ int phb_root_lnl(phb_ctx* c, int node_a, int node_b, double length, const double
     return PHB_OK;
 }
 
-int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* total, double* pattern_lnl) {
-    if (!c) return PHB_ERR_INVALID;
+static int lnl_resident_enqueue(phb_ctx* c, int node_a, int node_b, double length) {
     int st = activate(c);
     if (st) return st;
-    PHB_REQUIRE(c, total != nullptr, PHB_ERR_INVALID, "phb_lnl_resident: total is NULL");
     PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
                 "phb_lnl_resident: tips, schedule, model and edge lengths must be set");
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_resident: only 4-state models with K in {1,2,4,8}");
     st = build_eval_pmats(c, node_a, node_b, length);
     if (st) return st;
     // default: two patterns per lane (clv_dna_pair.cu); PHB_RESIDENT_V1 selects the one-pattern-per-lane walk
-    if (getenv("PHB_RESIDENT_V1") == nullptr) {
+    if (!tuning().resident_v1) {
         st = dna_pair_lnl(c, node_a, node_b);
     } else {
         PHB_REQUIRE(c, !c->codes_packed, PHB_ERR_STATE, "phb_lnl_resident: packed codes need the pair kernel");
         st = dna_resident(c, node_a, node_b, false, true);
     }
+    return st;
+}
+
+int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* total, double* pattern_lnl) {
+    if (!c) return PHB_ERR_INVALID;
+    PHB_REQUIRE(c, total != nullptr, PHB_ERR_INVALID, "phb_lnl_resident: total is NULL");
+    int st = lnl_resident_enqueue(c, node_a, node_b, length);
     if (st) return st;
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)
@@ -749,7 +805,7 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
     if (!c) return PHB_ERR_INVALID;
     int st = activate(c);
     if (st) return st;
-    PHB_REQUIRE(c, codes != nullptr && total != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host: NULL argument");
+    PHB_REQUIRE(c, codes != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host: NULL argument");
     PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
                 "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
@@ -759,29 +815,18 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
     c->have_partials = false;
     c->have_up = false;
     if (n_chunks <= 0) n_chunks = 64;   // measured at 1000 x 1M: 16 -> 68.6, 64 -> 69.9 evaluations/s
-    if (!packed && getenv("PHB_RESIDENT_V1") != nullptr) {
+    if (!packed && tuning().resident_v1) {
         c->codes_packed = false;
         st = dna_resident_from_host(c, codes, n_chunks, node_a, node_b);
     } else {
         st = dna_pair_from_host(c, codes, packed, n_chunks, node_a, node_b);
     }
     if (st) return st;
-    int late = 0;
+    if (total == nullptr) return PHB_OK;   // stream-ordered form: phb_result_fetch / phb_sync complete the evaluation
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
-    if (c->pipelined_pending)
-        PHB_CUDA(c, cudaMemcpyAsync(&late, c->d_flags + kMaxFlagChunks, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (pattern_lnl)
         PHB_CUDA(c, cudaMemcpyAsync(pattern_lnl, c->d_pattern_lnl, (size_t)c->S * 8, cudaMemcpyDeviceToHost, c->stream));
-    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->pipelined_pending) {
-        c->pipelined_pending = false;
-        PHB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-        if (late) {
-            cudaMemsetAsync(c->d_flags + kMaxFlagChunks, 0, sizeof(int), c->stream);
-            return c->fail(PHB_ERR_CUDA, "phb_lnl_from_host: a chunk of tip codes never arrived on the device");
-        }
-    }
-    return PHB_OK;
+    return finish_stream(c);
 }
 
 int phb_lnl_from_host(phb_ctx* c, const uint8_t* codes, int n_chunks, int node_a, int node_b, double length,
@@ -905,6 +950,52 @@ int phb_edge_derivatives(phb_ctx* c, int n_edges, const int32_t* nodes, const do
                 "phb_edge_derivatives: NULL argument");
     PHB_REQUIRE(c, c->have_up, PHB_ERR_STATE, "phb_edge_derivatives: run phb_compute_up_partials first");
     return launch_edge_derivatives(c, n_edges, nodes, lengths, chain_rule, out);
+}
+
+// ---- stream-ordered forms ------------------------------------------------------------------------------------
+int phb_lnl_resident_async(phb_ctx* c, int node_a, int node_b, double length) {
+    if (!c) return PHB_ERR_INVALID;
+    return lnl_resident_enqueue(c, node_a, node_b, length);
+}
+
+int phb_root_lnl_async(phb_ctx* c, int node_a, int node_b, double length) {
+    if (!c) return PHB_ERR_INVALID;
+    return root_lnl_enqueue(c, node_a, node_b, length, nullptr, false);
+}
+
+int phb_lnl_from_host_packed_async(phb_ctx* c, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
+                                   double length) {
+    return lnl_from_host(c, packed_codes, true, n_chunks, node_a, node_b, length, nullptr, nullptr);
+}
+
+int phb_edge_derivatives_async(phb_ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, n_edges >= 0 && (n_edges == 0 || (nodes && lengths)), PHB_ERR_INVALID,
+                "phb_edge_derivatives_async: NULL argument");
+    PHB_REQUIRE(c, 3 * (size_t)n_edges <= c->result_doubles, PHB_ERR_INVALID,
+                "phb_edge_derivatives_async: more edges than the device result buffer holds (3 doubles per edge)");
+    PHB_REQUIRE(c, c->have_up, PHB_ERR_STATE, "phb_edge_derivatives_async: run phb_compute_up_partials first");
+    return launch_edge_derivatives(c, n_edges, nodes, lengths, chain_rule, nullptr);
+}
+
+int phb_device_result(phb_ctx* c, void** device_ptr, int64_t* capacity_doubles) {
+    if (!c) return PHB_ERR_INVALID;
+    PHB_REQUIRE(c, device_ptr != nullptr, PHB_ERR_INVALID, "phb_device_result: NULL argument");
+    *device_ptr = c->d_result;
+    if (capacity_doubles) *capacity_doubles = (int64_t)c->result_doubles;
+    return PHB_OK;
+}
+
+int phb_result_fetch(phb_ctx* c, int n, double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, n >= 0 && (size_t)n <= c->result_doubles && (n == 0 || out), PHB_ERR_INVALID,
+                "phb_result_fetch: bad count or NULL output");
+    if (n) PHB_CUDA(c, cudaMemcpyAsync(out, c->d_result, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    return finish_stream(c);
 }
 
 }  // extern "C"

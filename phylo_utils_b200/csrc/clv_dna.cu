@@ -268,8 +268,7 @@ int launch_prune_u(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, int6
     // One tile per SM is enough to keep the biggest tile: every row costs a thread 32 loads for its two P blocks,
     // which a big tile amortises over 8 elements (cfg5 shard, 62.5k patterns: up pass 26.4 ms at four tiles per SM,
     // 17.4 ms at one).  PHB_TILE_WANT overrides (tuning knob).
-    const char* env_want = getenv("PHB_TILE_WANT");
-    const int64_t want = (int64_t)c->sm_count * (env_want ? atoi(env_want) : 1);
+    const int64_t want = (int64_t)c->sm_count * (tuning().tile_want > 0 ? tuning().tile_want : 1);
     const int spi = kThreads / K;
     auto tiles = [&](int u) { return ((c->S + (int64_t)spi * u - 1) / ((int64_t)spi * u)) * parallel_rows; };
     if (tiles(8) >= want) return launch_prune<K, 8, LEVEL>(c, d_rows, row_begin, row_end);

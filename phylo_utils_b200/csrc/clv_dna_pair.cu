@@ -612,8 +612,14 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     int per_sm = 0;
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
     if (per_sm < 1) per_sm = 1;
-    if (const char* f = getenv("PHB_PAIR_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(f)));
-    int64_t grid = std::min<int64_t>(tile_end - tile_begin, (int64_t)c->sm_count * per_sm);
+    if (tuning().pair_ctas > 0) per_sm = std::min(per_sm, tuning().pair_ctas);
+    const int64_t n_tiles = tile_end - tile_begin, resident = (int64_t)c->sm_count * per_sm;
+    int64_t grid = std::min<int64_t>(n_tiles, resident);
+    if (tuning().pair_grid == 2 && n_tiles > resident) {
+        // the same number of tiles for every warp: no tail round in which a few warps walk the tree on their own
+        const int64_t rounds = (n_tiles + resident - 1) / resident;
+        grid = (n_tiles + rounds - 1) / rounds;
+    }
     grid = std::min<int64_t>(grid, max_grid);
     // every resident warp needs its own scratch stripe
     const int64_t cap = (int64_t)(c->scratch_bytes / ((size_t)n_slots * L::SLOT_BYTES));
@@ -629,8 +635,7 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
 
 // patterns per lane: 2 everywhere; 4 is built for K = 4 and selected with PHB_PAIR_PPT=4 (tuning knob)
 int pair_ppt(const Ctx* c) {
-    const char* env = getenv("PHB_PAIR_PPT");
-    return (env != nullptr && atoi(env) == 4 && c->K == 4) ? 4 : 2;
+    return (tuning().pair_ppt == 4 && c->K == 4) ? 4 : 2;
 }
 
 template <int K, int NC, int PPT>

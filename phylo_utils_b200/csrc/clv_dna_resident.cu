@@ -474,7 +474,7 @@ int launch_resident(Ctx* c, const ResPlan& plan, int64_t wt_begin, int64_t wt_en
     // pick the CTA width that keeps the most warps resident per SM
     const size_t lut_bytes = 0, budget = c->smem_optin, sm_total = c->smem_per_sm;
     int best_w = 1, best_total = 0, best_ctas = 1;
-    const int force_w = getenv("PHB_RESIDENT_WARPS") ? atoi(getenv("PHB_RESIDENT_WARPS")) : 0;
+    const int force_w = tuning().resident_warps;
     for (int w = 1; w <= kMaxWarps; ++w) {
         if (force_w && w != force_w) continue;
         const size_t cta = lut_bytes + (size_t)w * a.warp_bytes + 1024;   // + per-CTA reservation

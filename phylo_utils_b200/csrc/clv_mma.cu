@@ -402,7 +402,7 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, const Mm
     a.pmats = c->d_pmats;
     // tables are staged in the P buffer (MROWS rows): usable when every code has a row there
     a.nc = tip_table_rows(c);
-    a.tiptab = (tip_tables_usable(c) && a.nc <= MROWS && getenv("PHB_DISABLE_TIPTAB") == nullptr) ? c->d_tiptab : nullptr;
+    a.tiptab = (tip_tables_usable(c) && a.nc <= MROWS && !tuning().disable_tiptab) ? c->d_tiptab : nullptr;
     a.codes = c->d_codes;
     a.pitch = c->code_pitch;
     a.lut = c->d_lut;
@@ -448,8 +448,7 @@ int run_rows_mma(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frows = nul
 bool mma_supported(const Ctx* c) { return c->A == 20 || c->A == 61; }
 
 static int mma_dispatch(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frows) {
-    const char* env = getenv("PHB_MMA_VARIANT");   // tuning knob: alternative tile shapes
-    const int variant = env ? atoi(env) : 0;
+    const int variant = tuning().mma_variant;   // tuning knob: alternative tile shapes
     if (c->A == 20) {
         if (variant == 1) return run_rows_mma<20, 3, 5, 4, 8>(c, rs, mode, d_frows);   // 256 patterns per CTA, 8 warps
         return run_rows_mma<20, 3, 5, 4, 4>(c, rs, mode, d_frows);                     // 128 patterns per CTA, 4 warps

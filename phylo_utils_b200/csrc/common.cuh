@@ -36,6 +36,28 @@ static_assert(sizeof(OpRow) == 32, "OpRow must stay 32 bytes");
 
 struct Ctx;
 
+// Developer switches (A/B measurements, what-if builds).  The environment is read ONCE, on first use, into this
+// struct (api.cu); nothing on an evaluation's path calls getenv.  Defaults = the shipped configuration.
+struct Tuning {
+    bool resident_v1 = false;        // PHB_RESIDENT_V1: one-pattern-per-lane walk instead of the pair kernels
+    bool disable_mma = false;        // PHB_DISABLE_MMA: generic kernels instead of the FP64 tensor-core ones
+    bool disable_tiptab = false;     // PHB_DISABLE_TIPTAB: DMMA rows multiply tip operands instead of reading P.lut rows
+    bool up_two_rows = false;        // PHB_UP_TWO_ROWS: pre-order pass as two pruning rows per parent
+    bool up_plain = false;           // PHB_UP_PLAIN: pre-order walk writes up partials, not per-edge sum tables
+    bool deriv_no_st = false;        // PHB_DERIV_NO_ST: DMMA derivative pass leaves no sum tables
+    bool deriv_matrix_form = false;  // PHB_DERIV_MATRIX_FORM: matrix-form derivative kernels
+    bool compress_timing = false;    // PHB_COMPRESS_TIMING: per-phase wall clock of phb_compress_patterns on stderr
+    int pair_ctas = 0;               // PHB_PAIR_CTAS: cap on resident warps per SM of the pair kernel
+    int pair_ppt = 0;                // PHB_PAIR_PPT: patterns per lane of the lnL-only pair kernel (0 = choose)
+    int pair_grid = 0;               // PHB_PAIR_GRID: 0 = choose, 1 = every resident warp, 2 = equal tiles per warp
+    int up_ppt = 0;                  // PHB_UP_PPT: patterns per lane of the pre-order walk
+    int up_warps = 0;                // PHB_UP_WARPS: cap on resident warps per SM of the pre-order walk
+    int resident_warps = 0;          // PHB_RESIDENT_WARPS: CTA width of the one-pattern-per-lane walk
+    int tile_want = 0;               // PHB_TILE_WANT: tiles per SM the streaming tile walk asks for
+    int mma_variant = 0;             // PHB_MMA_VARIANT: alternative DMMA tile shapes
+};
+const Tuning& tuning();
+
 // launch bookkeeping ------------------------------------------------------------------------
 #define PHB_CUDA(ctx, expr)                                                                     \
     do {                                                                                        \
@@ -128,7 +150,8 @@ struct Ctx {
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
     double* d_partial_sums = nullptr;  // [kPartialCap]
-    double* d_result = nullptr;        // [4 * kMaxEdgeBatch]
+    double* d_result = nullptr;        // [result_doubles] = max(4 * kMaxEdgeBatch, 6 * n_tips): lnL, or 3 sums per edge
+    size_t result_doubles = 0;
 
     // host mirrors
     std::vector<int32_t> node_tip;     // node id -> tip row, or -1

@@ -333,7 +333,7 @@ struct PhaseTimer {
         clock_gettime(CLOCK_MONOTONIC, &ts);
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     }
-    explicit PhaseTimer(cudaStream_t s) : on(getenv("PHB_COMPRESS_TIMING") != nullptr), stream(s), t0(now()) {}
+    explicit PhaseTimer(cudaStream_t s) : on(tuning().compress_timing), stream(s), t0(now()) {}
     void mark(const char* what) {
         if (!on) return;
         cudaStreamSynchronize(stream);

@@ -883,7 +883,7 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     c->st_ready.assign(c->n_nodes, 0);
     if (n_rows == 0) return PHB_OK;
     // 4-state models whose post-order pass was the operand-resident walk: one pre-order walk (up_dna_pair.cu)
-    if (c->resident_partials && getenv("PHB_UP_TWO_ROWS") == nullptr) {
+    if (c->resident_partials && !tuning().up_two_rows) {
         const int st = dna_up_walk(c, node_a, node_b);
         if (st != PHB_ERR_UNSUPPORTED) return st;
     }
@@ -892,7 +892,7 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     auto rank = [](int kind) { return kind == SRC_TIP ? 0 : 2; };
     // 20 / 61 states: one three-operand row per parent on the FP64 tensor cores (clv_mma.cu) - P.X once for both
     // children, three products instead of four
-    if (mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr && getenv("PHB_UP_TWO_ROWS") == nullptr) {
+    if (mma_supported(c) && !tuning().disable_mma && !tuning().up_two_rows) {
         std::vector<int32_t> parents, plevel;
         for (int r = n_rows - 1; r >= 0; --r) {
             const int par = c->rows_raw[3 * r];
@@ -1001,13 +1001,15 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
                             double* out) {
     const int A = c->A, K = c->K;
     const size_t blk = (size_t)K * A * A;
-    const bool use_mma = mma_supported(c) && getenv("PHB_DISABLE_MMA") == nullptr;
+    const bool use_mma = mma_supported(c) && !tuning().disable_mma;
     const int mrows = A == 20 ? 24 : 64;
     // edges per launch: as many as the matrix scratch area (or, for the sum-table kernel, the coefficient table), the
     // block-sum buffer and the grid's y dimension hold - all 2N-3 edges of a 4-state tree go out in one launch
     int cap = use_mma ? (int)std::min<size_t>((c->dmats_doubles - (size_t)A * A) / (3 * (size_t)K * mrows), 1 << 20)
                       : (int)std::min<size_t>(c->dmats_doubles / (3 * blk), 1 << 20);
-    cap = std::min(std::min(cap, c->n_nodes), std::min(kPartialCap / 3, 65535));
+    // the 4-state sum-table pass keeps the last kListArea doubles of the block-sum buffer for the root-edge list
+    constexpr int kListParts = 512, kListArea = 4 * 3 * kListParts;
+    cap = std::min(std::min(cap, c->n_nodes), std::min((kPartialCap - kListArea) / 3, 65535));
     if (cap < 1) return c->fail(PHB_ERR_NOMEM, "edge derivatives: scratch area too small");
     double* d_len = c->d_lengths + 2 * (size_t)c->max_rows() + 2;
     std::vector<EdgeDesc> edges;
@@ -1036,8 +1038,8 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             }
         }
         PHB_CUDA(c, cudaMemcpyAsync(d_len, lengths + start, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        // pageable sources: both copies are staged before the calls return, so `edges` may be refilled by the next batch
         PHB_CUDA(c, cudaMemcpyAsync(c->d_edges, edges.data(), (size_t)n * sizeof(EdgeDesc), cudaMemcpyHostToDevice, c->stream));
-        PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // `edges` is reused by the next batch
         const EdgeDesc* d_edges = static_cast<const EdgeDesc*>(c->d_edges);
         int n_parts = 0;
         int n_list_done = 0, list_done[4] = {0, 0, 0, 0}, list_parts_done = 0;   // edges reduced from their own block sums
@@ -1068,7 +1070,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             // later passes read that one block per edge (edge_st_kernel).  Needs 16-byte rows (K A even), a row that
             // fits the register-resident coefficient layouts, and every node at most once per launch.
             const int row_chunks = K * A / 2;
-            bool st_ok = getenv("PHB_DERIV_NO_ST") == nullptr && (K * A) % 2 == 0 && row_chunks <= 256 &&
+            bool st_ok = !tuning().deriv_no_st && (K * A) % 2 == 0 && row_chunks <= 256 &&
                          (int)c->st_ready.size() == c->n_nodes;
             int n_table = 0, n_fresh = 0;
             if (st_ok) {
@@ -1134,7 +1136,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
                         c->st_ready[nodes[start + i]] = 1;
             n_parts = m.n_parts;
         } else if (dna_supported(c) && (int)c->h_evecs.size() == A * A && (int)c->h_freqs.size() == A &&
-                   (c->up_sumtable || getenv("PHB_DERIV_MATRIX_FORM") == nullptr)) {
+                   (c->up_sumtable || !tuning().deriv_matrix_form)) {
             DnaSumArgs q;
             for (int m = 0; m < 4; ++m)
                 for (int i = 0; i < 4; ++i) {
@@ -1157,7 +1159,6 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             q.S = c->S;
             // edges of a sum-table pass without a table (the root edge): up to four go out as a list, with their own
             // (much finer) split of the pattern axis and their own block sums at the end of the buffer
-            constexpr int kListParts = 512, kListArea = 4 * 3 * kListParts;
             q.n_list = 0;
             int n_plain = 0;
             for (int i = 0; i < n; ++i)
@@ -1256,17 +1257,19 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             PHB_CUDA(c, cudaGetLastError());
             n_parts = (int)parts;
         }
-        int st = launch_final_reduce(c, c->d_partial_sums, n_parts, 3 * n, c->d_result);
+        // the sums of edge i of the call end up at d_result[3 i .. 3 i + 2] (what the stream-ordered form leaves behind)
+        double* const d_out = 3 * (size_t)(start + n) <= c->result_doubles ? c->d_result + 3 * (size_t)start : c->d_result;
+        int st = launch_final_reduce(c, c->d_partial_sums, n_parts, 3 * n, d_out);
         if (st) return st;
         for (int j = 0; j < n_list_done; ++j) {   // overwrites what the launch above left in the listed edges' slots
-            st = launch_final_reduce(c, c->d_partial_sums + (kPartialCap - 4 * 3 * 512) + (size_t)j * 3 * list_parts_done,
-                                     list_parts_done, 3, c->d_result + 3 * (size_t)list_done[j]);
+            st = launch_final_reduce(c, c->d_partial_sums + (kPartialCap - kListArea) + (size_t)j * 3 * list_parts_done,
+                                     list_parts_done, 3, d_out + 3 * (size_t)list_done[j]);
             if (st) return st;
         }
-        PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, c->d_result, (size_t)3 * n * 8, cudaMemcpyDeviceToHost,
-                                    c->stream));
-        PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (out != nullptr)
+            PHB_CUDA(c, cudaMemcpyAsync(out + 3 * (size_t)start, d_out, (size_t)3 * n * 8, cudaMemcpyDeviceToHost, c->stream));
     }
+    if (out != nullptr) PHB_CUDA(c, cudaStreamSynchronize(c->stream));
     return PHB_OK;
 }
 

@@ -33,6 +33,40 @@ int op_fail(cudaError_t e, const char* where) {
         if (_e != cudaSuccess) return op_fail(_e, where);     \
     } while (0)
 
+// fp64 throughput probes (phb_op_fp64_peak): eight independent dependency chains per thread
+__global__ void __launch_bounds__(256) fp64_fma_probe(double* out, int iters) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    const double m = 1.0 - 1e-12, c = 1e-12;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fma(v[j], m, c);
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) fp64_mma_probe(double* out, int iters) {
+    double d[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j][0] = d[j][1] = 0.0;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-3;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(d[j][0]), "+d"(d[j][1])
+                         : "d"(a), "d"(b));
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += d[j][0] + d[j][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // numba_likelihood_engine.py:14-46, one thread per (pattern, category)
 __global__ void op_clv_kernel(int64_t S, int K, int A, const double* __restrict__ p1, const double* __restrict__ p2,
                               const double* __restrict__ clv1, const double* __restrict__ clv2,
@@ -252,6 +286,44 @@ int phb_op_pmatrices(int device, int A, int n, const double* evecs, const double
                                dout.as<double>(), A, 1, n, order, 0),
             "phb_op_pmatrices launch");
     OP_CUDA(cudaMemcpy(out, dout.p, (size_t)n * AA, cudaMemcpyDeviceToHost), "phb_op_pmatrices d2h");
+    return PHB_OK;
+}
+
+// Measured fp64 ceilings of this GPU, the denominators bench.py's roofline uses for the compute-bound kernels
+// (MEASURED_PEAKS.json has HBM and bf16 figures only).  kind 0: independent DFMA chains on every SM (vector pipe);
+// kind 1: independent DMMA m8n8k4 chains (fp64 tensor pipe).  Best of five launches, CUDA events.
+int phb_op_fp64_peak(int device, int kind, double* tflops) {
+    if (tflops == nullptr || (kind != 0 && kind != 1)) {
+        set_thread_error("phb_op_fp64_peak: bad argument");
+        return PHB_ERR_INVALID;
+    }
+    int st = pick_device(device);
+    if (st) return st;
+    cudaDeviceProp prop;
+    OP_CUDA(cudaGetDeviceProperties(&prop, device), "phb_op_fp64_peak");
+    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 13;
+    DevBuf out;
+    OP_CUDA(out.alloc((size_t)blocks * threads * 8), "phb_op_fp64_peak alloc");
+    cudaEvent_t a, b;
+    OP_CUDA(cudaEventCreate(&a), "phb_op_fp64_peak");
+    OP_CUDA(cudaEventCreate(&b), "phb_op_fp64_peak");
+    // flops per thread and iteration: 8 chains x 2 (DFMA), or 8 chains x 512 / 32 (one m8n8k4 per warp = 512 flops)
+    const double flops = (double)blocks * threads * iters * (kind == 0 ? 16.0 : 8.0 * 512.0 / 32.0);
+    float best = 0.f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(a);
+        if (kind == 0) fp64_fma_probe<<<blocks, threads>>>(out.as<double>(), iters);
+        else fp64_mma_probe<<<blocks, threads>>>(out.as<double>(), iters);
+        cudaEventRecord(b);
+        OP_CUDA(cudaEventSynchronize(b), "phb_op_fp64_peak run");
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && (best == 0.f || ms < best)) best = ms;   // launch 0 is the warm-up
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    OP_CUDA(cudaGetLastError(), "phb_op_fp64_peak launch");
+    *tflops = flops / (best * 1e-3) / 1e12;
     return PHB_OK;
 }
 

@@ -542,7 +542,7 @@ int dna_up_walk(Ctx* c, int node_a, int node_b) {
     for (int r = 0; r < n_rows; ++r)
         weight[c->rows_raw[3 * r]] = 1 + weight[c->rows_raw[3 * r + 1]] + weight[c->rows_raw[3 * r + 2]];
     // sum-table form needs the host copy of the eigen-system and the scratch area; PHB_UP_PLAIN keeps plain up partials
-    const bool st_form = getenv("PHB_UP_PLAIN") == nullptr && c->d_scratch != nullptr && (int)c->h_evecs.size() == 16 &&
+    const bool st_form = !tuning().up_plain && c->d_scratch != nullptr && (int)c->h_evecs.size() == 16 &&
                          (int)c->h_ivecs.size() == 16 && (int)c->h_freqs.size() == 4;
     std::vector<UpStep> steps;
     steps.reserve(2 * (size_t)n_rows);
@@ -627,8 +627,7 @@ int dna_up_walk(Ctx* c, int node_a, int node_b) {
     const int n_steps = (int)steps.size();
     // one pattern per lane: smaller tiles, 6-7 warps per SM instead of 4 (measured faster at every size tried;
     // PHB_UP_PPT=2 selects two patterns per lane)
-    const char* env = getenv("PHB_UP_PPT");
-    const int ppt = K == 4 && !(env != nullptr && atoi(env) == 2) ? 1 : 2;
+    const int ppt = K == 4 && tuning().up_ppt != 2 ? 1 : 2;
     c->up_sumtable = st_form;
     switch (K * 1000 + tip_table_rows(c) * 10 + ppt) {
 #define PHB_UP_CASE(K_, NC_, PPT_) \

@@ -12,7 +12,14 @@ import numpy as np
 from . import _lib
 from ._lib import lib, check, dptr, iptr
 
-__all__ = ["LikelihoodEngine"]
+__all__ = ["LikelihoodEngine", "fp64_peak"]
+
+
+def fp64_peak(device=0, tensor=False):
+    """Measured fp64 throughput of ``device`` in TFLOP/s (vector DFMA pipe, or the DMMA tensor pipe)."""
+    out = ctypes.c_double(0.0)
+    check(lib().phb_op_fp64_peak(int(device), 1 if tensor else 0, ctypes.byref(out)))
+    return out.value
 
 
 def _f64(a):
@@ -212,6 +219,49 @@ class LikelihoodEngine(object):
         self._ok(fn(self._ctx, ctypes.c_void_p(codes.ctypes.data), int(n_chunks), int(node_a), int(node_b),
                     float(length), ctypes.byref(total), dptr(pattern) if want_pattern else None))
         return total.value, pattern
+
+    # ---- stream-ordered forms: enqueue only, sums stay on the device (multi-GPU drivers) ---------------
+    def lnl_resident_async(self, node_a, node_b, length):
+        self._ok(self._lib.phb_lnl_resident_async(self._ctx, int(node_a), int(node_b), float(length)))
+
+    def root_lnl_async(self, node_a, node_b, length):
+        self._ok(self._lib.phb_root_lnl_async(self._ctx, int(node_a), int(node_b), float(length)))
+
+    def lnl_from_host_packed_async(self, packed_codes, node_a, node_b, length, n_chunks=0):
+        codes = np.ascontiguousarray(packed_codes, dtype=np.uint8)
+        if codes.shape != (self.n_tips, (self.n_patterns + 1) // 2):
+            raise ValueError("codes must be {}".format((self.n_tips, (self.n_patterns + 1) // 2)))
+        self._keep["host_codes"] = codes          # the copy engine reads it until the evaluation is complete
+        self._ok(self._lib.phb_lnl_from_host_packed_async(self._ctx, ctypes.c_void_p(codes.ctypes.data), int(n_chunks),
+                                                          int(node_a), int(node_b), float(length)))
+
+    def edge_derivatives_async(self, nodes, lengths, chain_rule=True):
+        nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        lengths = _f64(lengths)
+        if nodes.shape != lengths.shape or nodes.ndim != 1:
+            raise ValueError("nodes and lengths must be 1-D and of equal length")
+        self._ok(self._lib.phb_edge_derivatives_async(self._ctx, nodes.shape[0], iptr(nodes), dptr(lengths),
+                                                      1 if chain_rule else 0))
+        return nodes.shape[0]
+
+    def result_tensor(self, n):
+        """The first ``n`` doubles of the context's device result buffer as a torch tensor VIEW (no copy): what a
+        collective on the same stream reduces in place.  Needs the torch-owned workspace."""
+        ws = self._keep.get("workspace")
+        if ws is None:
+            raise RuntimeError("result_tensor needs a torch-owned workspace (use_torch=True on a CUDA box)")
+        ptr, cap = ctypes.c_void_p(), ctypes.c_int64(0)
+        self._ok(self._lib.phb_device_result(self._ctx, ctypes.byref(ptr), ctypes.byref(cap)))
+        if not 0 <= n <= cap.value:
+            raise ValueError("the device result buffer holds {} doubles".format(cap.value))
+        import torch
+        off = ptr.value - ws.data_ptr()
+        return ws[off:off + 8 * int(n)].view(torch.float64)
+
+    def result_fetch(self, n):
+        out = np.empty(int(n))
+        self._ok(self._lib.phb_result_fetch(self._ctx, int(n), dptr(out)))
+        return out
 
     # ---- read-back --------------------------------------------------------------------------
     def get_partials(self, node):

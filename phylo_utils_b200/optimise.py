@@ -28,14 +28,11 @@ def edge_nodes(traversal):
 
 
 def _get_lengths(br, keys):
-    get = dict.__getitem__
-    return np.fromiter((get(br, k) for k in keys), dtype=np.double, count=len(keys))
+    return br.gather(br.slots(keys))
 
 
 def _set_lengths(br, keys, lengths):
-    put = dict.__setitem__
-    for k, t in zip(keys, np.asarray(lengths, dtype=np.double).tolist()):
-        put(br, k, t)
+    br.scatter(br.slots(keys), np.asarray(lengths, dtype=np.double))
 
 
 def newton_step(t, d1, d2, lo=MIN_BRANCH_LENGTH, hi=MAX_BRANCH_LENGTH):
@@ -57,8 +54,8 @@ def optimise_branch_lengths(tm, max_sweeps=20, inner_iterations=3, tol=1e-4, ver
     local = getattr(tm, "local", tm)
     nodes = edge_nodes(tm.traversal)
     br = local.traversal.brlens
-    keys = local.edge_keys(nodes)        # dictionary keys resolved once: the sweeps run next to millisecond kernels
-    lengths = _get_lengths(br, keys)
+    slots = br.slots(local.edge_keys(nodes))   # resolved once: the sweeps run next to millisecond kernels
+    lengths = br.gather(slots)
     lnl = tm.lnl()
     trace = [lnl]
     derivative_launches = 0
@@ -72,7 +69,7 @@ def optimise_branch_lengths(tm, max_sweeps=20, inner_iterations=3, tol=1e-4, ver
         step = trial - lengths
         alpha, accepted = 1.0, False
         while alpha > 1e-3:
-            _set_lengths(br, keys, lengths + alpha * step)
+            br.scatter(slots, lengths + alpha * step)
             tm.compute_partials()
             new_lnl = tm.lnl()
             if new_lnl >= lnl:
@@ -80,7 +77,7 @@ def optimise_branch_lengths(tm, max_sweeps=20, inner_iterations=3, tol=1e-4, ver
                 break
             alpha *= 0.5
         if not accepted:
-            _set_lengths(br, keys, lengths)
+            br.scatter(slots, lengths)
             tm.compute_partials()
             break
         gain = new_lnl - lnl

@@ -8,6 +8,12 @@ moves between GPUs inside an evaluation: the only exchange is an all-reduce of t
 3 x n_edges derivative sums), issued through torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU
 tests).  Per-site output, when asked for, is an all-gather of the per-pattern vector.
 
+The sums never visit the host on their way into the collective: the engine's stream-ordered entry points
+(phb_lnl_resident_async, phb_root_lnl_async, phb_edge_derivatives_async, phb_lnl_from_host_packed_async) leave
+them in the context's device result buffer, the collective reduces a tensor VIEW of that buffer in place, ordered
+behind the kernels on the same stream, and one 8-byte (or 3 x n_edges x 8-byte) copy brings the global value
+back: one host synchronisation per evaluation, the same as on one GPU.
+
 One process per GPU; launch with ``python -m torch.distributed.run --nproc-per-node N ...``.
 """
 import numpy as np
@@ -73,7 +79,7 @@ class ShardedTreeModel(object):
     Every rank calls every method (SPMD); scalar results are identical on all ranks.
     """
 
-    def __init__(self, device=None, up_partials=False, mode="auto"):
+    def __init__(self, device=None, up_partials=False, mode="auto", store_partials=True):
         dist = _dist()
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
@@ -81,9 +87,10 @@ class ShardedTreeModel(object):
             import os
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = device
-        self.local = TreeModel(device=device, up_partials=up_partials, mode=mode)
+        self.local = TreeModel(device=device, up_partials=up_partials, mode=mode, store_partials=store_partials)
         self._torch_device = None
         self.n_patterns = None
+        self.collectives = 0          # all-reduces / all-gathers issued so far (bench and tests read it)
 
     def _comm_device(self):
         dist = _dist()
@@ -105,11 +112,11 @@ class ShardedTreeModel(object):
     def set_tip_codes(self, codes, lut, names, siteweights=None, inverse_index=None):
         """``codes`` (ntax, npat) is the FULL compressed alignment; this rank keeps patterns [lo, hi)."""
         npat = codes.shape[1]
+        if npat < self.world:        # the same test on every rank: all of them raise, none is left waiting in a collective
+            raise ValueError("more ranks ({}) than site patterns ({})".format(self.world, npat))
         self.n_patterns = npat
         self.sizes = [hi - lo for lo, hi in shard_slices(npat, self.world)]
         lo, hi = shard_bounds(npat, self.rank, self.world)
-        if hi <= lo:
-            raise ValueError("more ranks than site patterns")
         self.lo, self.hi = lo, hi
         self.inverse_index = np.arange(npat) if inverse_index is None else np.asarray(inverse_index)
         w = None if siteweights is None else np.asarray(siteweights)[lo:hi]
@@ -119,6 +126,8 @@ class ShardedTreeModel(object):
         """This rank's shard only: ``codes`` (ntax, hi - lo) are patterns [lo, hi) = ``shard_bounds(n_patterns, rank,
         world)`` of an alignment of ``n_patterns`` patterns that no rank needs to hold in full (synthetic or
         pre-sharded data).  Per-site output (``compute_likelihood_at_edge``) is then in pattern order."""
+        if int(n_patterns) < self.world:
+            raise ValueError("more ranks ({}) than site patterns ({})".format(self.world, n_patterns))
         self.n_patterns = int(n_patterns)
         self.sizes = [hi - lo for lo, hi in shard_slices(self.n_patterns, self.world)]
         self.lo, self.hi = shard_bounds(self.n_patterns, self.rank, self.world)
@@ -132,6 +141,14 @@ class ShardedTreeModel(object):
         codes, lut, sw, ii, names = alignment_to_codes(alignment, alphabet, compress)
         self.set_tip_codes(codes, lut, names, sw, ii)
 
+    def set_ascertainment_bias_correction(self):
+        """Lewis correction under sharding (SURVEY.md 8(e) "exchange steps"): EVERY rank appends the reference's
+        one-constant-pattern-per-state dummy block (tree_model.py:151-156) to its own shard with weight 0, so each
+        rank derives the identical correction (tree_model.py:209-214) from its own evaluation - a pattern's value
+        does not depend on where in a shard it sits - and nothing has to be broadcast.  The dummy patterns never
+        reach the totals (weight 0) nor the gathered per-site vector (stripped before the all-gather)."""
+        self.local.set_ascertainment_bias_correction()
+
     def initialise(self):
         self.local.initialise()
 
@@ -143,11 +160,39 @@ class ShardedTreeModel(object):
         return self.local.traversal
 
     # -- results ----------------------------------------------------------------------------------------------
+    def _device_sums(self):
+        """True when the local sums can stay on the device on their way through the collective."""
+        m = self.local
+        return _dist() is not None and self.world > 1 and not m.ascbias and \
+            getattr(m.substitution_model, "has_real_eigensystem", True)
+
+    def _reduce_in_place(self, view):
+        """all-reduce (sum) of a device tensor view of the engine's result buffer, then one copy to the host."""
+        _dist().all_reduce(view)
+        self.collectives += 1
+        return self.local.engine.result_fetch(view.numel())
+
     def lnl(self, node_a=None, node_b=None):
+        if self._device_sums():
+            return float(self._reduce_in_place(self.local.lnl_enqueue(node_a, node_b))[0])
+        if self.world > 1:
+            self.collectives += 1
         return float(allreduce_sum([self.local.lnl(node_a, node_b)], self._comm_device())[0])
+
+    def lnl_from_host_codes(self, packed_codes, node_a=None, node_b=None, n_chunks=0):
+        """``TreeModel.lnl_from_host_codes`` on this rank's shard of a new alignment (pinned host memory, two codes
+        per byte), summed over the ranks on the device."""
+        if self._device_sums():
+            view = self.local.lnl_from_host_codes(packed_codes, node_a, node_b, n_chunks, enqueue_only=True)
+            return float(self._reduce_in_place(view)[0])
+        return float(allreduce_sum([self.local.lnl_from_host_codes(packed_codes, node_a, node_b, n_chunks)],
+                                   self._comm_device())[0])
 
     def compute_likelihood_at_edge(self, node_a, node_b):
         _, pattern = self.local._pattern_lnl(node_a, node_b)
+        pattern = pattern[:self.hi - self.lo]              # without the ascertainment-bias dummy patterns
+        if self.world > 1:
+            self.collectives += 1
         full = allgather_concat(pattern, self.sizes, self._comm_device())
         return full[self.inverse_index]
 
@@ -155,5 +200,10 @@ class ShardedTreeModel(object):
         self.local.compute_up_partials()
 
     def edge_derivatives(self, nodes, lengths=None, chain_rule=True):
+        if self._device_sums():
+            view = self.local.edge_derivatives_enqueue(nodes, lengths, chain_rule)
+            return self._reduce_in_place(view.view(-1)).reshape(-1, 3)
         part = self.local.edge_derivatives(nodes, lengths, chain_rule)
+        if self.world > 1:
+            self.collectives += 1
         return allreduce_sum(part.ravel(), self._comm_device()).reshape(part.shape)

@@ -149,6 +149,12 @@ class TreeModel(object):
         nodes = [self.traversal.names[nm] for nm in order]
         return np.asarray(rows), np.asarray(nodes, dtype=np.int32)
 
+    @property
+    def tip_row_order(self):
+        """Alignment row (index into ``alignment_codes``) of every device tip row: the row order of the host codes
+        ``lnl_from_host_codes`` expects."""
+        return self._tip_rows()[0]
+
     def _choose_mode(self, n_patterns):
         if self.mode == "tile":
             return _lib.PHB_MODE_TILE
@@ -216,10 +222,26 @@ class TreeModel(object):
         self._upload_model()
         self.compute_partials()
 
-    def _upload_model(self):
+    def _model_signature(self):
+        """Everything the device holds of the two model objects, as bytes: a few hundred bytes for a nucleotide
+        model, 60 kB for a codon model - cheap enough to compare on every evaluation."""
+        m, r = self.substitution_model, self.rate_model
+        parts = [np.asarray(r.rates, dtype=np.double).tobytes(), np.asarray(r.weights, dtype=np.double).tobytes(),
+                 np.asarray(m.freqs, dtype=np.double).tobytes()]
+        if getattr(m, "has_real_eigensystem", True):
+            e = m.eigen
+            parts += [np.asarray(e.evals).tobytes(), np.asarray(e.evecs).tobytes(), np.asarray(e.ivecs).tobytes()]
+        return b"".join(parts)
+
+    def _upload_model(self, only_if_changed=False):
         m, r = self.substitution_model, self.rate_model
         if m is None or r is None or self.engine is None:
             return
+        signature = self._model_signature()
+        if only_if_changed and signature == getattr(self, "_uploaded_signature", None) and \
+                getattr(self, "_uploaded_to", None) is self.engine:
+            return
+        self._uploaded_signature, self._uploaded_to = signature, self.engine
         if r.ncat != self.engine.n_cat:
             raise ValueError("rate model has {} categories, device layout was built for {}".format(r.ncat, self.engine.n_cat))
         if m.size != self.engine.n_states:
@@ -234,15 +256,14 @@ class TreeModel(object):
         """(n_rows, 2) branch lengths in schedule order.  The dictionary keys of the rows' edges are resolved once
         per schedule: this runs on every evaluation, next to kernels that take a few milliseconds."""
         br = self.traversal.brlens
-        cache = getattr(self, "_row_keys", None)
+        cache = getattr(self, "_row_slots", None)
         if cache is None or cache[0] is not self._rows or cache[1] is not br:
             keys = []
             for par, c1, c2 in self._rows:
-                keys.append(br.canonical_key((int(par), int(c1))))
-                keys.append(br.canonical_key((int(par), int(c2))))
-            cache = self._row_keys = (self._rows, br, keys)
-        get = dict.__getitem__
-        return np.fromiter((get(br, k) for k in cache[2]), dtype=np.double, count=len(cache[2])).reshape(-1, 2)
+                keys.append((int(par), int(c1)))
+                keys.append((int(par), int(c2)))
+            cache = self._row_slots = (self._rows, br, br.slots(keys))
+        return br.gather(cache[2]).reshape(-1, 2)
 
     # ------------------------------------------------------------------------------------------
     # the hot path
@@ -251,6 +272,9 @@ class TreeModel(object):
         """One post-order traversal over all internal nodes (reference: tree_model.py:160-176)."""
         if self.engine is None:
             raise ValueError("call initialise() first")
+        # the reference reads rate_model.rates and calls substitution_model.p on every pass (tree_model.py:166-169), so a
+        # model object mutated in place (rate_model.alpha = x) takes effect there; re-upload when anything changed
+        self._upload_model(only_if_changed=True)
         lengths = self._row_lengths()
         self.engine.set_edge_lengths(lengths)
         if not self.store_partials:
@@ -318,6 +342,37 @@ class TreeModel(object):
         total, _ = self._pattern_lnl(node_a, node_b, want_pattern=False)   # the per-pattern vector stays on the device
         return total
 
+    def lnl_enqueue(self, node_a=None, node_b=None):
+        """Stream-ordered ``lnl``: the evaluation is only enqueued and its sum stays on the device; returns a
+        one-element torch tensor VIEW of it (``engine.result_tensor``) that a collective on the same stream can
+        reduce in place.  No host synchronisation.  Not available with the ascertainment-bias correction or a
+        model without a real eigen-system (their last step runs on the host)."""
+        if node_a is None:
+            node_a, node_b = self.traversal.root_edge
+        if self.ascbias or not getattr(self.substitution_model, "has_real_eigensystem", True):
+            raise ValueError("lnl_enqueue: this model composes its likelihood on the host; use lnl()")
+        length = self._edge_length(node_a, node_b)
+        if self.store_partials:
+            self.engine.root_lnl_async(node_a, node_b, length)
+        else:
+            self.engine.lnl_resident_async(node_a, node_b, length)
+        return self.engine.result_tensor(1)
+
+    def lnl_from_host_codes(self, packed_codes, node_a=None, node_b=None, n_chunks=0, enqueue_only=False):
+        """lnL of a NEW alignment over the same taxa, tree and models, starting from pinned HOST codes (two 4-bit codes
+        per byte, ``LikelihoodEngine.pack_codes``; rows in the order of the alignment given to ``set_tip_codes``):
+        the host-to-device copy is pipelined with the pruning (``phb_lnl_from_host_packed``).  lnL-only models
+        (``store_partials=False``).  ``enqueue_only``: as ``lnl_enqueue``."""
+        if self.store_partials or self.ascbias:
+            raise ValueError("lnl_from_host_codes needs an lnL-only model (store_partials=False) without asc-bias correction")
+        if node_a is None:
+            node_a, node_b = self.traversal.root_edge
+        length = self._edge_length(node_a, node_b)
+        if enqueue_only:
+            self.engine.lnl_from_host_packed_async(packed_codes, node_a, node_b, length, n_chunks)
+            return self.engine.result_tensor(1)
+        return self.engine.lnl_from_host(packed_codes, node_a, node_b, length, n_chunks=n_chunks, packed=True)[0]
+
     # ------------------------------------------------------------------------------------------
     # attribute views of device state (reference attributes partials / scale / root_partials / root_scale)
     # ------------------------------------------------------------------------------------------
@@ -357,6 +412,14 @@ class TreeModel(object):
             lengths = self.lengths_above(nodes)
         return self.engine.edge_derivatives(nodes, lengths, chain_rule)
 
+    def edge_derivatives_enqueue(self, nodes, lengths=None, chain_rule=True):
+        """Stream-ordered ``edge_derivatives``: returns a torch tensor VIEW (n_edges, 3) of the device sums."""
+        nodes = np.asarray(nodes, dtype=np.int32)
+        if lengths is None:
+            lengths = self.lengths_above(nodes)
+        n = self.engine.edge_derivatives_async(nodes, lengths, chain_rule)
+        return self.engine.result_tensor(3 * n).view(n, 3)
+
     def edge_keys(self, nodes):
         """``brlens`` key of the edge above each node (the root edge for either root child)."""
         a, b = self.traversal.root_edge
@@ -375,9 +438,7 @@ class TreeModel(object):
 
     def lengths_above(self, nodes):
         br = self.traversal.brlens
-        get = dict.__getitem__
-        keys = self.edge_keys(nodes)
-        return np.fromiter((get(br, k) for k in keys), dtype=np.double, count=len(keys))
+        return br.gather(br.slots(self.edge_keys(nodes)))
 
     def _parents(self):
         parents = getattr(self, "_parent_map", None)

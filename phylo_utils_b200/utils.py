@@ -119,19 +119,23 @@ def get_optimising_traversal(tree, descriptor, node_dict):
 
 
 class BranchLengths(dict):
-    """``{(i, j): length}`` with order-insensitive lookup (reference: utils.py:191-199)."""
+    """
+    ``{(i, j): length}`` with order-insensitive lookup (reference: utils.py:191-199).
 
-    def __getitem__(self, key):
-        if dict.__contains__(self, key):
-            return dict.__getitem__(self, key)
-        flipped = tuple(key)[::-1]
-        if dict.__contains__(self, flipped):
-            return dict.__getitem__(self, flipped)
-        raise KeyError(key)
+    The lengths themselves live in one dense float64 array (``dict`` maps a key to its slot), because the
+    device path moves ALL branch lengths of a tree on every evaluation: ``slots(keys)`` resolves keys once
+    per schedule, ``gather(slots)`` / ``scatter(slots, values)`` are single numpy indexing operations where a
+    dictionary walk of 2 000 keys would cost as much as a tenth of an evaluation on eight GPUs.  Seen through
+    ``[]``, ``in``, ``get``, ``items``, ``values``, ``keys``, ``len`` it is the reference's dictionary.
+    """
 
-    def __contains__(self, key):
-        return dict.__contains__(self, key) or dict.__contains__(self, tuple(key)[::-1])
+    def __init__(self, *args, **kwargs):
+        dict.__init__(self)
+        self._dense = np.empty(16, dtype=np.double)
+        for key, value in dict(*args, **kwargs).items():
+            self[key] = value
 
+    # -- dictionary face --------------------------------------------------------------------
     def canonical_key(self, key):
         if dict.__contains__(self, key):
             return key
@@ -139,6 +143,74 @@ class BranchLengths(dict):
         if dict.__contains__(self, flipped):
             return flipped
         raise KeyError(key)
+
+    def __getitem__(self, key):
+        return float(self._dense[dict.__getitem__(self, self.canonical_key(key))])
+
+    def __setitem__(self, key, value):
+        try:
+            slot = dict.__getitem__(self, self.canonical_key(key))
+        except KeyError:
+            slot = dict.__len__(self)
+            if slot == self._dense.shape[0]:
+                self._dense = np.concatenate([self._dense, np.empty(slot, dtype=np.double)])
+            dict.__setitem__(self, tuple(key), slot)
+        self._dense[slot] = value
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or dict.__contains__(self, tuple(key)[::-1])
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def values(self):
+        return [float(v) for v in self._dense[:dict.__len__(self)]]     # slots are handed out in insertion order
+
+    def items(self):
+        return list(zip(dict.keys(self), self.values()))
+
+    def __eq__(self, other):
+        return dict(self.items()) == (dict(other.items()) if isinstance(other, BranchLengths) else other)
+
+    def __ne__(self, other):
+        return not self == other
+
+    __hash__ = None
+
+    def __repr__(self):
+        return "BranchLengths({!r})".format(dict(self.items()))
+
+    def __delitem__(self, key):
+        raise TypeError("edges cannot be removed from a BranchLengths table")
+
+    pop = popitem = clear = setdefault = lambda self, *a, **k: BranchLengths.__delitem__(self, None)
+
+    def update(self, *args, **kwargs):
+        for key, value in dict(*args, **kwargs).items():
+            self[key] = value
+
+    def copy(self):
+        return BranchLengths(self.items())
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
+    def __reduce__(self):
+        return (BranchLengths, (self.items(),))
+
+    # -- array face (what TreeModel and the optimiser use) ---------------------------------------
+    def slots(self, keys):
+        """Slot index of every key (either orientation) - resolve once, then ``gather`` / ``scatter``."""
+        return np.fromiter((dict.__getitem__(self, self.canonical_key(k)) for k in keys), dtype=np.intp, count=len(keys))
+
+    def gather(self, slots):
+        return self._dense[slots]
+
+    def scatter(self, slots, values):
+        self._dense[slots] = values
 
 
 def get_branch_lengths(node_dict):

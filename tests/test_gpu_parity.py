@@ -255,3 +255,82 @@ def test_resident_rejects_unsupported_shapes():
     tm.initialise()
     with pytest.raises(ValueError):
         tm.lnl()
+
+
+# ---- regressions for state that must not go stale ----------------------------------------------------------------
+def _engine_lnl(eng, tr, rows, lengths):
+    a, b = tr.root_edge
+    eng.set_edge_lengths(lengths)
+    eng.build_pmatrices()
+    eng.compute_partials()
+    return eng.root_lnl(a, b, tr.brlens[(a, b)])[0]
+
+
+@pytest.mark.parametrize("mode_patterns", [200, 20000])      # level / tile kernels, and the operand-resident pair kernels
+def test_set_tips_twice_rebuilds_the_tip_tables(mode_patterns):
+    """phb_set_tips after phb_build_pmatrices: the P.lut tip tables depend on the look-up table and on n_codes (8 vs 16
+    rows per category) - a second phb_set_tips must invalidate them, or the next pass reads the old tables."""
+    rng = np.random.default_rng(11)
+    n_taxa, n_pat = 9, mode_patterns
+    t = phy.tree.random_tree(n_taxa, 11)
+    tr = phy.traversal.Traversal(phy.utils.deepcopy_tree(t))
+    labels = [lf.taxon.label for lf in t.leaf_node_iter()]
+    tip_nodes = np.asarray([tr.names[n] for n in labels], dtype=np.int32)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    rows = tr.locality_order()
+    lengths = np.asarray([[tr.brlens[(int(p), int(c1))], tr.brlens[(int(p), int(c2))]] for p, c1, c2 in rows])
+    lut5 = np.vstack([np.eye(4)[::-1], np.ones((1, 4))])                                   # 5 codes: 8-row tip tables
+    lut12 = np.vstack([lut5, rng.integers(0, 2, size=(7, 4)).astype(float) + np.eye(4)[rng.integers(0, 4, 7)]]).clip(0, 1)
+    codes5 = rng.integers(0, 5, size=(n_taxa, n_pat)).astype(np.uint8)
+    codes12 = rng.integers(0, 12, size=(n_taxa, n_pat)).astype(np.uint8)                   # 12 codes: 16-row tip tables
+
+    def want(codes, lut):
+        tips = {tr.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(labels)}
+        return float(oracle.tree_lnl(tr, tips, model.p, model.freqs, rate.rates, rate.weights).sum())
+
+    eng = phy.LikelihoodEngine(n_taxa, n_pat, 4, 4)
+    e = model.eigen
+    eng.set_model(e.evecs, e.evals, np.ascontiguousarray(e.ivecs), model.freqs, rate.rates, rate.weights)
+    eng.set_tips(codes5, lut5, tip_nodes)
+    eng.set_schedule(rows)
+    assert_lnl_close(_engine_lnl(eng, tr, rows, lengths), want(codes5, lut5))
+    eng.set_tips(codes12, lut12, tip_nodes)                  # other table, other geometry, SAME matrices
+    with pytest.raises(RuntimeError):
+        eng.compute_partials()                               # the matrices (and their tip tables) are stale now
+    assert_lnl_close(_engine_lnl(eng, tr, rows, lengths), want(codes12, lut12))
+    eng.set_tips(codes5, lut5[[4, 3, 2, 1, 0]], tip_nodes)   # back to 5 codes, rows permuted
+    assert_lnl_close(_engine_lnl(eng, tr, rows, lengths), want(codes5, lut5[[4, 3, 2, 1, 0]]))
+    eng.close()
+
+
+@pytest.mark.parametrize("store", [True, False])
+def test_mutating_the_rate_model_in_place_takes_effect(store):
+    """The reference reads rate_model.rates on every compute_partials (tree_model.py:166-169): `tm.rate_model.alpha = x`
+    followed by compute_partials() must evaluate the new categories here too."""
+    g, tr, codes, lut, sw, ii, names, model, _ = problem("cfg1_gtr_g4")
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(store_partials=store)
+    tm.set_tree(tree(g))
+    tm.set_alignment(records(g), 0)
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    assert_lnl_close(tm.lnl(), g["total_lnl"])
+    rate.alpha = 2.0
+    tm.compute_partials()
+    fresh = phy.rate_models.GammaRateModel(4, 2.0)
+    want = oracle.tree_lnl(tr, tip_partials(tr, codes, lut, names), model.p, model.freqs, fresh.rates, fresh.weights)
+    assert_lnl_close(tm.lnl(), float(np.dot(want, sw)))
+    rate.alpha = 0.5
+    tm.compute_partials()
+    assert_lnl_close(tm.lnl(), g["total_lnl"])
+    # +I+G: pinvar changes rates AND weights
+    ig = phy.rate_models.InvariantGammaModel(0.1, 3, 0.7)
+    tm.set_rate_model(ig)
+    tm.compute_partials()
+    ig.pinvar = 0.35
+    tm.compute_partials()
+    fresh = phy.rate_models.InvariantGammaModel(0.35, 3, 0.7)
+    want = oracle.tree_lnl(tr, tip_partials(tr, codes, lut, names), model.p, model.freqs, fresh.rates, fresh.weights)
+    assert_lnl_close(tm.lnl(), float(np.dot(want, sw)))

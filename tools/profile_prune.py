@@ -25,11 +25,12 @@ def main():
     ap.add_argument("--lnl-only", action="store_true")
     args = ap.parse_args()
     import torch
-    tree, names = bench.make_tree(args.taxa, args.seed)
+    tree = phy.tree.random_tree(args.taxa, args.seed)
+    names = [lf.taxon.label for lf in tree.leaf_node_iter()]
     trav = phy.traversal.Traversal(phy.utils.deepcopy_tree(tree))
     model = phy.substitution_models.GTR(bench.GTR_RATES, bench.GTR_FREQS)
     rate = phy.rate_models.GammaRateModel(4, 0.5)
-    codes = torch.from_numpy(bench.make_codes(args.taxa, args.patterns, args.seed)).cuda()
+    codes = torch.from_numpy(bench.make_codes(args.taxa, 0, args.patterns, args.seed)).cuda()
     eng = phy.LikelihoodEngine(args.taxa, args.patterns, 4, 4, store_partials=not args.lnl_only)
     mode = {"tile": _lib.PHB_MODE_TILE, "level": _lib.PHB_MODE_LEVEL, "resident": _lib.PHB_MODE_RESIDENT}[args.mode]
     if mode == _lib.PHB_MODE_LEVEL:
