@@ -66,6 +66,9 @@ const char* phb_status_name(int status);
 /* message of the last failure on this ctx, or (ctx == NULL) of the last failed phb_create /
  * context-free call on the calling thread */
 const char* phb_last_error(const phb_ctx* ctx);
+/* The PHB_* developer switches (A/B measurements; csrc/common.cuh `Tuning`) are read from the environment once, on
+ * first use; this re-reads them (tests and tuning scripts that change a switch inside one process). */
+int phb_reload_tuning(void);
 /* number of kernel launches issued by this ctx since creation (bench.py's gpu_launches) */
 int64_t phb_launch_count(const phb_ctx* ctx);
 

@@ -28,6 +28,7 @@ SIGNATURES = {
     "phb_version": (c_int, []),
     "phb_status_name": (c_char_p, [c_int]),
     "phb_last_error": (c_char_p, [c_void_p]),
+    "phb_reload_tuning": (c_int, []),
     "phb_launch_count": (c_int64, [c_void_p]),
     "phb_discrete_gamma": (c_int, [c_double, c_double, c_int, c_int, _dp, _dp]),
     "phb_compress_patterns": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_void_p, _lp, _lp, _lp, _lp]),

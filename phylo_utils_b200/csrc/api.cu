@@ -13,8 +13,8 @@ namespace phb {
 static thread_local std::string g_thread_error;
 void set_thread_error(const std::string& msg) { g_thread_error = msg; }
 
-const Tuning& tuning() {
-    static const Tuning t = [] {
+static Tuning read_tuning() {
+    {
         Tuning v;
         auto flag = [](const char* name) { return getenv(name) != nullptr; };
         auto num = [](const char* name) { const char* s = getenv(name); return s ? atoi(s) : 0; };
@@ -35,9 +35,15 @@ const Tuning& tuning() {
         v.tile_want = num("PHB_TILE_WANT");
         v.mma_variant = num("PHB_MMA_VARIANT");
         return v;
-    }();
+    }
+}
+
+static Tuning& tuning_slot() {
+    static Tuning t = read_tuning();
     return t;
 }
+
+const Tuning& tuning() { return tuning_slot(); }
 const char* thread_error() { return g_thread_error.c_str(); }
 
 namespace {
@@ -226,6 +232,11 @@ using namespace phb;
 extern "C" {
 
 int phb_version(void) { return PHB_VERSION; }
+
+int phb_reload_tuning(void) {
+    tuning_slot() = read_tuning();
+    return PHB_OK;
+}
 
 const char* phb_status_name(int status) {
     switch (status) {

@@ -635,7 +635,15 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
 
 // patterns per lane: 2 everywhere; 4 is built for K = 4 and selected with PHB_PAIR_PPT=4 (tuning knob)
 int pair_ppt(const Ctx* c) {
-    return (tuning().pair_ppt == 4 && c->K == 4) ? 4 : 2;
+    if (c->K != 4) return 2;
+    if (tuning().pair_ppt == 2 || tuning().pair_ppt == 4) return tuning().pair_ppt;
+    // A tile is one long sequential job (a walk over the whole tree), so what counts is the number of WAVES: when the
+    // 64-pattern tiles need a second, nearly empty wave of warps but the 128-pattern tiles fit in one, the bigger
+    // tiles win (125k patterns - the 8-GPU shard of the 1M-pattern alignment: 2.19 vs 2.36 ms); otherwise the
+    // 64-pattern tiles do (250k: 4.00 vs 4.47 ms; 1M: 15.3 vs 15.8 ms on the same box).
+    const int64_t t64 = (c->S + 63) / 64, t128 = (c->S + 127) / 128;
+    const int64_t wave2 = (int64_t)c->sm_count * PairLayout<4, 8, 2>::MIN_CTAS, wave4 = (int64_t)c->sm_count * PairLayout<4, 8, 4>::MIN_CTAS;
+    return (t64 > wave2 && t128 <= wave4) ? 4 : 2;
 }
 
 template <int K, int NC, int PPT>

@@ -40,9 +40,11 @@ __global__ void __launch_bounds__(256) fp64_fma_probe(double* out, int iters) {
     for (int j = 0; j < 8; ++j) v[j] = 1.0 + 1e-9 * (threadIdx.x + j);
     const double m = 1.0 - 1e-12, c = 1e-12;
 #pragma unroll 1
-    for (int i = 0; i < iters; ++i)
+    for (int i = 0; i < iters; i += 16)          // 128 DFMA per trip: loop control is ~2 % of the instructions
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fma(v[j], m, c);
+        for (int u = 0; u < 16; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fma(v[j], m, c);
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += v[j];
@@ -55,10 +57,12 @@ __global__ void __launch_bounds__(256) fp64_mma_probe(double* out, int iters) {
     for (int j = 0; j < 8; ++j) d[j][0] = d[j][1] = 0.0;
     const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-3;
 #pragma unroll 1
-    for (int i = 0; i < iters; ++i)
+    for (int i = 0; i < iters; i += 8)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                          : "+d"(d[j][0]), "+d"(d[j][1])
                          : "d"(a), "d"(b));
     double s = 0.0;

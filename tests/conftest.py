@@ -13,6 +13,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the read-only reference checkout at /root/reference")
 
 
+@pytest.fixture(autouse=True)
+def _developer_switches_follow_the_environment():
+    """The library reads its PHB_* switches once; tests that monkeypatch one call ``phb_reload_tuning()`` and this
+    fixture - set up before, hence torn down after, monkeypatch - re-reads the restored environment afterwards."""
+    yield
+    from phylo_utils_b200 import _lib
+    _lib.lib().phb_reload_tuning()
+
+
 def _gpu_available():
     try:
         import torch

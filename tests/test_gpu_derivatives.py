@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import phylo_utils_b200 as phy
+from phylo_utils_b200 import _lib
 from phylo_utils_b200.tree import random_tree, caterpillar_tree, balanced_tree
 from helpers import (problem, records, tree, tip_partials, oracle_up_partials, oracle_edge_derivatives, assert_lnl_close)
 from oracle import oracle
@@ -165,6 +166,7 @@ def _walk_vs_two_rows(tree_fn, n_taxa, n_pat, ppt, monkeypatch, n_cat=4, iupac=F
             monkeypatch.setenv("PHB_UP_TWO_ROWS", "1")
         elif env == "plain":
             monkeypatch.setenv("PHB_UP_PLAIN", "1")       # the walk storing up partials instead of sum tables
+        _lib.lib().phb_reload_tuning()
         tm = phy.TreeModel(mode="resident", up_partials=True)
         tm.set_tree(tr_tree)
         tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)}, siteweights=weights)

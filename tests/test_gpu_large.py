@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import phylo_utils_b200 as phy
+from phylo_utils_b200 import _lib
 from phylo_utils_b200.tree import random_tree, caterpillar_tree, balanced_tree
 from helpers import assert_lnl_close
 from oracle import oracle
@@ -247,12 +248,16 @@ def test_four_patterns_per_lane_knob_gives_the_same_answer(monkeypatch):
     tm.initialise()
     a, b = tm.traversal.root_edge
     length = tm.traversal.brlens[(a, b)]
+    monkeypatch.setenv("PHB_PAIR_PPT", "2")
+    _lib.lib().phb_reload_tuning()
     t2, p2 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
     monkeypatch.setenv("PHB_PAIR_PPT", "4")
+    _lib.lib().phb_reload_tuning()
     t4, p4 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
     packed = phy.LikelihoodEngine.pack_codes(codes)
     t4p, p4p = tm.engine.lnl_from_host(packed, a, b, length, n_chunks=7, want_pattern=True, packed=True)
     monkeypatch.delenv("PHB_PAIR_PPT")
+    _lib.lib().phb_reload_tuning()
     assert_lnl_close(p4, p2)
     assert np.array_equal(p4p, p4)
     assert_lnl_close(t4, t2)
@@ -293,11 +298,11 @@ def test_headline_shape_full_size_properties():
     assert np.array_equal(p2, pattern) and t2 == total
 
 
-@pytest.mark.parametrize("shape", ["cfg5_shard", "cfg3"])
+@pytest.mark.parametrize("shape", ["cfg5_shard", "cfg3", "cfg4"])
 def test_derivative_configs_full_size_properties(shape):
     """
-    BASELINE configs 5 (one GPU's shard: 2000 taxa x 62,500 patterns, GTR+G4) and 3 (500 taxa x 100,000 patterns, LG+G4)
-    at full size through the derivative path - post-order pass, pre-order pass, all edges in one launch.  The alignment
+    BASELINE configs 5 (one GPU's shard: 2000 taxa x 62,500 patterns, GTR+G4), 3 (500 taxa x 100,000 patterns, LG+G4) and
+    4 (100 taxa x 50,000 codons, GY94+G4, 61 states on the FP64 tensor cores) at full size through the derivative path - post-order pass, pre-order pass, all edges in one launch.  The alignment
     is a small block repeated, so (size-independent properties): the total is reps x the block total, which the oracle
     gives to 1e-10; EVERY edge reproduces that total (pulley principle); derivatives at other trial lengths agree between
     the first pass and the passes that read the per-edge sum tables; a Newton sweep does not lower lnL.
@@ -306,9 +311,13 @@ def test_derivative_configs_full_size_properties(shape):
     if shape == "cfg5_shard":
         n_taxa, block, reps, n_states = 2000, 250, 250, 4
         model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
-    else:
+    elif shape == "cfg3":
         n_taxa, block, reps, n_states = 500, 200, 500, 20
         model = phy.substitution_models.LG()
+    else:
+        from phylo_utils_b200.substitution_models.codon import f3x4
+        n_taxa, block, reps, n_states = 100, 125, 400, 61
+        model = phy.substitution_models.GY94(2.0, 0.2, f3x4(np.random.default_rng(4).dirichlet(np.ones(4) * 5, size=3)))
     tree, names, codes, lut = synthetic(n_taxa, block, n_states, seed=5)
     big = np.ascontiguousarray(np.tile(codes, (1, reps)))
     rate = phy.rate_models.GammaRateModel(4, 0.5)
@@ -322,6 +331,12 @@ def test_derivative_configs_full_size_properties(shape):
     want = reps * oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights).sum()
     total = tm.lnl()
     assert_lnl_close(total, want)
+    if shape == "cfg4":
+        # per-pattern values: bitwise periodic in the block, the block itself against the oracle
+        pattern = tm.compute_likelihood_at_edge(*tm.traversal.root_edge)
+        assert pattern.shape == (50000,)
+        assert np.array_equal(pattern.reshape(reps, block), np.tile(pattern[:block], (reps, 1)))
+        assert_lnl_close(pattern[:block], oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights))
     tm.compute_up_partials()
     nodes = edge_nodes(tm.traversal)
     lengths = tm.lengths_above(nodes)

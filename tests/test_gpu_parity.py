@@ -334,3 +334,19 @@ def test_mutating_the_rate_model_in_place_takes_effect(store):
     fresh = phy.rate_models.InvariantGammaModel(0.35, 3, 0.7)
     want = oracle.tree_lnl(tr, tip_partials(tr, codes, lut, names), model.p, model.freqs, fresh.rates, fresh.weights)
     assert_lnl_close(tm.lnl(), float(np.dot(want, sw)))
+
+
+def test_device_codon_matrices_match_the_textbook_definition():
+    """GY94 has no counterpart in the reference: pin the device-built P (csrc/pmatrix.cu, A = 61) against
+    scipy's expm of the rate matrix written out from the published definition (tests/test_substitution_models.py)."""
+    from scipy.linalg import expm
+    from test_substitution_models import _textbook_gy94
+    from phylo_utils_b200.substitution_models.codon import f3x4, SENSE_CODONS
+    pi = f3x4(np.random.default_rng(4).dirichlet(np.ones(4) * 5, size=3))
+    m = phy.substitution_models.GY94(2.0, 0.2, pi)
+    q = _textbook_gy94(2.0, 0.2, pi, SENSE_CODONS)
+    times = np.array([0.003, 0.11, 0.9, 2.7])
+    got = transition_matrices(m.eigen, times, 0)
+    want = np.stack([expm(q * t) for t in times])
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-13)
+    assert np.allclose(transition_matrices(m.eigen, times, 1), np.stack([q.dot(expm(q * t)) for t in times]), rtol=1e-8, atol=1e-12)

@@ -127,3 +127,58 @@ def test_gy94_structure():
     assert q[i, l] == 0
     p = m.p(0.3, [0.5, 1.5])
     assert np.allclose(p.sum(axis=2), 1.0, atol=1e-11) and p.min() > -1e-12
+
+
+# The standard genetic code written out per amino acid (NCBI translation table 1) - deliberately NOT the packed
+# 64-character string codon.py uses, so that the two encodings check each other.
+_CODE_BY_AA = {
+    "F": "TTT TTC", "L": "TTA TTG CTT CTC CTA CTG", "I": "ATT ATC ATA", "M": "ATG", "V": "GTT GTC GTA GTG",
+    "S": "TCT TCC TCA TCG AGT AGC", "P": "CCT CCC CCA CCG", "T": "ACT ACC ACA ACG", "A": "GCT GCC GCA GCG",
+    "Y": "TAT TAC", "H": "CAT CAC", "Q": "CAA CAG", "N": "AAT AAC", "K": "AAA AAG", "D": "GAT GAC", "E": "GAA GAG",
+    "C": "TGT TGC", "W": "TGG", "R": "CGT CGC CGA CGG AGA AGG", "G": "GGT GGC GGA GGG",
+}
+
+
+def _textbook_gy94(kappa, omega, pi, codons):
+    """Goldman & Yang (1994) / Yang (2006, eq. 2.7) rate matrix built entry by entry from the definition."""
+    aa = {cod: a for a, cods in _CODE_BY_AA.items() for cod in cods.split()}
+    assert len(aa) == 61 and sorted(aa) == sorted(codons)
+    purines = set("AG")
+    n = len(codons)
+    q = np.zeros((n, n))
+    for i, ci in enumerate(codons):
+        for j, cj in enumerate(codons):
+            where = [p for p in range(3) if ci[p] != cj[p]]
+            if i == j or len(where) != 1:
+                continue
+            x, y = ci[where[0]], cj[where[0]]
+            rate = pi[j]
+            if (x in purines) == (y in purines):       # purine <-> purine or pyrimidine <-> pyrimidine: transition
+                rate *= kappa
+            if aa[ci] != aa[cj]:
+                rate *= omega
+            q[i, j] = rate
+        q[i, i] = -q[i].sum()
+    return q / -(pi * np.diag(q)).sum()                # one expected substitution per codon per unit time
+
+
+def test_gy94_q_and_p_against_the_textbook_definition():
+    """Independent pin for the codon model (it has no counterpart in the reference): Q from the published definition,
+    P = expm(Q t r) from scipy, against GY94.q() and the eigen-decomposition route of Model.p."""
+    from scipy.linalg import expm
+    from phylo_utils_b200.substitution_models.codon import f3x4, SENSE_CODONS
+    rng = np.random.default_rng(4)
+    for kappa, omega in ((2.0, 0.2), (1.0, 1.0), (5.5, 1.7)):
+        pi = f3x4(rng.dirichlet(np.ones(4) * 5, size=3))
+        m = GY94(kappa, omega, pi)
+        q = _textbook_gy94(kappa, omega, pi, SENSE_CODONS)
+        assert np.allclose(m.q(), q, rtol=1e-13, atol=1e-16)
+        rates = np.array([0.03, 0.25, 0.82, 2.89])
+        for t in (0.01, 0.3, 2.0):
+            want = np.stack([expm(q * t * r) for r in rates])
+            got = m.p(t, rates)
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-13)
+    # f3x4 itself: product of the position frequencies over the sense codons, renormalised
+    pf = rng.dirichlet(np.ones(4) * 5, size=3)
+    want = np.array([pf[0]["ACGT".index(c[0])] * pf[1]["ACGT".index(c[1])] * pf[2]["ACGT".index(c[2])] for c in SENSE_CODONS])
+    assert np.allclose(f3x4(pf), want / want.sum(), rtol=1e-14)
