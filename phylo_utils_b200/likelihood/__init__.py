@@ -8,5 +8,9 @@ import sys
 from . import cuda_likelihood_engine
 from .cuda_likelihood_engine import clv, lnl_node, lnl_branch, lnl_branch_derivs
 
+from . import legacy
+from .legacy import (Leaf, LnlNode, LnlModel, Mixture, GammaMixture, OptWrapper, BranchLengthOptimiser, optimise,
+                     brent_optimise)
+
 numba_likelihood_engine = cuda_likelihood_engine
 sys.modules[__name__ + ".numba_likelihood_engine"] = cuda_likelihood_engine
