@@ -198,6 +198,19 @@ int phb_compute_up_partials(phb_ctx* ctx, int node_a, int node_b, double length)
 int phb_edge_derivatives(phb_ctx* ctx, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
                          double* out);
 
+/* ---- re-rooting in place -------------------------------------------------------------------
+ * The reference's one-edge-at-a-time optimisation order (Traversal.optimising_traversal, utils.py:137-188; rows
+ * [PAR, SIB, GPA, NOD, PAR] and [NOD, CH1, CH2, -1, -1]) re-computes one node's partial from two neighbours so that it
+ * faces the edge about to be optimised.  phb_update_node is that single `clv` call on the device
+ * (numba_likelihood_engine.py:10-46 with P(len_a), P(len_b) built on the device): node's block := combine(child_a over
+ * len_a, child_b over len_b), children being tips or internal nodes as they currently stand.
+ * phb_branch_derivatives evaluates { lnL, dlnL/dt, d2lnL/dt2 } ACROSS the edge (node_a, node_b) at n trial lengths in
+ * one launch, from the two nodes' current partials (lnl_branch_derivs, :49-57, composed over the Gamma mixture): the
+ * line search of one edge.  Neither needs the pre-order pass; both invalidate what it left. */
+int phb_update_node(phb_ctx* ctx, int node, int child_a, double len_a, int child_b, double len_b);
+int phb_branch_derivatives(phb_ctx* ctx, int node_a, int node_b, int n_lengths, const double* lengths, int chain_rule,
+                           double* out);
+
 /* ---- stream-ordered forms (multi-GPU drivers) ------------------------------------------------
  * The reference is one process and sums per-site lnL on the host (bin/phy.py:146).  With the site patterns sharded
  * over several GPUs the only exchange is the sum of the per-shard scalars, and it must not cost a

@@ -57,6 +57,8 @@ SIGNATURES = {
     "phb_get_root_partials": (c_int, [c_void_p, _dp, _dp]),
     "phb_compute_up_partials": (c_int, [c_void_p, c_int, c_int, c_double]),
     "phb_edge_derivatives": (c_int, [c_void_p, c_int, _ip, _dp, c_int, _dp]),
+    "phb_update_node": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_double]),
+    "phb_branch_derivatives": (c_int, [c_void_p, c_int, c_int, c_int, _dp, c_int, _dp]),
     "phb_lnl_resident_async": (c_int, [c_void_p, c_int, c_int, c_double]),
     "phb_root_lnl_async": (c_int, [c_void_p, c_int, c_int, c_double]),
     "phb_lnl_from_host_packed_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double]),

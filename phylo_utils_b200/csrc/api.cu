@@ -963,6 +963,78 @@ int phb_edge_derivatives(phb_ctx* c, int n_edges, const int32_t* nodes, const do
     return launch_edge_derivatives(c, n_edges, nodes, lengths, chain_rule, out);
 }
 
+// ---- re-rooting in place (Traversal.optimising_traversal, utils.py:137-188) --------------------------------------
+int phb_update_node(phb_ctx* c, int node, int child_a, double len_a, int child_b, double len_b) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS), PHB_ERR_STATE, "phb_update_node: context has no partial storage");
+    PHB_REQUIRE(c, c->have_tips && !c->codes_packed && c->have_schedule && c->have_model, PHB_ERR_STATE,
+                "phb_update_node: tips, schedule and eigen-system must be set");
+    PHB_REQUIRE(c, c->have_partials, PHB_ERR_STATE, "phb_update_node: run phb_compute_partials first");
+    PHB_REQUIRE(c, node >= 0 && node < c->n_nodes && c->node_tip[node] < 0 && c->node_slot[node] >= 0, PHB_ERR_INVALID,
+                "phb_update_node: node must be an internal node of the schedule");
+    const int kids[2] = {child_a, child_b};
+    const double lens[2] = {len_a, len_b};
+    OpRow row{};
+    row.dst = c->node_slot[node];
+    for (int i = 0; i < 2; ++i) {
+        st = node_operand_ok(c, kids[i]);
+        if (st) return st;
+        PHB_REQUIRE(c, kids[i] != node && lens[i] >= 0 && std::isfinite(lens[i]), PHB_ERR_INVALID,
+                    "phb_update_node: bad child or branch length");
+        row.kind[i] = c->node_tip[kids[i]] >= 0 ? SRC_TIP : SRC_GLOBAL;
+        row.src[i] = c->node_tip[kids[i]] >= 0 ? c->node_tip[kids[i]] : c->node_slot[kids[i]];
+        row.pidx[i] = 2 * c->max_rows() + i;
+    }
+    PHB_REQUIRE(c, child_a != child_b, PHB_ERR_INVALID, "phb_update_node: both children are the same node");
+    if (row.kind[0] != SRC_TIP && row.kind[1] == SRC_TIP) {   // canonical order: tips first
+        std::swap(row.kind[0], row.kind[1]);
+        std::swap(row.src[0], row.src[1]);
+        std::swap(row.pidx[0], row.pidx[1]);
+    }
+    // the two matrices go where the root edge's would (the two spare blocks behind the rows' matrices)
+    c->h_root_two[0] = len_a;
+    c->h_root_two[1] = len_b;
+    const size_t blk = (size_t)c->K * c->A * c->A;
+    double* d_len = c->d_lengths + 2 * (size_t)c->max_rows();
+    PHB_CUDA(c, cudaMemcpyAsync(d_len, c->h_root_two, sizeof c->h_root_two, cudaMemcpyHostToDevice, c->stream));
+    st = launch_build_pmatrices(c, d_len, 2, c->d_pmats + (size_t)(2 * c->max_rows()) * blk, 0, 0);
+    if (st) return st;
+    st = launch_tip_tables(c, 2 * c->max_rows(), 2);
+    if (st) return st;
+    c->h_spare_row = row;   // member: the source of an asynchronous copy must outlive the call
+    OpRow* d_row = c->d_rows + c->max_rows();
+    PHB_CUDA(c, cudaMemcpyAsync(d_row, &c->h_spare_row, sizeof(OpRow), cudaMemcpyHostToDevice, c->stream));
+    static const std::vector<int32_t> one_level = {0, 1};
+    const RowSet rs{d_row, 1, &one_level};
+    st = run_rows(c, rs, PHB_MODE_LEVEL);
+    if (st) return st;
+    c->have_up = false;        // whatever the pre-order pass left refers to the old rooting
+    c->have_root = false;
+    c->resident_partials = false;
+    return PHB_OK;
+}
+
+int phb_branch_derivatives(phb_ctx* c, int node_a, int node_b, int n_lengths, const double* lengths, int chain_rule,
+                           double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, n_lengths >= 0 && (n_lengths == 0 || (lengths && out)), PHB_ERR_INVALID,
+                "phb_branch_derivatives: NULL argument");
+    PHB_REQUIRE(c, !(c->flags & PHB_FLAG_NO_PARTIALS) && c->have_tips && !c->codes_packed && c->have_model && c->have_mixture,
+                PHB_ERR_STATE, "phb_branch_derivatives: needs stored partials, tips and a reversible model");
+    PHB_REQUIRE(c, c->have_partials || c->n_rows() == 0, PHB_ERR_STATE, "phb_branch_derivatives: run phb_compute_partials first");
+    st = node_operand_ok(c, node_a);
+    if (st) return st;
+    st = node_operand_ok(c, node_b);
+    if (st) return st;
+    PHB_REQUIRE(c, node_a != node_b, PHB_ERR_INVALID, "phb_branch_derivatives: both ends are the same node");
+    std::vector<int32_t> near((size_t)n_lengths, node_a), far((size_t)n_lengths, node_b);
+    return launch_edge_derivatives(c, n_lengths, near.data(), lengths, chain_rule, out, far.data());
+}
+
 // ---- stream-ordered forms ------------------------------------------------------------------------------------
 int phb_lnl_resident_async(phb_ctx* c, int node_a, int node_b, double length) {
     if (!c) return PHB_ERR_INVALID;

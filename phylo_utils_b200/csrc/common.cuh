@@ -131,6 +131,7 @@ struct Ctx {
         int n_steps = 0, n_slots = 0;
     } res_cache;
     double h_root_two[2] = {0.0, 0.0}; // P(0), P(root length): source of the asynchronous copy behind the row lengths
+    OpRow h_spare_row{};               // the one-row schedule of phb_update_node (same reason)
     int resident_u = 0;                // 0 = choose, else forced patterns-per-warp multiplier (tuning / tests)
     int resident_slots = 0;            // parked blocks the last resident launch needed
     int resident_warps = 0;            // warps per SM of the last resident launch
@@ -249,7 +250,7 @@ int generic_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 // derivs.cu
 int launch_up_partials(Ctx* c, int node_a, int node_b);
 int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
-                            double* out);
+                            double* out, const int32_t* far_nodes = nullptr);
 // max over a byte array (in clv_generic.cu); synchronises the stream
 int launch_max_code(Ctx* c, const uint8_t* d_codes, size_t n, int* worst);
 // reduce (in clv_generic.cu): sums n_parts partial sums (stride 1) into d_result[0..n_out)

@@ -997,8 +997,11 @@ int launch_up_partials(Ctx* c, int node_a, int node_b) {
     return run_rows(c, rs, mode);
 }
 
+// far_nodes == nullptr: edge i is the one ABOVE nodes[i] (its other end is the node's up block, or the other root
+// child).  far_nodes != nullptr: edge i connects the down-array partials of nodes[i] and far_nodes[i] as they are now -
+// the re-rooting sweep, where every partial faces the edge being optimised (phb_branch_derivatives).
 int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule,
-                            double* out) {
+                            double* out, const int32_t* far_nodes) {
     const int A = c->A, K = c->K;
     const size_t blk = (size_t)K * A * A;
     const bool use_mma = mma_supported(c) && !tuning().disable_mma;
@@ -1021,7 +1024,11 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             PHB_REQUIRE(c, node >= 0 && node < c->n_nodes, PHB_ERR_INVALID, "edge derivatives: node id out of range");
             PHB_REQUIRE(c, lengths[start + i] >= 0, PHB_ERR_INVALID, "edge derivatives: negative branch length");
             fill_operand(c, node, &edges[i].src_a, &edges[i].kind_a);
-            if (node == c->root_a || node == c->root_b) {
+            if (far_nodes != nullptr) {
+                const int far = far_nodes[start + i];
+                PHB_REQUIRE(c, far >= 0 && far < c->n_nodes && far != node, PHB_ERR_INVALID, "branch derivatives: bad far node");
+                fill_operand(c, far, &edges[i].src_b, &edges[i].kind_b);
+            } else if (node == c->root_a || node == c->root_b) {
                 fill_operand(c, node == c->root_a ? c->root_b : c->root_a, &edges[i].src_b, &edges[i].kind_b);
                 if (use_mma && (int)c->st_ready.size() == c->n_nodes && c->st_ready[node]) {
                     edges[i].src_a = c->n_internal + node;   // the root edge's table sits in this root child's up block
@@ -1070,7 +1077,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
             // later passes read that one block per edge (edge_st_kernel).  Needs 16-byte rows (K A even), a row that
             // fits the register-resident coefficient layouts, and every node at most once per launch.
             const int row_chunks = K * A / 2;
-            bool st_ok = !tuning().deriv_no_st && (K * A) % 2 == 0 && row_chunks <= 256 &&
+            bool st_ok = far_nodes == nullptr && !tuning().deriv_no_st && (K * A) % 2 == 0 && row_chunks <= 256 &&
                          (int)c->st_ready.size() == c->n_nodes;
             int n_table = 0, n_fresh = 0;
             if (st_ok) {
@@ -1166,7 +1173,7 @@ int launch_edge_derivatives(Ctx* c, int n_edges, const int32_t* nodes, const dou
                     if (n_plain < 4) q.list[n_plain] = i;
                     ++n_plain;
                 }
-            if (c->up_sumtable && n_plain <= 4) q.n_list = n_plain;
+            if (far_nodes == nullptr && c->up_sumtable && n_plain <= 4) q.n_list = n_plain;
             const int64_t span = 128 / K;
             int64_t parts = (c->S + span * K - 1) / (span * K);
             const int64_t lim = std::max<int64_t>(1, std::min<int64_t>((kPartialCap - kListArea) / (3 * n), std::max<int64_t>(8, (int64_t)c->sm_count * 16 / n)));

@@ -220,6 +220,17 @@ class LikelihoodEngine(object):
                     float(length), ctypes.byref(total), dptr(pattern) if want_pattern else None))
         return total.value, pattern
 
+    # ---- re-rooting in place -----------------------------------------------------------------
+    def update_node(self, node, child_a, len_a, child_b, len_b):
+        self._ok(self._lib.phb_update_node(self._ctx, int(node), int(child_a), float(len_a), int(child_b), float(len_b)))
+
+    def branch_derivatives(self, node_a, node_b, lengths, chain_rule=True):
+        lengths = _f64(np.atleast_1d(lengths))
+        out = np.empty((lengths.shape[0], 3))
+        self._ok(self._lib.phb_branch_derivatives(self._ctx, int(node_a), int(node_b), lengths.shape[0], dptr(lengths),
+                                                  1 if chain_rule else 0, dptr(out)))
+        return out
+
     # ---- stream-ordered forms: enqueue only, sums stay on the device (multi-GPU drivers) ---------------
     def lnl_resident_async(self, node_a, node_b, length):
         self._ok(self._lib.phb_lnl_resident_async(self._ctx, int(node_a), int(node_b), float(length)))

@@ -135,3 +135,23 @@ def oracle_edge_derivatives(tr, ot, up, model, rate, node, t, siteweights, chain
     d2 = (post * (g2 + g1 * g1)).sum(axis=1) - d1 * d1     # L''/L - (L'/L)^2
     w = np.asarray(siteweights, dtype=float)
     return np.array([np.dot(w, lnL), np.dot(w, d1), np.dot(w, d2)])
+
+
+# ---- a tiny sequence simulator for the optimiser tests (sites evolved down the tree under the model) --------------------
+def simulate_codes(tr_tree, model, rate, n_sites, seed):
+    """-> (codes uint8 (ntax, nsites) in state order, lut = identity, names {label: row}); one Gamma category per site."""
+    rng = np.random.default_rng(seed)
+    A = model.size
+    cats = rng.integers(0, rate.ncat, n_sites)
+    states = {}
+    for nd in tr_tree.preorder_node_iter():
+        if nd.parent_node is None:
+            states[nd] = rng.choice(A, size=n_sites, p=np.asarray(model.freqs) / np.sum(model.freqs))
+            continue
+        pm = np.stack([model.p(nd.edge_length * r) for r in rate.rates])          # (K, A, A)
+        rows = np.clip(pm[cats, states[nd.parent_node]], 0, None)                  # (n_sites, A) transition rows
+        cdf = np.cumsum(rows / rows.sum(1, keepdims=True), axis=1)
+        states[nd] = np.minimum((rng.random(n_sites)[:, None] > cdf).sum(1), A - 1)
+    leaves = list(tr_tree.leaf_node_iter())
+    codes = np.stack([states[lf] for lf in leaves]).astype(np.uint8)
+    return codes, np.eye(A), {lf.taxon.label: i for i, lf in enumerate(leaves)}
