@@ -248,6 +248,38 @@ class ClockSampler(object):
                 "samples": len(sm), "sm_min_mhz": float(min(sm)) if sm else None}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are
+    allocated (first touch places them on that node): the e2e path streams tip codes from host memory on every step,
+    and at 4 - 8 GPUs the box's aggregate host-to-device bandwidth is what bounds it.  Returns what was found / done."""
+    info = {"gpu": index}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/{:04x}:{:02x}:{:02x}.0/numa_node".format(dom, bus, dev)
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes_on_host"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node{}/cpulist".format(node)).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound_to_cpus"] = len(cpus)
+        else:
+            info["bound_to_cpus"] = None      # one node (or unknown): nothing to choose
+    except Exception as exc:                   # sysfs layout differs, containers hide it, ...: measurement goes on unbound
+        info["error"] = repr(exc)[:120]
+    info["cpus_available"] = len(os.sched_getaffinity(0))
+    return info
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -399,6 +431,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: phylo_utils_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -589,7 +622,7 @@ def main():
             "collectives_in_timed_region": int(collectives),
             "path": "ShardedTreeModel(store_partials=False): lnL-only operand-resident walk per shard, device all-reduce",
             "with_stored_partials": stored, "weak_scaling": weak, "configs": configs, "sharded_parity": parity,
-            "clocks": clocks.summary(), "lnl": lnl,
+            "clocks": clocks.summary(), "lnl": lnl, "host_placement_rank0": numa,
             "site_node_updates_per_s": (n_taxa - 2) * n_pat * 1e3 / ms_per_step,
         }
         print(json.dumps(line), flush=True)

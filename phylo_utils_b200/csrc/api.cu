@@ -52,7 +52,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, flags, edges, dmats_doubles,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, pimg, pimg_size, flags, edges, dmats_doubles,
         pattern_lnl, cat_lnl, partial, result, total;
     int root_block;
 };
@@ -97,6 +97,9 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     }
     p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32
                            : ((A == 20 || A == 61) ? (2 * max_rows + 2) * (size_t)K * 64 * A * 8 : 0));
+    // 61 states: padded staging images (64 rows x 68 doubles) of every P block and tip table for the DMMA kernels
+    p.pimg_size = A == 61 ? (2 * max_rows + 2) * (size_t)K * 2 * 64 * 68 * 8 : 0;
+    p.pimg = take(p.pimg_size);
     p.model = take((2 * (size_t)A * A + 2 * A + 2 * K) * 8);
     p.lengths = take((2 * max_rows + 2 + 2 * (size_t)n_tips) * 8);   // rows, root, + trial lengths of a derivative launch
     p.rows = take((max_rows + 1) * sizeof(OpRow));   // + the root pseudo-row
@@ -353,6 +356,9 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->dmats_doubles = p.dmats_doubles;
     c->d_edges = (void*)(w + p.edges);
     c->d_tiptab = (n_states == 4 || n_states == 20 || n_states == 61) ? (double*)(w + p.tiptab) : nullptr;
+    c->d_pimg = p.pimg_size ? (double*)(w + p.pimg) : nullptr;
+    c->pimg_rows = p.pimg_size ? 64 : 0;
+    c->pimg_pitch = p.pimg_size ? 68 : 0;
     c->d_model = (double*)(w + p.model);
     c->d_lengths = (double*)(w + p.lengths);
     c->d_rows = (OpRow*)(w + p.rows);

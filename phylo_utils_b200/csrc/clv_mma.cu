@@ -46,6 +46,9 @@ struct MmaArgs {
     int row_begin, row_end;
     const double* pmats;  // [pidx][K][A][A]
     const double* tiptab; // [pidx][K][nc][A] = P . lut[code], or null
+    // odd state counts (61): zero-padded staging images [pidx][K][2][MROWS][LDP] of the P blocks (0) and the tip
+    // tables (1), 16-byte aligned and contiguous, so that a block is staged by a flat 16-byte copy; or null
+    const double* pimg;
     int nc;
     const uint8_t* codes;
     size_t pitch;
@@ -100,9 +103,34 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     const size_t S = (size_t)p.S;
     for (int e = threadIdx.x; e < 2 * MROWS * LDP + 2 * TS * LDL; e += WARPS * 32) sm[e] = 0.0;
     __syncthreads();
+    // Rows of an odd number of doubles (61 states) start on a 16-byte boundary only every second row.  With an even
+    // category count every row of a phase shares the parity of k: shifted by one double in shared memory (element j of
+    // a row sits in column j + sh, sh = k & 1), both ends of every copy are 16-byte aligned, and a row moves as 30
+    // 16-byte pieces and one 8-byte piece - lane = piece, no index arithmetic - instead of 61 8-byte pieces that each
+    // cost a division (profiles/r02a_cfg4_mma.txt: 69 % of the kernel's instructions were in the three copy loops).
+    constexpr bool ODD = (A % 2) == 1;
+    constexpr int HALF = (A - 1) / 2;                 // 16-byte pieces of an odd row
+    static_assert(!ODD || (HALF + 2 <= 32 && A + 1 <= LDL), "one piece per lane; room for the shift");
+    const bool fast = ODD && (p.K % 2 == 0) && p.pimg != nullptr;
+    // piece `lane` of a row whose first element is 16-byte aligned (sh == 0) or 8 bytes off (sh == 1)
+    auto piece_of = [&](int sh, int& j0, int& bytes) {
+        if (sh == 0) {
+            j0 = 2 * lane;
+            bytes = lane < HALF ? 16 : (lane == HALF ? 8 : 0);
+        } else {
+            j0 = lane == 0 ? 0 : 2 * lane - 1;
+            bytes = lane == 0 ? 8 : (lane <= HALF ? 16 : 0);
+        }
+    };
 
     // a P block or tip table -> the staging buffer: rows of A doubles, contiguous in shared memory too when LDP == A
     // (20 states: one 16-byte copy per two doubles instead of two 8-byte ones)
+    auto stage_image = [&](double* Pd, const double* img) {
+        for (int e = threadIdx.x; e < MROWS * LDP / 2; e += WARPS * 32) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(Pd + 2 * e);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(img + 2 * e) : "memory");
+        }
+    };
     auto stage_matrix = [&](double* Pd, const double* q, int n_rows) {
         if (LDP == A && A % 2 == 0) {
             for (int e = threadIdx.x; e < n_rows * A / 2; e += WARPS * 32) {
@@ -179,19 +207,39 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
             auto prefetch = [&](int ph, int k, int c) {
                 const int buf = ph & 1;
                 double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
+                const int sh = fast ? (k & 1) : 0;
                 if (kind_of(c) == SRC_TIP && p.tiptab != nullptr) {
                     // a tip child needs no product at all: its contribution is row `code` of T = P . lut, staged
                     // where the P block would go (row = code, n_codes <= MROWS rows)
-                    stage_matrix(Pd, p.tiptab + ((size_t)pidx_of(c) * K + k) * p.nc * A, p.nc);
+                    if (fast) stage_image(Pd, p.pimg + (((size_t)pidx_of(c) * K + k) * 2 + 1) * (MROWS * LDP));
+                    else stage_matrix(Pd, p.tiptab + ((size_t)pidx_of(c) * K + k) * p.nc * A, p.nc);
                     cp_async_commit_all();
                     return;
                 }
-                stage_matrix(Pd, p.pmats + ((size_t)pidx_of(c) * K + k) * A * A, A);
+                if (fast) stage_image(Pd, p.pimg + (((size_t)pidx_of(c) * K + k) * 2) * (MROWS * LDP));
+                else stage_matrix(Pd, p.pmats + ((size_t)pidx_of(c) * K + k) * A * A, A);
                 double* Ld = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
                 if (kind_of(c) == SRC_TIP) {
                     for (int e = lane; e < WR * A; e += 32) {
                         const int n = e / A, j = e - n * A;
-                        Ld[n * LDL + j] = __ldg(p.lut + (size_t)s_codes[c * TS + warp * WR + n] * A + j);
+                        Ld[n * LDL + j + sh] = __ldg(p.lut + (size_t)s_codes[c * TS + warp * WR + n] * A + j);
+                    }
+                    if (fast && sh == 0 && lane < WR) Ld[lane * LDL + A] = 0.0;   // column A may hold element A-1 of a shifted row
+                } else if (fast) {
+                    const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
+                    const double* g = p.clv + (((size_t)src_of(c) * S + wsite0) * K + k) * A;
+                    int j0, bytes;
+                    piece_of(sh, j0, bytes);
+                    const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld + j0 + sh);
+                    const double* q = g + j0;
+                    if (bytes == 16) {
+                        for (int n = 0; n < n_valid; ++n)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + n * (LDL * 8)), "l"(q + (size_t)n * (K * A)) : "memory");
+                    } else if (bytes == 8) {
+                        for (int n = 0; n < n_valid; ++n)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + n * (LDL * 8)), "l"(q + (size_t)n * (K * A)) : "memory");
+                    } else if (sh == 0 && lane == 31) {
+                        for (int n = 0; n < n_valid; ++n) Ld[n * LDL + A] = 0.0;   // stale element A-1 of a shifted row
                     }
                 } else {
                     // rows of A doubles are 16-byte aligned when A is even (A = 20: ten 16-byte pieces per row)
@@ -225,7 +273,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     prefetch(ph + 1, cn == 0 ? k + 1 : k, cn);
                 }
                 const double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
-                const double* myLr = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL;
+                const double* myLr = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL + (fast ? (k & 1) : 0);
                 if (kind_of(c) == SRC_TIP && p.tiptab != nullptr) {
                     // gather in fragment layout: acc[mt][nt][q] = T[code(pattern nt*8 + 2fc + q)][state mt*8 + fr]
 #pragma unroll
@@ -273,7 +321,8 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     __syncwarp();      // all lanes have read their operand rows; they now become the output rows
                     // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q.  Padding states (>= A) are
                     // neither stored nor allowed into the maximum: a tip-table gather reads past its row for them.
-                    double* corner = myL + (2 * fc) * LDL + fr;
+                    const int sh = fast ? (k & 1) : 0;        // the output rows have the parity of their category too
+                    double* corner = myL + (2 * fc) * LDL + fr + sh;
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
                         if (mt * 8 + 8 > A && mt * 8 + fr >= A) continue;
@@ -288,7 +337,20 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                             }
                     }
                     __syncwarp();
-                    {
+                    if (fast) {
+                        // lane = piece, as on the way in: 16-byte loads from the shifted rows, 16-byte stores
+                        const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
+                        int j0, bytes;
+                        piece_of(sh, j0, bytes);
+                        double* g = out + ((size_t)wsite0 * K + k) * A + j0;
+                        const double* src = myL + j0 + sh;
+                        if (bytes == 16) {
+                            for (int n = 0; n < n_valid; ++n)
+                                *reinterpret_cast<double2*>(g + (size_t)n * (K * A)) = *reinterpret_cast<const double2*>(src + n * LDL);
+                        } else if (bytes == 8) {
+                            for (int n = 0; n < n_valid; ++n) g[(size_t)n * (K * A)] = src[n * LDL];
+                        }
+                    } else {
                         // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  Columns >= A of
                         // the rows are never written (they stay zero for their next life as an operand row).
                         constexpr int PB = (A % 2 == 0) ? 16 : 8, PIECES = A * 8 / PB;
@@ -403,6 +465,7 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, const Mm
     // tables are staged in the P buffer (MROWS rows): usable when every code has a row there
     a.nc = tip_table_rows(c);
     a.tiptab = (tip_tables_usable(c) && a.nc <= MROWS && !tuning().disable_tiptab) ? c->d_tiptab : nullptr;
+    a.pimg = (AA % 2 == 1 && c->pimg_rows == MROWS && c->pimg_pitch == LDP) ? c->d_pimg : nullptr;
     a.codes = c->d_codes;
     a.pitch = c->code_pitch;
     a.lut = c->d_lut;
@@ -446,6 +509,31 @@ int run_rows_mma(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frows = nul
 }  // namespace
 
 bool mma_supported(const Ctx* c) { return c->A == 20 || c->A == 61; }
+
+// Padded staging images of the P blocks and tip tables [first_mat, first_mat + n_mats) (see MmaArgs::pimg)
+__global__ void mma_image_kernel(const double* __restrict__ pmats, const double* __restrict__ tiptab, int A, int K, int nc,
+                                 int rows, int pitch, int first_mat, double* __restrict__ out) {
+    const int m = first_mat + blockIdx.x, k = blockIdx.y, which = blockIdx.z;
+    const double* src = which == 0 ? pmats + ((size_t)m * K + k) * A * A : (tiptab ? tiptab + ((size_t)m * K + k) * nc * A : nullptr);
+    const int n_src_rows = which == 0 ? A : (tiptab ? nc : 0);
+    double* dst = out + (((size_t)m * K + k) * 2 + which) * rows * pitch;
+    for (int e = threadIdx.x; e < rows * pitch; e += blockDim.x) {
+        const int i = e / pitch, j = e - i * pitch;
+        dst[e] = (i < n_src_rows && j < A) ? src[(size_t)i * A + j] : 0.0;
+    }
+}
+
+int launch_mma_images(Ctx* c, int first_mat, int n_mats) {
+    if (c->d_pimg == nullptr || n_mats <= 0) return PHB_OK;
+    const int nc = tip_table_rows(c);
+    const bool tables = tip_tables_usable(c) && nc <= c->pimg_rows;
+    dim3 grid(n_mats, c->K, 2);
+    mma_image_kernel<<<grid, 256, 0, c->stream>>>(c->d_pmats, tables ? c->d_tiptab : nullptr, c->A, c->K, nc, c->pimg_rows,
+                                                  c->pimg_pitch, first_mat, c->d_pimg);
+    c->launches++;
+    PHB_CUDA(c, cudaGetLastError());
+    return PHB_OK;
+}
 
 static int mma_dispatch(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frows) {
     const int variant = tuning().mma_variant;   // tuning knob: alternative tile shapes

@@ -117,6 +117,10 @@ struct Ctx {
     // 4-state models: T[m][k][code][:] = P[m][k] . lut[code] for every P block m, so that a tip operand is
     // a 32-byte table look-up instead of a matrix-vector product (codes padded to kTipTabCodes rows)
     double* d_tiptab = nullptr;
+    // 61-state models: zero-padded, 16-byte aligned staging images of every P block and tip table for the DMMA
+    // kernels ([mat][K][2][pimg_rows][pimg_pitch], clv_mma.cu), rebuilt with the matrices
+    double* d_pimg = nullptr;
+    int pimg_rows = 0, pimg_pitch = 0;
     double* d_model = nullptr;         // evecs | evals | ivecs | freqs | rates | catw
     double* d_lengths = nullptr;       // [2*max_rows + 2]
     OpRow* d_rows = nullptr;           // [max_rows]
@@ -243,6 +247,7 @@ int generic_run_rows(Ctx* c, const RowSet& rs, int mode);
 // clv_mma.cu (A == 20 or 61, FP64 tensor cores)
 bool mma_supported(const Ctx* c);
 int mma_run_rows(Ctx* c, const RowSet& rs, int mode);
+int launch_mma_images(Ctx* c, int first_mat, int n_mats);   // after every (re)build of P blocks / tip tables
 int mma_run_parent_rows(Ctx* c, const std::vector<int32_t>& parents, const std::vector<int32_t>& levels);   // pre-order pass
 // picks the kernel family for this context's shape
 int run_rows(Ctx* c, const RowSet& rs, int mode);

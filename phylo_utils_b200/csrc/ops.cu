@@ -297,7 +297,7 @@ int phb_op_pmatrices(int device, int A, int n, const double* evecs, const double
 // (MEASURED_PEAKS.json has HBM and bf16 figures only).  kind 0: independent DFMA chains on every SM (vector pipe);
 // kind 1: independent DMMA m8n8k4 chains (fp64 tensor pipe).  Best of five launches, CUDA events.
 int phb_op_fp64_peak(int device, int kind, double* tflops) {
-    if (tflops == nullptr || (kind != 0 && kind != 1)) {
+    if (tflops == nullptr || kind < 0 || kind > 3) {
         set_thread_error("phb_op_fp64_peak: bad argument");
         return PHB_ERR_INVALID;
     }
@@ -305,7 +305,9 @@ int phb_op_fp64_peak(int device, int kind, double* tflops) {
     if (st) return st;
     cudaDeviceProp prop;
     OP_CUDA(cudaGetDeviceProperties(&prop, device), "phb_op_fp64_peak");
-    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 1 << 13;
+    // kinds 2 / 3 (tuning aid): the DMMA probe with only 8 / 16 warps per SM - the occupancy of the 61-state pruning
+    // kernel and twice that - to see how many warps it takes to keep the fp64 tensor pipe busy
+    const int blocks = prop.multiProcessorCount * (kind == 2 ? 1 : (kind == 3 ? 2 : 4)), threads = 256, iters = 1 << 13;
     DevBuf out;
     OP_CUDA(out.alloc((size_t)blocks * threads * 8), "phb_op_fp64_peak alloc");
     cudaEvent_t a, b;
@@ -316,7 +318,7 @@ int phb_op_fp64_peak(int device, int kind, double* tflops) {
     float best = 0.f;
     for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(a);
-        if (kind == 0) fp64_fma_probe<<<blocks, threads>>>(out.as<double>(), iters);
+        if (kind == 0) fp64_fma_probe<<<blocks, threads, 0>>>(out.as<double>(), iters);
         else fp64_mma_probe<<<blocks, threads>>>(out.as<double>(), iters);
         cudaEventRecord(b);
         OP_CUDA(cudaEventSynchronize(b), "phb_op_fp64_peak run");

@@ -92,15 +92,18 @@ __global__ void tip_table_generic_kernel(const double* __restrict__ pmats, const
 }
 
 int launch_tip_tables(Ctx* c, int first_mat, int n_mats) {
-    if (n_mats <= 0 || !tip_tables_usable(c)) return PHB_OK;
+    if (n_mats <= 0) return PHB_OK;
     if (c->A != 4) {
-        dim3 grid(n_mats, c->K);
-        tip_table_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->A,
-                                                              c->K, first_mat, c->d_tiptab);
-        c->launches++;
-        PHB_CUDA(c, cudaGetLastError());
-        return PHB_OK;
+        if (tip_tables_usable(c)) {
+            dim3 grid(n_mats, c->K);
+            tip_table_generic_kernel<<<grid, 256, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->A,
+                                                                  c->K, first_mat, c->d_tiptab);
+            c->launches++;
+            PHB_CUDA(c, cudaGetLastError());
+        }
+        return launch_mma_images(c, first_mat, n_mats);   // padded staging images for the DMMA kernels (61 states)
     }
+    if (!tip_tables_usable(c)) return PHB_OK;
     tip_table_kernel<<<n_mats, 128, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->K, first_mat,
                                                     c->d_tiptab);
     c->launches++;
