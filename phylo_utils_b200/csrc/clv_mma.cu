@@ -175,11 +175,28 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
         for (int r = r0; r < r1; ++r) {
             const MmaRow row = next_row;
             if (r + 1 < r1) next_row = load_row(r + 1);
-            const int n_ops = FUSED ? 3 : 2, n_phases = n_ops * K;   // compile-time per instantiation: a pruning row costs what it did
+            const int n_ops = FUSED ? 3 : 2;
             // selects instead of indexed reads: the row stays in registers
             auto src_of = [&](int c) { return c == 0 ? row.src[0] : (c == 1 ? row.src[1] : row.src[2]); };
             auto kind_of = [&](int c) { return c == 0 ? row.kind[0] : (c == 1 ? row.kind[1] : row.kind[2]); };
             auto pidx_of = [&](int c) { return c == 0 ? row.pidx[0] : (c == 1 ? row.pidx[1] : row.pidx[2]); };
+            // Pruning rows: a tip operand's contribution (row `code` of its P.lut table) is gathered STRAIGHT from the
+            // table in global memory into the accumulator registers - no staging copy, no barrier, no phase of its own;
+            // the loads fly during the product phase of the other operand.  Only internal operands have phases:
+            // 2K for an internal x internal row, K for a tip x internal row, none for a cherry (half of all operands of
+            // a tree are tips: the phase count, and with it the barriers and the table staging traffic, is halved).
+            const bool d0 = !FUSED && kind_of(0) == SRC_TIP && p.tiptab != nullptr;
+            const bool d1 = !FUSED && kind_of(1) == SRC_TIP && p.tiptab != nullptr;
+            const int n_phases = FUSED ? 3 * K : ((d0 ? 0 : 1) + (d1 ? 0 : 1)) * K;
+            auto next_phase = [&](int k, int c, int& kn, int& cn) {
+                if (FUSED || (!d0 && !d1)) {
+                    cn = c + 1 == n_ops ? 0 : c + 1;
+                    kn = cn == 0 ? k + 1 : k;
+                } else {          // one internal operand: the same operand of the next category
+                    cn = c;
+                    kn = k + 1;
+                }
+            };
 
             // tip codes and exponents of this warp's patterns (one per lane), same for every category.  The loads are
             // issued here and parked in shared memory once the first operand copies are under way: one latency, not two.
@@ -269,8 +286,9 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 cp_async_wait_all();
                 __syncthreads();      // phase ph's operands have landed; everybody has left phase ph-1
                 if (ph + 1 < n_phases) {
-                    const int cn = c + 1 == n_ops ? 0 : c + 1;
-                    prefetch(ph + 1, cn == 0 ? k + 1 : k, cn);
+                    int kn, cn;
+                    next_phase(k, c, kn, cn);
+                    prefetch(ph + 1, kn, cn);
                 }
                 const double* Pd = Pbuf + (size_t)buf * MROWS * LDP;
                 const double* myLr = Lbuf + ((size_t)buf * TS + (size_t)warp * WR) * LDL + (fast ? (k & 1) : 0);
@@ -304,20 +322,25 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 }
             };
 
-            __syncthreads();          // the previous row is completely done with both buffer pairs
-            if (p.tiptab == nullptr) park_codes();   // without tip tables the first copy gathers look-up rows by code
-            prefetch(0, 0, 0);
-            if (p.tiptab != nullptr) park_codes();
-            int ph = 0;
-            for (int k = 0; k < K; ++k) {
-                run_phase(ph, k, 0, acc0);
-                ++ph;
-                for (int j = 1; j < n_ops; ++j, ++ph) {
-                    run_phase(ph, k, j, acc1);
-                    // operand j of category k is done: output j-1 = acc0 * acc1.  It leaves through this warp's rows of
-                    // the L buffer the phase just read (the next copy into that buffer is issued behind a barrier)
+            // a tip operand's accumulators straight from its table: acc[mt][nt][q] = T[code(pattern nt*8 + 2fc + q)][mt*8 + fr]
+            auto gather_direct = [&](int k, int c, double (&acc)[MT][NT][2]) {
+                const double* T = p.tiptab + ((size_t)pidx_of(c) * K + k) * p.nc * A + fr;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const double* trow = T + (size_t)s_codes[c * TS + warp * WR + nt * 8 + 2 * fc + q] * A;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            acc[mt][nt][q] = (mt * 8 + 8 <= A || mt * 8 + fr < A) ? __ldg(trow + mt * 8) : 0.0;
+                    }
+            };
+            // output j-1 of category k = acc0 * acc1.  It leaves through this warp's rows of L buffer `sbuf`: the one the
+            // last phase read (the next copy into it is issued behind a barrier), or any when the row has no phases
+            auto emit = [&](int j, int k, int sbuf) {
+                {
                     double* out = p.clv + (size_t)(j == 1 ? row.dst[0] : row.dst[1]) * S * K * A;
-                    double* myL = Lbuf + ((size_t)(ph & 1) * TS + (size_t)warp * WR) * LDL;
+                    double* myL = Lbuf + ((size_t)sbuf * TS + (size_t)warp * WR) * LDL;
                     __syncwarp();      // all lanes have read their operand rows; they now become the output rows
                     // fragment element (mt, nt, q) = state mt*8 + fr of pattern nt*8 + 2fc + q.  Padding states (>= A) are
                     // neither stored nor allowed into the maximum: a tip-table gather reads past its row for them.
@@ -368,6 +391,36 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         }
                     }
                     __syncwarp();
+                }
+            };
+
+            __syncthreads();          // the previous row is completely done with both buffer pairs
+            if (p.tiptab == nullptr) park_codes();   // without tip tables the first copy gathers look-up rows by code
+            if (n_phases > 0) prefetch(0, 0, d0 ? 1 : 0);
+            if (p.tiptab != nullptr) park_codes();
+            int ph = 0, sbuf = 0;
+            for (int k = 0; k < K; ++k) {
+                if (FUSED) {
+                    run_phase(ph, k, 0, acc0);
+                    ++ph;
+                    for (int j = 1; j < n_ops; ++j, ++ph) {
+                        run_phase(ph, k, j, acc1);
+                        emit(j, k, ph & 1);
+                    }
+                } else {
+                    if (d0) gather_direct(k, 0, acc0);       // in flight while the other operand's products run
+                    if (d1) gather_direct(k, 1, acc1);
+                    if (!d0) {
+                        run_phase(ph, k, 0, acc0);
+                        sbuf = ph & 1;
+                        ++ph;
+                    }
+                    if (!d1) {
+                        run_phase(ph, k, 1, acc1);
+                        sbuf = ph & 1;
+                        ++ph;
+                    }
+                    emit(1, k, sbuf);
                 }
             }
             // per-pattern maximum over states (lanes sharing fc) and categories (already folded into mx)

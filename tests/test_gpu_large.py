@@ -344,8 +344,10 @@ def test_derivative_configs_full_size_properties(shape):
     assert np.all(np.isfinite(first))
     assert np.all(np.abs(first[:, 0] - want) <= 1e-10 * abs(want))
     again = tm.edge_derivatives(nodes, lengths)                      # from the sum tables
-    # two summation orders of the same terms; 61-state rows are three times longer than 20-state ones
-    rtol = 1e-9 if shape == "cfg4" else 1e-12
+    # two summation orders of the same terms.  At 61 states the derivative sums cancel heavily (244 terms of both signs
+    # per pattern): both passes sit 1e-10 .. 4e-9 from the composed oracle (tools/diag_codon_derivs.py), hence the
+    # derivative tolerance of DESIGN.md section 5 (1e-8) here instead of 1e-12
+    rtol = 1e-8 if shape == "cfg4" else 1e-12
     assert np.allclose(first, again, rtol=rtol, atol=1e-6)
     other = tm.edge_derivatives(nodes, lengths * 1.5)
     tm.compute_up_partials()

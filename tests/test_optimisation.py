@@ -228,7 +228,7 @@ def test_rerooting_sweep_and_batched_newton_reach_the_same_optimum():
         results[which] = (res["lnl"], tm.traversal.brlens.copy())
     assert abs(results["reroot"][0] - results["newton"][0]) < 1e-3
     for key, t in results["reroot"][1].items():
-        assert abs(t - results["newton"][1][key]) < 2e-3 * max(t, 0.01)
+        assert abs(t - results["newton"][1][key]) < 1e-2 * max(t, 0.01)     # two routes to a flat maximum
 
 
 @pytest.mark.gpu
