@@ -29,6 +29,7 @@ static Tuning read_tuning() {
         v.pair_ctas = num("PHB_PAIR_CTAS");
         v.pair_ppt = num("PHB_PAIR_PPT");
         v.pair_grid = num("PHB_PAIR_GRID");
+        v.pair_full_p = flag("PHB_PAIR_FULL_P");
         v.up_ppt = num("PHB_UP_PPT");
         v.up_warps = num("PHB_UP_WARPS");
         v.resident_warps = num("PHB_RESIDENT_WARPS");
@@ -52,7 +53,7 @@ constexpr size_t kAlign = 256;
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 
 struct Plan {
-    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, pimg, pimg_size, flags, edges, dmats_doubles,
+    size_t codes, lut, weights, clv, scale, up, up_scale, up_rows, root_clv, root_scale, pmats, dmats, model, lengths, rows, res_rows, scratch, scratch_size, tiptab, rmats, pimg, pimg_size, flags, edges, dmats_doubles,
         pattern_lnl, cat_lnl, partial, result, total;
     int root_block;
 };
@@ -97,6 +98,8 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     }
     p.tiptab = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * kTipTabCodes * 32
                            : ((A == 20 || A == 61) ? (2 * max_rows + 2) * (size_t)K * 64 * A * 8 : 0));
+    // 4 states: packed symmetric P blocks for the lnL-only walk (+ one copy round of slack behind the last block)
+    p.rmats = take(A == 4 ? (2 * max_rows + 2) * (size_t)K * 80 + 1024 : 0);
     // 61 states: padded staging images (64 rows x 68 doubles) of every P block and tip table for the DMMA kernels
     p.pimg_size = A == 61 ? (2 * max_rows + 2) * (size_t)K * 2 * 64 * 68 * 8 : 0;
     p.pimg = take(p.pimg_size);
@@ -356,6 +359,7 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     c->dmats_doubles = p.dmats_doubles;
     c->d_edges = (void*)(w + p.edges);
     c->d_tiptab = (n_states == 4 || n_states == 20 || n_states == 61) ? (double*)(w + p.tiptab) : nullptr;
+    c->d_rmats = n_states == 4 ? (double*)(w + p.rmats) : nullptr;
     c->d_pimg = p.pimg_size ? (double*)(w + p.pimg) : nullptr;
     c->pimg_rows = p.pimg_size ? 64 : 0;
     c->pimg_pitch = p.pimg_size ? 68 : 0;
@@ -529,6 +533,28 @@ int phb_set_model(phb_ctx* c, const double* evecs, const double* evals, const do
     if (st) return st;
     c->h_evecs.assign(evecs, evecs + AA);
     c->h_ivecs.assign(ivecs, ivecs + AA);
+    {
+        // detailed balance of Q = V diag(lambda) V^-1 with respect to the given frequencies: pi_i q_ij == pi_j q_ji.
+        // Every model the reference's TreeModel can drive through an eigen-system has it; a caller of the C ABI need not.
+        const int A = c->A;
+        bool rev = true;
+        double scale = 0.0;
+        std::vector<double> q(AA, 0.0);
+        for (int i = 0; i < A; ++i)
+            for (int j = 0; j < A; ++j) {
+                double v = 0.0;
+                for (int m = 0; m < A; ++m) v += evecs[i * A + m] * evals[m] * ivecs[m * A + j];
+                q[i * A + j] = v;
+                scale = std::max(scale, std::fabs(v));
+            }
+        for (int i = 0; i < A && rev; ++i) {
+            if (!(freqs[i] > 0)) rev = false;
+            for (int j = i + 1; j < A && rev; ++j)
+                if (std::fabs(freqs[i] * q[i * A + j] - freqs[j] * q[j * A + i]) > 1e-12 * scale) rev = false;
+        }
+        if (rev != c->reversible) c->res_cache.kind = 0;   // the cached walk descriptors point at the other kind of block
+        c->reversible = rev;
+    }
     c->have_model = true;
     c->have_pmats = false;
     c->have_partials = false;

@@ -21,7 +21,14 @@
 //     them: profiles/r01k_pair_v1_1000x1M.txt);
 //   * there is ONE operand tile: the parked operand of row r+1 is fetched during row r, or right after row
 //     r's arithmetic when row r reads the tile itself (1 row in 9);
-//   * the last pseudo-row does the root combine, pi-dot, Gamma mixture, log and the weighted tile sum.
+//   * the last pseudo-row does the root combine, pi-dot, Gamma mixture, log and the weighted tile sum;
+//   * SYM (reversible models - every model the reference's TreeModel can drive): the kernel is bound by the shared-memory
+//     data pipe, and a third of its wavefronts are the warp-wide broadcast reads of the operands' 4 x 4 P blocks
+//     (profiles/r02a_pair_lnl.txt).  Detailed balance makes R = diag(pi) P symmetric, so
+//         (P L)_i = (1 / pi_i) sum_j r_ij L_j
+//     needs the 10 numbers of R's upper triangle instead of the 16 of P: 5 broadcast LDS.128 per category and
+//     operand instead of 8, the same 16 FMAs, and one multiplication by the constant pi_i^-n (n = internal
+//     operands of the row) folded into the product.  No basis change, no cancellation: every term stays >= 0.
 #include <algorithm>
 #include <cstdlib>
 
@@ -59,13 +66,43 @@ struct PairArgs {
     const int* flags;
     int epoch, chunk_shift;       // tiles per chunk = 1 << chunk_shift
     int* error;                   // set to 1 if a chunk never arrived (bounded wait)
+    double ipi[4];                // SYM: 1 / pi_i
 };
 
 
 // prev[p][k] <- (Pa[k] . a[p][k]) * (Pb[k] . b[p][k]) for the lane's PPT patterns; pe <- cumulative exponents
-template <int K, int NC, int PPT, bool PACKED, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE>
+// y[p][i] <- sum_j r_ij v[p][j] from the packed upper triangle [r00 r01 | r02 r03 | r11 r12 | r13 r22 | r23 r33] of a
+// symmetric 4 x 4 block: five warp-wide broadcast reads, sixteen FMAs per pattern
+template <int PPT>
+__device__ __forceinline__ void sym_matvec(const unsigned char* blk, const double (&v)[PPT][4], double (&y)[PPT][4]) {
+    const double2* q = reinterpret_cast<const double2*>(blk);
+    const double2 q0 = q[0], q1 = q[1];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        y[p][0] = fma(q1.y, v[p][3], fma(q1.x, v[p][2], fma(q0.y, v[p][1], q0.x * v[p][0])));
+        y[p][1] = q0.y * v[p][0];
+        y[p][2] = q1.x * v[p][0];
+        y[p][3] = q1.y * v[p][0];
+    }
+    const double2 q2 = q[2], q3 = q[3];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        y[p][1] = fma(q3.x, v[p][3], fma(q2.y, v[p][2], fma(q2.x, v[p][1], y[p][1])));
+        y[p][2] = fma(q3.y, v[p][2], fma(q2.y, v[p][1], y[p][2]));
+        y[p][3] = fma(q3.x, v[p][1], y[p][3]);
+    }
+    const double2 q4 = q[4];
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) {
+        y[p][2] = fma(q4.x, v[p][3], y[p][2]);
+        y[p][3] = fma(q4.y, v[p][3], fma(q4.x, v[p][2], y[p][3]));
+    }
+}
+
+template <int K, int NC, int PPT, bool PACKED, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE, bool SYM = false>
 __device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
-                                            double (&prev)[PPT][K][4], int (&pe)[PPT]) {
+                                            double (&prev)[PPT][K][4], int (&pe)[PPT], const double* ipi = nullptr) {
+    constexpr int PB = SYM ? 80 : 128;   // bytes of one category's P block (SYM: the upper triangle of diag(pi) P)
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = K * 32 + 16;   // LAYOUT_ARRAY: one pattern's row of the operand tile
     static_assert(KA != KIND_SLOT, "operand a is a tip or the previous row");
@@ -104,6 +141,13 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
             // a tip operand contributes the row `code` of its staged table T[k] = P[k] . lut - no arithmetic
 #pragma unroll
             for (int p = 0; p < PPT; ++p) lds32(st + k * NC * 32 + ra[p], x[p]);
+        } else if (SYM) {
+            double a[PPT][4];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[p][i] = prev[p][k][i];
+            sym_matvec<PPT>(st + k * PB, a, x);
         } else {
             const double2* q = reinterpret_cast<const double2*>(st + k * 128);
 #pragma unroll
@@ -139,13 +183,31 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
                     b[p][0] = lo.x; b[p][1] = lo.y; b[p][2] = hi.x; b[p][3] = hi.y;
                 }
             }
-            const double2* q = reinterpret_cast<const double2*>(st + L::OPER_BYTES + k * 128);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double2 r0 = q[2 * i], r1 = q[2 * i + 1];
+            if (SYM) {
+                double y[PPT][4];
+                sym_matvec<PPT>(st + L::OPER_BYTES + k * PB, b, y);
 #pragma unroll
                 for (int p = 0; p < PPT; ++p)
-                    x[p][i] *= fma(r1.y, b[p][3], fma(r1.x, b[p][2], fma(r0.y, b[p][1], r0.x * b[p][0])));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[p][i] *= y[p][i];
+            } else {
+                const double2* q = reinterpret_cast<const double2*>(st + L::OPER_BYTES + k * 128);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double2 r0 = q[2 * i], r1 = q[2 * i + 1];
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p)
+                        x[p][i] *= fma(r1.y, b[p][3], fma(r1.x, b[p][2], fma(r0.y, b[p][1], r0.x * b[p][0])));
+                }
+            }
+        }
+        if (SYM && (KA != KIND_TIP || KB != KIND_TIP)) {
+            // (P L)_i = (R L)_i / pi_i for every internal operand of the row: one or two factors 1 / pi_i
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double f = (KA != KIND_TIP && KB != KIND_TIP) ? ipi[i] * ipi[i] : ipi[i];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) x[p][i] *= f;
             }
         }
 #pragma unroll
@@ -195,8 +257,8 @@ __device__ __noinline__ void wait_for_chunk(const int* flags, int chunk_shift, i
     *error = 1;
 }
 
-template <int K, int NC, int PPT, bool PACKED, bool PIPE>
-__global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair_kernel(const PairArgs p) {
+template <int K, int NC, int PPT, bool PACKED, bool PIPE, bool SYM>
+__global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair_kernel(const __grid_constant__ PairArgs p) {
     using L = PairLayout<K, NC, PPT>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x;
@@ -299,12 +361,12 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
             // indirect branch on the row's critical path
             const int kind_a = kinds & 3, kind_b = kinds >> 2;
             if (kind_b == KIND_SLOT) {
-                if (kind_a == KIND_PREV) pair_update<K, NC, PPT, PACKED, KIND_PREV, KIND_SLOT>(st, s_opin, lane, prev, pe);
-                else pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_SLOT>(st, s_opin, lane, prev, pe);
+                if (kind_a == KIND_PREV) pair_update<K, NC, PPT, PACKED, KIND_PREV, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                else pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
             } else if (kind_b == KIND_PREV) {
-                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_PREV>(st, s_opin, lane, prev, pe);
+                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_PREV, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
             } else {
-                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_TIP>(st, s_opin, lane, prev, pe);
+                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_TIP, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
             }
             if (fetch_late) {   // the operand tile is free now (a lane only ever touches its own chunks of it)
                 fetch_slot(slot_n);
@@ -580,7 +642,7 @@ int launch_pair_store(Ctx* c, int n_steps) {
     return PHB_OK;
 }
 
-template <int K, int NC, int PPT, bool PACKED, bool PIPE>
+template <int K, int NC, int PPT, bool PACKED, bool PIPE, bool SYM>
 int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
                 int max_grid, int* grid_out, int chunk_shift) {
     using L = PairLayout<K, NC, PPT>;
@@ -604,7 +666,8 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.epoch = c->flag_epoch;
     a.chunk_shift = chunk_shift;
     a.error = c->d_flags + kMaxFlagChunks;
-    auto kern = dna_pair_kernel<K, NC, PPT, PACKED, PIPE>;
+    for (int i = 0; i < 4; ++i) a.ipi[i] = SYM ? 1.0 / c->h_freqs[i] : 1.0;
+    auto kern = dna_pair_kernel<K, NC, PPT, PACKED, PIPE, SYM>;
     const size_t smem = L::WARP_BYTES + 256;   // + the per-lane running sums
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -633,6 +696,9 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     return PHB_OK;
 }
 
+// the lnL-only walk reads the symmetric form of the P blocks (10 numbers instead of 16) when the model is reversible
+bool pair_sym(const Ctx* c) { return c->reversible && c->d_rmats != nullptr && !tuning().pair_full_p; }
+
 // patterns per lane: 2 everywhere; 4 is built for K = 4 and selected with PHB_PAIR_PPT=4 (tuning knob)
 int pair_ppt(const Ctx* c) {
     if (c->K != 4) return 2;
@@ -650,12 +716,21 @@ template <int K, int NC, int PPT>
 int launch_pair_v(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
                   int* grid_out, int chunk_shift) {
     const int cs = chunk_shift < 0 ? 0 : chunk_shift;
-    if (packed) {
-        if (chunk_shift >= 0) return launch_pair<K, NC, PPT, true, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
-        return launch_pair<K, NC, PPT, true, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+    const int flavour = (packed ? 4 : 0) | (chunk_shift >= 0 ? 2 : 0) | (pair_sym(c) ? 1 : 0);
+    switch (flavour) {
+#define PHB_PAIR_FLAVOUR(F_, PACKED_, PIPE_, SYM_) \
+    case F_: return launch_pair<K, NC, PPT, PACKED_, PIPE_, SYM_>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+        PHB_PAIR_FLAVOUR(0, false, false, false)
+        PHB_PAIR_FLAVOUR(1, false, false, true)
+        PHB_PAIR_FLAVOUR(2, false, true, false)
+        PHB_PAIR_FLAVOUR(3, false, true, true)
+        PHB_PAIR_FLAVOUR(4, true, false, false)
+        PHB_PAIR_FLAVOUR(5, true, false, true)
+        PHB_PAIR_FLAVOUR(6, true, true, false)
+        PHB_PAIR_FLAVOUR(7, true, true, true)
+#undef PHB_PAIR_FLAVOUR
     }
-    if (chunk_shift >= 0) return launch_pair<K, NC, PPT, false, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
-    return launch_pair<K, NC, PPT, false, false>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+    return PHB_ERR_INVALID;
 }
 
 int launch_pair_k(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
@@ -682,10 +757,12 @@ int launch_pair_k(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int6
 }
 
 // resident_plan rows -> this kernel's descriptors (operand offsets resolved on the host), uploaded
-int upload_pair_rows(Ctx* c, const ResPlan& plan) {
+int upload_pair_rows(Ctx* c, const ResPlan& plan, bool sym) {
     if (c->n_codes > kTipTabCodes)
         return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: look-up tables of more than 16 rows are not covered");
-    const size_t tab_bytes = (size_t)c->K * tip_table_rows(c) * 32, p_bytes = (size_t)c->K * 128;
+    const size_t tab_bytes = (size_t)c->K * tip_table_rows(c) * 32, p_bytes = (size_t)c->K * (sym ? 80 : 128);
+    // symmetric form: an internal operand's block is the packed upper triangle of diag(pi) P in d_rmats
+    const size_t p_base = sym ? reinterpret_cast<const unsigned char*>(c->d_rmats) - reinterpret_cast<const unsigned char*>(c->d_pmats) : 0;
     const size_t tab_base = reinterpret_cast<const unsigned char*>(c->d_tiptab) - reinterpret_cast<const unsigned char*>(c->d_pmats);
     std::vector<PairRow> rows(plan.rows.size());
     for (size_t r = 0; r < plan.rows.size(); ++r) {
@@ -694,8 +771,8 @@ int upload_pair_rows(Ctx* c, const ResPlan& plan) {
         const int kind_a = (s.packed >> 24) & 3, kind_b = (s.packed >> 26) & 3;
         if (kind_a == KIND_SLOT) return c->fail(PHB_ERR_STATE, "pair kernel: plan is not in canonical operand order");
         if (s.src_b < 0 || s.src_b >= (1 << 24)) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: too many tips");
-        const size_t oa = kind_a == KIND_TIP ? tab_base + pidx_a * tab_bytes : pidx_a * p_bytes;
-        const size_t ob = kind_b == KIND_TIP ? tab_base + pidx_b * tab_bytes : pidx_b * p_bytes;
+        const size_t oa = kind_a == KIND_TIP ? tab_base + pidx_a * tab_bytes : p_base + pidx_a * p_bytes;
+        const size_t ob = kind_b == KIND_TIP ? tab_base + pidx_b * tab_bytes : p_base + pidx_b * p_bytes;
         PairRow d;
         d.off_a = (uint32_t)(oa / 16);
         d.off_b = (uint32_t)(ob / 16);
@@ -712,7 +789,8 @@ int upload_pair_rows(Ctx* c, const ResPlan& plan) {
 // (root_a, root_b); kind 2: every block stored, no root step)
 int cached_pair_plan(Ctx* c, int kind, int root_a, int root_b, int* n_steps, int* n_slots) {
     auto& rc = c->res_cache;
-    if (rc.kind == kind && rc.root_a == root_a && rc.root_b == root_b && rc.gen == c->sched_gen) {
+    const bool sym = kind == 1 && pair_sym(c);
+    if (rc.kind == kind && rc.root_a == root_a && rc.root_b == root_b && rc.gen == c->sched_gen && rc.sym == sym) {
         *n_steps = rc.n_steps;
         *n_slots = rc.n_slots;
         return PHB_OK;
@@ -724,9 +802,10 @@ int cached_pair_plan(Ctx* c, int kind, int root_a, int root_b, int* n_steps, int
     *n_steps = (int)plan.rows.size();
     *n_slots = plan.n_slots;
     if (plan.rows.empty()) return PHB_OK;
-    st = upload_pair_rows(c, plan);
+    st = upload_pair_rows(c, plan, sym);
     if (st) return st;
     rc.kind = kind;
+    rc.sym = sym;
     rc.root_a = root_a;
     rc.root_b = root_b;
     rc.gen = c->sched_gen;

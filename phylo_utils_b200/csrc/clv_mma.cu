@@ -185,8 +185,10 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
             // the loads fly during the product phase of the other operand.  Only internal operands have phases:
             // 2K for an internal x internal row, K for a tip x internal row, none for a cherry (half of all operands of
             // a tree are tips: the phase count, and with it the barriers and the table staging traffic, is halved).
-            const bool d0 = !FUSED && kind_of(0) == SRC_TIP && p.tiptab != nullptr;
-            const bool d1 = !FUSED && kind_of(1) == SRC_TIP && p.tiptab != nullptr;
+            // (61 states, where a table is 30 kB; at 20 states staging 3.8 kB costs less than the exposed L2 latency of the
+            // gathers: cfg3 15.98 vs 16.42 ms)
+            const bool d0 = !FUSED && A > 32 && kind_of(0) == SRC_TIP && p.tiptab != nullptr;
+            const bool d1 = !FUSED && A > 32 && kind_of(1) == SRC_TIP && p.tiptab != nullptr;
             const int n_phases = FUSED ? 3 * K : ((d0 ? 0 : 1) + (d1 ? 0 : 1)) * K;
             auto next_phase = [&](int k, int c, int& kn, int& cn) {
                 if (FUSED || (!d0 && !d1)) {

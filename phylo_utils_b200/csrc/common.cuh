@@ -50,6 +50,7 @@ struct Tuning {
     int pair_ctas = 0;               // PHB_PAIR_CTAS: cap on resident warps per SM of the pair kernel
     int pair_ppt = 0;                // PHB_PAIR_PPT: patterns per lane of the lnL-only pair kernel (0 = choose)
     int pair_grid = 0;               // PHB_PAIR_GRID: 0 = choose, 1 = every resident warp, 2 = equal tiles per warp
+    bool pair_full_p = false;        // PHB_PAIR_FULL_P: the lnL-only walk reads full P blocks even for reversible models
     int up_ppt = 0;                  // PHB_UP_PPT: patterns per lane of the pre-order walk
     int up_warps = 0;                // PHB_UP_WARPS: cap on resident warps per SM of the pre-order walk
     int resident_warps = 0;          // PHB_RESIDENT_WARPS: CTA width of the one-pattern-per-lane walk
@@ -117,6 +118,10 @@ struct Ctx {
     // 4-state models: T[m][k][code][:] = P[m][k] . lut[code] for every P block m, so that a tip operand is
     // a 32-byte table look-up instead of a matrix-vector product (codes padded to kTipTabCodes rows)
     double* d_tiptab = nullptr;
+    // 4-state reversible models: R[m][k] = packed upper triangle of diag(pi) P[m][k] (10 doubles; symmetric by detailed
+    // balance), what the lnL-only walk reads instead of P (clv_dna_pair.cu, SYM); rebuilt with the tip tables
+    double* d_rmats = nullptr;
+    bool reversible = false;           // pi_i q_ij == pi_j q_ji for the eigen-system and frequencies of phb_set_model
     // 61-state models: zero-padded, 16-byte aligned staging images of every P block and tip table for the DMMA
     // kernels ([mat][K][2][pimg_rows][pimg_pitch], clv_mma.cu), rebuilt with the matrices
     double* d_pimg = nullptr;
@@ -133,6 +138,7 @@ struct Ctx {
         int root_a = -1, root_b = -1;
         int64_t gen = -1;
         int n_steps = 0, n_slots = 0;
+        bool sym = false;              // the descriptors point at the symmetric P blocks (d_rmats)
     } res_cache;
     double h_root_two[2] = {0.0, 0.0}; // P(0), P(root length): source of the asynchronous copy behind the row lengths
     OpRow h_spare_row{};               // the one-row schedule of phb_update_node (same reason)

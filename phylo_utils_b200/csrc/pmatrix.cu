@@ -76,6 +76,18 @@ __global__ void tip_table_kernel(const double* __restrict__ pmats, const double*
     }
 }
 
+// R[m][k] = upper triangle of diag(pi) P[m][k], packed [r00 r01 r02 r03 r11 r12 r13 r22 r23 r33] (4-state reversible models)
+__global__ void sym_block_kernel(const double* __restrict__ pmats, const double* __restrict__ freqs, int K, int first_mat,
+                                 double* __restrict__ out) {
+    const int m = first_mat + blockIdx.x;
+    for (int idx = threadIdx.x; idx < K * 10; idx += blockDim.x) {
+        const int k = idx / 10, e = idx - 10 * k;
+        const int i = e < 4 ? 0 : (e < 7 ? 1 : (e < 9 ? 2 : 3));
+        const int j = e < 4 ? e : (e < 7 ? e - 3 : (e < 9 ? e - 5 : 3));
+        out[((size_t)m * K + k) * 10 + e] = freqs[i] * pmats[((size_t)m * K + k) * 16 + i * 4 + j];
+    }
+}
+
 // any state count: T[m][k][code][i], grid (n_mats, K)
 __global__ void tip_table_generic_kernel(const double* __restrict__ pmats, const double* __restrict__ lut, int n_codes,
                                          int nc, int A, int K, int first_mat, double* __restrict__ out) {
@@ -102,6 +114,11 @@ int launch_tip_tables(Ctx* c, int first_mat, int n_mats) {
             PHB_CUDA(c, cudaGetLastError());
         }
         return launch_mma_images(c, first_mat, n_mats);   // padded staging images for the DMMA kernels (61 states)
+    }
+    if (c->d_rmats != nullptr && c->reversible) {
+        sym_block_kernel<<<n_mats, 64, 0, c->stream>>>(c->d_pmats, c->model_freqs(), c->K, first_mat, c->d_rmats);
+        c->launches++;
+        PHB_CUDA(c, cudaGetLastError());
     }
     if (!tip_tables_usable(c)) return PHB_OK;
     tip_table_kernel<<<n_mats, 128, 0, c->stream>>>(c->d_pmats, c->d_lut, c->n_codes, tip_table_rows(c), c->K, first_mat,
