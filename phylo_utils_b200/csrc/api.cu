@@ -18,7 +18,6 @@ static Tuning read_tuning() {
         Tuning v;
         auto flag = [](const char* name) { return getenv(name) != nullptr; };
         auto num = [](const char* name) { const char* s = getenv(name); return s ? atoi(s) : 0; };
-        v.resident_v1 = flag("PHB_RESIDENT_V1");
         v.disable_mma = flag("PHB_DISABLE_MMA");
         v.disable_tiptab = flag("PHB_DISABLE_TIPTAB");
         v.up_two_rows = flag("PHB_UP_TWO_ROWS");
@@ -32,7 +31,6 @@ static Tuning read_tuning() {
         v.pair_full_p = flag("PHB_PAIR_FULL_P");
         v.up_ppt = num("PHB_UP_PPT");
         v.up_warps = num("PHB_UP_WARPS");
-        v.resident_warps = num("PHB_RESIDENT_WARPS");
         v.tile_want = num("PHB_TILE_WANT");
         v.mma_variant = num("PHB_MMA_VARIANT");
         return v;
@@ -129,15 +127,8 @@ bool shape_ok(int n_tips, int64_t S, int K, int A, std::string* why) {
 
 }  // namespace
 
-// operand-resident post-order pass with all blocks stored: two patterns per lane (clv_dna_pair.cu) where that kernel
-// covers the shape, the one-pattern-per-lane walk (clv_dna_resident.cu) otherwise or with PHB_RESIDENT_V1
-int resident_store(Ctx* c) {
-    if (!tuning().resident_v1) {
-        const int st = dna_pair_store(c);
-        if (st != PHB_ERR_UNSUPPORTED) return st;
-    }
-    return dna_resident(c, -1, -1, true, false);
-}
+// operand-resident post-order pass with all blocks stored (clv_dna_pair.cu)
+int resident_store(Ctx* c) { return dna_pair_store(c); }
 
 int run_rows(Ctx* c, const RowSet& rs, int mode) {
     if (dna_supported(c)) return dna_run_rows(c, rs, mode);
@@ -821,14 +812,7 @@ static int lnl_resident_enqueue(phb_ctx* c, int node_a, int node_b, double lengt
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_resident: only 4-state models with K in {1,2,4,8}");
     st = build_eval_pmats(c, node_a, node_b, length);
     if (st) return st;
-    // default: two patterns per lane (clv_dna_pair.cu); PHB_RESIDENT_V1 selects the one-pattern-per-lane walk
-    if (!tuning().resident_v1) {
-        st = dna_pair_lnl(c, node_a, node_b);
-    } else {
-        PHB_REQUIRE(c, !c->codes_packed, PHB_ERR_STATE, "phb_lnl_resident: packed codes need the pair kernel");
-        st = dna_resident(c, node_a, node_b, false, true);
-    }
-    return st;
+    return dna_pair_lnl(c, node_a, node_b);
 }
 
 int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* total, double* pattern_lnl) {
@@ -858,12 +842,7 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
     c->have_partials = false;
     c->have_up = false;
     if (n_chunks <= 0) n_chunks = 64;   // measured at 1000 x 1M: 16 -> 68.6, 64 -> 69.9 evaluations/s
-    if (!packed && tuning().resident_v1) {
-        c->codes_packed = false;
-        st = dna_resident_from_host(c, codes, n_chunks, node_a, node_b);
-    } else {
-        st = dna_pair_from_host(c, codes, packed, n_chunks, node_a, node_b);
-    }
+    st = dna_pair_from_host(c, codes, packed, n_chunks, node_a, node_b);
     if (st) return st;
     if (total == nullptr) return PHB_OK;   // stream-ordered form: phb_result_fetch / phb_sync complete the evaluation
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));

@@ -1,6 +1,6 @@
 // lnL-only operand-resident pruning for 4-state models, two patterns per lane.
 //
-// Same arithmetic as clv_dna.cu / clv_dna_resident.cu (reference `clv`, numba_likelihood_engine.py:10-46; root
+// Same arithmetic as clv_dna.cu (reference `clv`, numba_likelihood_engine.py:10-46; root
 // step = tree_model.py:178-217 with lnl_node, numba_likelihood_engine.py:82-87), same parking plan
 // (resident_plan.cuh), different mapping:
 //
@@ -457,9 +457,8 @@ struct PairStoreArgs {
     int64_t S, n_tiles;
 };
 
-template <int K, int NC>
+template <int K, int NC, int PPT>
 __global__ void __launch_bounds__(32, 11) dna_pair_store_kernel(const PairStoreArgs p) {
-    constexpr int PPT = 2;
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = K * 32 + 16, TILE_BYTES = L::TILE * ROWB, OPIN_BYTES = TILE_BYTES;   // exponents sit in the row padding
     constexpr int PIECES = K * 2;                        // 16-byte pieces per pattern
@@ -612,9 +611,9 @@ __global__ void __launch_bounds__(32, 11) dna_pair_store_kernel(const PairStoreA
     cp_async_wait_all();
 }
 
-template <int K, int NC>
+template <int K, int NC, int PPT>
 int launch_pair_store(Ctx* c, int n_steps) {
-    using L = PairLayout<K, NC, 2>;
+    using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = K * 32 + 16;
     PairStoreArgs a;
     a.rows = static_cast<const PairRow*>(c->d_res_rows);
@@ -626,7 +625,7 @@ int launch_pair_store(Ctx* c, int n_steps) {
     a.scale = c->d_scale;
     a.S = c->S;
     a.n_tiles = (c->S + L::TILE - 1) / L::TILE;
-    auto kern = dna_pair_store_kernel<K, NC>;
+    auto kern = dna_pair_store_kernel<K, NC, PPT>;
     const size_t smem = L::DESC_BYTES + 2 * L::STAGE_BYTES + (size_t)L::TILE * ROWB + 32 * ROWB;   // operand tile + half-size staging tile
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair store kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -816,20 +815,101 @@ int cached_pair_plan(Ctx* c, int kind, int root_a, int root_b, int* n_steps, int
 
 }  // namespace
 
+// Parking plan of the operand-resident walks: the schedule is walked like a register allocator - a finished block that
+// the next row does not consume is parked in the lowest free scratch slot (lnL-only walk) or simply lives in the partials
+// array (store walk); a slot is recycled once its block has been read.  Operands come out in the canonical order
+// TIP <= PREV <= SLOT; a row with two parked operands means the schedule is not a post-order walk: rejected.
+int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPlan* out) {
+    const int n_rows = c->n_rows();
+    std::vector<int> park_of_node(c->n_nodes, -1);
+    std::vector<int> consumer_row(c->n_nodes, -1);
+    for (int r = 0; r < n_rows; ++r)
+        for (int i = 1; i <= 2; ++i) consumer_row[c->rows_raw[3 * r + i]] = r;
+    if (with_root) {
+        if (c->node_tip[root_a] < 0) consumer_row[root_a] = n_rows;
+        if (c->node_tip[root_b] < 0) consumer_row[root_b] = n_rows;
+    }
+    std::vector<char> busy;
+    auto grab = [&]() {
+        for (size_t i = 0; i < busy.size(); ++i)
+            if (!busy[i]) {
+                busy[i] = 1;
+                return (int)i;
+            }
+        busy.push_back(1);
+        return (int)busy.size() - 1;
+    };
+    auto make = [&](int r, int node_a, int node_b, int pidx_a, int pidx_b, int dst_node) -> int {
+        int nodes[2] = {node_a, node_b}, pidx[2] = {pidx_a, pidx_b}, kind[2], src[2];
+        for (int i = 0; i < 2; ++i) {
+            const int nd = nodes[i];
+            if (c->node_tip[nd] >= 0) {
+                kind[i] = KIND_TIP;
+                src[i] = c->node_tip[nd];
+            } else if (c->node_row[nd] == r - 1) {
+                kind[i] = KIND_PREV;
+                src[i] = 0;
+            } else {
+                kind[i] = KIND_SLOT;
+                src[i] = store ? c->node_row[nd] : park_of_node[nd];
+                if (src[i] < 0) return c->fail(PHB_ERR_STATE, "resident plan: operand was never parked");
+                if (!store) busy[src[i]] = 0;   // recycled after this row has read it
+            }
+        }
+        if (kind[0] == KIND_SLOT && kind[1] == KIND_SLOT)
+            return c->fail(PHB_ERR_UNSUPPORTED,
+                           "resident kernel needs a post-order schedule (second child = previous row); "
+                           "use Traversal.locality_order() or another mode");
+        if (kind[0] > kind[1]) {   // canonical operand order TIP <= PREV <= SLOT (children commute)
+            std::swap(kind[0], kind[1]);
+            std::swap(src[0], src[1]);
+            std::swap(pidx[0], pidx[1]);
+        }
+        int dst = 15;
+        if (!store && dst_node >= 0 && consumer_row[dst_node] != r + 1 && consumer_row[dst_node] >= 0) {
+            dst = grab();
+            if (dst >= kScratchSlots) return c->fail(PHB_ERR_UNSUPPORTED, "resident plan: tree needs more than 15 parked blocks");
+            park_of_node[dst_node] = dst;
+        }
+        if (pidx[1] >= (1 << 24)) return c->fail(PHB_ERR_UNSUPPORTED, "resident plan: too many rows");
+        ResRow row;
+        row.src_a = src[0];
+        row.src_b = src[1];
+        row.pidx_a = pidx[0];
+        row.packed = (uint32_t)pidx[1] | ((uint32_t)kind[0] << 24) | ((uint32_t)kind[1] << 26) | ((uint32_t)dst << 28);
+        out->rows.push_back(row);
+        return PHB_OK;
+    };
+    out->rows.clear();
+    for (int r = 0; r < n_rows; ++r) {
+        int st = make(r, c->rows_raw[3 * r + 1], c->rows_raw[3 * r + 2], 2 * r, 2 * r + 1, c->rows_raw[3 * r]);
+        if (st) return st;
+    }
+    if (with_root) {
+        const int rp = 2 * c->max_rows();
+        int st = make(n_rows, root_a, root_b, rp, rp + 1, -1);
+        if (st) return st;
+    }
+    out->n_slots = std::max<int>((int)busy.size(), 1);
+    return PHB_OK;
+}
+
 // Post-order pass with every node block stored (PHB_MODE_RESIDENT / PHB_MODE_AUTO of phb_compute_partials)
 int dna_pair_store(Ctx* c) {
-    if (c->K > 4) return PHB_ERR_UNSUPPORTED;   // K = 8 keeps the one-pattern-per-lane walk (register budget)
     int n_steps = 0, n_slots = 0;
     int st = cached_pair_plan(c, 2, -1, -1, &n_steps, &n_slots);
     if (st) return st;
     if (n_steps == 0) return PHB_OK;
     switch (c->K * 100 + tip_table_rows(c)) {
-        case 108: return launch_pair_store<1, 8>(c, n_steps);
-        case 116: return launch_pair_store<1, 16>(c, n_steps);
-        case 208: return launch_pair_store<2, 8>(c, n_steps);
-        case 216: return launch_pair_store<2, 16>(c, n_steps);
-        case 408: return launch_pair_store<4, 8>(c, n_steps);
-        case 416: return launch_pair_store<4, 16>(c, n_steps);
+        case 108: return launch_pair_store<1, 8, 2>(c, n_steps);
+        case 116: return launch_pair_store<1, 16, 2>(c, n_steps);
+        case 208: return launch_pair_store<2, 8, 2>(c, n_steps);
+        case 216: return launch_pair_store<2, 16, 2>(c, n_steps);
+        case 408: return launch_pair_store<4, 8, 2>(c, n_steps);
+        case 416: return launch_pair_store<4, 16, 2>(c, n_steps);
+        // eight categories: one pattern per lane (two would need 128 registers for the block alone)
+        case 808: return launch_pair_store<8, 8, 1>(c, n_steps);
+        case 816: return launch_pair_store<8, 16, 1>(c, n_steps);
     }
     return PHB_ERR_UNSUPPORTED;
 }

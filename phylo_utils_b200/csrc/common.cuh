@@ -39,7 +39,6 @@ struct Ctx;
 // Developer switches (A/B measurements, what-if builds).  The environment is read ONCE, on first use, into this
 // struct (api.cu); nothing on an evaluation's path calls getenv.  Defaults = the shipped configuration.
 struct Tuning {
-    bool resident_v1 = false;        // PHB_RESIDENT_V1: one-pattern-per-lane walk instead of the pair kernels
     bool disable_mma = false;        // PHB_DISABLE_MMA: generic kernels instead of the FP64 tensor-core ones
     bool disable_tiptab = false;     // PHB_DISABLE_TIPTAB: DMMA rows multiply tip operands instead of reading P.lut rows
     bool up_two_rows = false;        // PHB_UP_TWO_ROWS: pre-order pass as two pruning rows per parent
@@ -53,7 +52,6 @@ struct Tuning {
     bool pair_full_p = false;        // PHB_PAIR_FULL_P: the lnL-only walk reads full P blocks even for reversible models
     int up_ppt = 0;                  // PHB_UP_PPT: patterns per lane of the pre-order walk
     int up_warps = 0;                // PHB_UP_WARPS: cap on resident warps per SM of the pre-order walk
-    int resident_warps = 0;          // PHB_RESIDENT_WARPS: CTA width of the one-pattern-per-lane walk
     int tile_want = 0;               // PHB_TILE_WANT: tiles per SM the streaming tile walk asks for
     int mma_variant = 0;             // PHB_MMA_VARIANT: alternative DMMA tile shapes
 };
@@ -142,7 +140,6 @@ struct Ctx {
     } res_cache;
     double h_root_two[2] = {0.0, 0.0}; // P(0), P(root length): source of the asynchronous copy behind the row lengths
     OpRow h_spare_row{};               // the one-row schedule of phb_update_node (same reason)
-    int resident_u = 0;                // 0 = choose, else forced patterns-per-warp multiplier (tuning / tests)
     int resident_slots = 0;            // parked blocks the last resident launch needed
     int resident_warps = 0;            // warps per SM of the last resident launch
     unsigned char* d_scratch = nullptr;  // L2-resident parking area of the lnL-only resident kernel
@@ -240,8 +237,6 @@ struct RowSet {
 bool dna_supported(const Ctx* c);
 int dna_run_rows(Ctx* c, const RowSet& rs, int mode);
 int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
-int dna_resident(Ctx* c, int root_a, int root_b, bool store, bool with_root);   // clv_dna_resident.cu
-int dna_resident_from_host(Ctx* c, const uint8_t* codes_host, int n_chunks, int root_a, int root_b);
 // clv_dna_pair.cu: lnL-only walk, two patterns per lane (the default lnL-only path)
 int dna_pair_lnl(Ctx* c, int root_a, int root_b);
 int dna_pair_store(Ctx* c);   // all partials stored; PHB_ERR_UNSUPPORTED (no message) when the shape is not covered

@@ -1,4 +1,4 @@
-// Parking plan shared by the operand-resident 4-state kernels (clv_dna_resident.cu, clv_dna_pair.cu).
+// Parking plan of the operand-resident 4-state walks (clv_dna_pair.cu, up_dna_pair.cu).
 #pragma once
 
 #include <vector>
@@ -23,7 +23,7 @@ struct ResPlan {
     int n_slots = 0;
 };
 
-// Walks the schedule like a register allocator (defined in clv_dna_resident.cu).  Operands come out in the
+// Walks the schedule like a register allocator (defined in clv_dna_pair.cu).  Operands come out in the
 // canonical order TIP <= PREV <= SLOT; rows with two parked operands are rejected (PHB_ERR_UNSUPPORTED).
 int plan_rows(Ctx* c, int root_a, int root_b, bool with_root, bool store, ResPlan* out);
 
