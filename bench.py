@@ -514,12 +514,15 @@ def main():
     prune_bytes, _ = algorithmic_bytes(n_taxa, n_local)
     flops = algorithmic_flops(n_taxa, n_local)
     ncu = ncu_record("dna_pair_kernel_lnl_only_1000x1M") or {}
+    # the launch's own rule (clv_dna_pair.cu: pair_ppt): 128-pattern tiles when the 64-pattern tiles need a second wave
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    ppt = 4 if ((n_local + 63) // 64 > 12 * sms and (n_local + 127) // 128 <= 8 * sms) else 2
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tf / dfma_peak,
         "traffic": ncu.get("dram_bytes_per_launch"),
-        "kernel": "dna_pair_kernel<K=4,NC=8,PPT=2> (two patterns per lane, whole post-order walk + root + reduction in one "
-                  "launch, operands on chip, no partials stored)",
+        "kernel": "dna_pair_kernel<K=4,NC=8,PPT={},SYM> ({} patterns per lane, whole post-order walk + root + reduction in one "
+                  "launch, operands on chip, symmetric P blocks, no partials stored)".format(ppt, {2: "two", 4: "four"}[ppt]),
         "kernel_ms": kernel_ms, "patterns_per_launch": n_local, "share_of_step": kernel_ms / ms_per_step,
         "algorithmic_flops_per_launch": flops,
         "flops_per_unit": "272 fp64 flop per site-node update (SURVEY.md 8(d): K (4 A^2 + A)), x (N-2) x patterns of the shard",
@@ -538,23 +541,35 @@ def main():
     # ---- e2e: the same evaluation from pinned HOST codes every step (TreeModel-level API) ---------------------------
     e2e = None
     if not args.no_e2e:
+        # the alphabet has 5 code rows (<= 8): 3 bits per code in two planes (phb_split_codes, done once when an alignment
+        # is loaded); the two-codes-per-byte format of round 1 is measured next to it
+        planes = tuple(torch.from_numpy(x).pin_memory().numpy() for x in phy.LikelihoodEngine.split_codes(codes_host.numpy()))
         packed = torch.from_numpy(phy.LikelihoodEngine.pack_codes(codes_host.numpy())).pin_memory().numpy()
 
-        def evaluate_e2e():
+        def evaluate_e2e(host_codes):
             tm.compute_partials()
-            return tm.lnl_from_host_codes(packed, n_chunks=args.chunks)
-        for _ in range(2):
-            evaluate_e2e()
-        e_ms, e_lnl = timed(evaluate_e2e, args.steps)
-        e_ms /= args.steps
-        e2e = {"value": 1e3 / e_ms, "unit": "lnL evals/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(packed.nbytes + (2 * (n_taxa - 2)) * 8 + 16), "d2h_bytes_per_step": 8,
-               "bytes_are": "per GPU (its shard's packed codes + the branch lengths); x{} over the box".format(world),
-               "api": "ShardedTreeModel.compute_partials() + lnl_from_host_codes(packed) -> TreeModel.lnl_from_host_codes -> C ABI "
-                      "phb_set_edge_lengths + phb_lnl_from_host_packed_async (pinned host tip codes, two 4-bit codes per byte, "
-                      "{} chunks, copy pipelined with the pruning), device all-reduce, phb_result_fetch".format(args.chunks),
-               "lnl": e_lnl}
-        del packed
+            return tm.lnl_from_host_codes(host_codes, n_chunks=args.chunks)
+
+        def measure_e2e(host_codes, code_bytes, what):
+            for _ in range(2):
+                evaluate_e2e(host_codes)
+            e_ms, e_lnl = timed(lambda: evaluate_e2e(host_codes), args.steps)
+            e_ms /= args.steps
+            return {"value": 1e3 / e_ms, "unit": "lnL evals/s", "ms_per_step": e_ms,
+                    "h2d_bytes_per_step": int(code_bytes + (2 * (n_taxa - 2)) * 8 + 16), "d2h_bytes_per_step": 8,
+                    "host_to_device_gbs_per_gpu": code_bytes / (e_ms * 1e-3) / 1e9, "tip_code_format": what, "lnl": e_lnl}
+        split = measure_e2e(planes, int(planes[0].nbytes + planes[1].nbytes), "3 bits per code: a plane of 2-bit values + a plane of high bits (phb_lnl_from_host_split_async)")
+        nibble = measure_e2e(packed, int(packed.nbytes), "two 4-bit codes per byte (phb_lnl_from_host_packed_async)")
+        # which format a deployment uses is a property of the box, decided before the run: one or two GPUs decode nibbles
+        # faster than the copy engine delivers them (the 3-bit decode costs the kernel 3 %); from four GPUs on the shared
+        # host-to-device link is the bound and fewer bytes win
+        e2e, other = (split, nibble) if world > 2 else (nibble, split)
+        e2e["bytes_are"] = "per GPU (its shard's tip codes + the branch lengths); x{} over the box".format(world)
+        e2e["api"] = ("ShardedTreeModel.compute_partials() + lnl_from_host_codes(codes) -> TreeModel.lnl_from_host_codes -> C ABI "
+                      "phb_set_edge_lengths + phb_lnl_from_host_{{packed,split}}_async (pinned host tip codes, {} chunks, copy pipelined "
+                      "with the pruning), device all-reduce, phb_result_fetch".format(args.chunks))
+        e2e["other_format"] = other
+        del packed, planes
 
     # ---- parity inside the run ------------------------------------------------------------------------------------
     # (a) the sharded product path against the reference-generated golden case cfg1 (10 taxa x 1000 patterns, numba
@@ -596,7 +611,10 @@ def main():
     configs = None
     if not args.no_configs and world in (1, 8):
         from tools import bench_configs
-        configs = bench_configs.sub_records(world, rank, local_rank, peak_hbm, fp64_peak(local_rank, tensor=True), dfma_peak)
+        try:
+            configs = bench_configs.sub_records(world, rank, local_rank, peak_hbm, fp64_peak(local_rank, tensor=True), dfma_peak)
+        except Exception as exc:            # a sub-record must never cost the headline line
+            configs = {"error": repr(exc)[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

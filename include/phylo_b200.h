@@ -172,6 +172,16 @@ int phb_lnl_from_host_packed(phb_ctx* ctx, const uint8_t* packed_codes, int n_ch
 /* host helper: codes[n_tips][n_patterns] (values < 16) -> out[n_tips][(n_patterns + 1) / 2] as described above */
 int phb_pack_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* out);
 
+/* phb_lnl_from_host for look-up tables of at most 8 rows (any alignment without partial ambiguity codes: the four
+ * nucleotides, the gap / N row, up to three more) and a reversible model: 3 bits per code, split into a plane of 2-bit
+ * values low_plane[n_tips][(n_patterns + 3) / 4] (pattern s in bits 2 (s % 4) .. of byte s / 4) and a plane of high
+ * bits high_plane[n_tips][(n_patterns + 7) / 8] (pattern s in bit s % 8 of byte s / 8) - 3/8 of a byte per code over
+ * PCIe, where the host-to-device link bounds the evaluation once several GPUs of a box are fed at the same time.
+ * Afterwards the device holds split codes (as after phb_lnl_from_host_packed). phb_split_codes builds the planes. */
+int phb_lnl_from_host_split(phb_ctx* ctx, const uint8_t* low_plane, const uint8_t* high_plane, int n_chunks, int node_a,
+                            int node_b, double length, double* total, double* pattern_lnl);
+int phb_split_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* low_plane, uint8_t* high_plane);
+
 /* ---- read-back for parity tests (TreeModel.partials / .scale / .root_partials attributes) --- */
 /* out[S][K][A]; tips are expanded from their codes */
 int phb_get_partials(phb_ctx* ctx, int node, double* out);
@@ -224,6 +234,8 @@ int phb_lnl_resident_async(phb_ctx* ctx, int node_a, int node_b, double length);
 int phb_root_lnl_async(phb_ctx* ctx, int node_a, int node_b, double length);
 int phb_lnl_from_host_packed_async(phb_ctx* ctx, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
                                    double length);
+int phb_lnl_from_host_split_async(phb_ctx* ctx, const uint8_t* low_plane, const uint8_t* high_plane, int n_chunks,
+                                  int node_a, int node_b, double length);
 int phb_edge_derivatives_async(phb_ctx* ctx, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule);
 /* device address and capacity (in doubles) of the result buffer; it lies inside the caller's workspace when one
  * was given to phb_create */

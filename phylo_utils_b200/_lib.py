@@ -52,6 +52,9 @@ SIGNATURES = {
     "phb_lnl_from_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, _dp, _dp]),
     "phb_lnl_from_host_packed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, _dp, _dp]),
     "phb_pack_codes": (c_int, [c_void_p, c_int, c_int64, c_void_p]),
+    "phb_lnl_from_host_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, _dp, _dp]),
+    "phb_split_codes": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "phb_lnl_from_host_split_async": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double]),
     "phb_get_partials": (c_int, [c_void_p, c_int, _dp]),
     "phb_get_scalers": (c_int, [c_void_p, c_int, _dp]),
     "phb_get_root_partials": (c_int, [c_void_p, _dp, _dp]),

@@ -434,6 +434,7 @@ int phb_set_tips(phb_ctx* c, const uint8_t* codes, int codes_on_device, int n_co
     if (c->code_pitch != (size_t)c->S && (!c->have_tips || c->codes_packed))
         PHB_CUDA(c, cudaMemsetAsync(c->d_codes_ws, 0, n_code_bytes, c->stream));
     c->codes_packed = false;
+    c->codes_mode = 0;
     PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws, c->code_pitch, codes, (size_t)c->S, (size_t)c->S, (size_t)c->n_tips,
                                   codes_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     c->d_codes = c->d_codes_ws;
@@ -827,8 +828,10 @@ int phb_lnl_resident(phb_ctx* c, int node_a, int node_b, double length, double* 
     return PHB_OK;
 }
 
-static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_chunks, int node_a, int node_b,
-                         double length, double* total, double* pattern_lnl) {
+// mode: 0 one byte per code, 1 two 4-bit codes per byte, 2 split 3-bit planes (codes = low plane, codes_hi = high plane)
+static int lnl_from_host(phb_ctx* c, const uint8_t* codes, const uint8_t* codes_hi, int mode, int n_chunks, int node_a,
+                         int node_b, double length, double* total, double* pattern_lnl) {
+    const bool packed = mode == 1;
     if (!c) return PHB_ERR_INVALID;
     int st = activate(c);
     if (st) return st;
@@ -837,12 +840,14 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
                 "phb_lnl_from_host: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
     PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host: only 4-state models with K in {1,2,4,8}");
     PHB_REQUIRE(c, !packed || c->n_codes <= 16, PHB_ERR_UNSUPPORTED, "phb_lnl_from_host_packed: more than 16 codes");
+    PHB_REQUIRE(c, mode != 2 || (codes_hi != nullptr && c->n_codes <= 8), PHB_ERR_UNSUPPORTED,
+                "phb_lnl_from_host_split: needs both planes and a look-up table of at most 8 rows");
     st = build_eval_pmats(c, node_a, node_b, length);
     if (st) return st;
     c->have_partials = false;
     c->have_up = false;
     if (n_chunks <= 0) n_chunks = 64;   // measured at 1000 x 1M: 16 -> 68.6, 64 -> 69.9 evaluations/s
-    st = dna_pair_from_host(c, codes, packed, n_chunks, node_a, node_b);
+    st = dna_pair_from_host(c, codes, codes_hi, mode, n_chunks, node_a, node_b);
     if (st) return st;
     if (total == nullptr) return PHB_OK;   // stream-ordered form: phb_result_fetch / phb_sync complete the evaluation
     PHB_CUDA(c, cudaMemcpyAsync(total, c->d_result, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -853,12 +858,48 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, bool packed, int n_ch
 
 int phb_lnl_from_host(phb_ctx* c, const uint8_t* codes, int n_chunks, int node_a, int node_b, double length,
                       double* total, double* pattern_lnl) {
-    return lnl_from_host(c, codes, false, n_chunks, node_a, node_b, length, total, pattern_lnl);
+    return lnl_from_host(c, codes, nullptr, 0, n_chunks, node_a, node_b, length, total, pattern_lnl);
 }
 
 int phb_lnl_from_host_packed(phb_ctx* c, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
                              double length, double* total, double* pattern_lnl) {
-    return lnl_from_host(c, packed_codes, true, n_chunks, node_a, node_b, length, total, pattern_lnl);
+    return lnl_from_host(c, packed_codes, nullptr, 1, n_chunks, node_a, node_b, length, total, pattern_lnl);
+}
+
+int phb_lnl_from_host_split(phb_ctx* c, const uint8_t* low_plane, const uint8_t* high_plane, int n_chunks, int node_a,
+                            int node_b, double length, double* total, double* pattern_lnl) {
+    if (c != nullptr && total == nullptr) return c->fail(PHB_ERR_INVALID, "phb_lnl_from_host_split: total is NULL");
+    return lnl_from_host(c, low_plane, high_plane, 2, n_chunks, node_a, node_b, length, total, pattern_lnl);
+}
+
+int phb_lnl_from_host_split_async(phb_ctx* c, const uint8_t* low_plane, const uint8_t* high_plane, int n_chunks, int node_a,
+                                  int node_b, double length) {
+    return lnl_from_host(c, low_plane, high_plane, 2, n_chunks, node_a, node_b, length, nullptr, nullptr);
+}
+
+int phb_split_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* low_plane, uint8_t* high_plane) {
+    if (codes == nullptr || low_plane == nullptr || high_plane == nullptr || n_tips < 0 || n_patterns < 0) {
+        set_thread_error("phb_split_codes: bad argument");
+        return PHB_ERR_INVALID;
+    }
+    const int64_t row_lo = (n_patterns + 3) / 4, row_hi = (n_patterns + 7) / 8;
+    for (int t = 0; t < n_tips; ++t) {
+        const uint8_t* src = codes + (size_t)t * n_patterns;
+        uint8_t* lo = low_plane + (size_t)t * row_lo;
+        uint8_t* hi = high_plane + (size_t)t * row_hi;
+        std::memset(lo, 0, (size_t)row_lo);
+        std::memset(hi, 0, (size_t)row_hi);
+        for (int64_t s = 0; s < n_patterns; ++s) {
+            const unsigned v = src[s];
+            if (v > 7u) {
+                set_thread_error("phb_split_codes: a code does not fit in 3 bits");
+                return PHB_ERR_INVALID;
+            }
+            lo[s >> 2] |= (uint8_t)((v & 3u) << (2 * (s & 3)));
+            hi[s >> 3] |= (uint8_t)((v >> 2) << (s & 7));
+        }
+    }
+    return PHB_OK;
 }
 
 int phb_pack_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* out) {
@@ -1059,7 +1100,7 @@ int phb_root_lnl_async(phb_ctx* c, int node_a, int node_b, double length) {
 
 int phb_lnl_from_host_packed_async(phb_ctx* c, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
                                    double length) {
-    return lnl_from_host(c, packed_codes, true, n_chunks, node_a, node_b, length, nullptr, nullptr);
+    return lnl_from_host(c, packed_codes, nullptr, 1, n_chunks, node_a, node_b, length, nullptr, nullptr);
 }
 
 int phb_edge_derivatives_async(phb_ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule) {

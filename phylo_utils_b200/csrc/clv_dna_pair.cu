@@ -52,6 +52,8 @@ struct PairArgs {
     const unsigned char* opbase;  // base the descriptors' operand offsets refer to
     const uint8_t* codes;
     size_t pitch;                 // bytes between tip rows of `codes`
+    const uint8_t* codes_hi;      // CODES_SPLIT3: the plane of high bits and its row pitch
+    size_t pitch_hi;
     unsigned char* scratch;
     int n_slots;
     const double* freqs;
@@ -99,7 +101,7 @@ __device__ __forceinline__ void sym_matvec(const unsigned char* blk, const doubl
     }
 }
 
-template <int K, int NC, int PPT, bool PACKED, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE, bool SYM = false>
+template <int K, int NC, int PPT, int CM, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE, bool SYM = false>
 __device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
                                             double (&prev)[PPT][K][4], int (&pe)[PPT], const double* ipi = nullptr) {
     constexpr int PB = SYM ? 80 : 128;   // bytes of one category's P block (SYM: the upper triangle of diag(pi) P)
@@ -129,8 +131,8 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
     int ra[PPT], rb[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) ra[p] = rb[p] = 0;
-    if (KA == KIND_TIP) table_rows<NC, PPT, PACKED, LAYOUT>(st + L::CODES_OFF, lane, ra);
-    if (KB == KIND_TIP) table_rows<NC, PPT, PACKED, LAYOUT>(st + L::CODES_OFF + L::TILE, lane, rb);
+    if (KA == KIND_TIP) table_rows<NC, PPT, CM, LAYOUT>(st + L::CODES_OFF, lane, ra);
+    if (KB == KIND_TIP) table_rows<NC, PPT, CM, LAYOUT>(st + L::CODES_OFF + L::TILE, lane, rb);
     int mh[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) mh[p] = 0;
@@ -257,7 +259,7 @@ __device__ __noinline__ void wait_for_chunk(const int* flags, int chunk_shift, i
     *error = 1;
 }
 
-template <int K, int NC, int PPT, bool PACKED, bool PIPE, bool SYM>
+template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
 __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair_kernel(const __grid_constant__ PairArgs p) {
     using L = PairLayout<K, NC, PPT>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -290,14 +292,22 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
 #pragma unroll
         for (int j = 0; j < L::ROUNDS; ++j)
             if (j < L::P_ROUNDS || kind_b == KIND_TIP) cp_async16(st + L::OPER_BYTES + j * 512 + lane * 16, gb + j * 512);
-        // codes of the tile: TILE (TILE / 2 when packed) bytes per tip operand; lanes 0..7 serve operand a, 8..15 operand b
-        constexpr int CL = (PACKED ? L::TILE / 2 : L::TILE) / 16;
+        // codes of the tile: TILE bytes per tip operand (TILE / 2 as nibbles; TILE / 4 + TILE / 8 as split 3-bit codes);
+        // lanes 0..7 serve operand a, 8..15 operand b
+        constexpr int CL = (CM == CODES_BYTE ? L::TILE : (CM == CODES_NIBBLE ? L::TILE / 2 : L::TILE / 4)) / 16;
         const int which = lane >> 3, piece = lane & 7;
         const bool tip = which == 0 ? kind_a == KIND_TIP : kind_b == KIND_TIP;
-        if (which < 2 && piece < CL && tip) {
+        if (which < 2 && tip) {
             const int tip_row = which == 0 ? d.src_a : (int)(d.packed & 0xffffff);
-            cp_async16(st + L::CODES_OFF + which * L::TILE + piece * 16,
-                       p.codes + (size_t)tip_row * p.pitch + (size_t)t * (CL * 16) + piece * 16);
+            if (piece < CL)
+                cp_async16(st + L::CODES_OFF + which * L::TILE + piece * 16,
+                           p.codes + (size_t)tip_row * p.pitch + (size_t)t * (CL * 16) + piece * 16);
+            if (CM == CODES_SPLIT3 && piece == CL) {   // the plane of high bits: TILE / 8 bytes, right behind the low plane
+                unsigned char* dst = st + L::CODES_OFF + which * L::TILE + L::TILE / 4;
+                const unsigned char* src = p.codes_hi + (size_t)tip_row * p.pitch_hi + (size_t)t * (L::TILE / 8);
+                if (PPT == 2) cp_async8(dst, src);
+                else cp_async16(dst, src);
+            }
         }
     };
 
@@ -361,12 +371,12 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
             // indirect branch on the row's critical path
             const int kind_a = kinds & 3, kind_b = kinds >> 2;
             if (kind_b == KIND_SLOT) {
-                if (kind_a == KIND_PREV) pair_update<K, NC, PPT, PACKED, KIND_PREV, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
-                else pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                if (kind_a == KIND_PREV) pair_update<K, NC, PPT, CM, KIND_PREV, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                else pair_update<K, NC, PPT, CM, KIND_TIP, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
             } else if (kind_b == KIND_PREV) {
-                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_PREV, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                pair_update<K, NC, PPT, CM, KIND_TIP, KIND_PREV, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
             } else {
-                pair_update<K, NC, PPT, PACKED, KIND_TIP, KIND_TIP, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                pair_update<K, NC, PPT, CM, KIND_TIP, KIND_TIP, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
             }
             if (fetch_late) {   // the operand tile is free now (a lane only ever touches its own chunks of it)
                 fetch_slot(slot_n);
@@ -562,12 +572,12 @@ __global__ void __launch_bounds__(32, 11) dna_pair_store_kernel(const PairStoreA
         const unsigned char* st = s_stage + (q & 1) * L::STAGE_BYTES;
         const int kind_a = kinds & 3, kind_b = kinds >> 2;
         if (kind_b == KIND_SLOT) {
-            if (kind_a == KIND_PREV) pair_update<K, NC, PPT, false, KIND_PREV, KIND_SLOT, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
-            else pair_update<K, NC, PPT, false, KIND_TIP, KIND_SLOT, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+            if (kind_a == KIND_PREV) pair_update<K, NC, PPT, CODES_BYTE, KIND_PREV, KIND_SLOT, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+            else pair_update<K, NC, PPT, CODES_BYTE, KIND_TIP, KIND_SLOT, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
         } else if (kind_b == KIND_PREV) {
-            pair_update<K, NC, PPT, false, KIND_TIP, KIND_PREV, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+            pair_update<K, NC, PPT, CODES_BYTE, KIND_TIP, KIND_PREV, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
         } else {
-            pair_update<K, NC, PPT, false, KIND_TIP, KIND_TIP, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
+            pair_update<K, NC, PPT, CODES_BYTE, KIND_TIP, KIND_TIP, LAYOUT_ARRAY>(st, s_opin, lane, prev, pe);
         }
         if (fetch_late) {   // each lane only ever touches its own rows of the operand tile
             __syncwarp();
@@ -641,7 +651,7 @@ int launch_pair_store(Ctx* c, int n_steps) {
     return PHB_OK;
 }
 
-template <int K, int NC, int PPT, bool PACKED, bool PIPE, bool SYM>
+template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
 int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
                 int max_grid, int* grid_out, int chunk_shift) {
     using L = PairLayout<K, NC, PPT>;
@@ -650,7 +660,9 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.n_steps = n_steps;
     a.opbase = reinterpret_cast<const unsigned char*>(c->d_pmats);
     a.codes = c->d_codes;
-    a.pitch = PACKED ? c->code_pitch / 2 : c->code_pitch;
+    a.pitch = CM == CODES_BYTE ? c->code_pitch : (CM == CODES_NIBBLE ? c->code_pitch / 2 : c->code_pitch / 4);
+    a.codes_hi = c->d_codes + (size_t)c->n_tips * (c->code_pitch / 4);
+    a.pitch_hi = c->code_pitch / 8;
     a.scratch = c->d_scratch;
     a.n_slots = n_slots;
     a.freqs = c->model_freqs();
@@ -666,7 +678,7 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.chunk_shift = chunk_shift;
     a.error = c->d_flags + kMaxFlagChunks;
     for (int i = 0; i < 4; ++i) a.ipi[i] = SYM ? 1.0 / c->h_freqs[i] : 1.0;
-    auto kern = dna_pair_kernel<K, NC, PPT, PACKED, PIPE, SYM>;
+    auto kern = dna_pair_kernel<K, NC, PPT, CM, PIPE, SYM>;
     const size_t smem = L::WARP_BYTES + 256;   // + the per-lane running sums
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -712,34 +724,39 @@ int pair_ppt(const Ctx* c) {
 }
 
 template <int K, int NC, int PPT>
-int launch_pair_v(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
+int launch_pair_v(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
                   int* grid_out, int chunk_shift) {
     const int cs = chunk_shift < 0 ? 0 : chunk_shift;
-    const int flavour = (packed ? 4 : 0) | (chunk_shift >= 0 ? 2 : 0) | (pair_sym(c) ? 1 : 0);
+    const int flavour = mode * 4 + (chunk_shift >= 0 ? 2 : 0) + (pair_sym(c) ? 1 : 0);
     switch (flavour) {
-#define PHB_PAIR_FLAVOUR(F_, PACKED_, PIPE_, SYM_) \
-    case F_: return launch_pair<K, NC, PPT, PACKED_, PIPE_, SYM_>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
-        PHB_PAIR_FLAVOUR(0, false, false, false)
-        PHB_PAIR_FLAVOUR(1, false, false, true)
-        PHB_PAIR_FLAVOUR(2, false, true, false)
-        PHB_PAIR_FLAVOUR(3, false, true, true)
-        PHB_PAIR_FLAVOUR(4, true, false, false)
-        PHB_PAIR_FLAVOUR(5, true, false, true)
-        PHB_PAIR_FLAVOUR(6, true, true, false)
-        PHB_PAIR_FLAVOUR(7, true, true, true)
+#define PHB_PAIR_FLAVOUR(F_, CM_, PIPE_, SYM_) \
+    case F_: return launch_pair<K, NC, PPT, CM_, PIPE_, SYM_>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+        PHB_PAIR_FLAVOUR(0, CODES_BYTE, false, false)
+        PHB_PAIR_FLAVOUR(1, CODES_BYTE, false, true)
+        PHB_PAIR_FLAVOUR(2, CODES_BYTE, true, false)
+        PHB_PAIR_FLAVOUR(3, CODES_BYTE, true, true)
+        PHB_PAIR_FLAVOUR(4, CODES_NIBBLE, false, false)
+        PHB_PAIR_FLAVOUR(5, CODES_NIBBLE, false, true)
+        PHB_PAIR_FLAVOUR(6, CODES_NIBBLE, true, false)
+        PHB_PAIR_FLAVOUR(7, CODES_NIBBLE, true, true)
 #undef PHB_PAIR_FLAVOUR
     }
-    return PHB_ERR_INVALID;
+    // split 3-bit codes: look-up tables of at most 8 rows, reversible models (the symmetric-block walk)
+    if constexpr (NC == 8) {
+        if (flavour == 9) return launch_pair<K, NC, PPT, CODES_SPLIT3, false, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+        if (flavour == 11) return launch_pair<K, NC, PPT, CODES_SPLIT3, true, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
+    }
+    return c->fail(PHB_ERR_UNSUPPORTED, "split 3-bit tip codes need a look-up table of at most 8 rows and a reversible model");
 }
 
-int launch_pair_k(Ctx* c, bool packed, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
+int launch_pair_k(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
                   int* grid_out, int chunk_shift = -1) {
     static_assert(kTipTabCodes == 16, "tip tables are staged with 8 or 16 rows per category");
     const int key = c->K * 1000 + tip_table_rows(c) * 10 + pair_ppt(c);
     switch (key) {
 #define PHB_PAIR_CASE(K_, NC_, PPT_) \
     case K_ * 1000 + NC_ * 10 + PPT_: \
-        return launch_pair_v<K_, NC_, PPT_>(c, packed, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift);
+        return launch_pair_v<K_, NC_, PPT_>(c, mode, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift);
         PHB_PAIR_CASE(1, 8, 2)
         PHB_PAIR_CASE(1, 16, 2)
         PHB_PAIR_CASE(2, 8, 2)
@@ -922,7 +939,7 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
     int grid = 0;
     const int tile = 32 * pair_ppt(c);
     const int64_t n_tiles = (c->S + tile - 1) / tile;
-    st = launch_pair_k(c, c->codes_packed, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
+    st = launch_pair_k(c, c->codes_mode, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
     if (st) return st;
     c->resident_slots = n_slots;
     return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
@@ -935,7 +952,11 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
 // packed: two 4-bit codes per byte (even pattern in the low nibble), rows of (S + 1) / 2 bytes - half the bytes over
 // PCIe.  Flags and data are written by memcpy from pinned memory only (copy engine): nothing here needs an SM while
 // the kernel occupies all of them.  One synchronisation at the very end (caller).
-int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b) {
+// mode CODES_SPLIT3: codes_host is the plane of 2-bit values, rows of (S + 3) / 4 bytes, codes_hi_host the plane of high
+// bits, rows of (S + 7) / 8 bytes - 3 / 8 of a byte per code over PCIe.
+int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_hi_host, int mode, int n_chunks, int root_a,
+                       int root_b) {
+    const bool packed = mode == CODES_NIBBLE;
     int n_steps = 0, n_slots = 0;
     int st = cached_pair_plan(c, 1, root_a, root_b, &n_steps, &n_slots);
     if (st) return st;
@@ -960,20 +981,29 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chu
     // the copy stream must not overtake work already queued on the compute stream (previous evaluation, flag reset)
     PHB_CUDA(c, cudaEventRecord(c->start_event, c->stream));
     PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
-    const size_t host_row = packed ? ((size_t)c->S + 1) / 2 : (size_t)c->S;
-    const size_t dev_pitch = packed ? c->code_pitch / 2 : c->code_pitch;
-    const int per_tile = packed ? tile / 2 : tile;   // bytes of one tile in a code row
-    c->codes_packed = packed;
+    const bool split = mode == CODES_SPLIT3;
+    const size_t host_row = split ? ((size_t)c->S + 3) / 4 : (packed ? ((size_t)c->S + 1) / 2 : (size_t)c->S);
+    const size_t dev_pitch = split ? c->code_pitch / 4 : (packed ? c->code_pitch / 2 : c->code_pitch);
+    const int per_tile = split ? tile / 4 : (packed ? tile / 2 : tile);   // bytes of one tile in a code row
+    const size_t host_row_hi = ((size_t)c->S + 7) / 8, dev_pitch_hi = c->code_pitch / 8;
+    uint8_t* const d_hi = c->d_codes_ws + (size_t)c->n_tips * (c->code_pitch / 4);
+    c->codes_packed = mode != CODES_BYTE;
+    c->codes_mode = mode;
     c->d_codes = c->d_codes_ws;
     for (int i = 0; i < n_chunks; ++i) {
         const int64_t b = tpc * i, e = std::min<int64_t>(tpc * (i + 1), n_tiles);
         const size_t c0 = (size_t)b * per_tile, c1 = std::min<size_t>((size_t)e * per_tile, host_row);
         PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws + c0, dev_pitch, codes_host + c0, host_row, c1 - c0, (size_t)c->n_tips,
                                       cudaMemcpyHostToDevice, c->copy_stream));
+        if (split) {
+            const size_t h0 = (size_t)b * (tile / 8), h1 = std::min<size_t>((size_t)e * (tile / 8), host_row_hi);
+            PHB_CUDA(c, cudaMemcpy2DAsync(d_hi + h0, dev_pitch_hi, codes_hi_host + h0, host_row_hi, h1 - h0, (size_t)c->n_tips,
+                                          cudaMemcpyHostToDevice, c->copy_stream));
+        }
         PHB_CUDA(c, cudaMemcpyAsync(c->d_flags + i, c->h_epoch, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
     }
     int grid = 0;
-    st = launch_pair_k(c, packed, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid, chunk_shift);
+    st = launch_pair_k(c, mode, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid, chunk_shift);
     if (st) return st;
     c->resident_slots = n_slots;
     c->pipelined_pending = true;

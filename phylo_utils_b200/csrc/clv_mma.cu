@@ -598,7 +598,6 @@ static int mma_dispatch(Ctx* c, const RowSet& rs, int mode, const MmaRow* d_frow
     }
     if (c->A == 61) {
         if (variant == 1) return run_rows_mma<61, 8, 16, 1, 8>(c, rs, mode, d_frows);  // 64 patterns per CTA
-        if (variant == 2) return run_rows_mma<61, 8, 16, 1, 16>(c, rs, mode, d_frows); // 128 patterns per CTA, 16 warps of 8
         return run_rows_mma<61, 8, 16, 2, 8>(c, rs, mode, d_frows);                    // 128 patterns per CTA
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "DMMA kernels cover 20 and 61 states");

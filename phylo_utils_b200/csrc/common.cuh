@@ -95,6 +95,7 @@ struct Ctx {
     // true after phb_lnl_from_host_packed: the buffer holds two 4-bit codes per byte (rows of code_pitch / 2
     // bytes), which only the pair kernel reads; every other consumer asks for phb_set_tips first
     bool codes_packed = false;
+    int codes_mode = 0;                // 0 one byte per code, 1 nibbles, 2 split 3-bit planes (pair_common.cuh CODES_*)
     double* d_lut = nullptr;           // [256][A]
     double* d_weights = nullptr;       // [S]
     double* d_clv = nullptr;           // [n_internal][S][K][A]
@@ -240,7 +241,8 @@ int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 // clv_dna_pair.cu: lnL-only walk, two patterns per lane (the default lnL-only path)
 int dna_pair_lnl(Ctx* c, int root_a, int root_b);
 int dna_pair_store(Ctx* c);   // all partials stored; PHB_ERR_UNSUPPORTED (no message) when the shape is not covered
-int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, bool packed, int n_chunks, int root_a, int root_b);
+int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_hi_host, int mode, int n_chunks, int root_a,
+                       int root_b);
 // up_dna_pair.cu: pre-order pass as one operand-resident walk; PHB_ERR_UNSUPPORTED (no message) when not covered
 int dna_up_walk(Ctx* c, int node_a, int node_b);
 // clv_generic.cu (any A <= 64, any K <= 16)

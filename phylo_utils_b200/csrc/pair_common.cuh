@@ -45,14 +45,30 @@ struct PairLayout {
 //                   (pattern-major rows, padded to ROWB bytes so that 128-bit accesses are conflict-free)
 constexpr int LAYOUT_PRIVATE = 0, LAYOUT_ARRAY = 1;
 
+// How the tip codes of a tile reach the kernel (CM): one byte per code; two 4-bit codes per byte; or - look-up tables of
+// at most 8 rows, i.e. any alignment without partial ambiguity codes - 3 bits per code split into a plane of 2-bit
+// values (the low bits, TILE / 4 bytes per tile) and a plane of single bits (the high bit, TILE / 8 bytes per tile).
+constexpr int CODES_BYTE = 0, CODES_NIBBLE = 1, CODES_SPLIT3 = 2;
+
 // the PPT codes of a lane, as byte offsets of their tip-table rows
-template <int NC, int PPT, bool PACKED, int LAYOUT>
+template <int NC, int PPT, int CM, int LAYOUT>
 __device__ __forceinline__ void table_rows(const unsigned char* codes, int lane, int (&row)[PPT]) {
     if (LAYOUT == LAYOUT_ARRAY) {
 #pragma unroll
         for (int p = 0; p < PPT; ++p) row[p] = (int)(codes[lane + 32 * p] & (NC - 1)) * 32;
         return;
     }
+    if (CM == CODES_SPLIT3) {
+        // low plane at [0, TILE / 4), high plane behind it; the lane's PPT patterns are adjacent
+        constexpr int TILE = 32 * PPT;
+        const unsigned lo = PPT == 2 ? ((unsigned)codes[lane >> 1] >> (4 * (lane & 1))) & 15u : (unsigned)codes[lane];
+        const unsigned hi = PPT == 2 ? ((unsigned)codes[TILE / 4 + (lane >> 2)] >> (2 * (lane & 3))) & 3u
+                                     : ((unsigned)codes[TILE / 4 + (lane >> 1)] >> (4 * (lane & 1))) & 15u;
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) row[p] = (int)((((lo >> (2 * p)) & 3u) | (((hi >> p) & 1u) << 2)) & (NC - 1)) * 32;
+        return;
+    }
+    constexpr bool PACKED = CM == CODES_NIBBLE;
     unsigned raw;
     if (PACKED) raw = PPT == 2 ? (unsigned)codes[lane] : (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane);
     else raw = PPT == 2 ? (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane)

@@ -206,6 +206,41 @@ class LikelihoodEngine(object):
                                    ctypes.c_void_p(out.ctypes.data)))
         return out
 
+    @staticmethod
+    def split_codes(codes):
+        """uint8 (n_tips, n_patterns) codes < 8 -> (low plane (n_tips, ceil(n/4)), high plane (n_tips, ceil(n/8))): 3 bits per
+        code, the input format of ``lnl_from_host_split`` (look-up tables of at most 8 rows)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        if codes.ndim != 2:
+            raise ValueError("codes must be (n_tips, n_patterns)")
+        low = np.empty((codes.shape[0], (codes.shape[1] + 3) // 4), dtype=np.uint8)
+        high = np.empty((codes.shape[0], (codes.shape[1] + 7) // 8), dtype=np.uint8)
+        check(lib().phb_split_codes(ctypes.c_void_p(codes.ctypes.data), codes.shape[0], codes.shape[1],
+                                    ctypes.c_void_p(low.ctypes.data), ctypes.c_void_p(high.ctypes.data)))
+        return low, high
+
+    def _split_planes(self, planes):
+        low, high = (np.ascontiguousarray(p, dtype=np.uint8) for p in planes)
+        if low.shape != (self.n_tips, (self.n_patterns + 3) // 4) or high.shape != (self.n_tips, (self.n_patterns + 7) // 8):
+            raise ValueError("split codes must be ({0}, ceil({1}/4)) and ({0}, ceil({1}/8))".format(self.n_tips, self.n_patterns))
+        return low, high
+
+    def lnl_from_host_split(self, planes, node_a, node_b, length, n_chunks=0, want_pattern=False):
+        """``lnl_from_host`` from the two planes of ``split_codes`` (pinned host memory)."""
+        low, high = self._split_planes(planes)
+        total = ctypes.c_double(0.0)
+        pattern = np.empty(self.n_patterns) if want_pattern else None
+        self._ok(self._lib.phb_lnl_from_host_split(self._ctx, ctypes.c_void_p(low.ctypes.data), ctypes.c_void_p(high.ctypes.data),
+                                                   int(n_chunks), int(node_a), int(node_b), float(length), ctypes.byref(total),
+                                                   dptr(pattern) if want_pattern else None))
+        return total.value, pattern
+
+    def lnl_from_host_split_async(self, planes, node_a, node_b, length, n_chunks=0):
+        low, high = self._split_planes(planes)
+        self._keep["host_codes"] = (low, high)    # the copy engine reads them until the evaluation is complete
+        self._ok(self._lib.phb_lnl_from_host_split_async(self._ctx, ctypes.c_void_p(low.ctypes.data), ctypes.c_void_p(high.ctypes.data),
+                                                         int(n_chunks), int(node_a), int(node_b), float(length)))
+
     def lnl_from_host(self, codes, node_a, node_b, length, n_chunks=0, want_pattern=False, packed=False):
         """Evaluate starting from host tip codes (numpy uint8, ideally pinned); copy and compute overlap.
         codes is (n_tips, n_patterns), or with packed=True the output of ``pack_codes``."""
@@ -254,6 +289,13 @@ class LikelihoodEngine(object):
         self._ok(self._lib.phb_edge_derivatives_async(self._ctx, nodes.shape[0], iptr(nodes), dptr(lengths),
                                                       1 if chain_rule else 0))
         return nodes.shape[0]
+
+    @property
+    def result_capacity(self):
+        """Doubles the context's device result buffer holds (3 per edge of the tree, at least 256)."""
+        ptr, cap = ctypes.c_void_p(), ctypes.c_int64(0)
+        self._ok(self._lib.phb_device_result(self._ctx, ctypes.byref(ptr), ctypes.byref(cap)))
+        return int(cap.value)
 
     def result_tensor(self, n):
         """The first ``n`` doubles of the context's device result buffer as a torch tensor VIEW (no copy): what a

@@ -201,8 +201,18 @@ class ShardedTreeModel(object):
 
     def edge_derivatives(self, nodes, lengths=None, chain_rule=True):
         if self._device_sums():
-            view = self.local.edge_derivatives_enqueue(nodes, lengths, chain_rule)
-            return self._reduce_in_place(view.view(-1)).reshape(-1, 3)
+            nodes = np.asarray(nodes, dtype=np.int32)
+            if lengths is None:
+                lengths = self.local.lengths_above(nodes)
+            lengths = np.asarray(lengths, dtype=np.double)
+            # the device result buffer holds 3 sums for every edge of the tree; longer lists (the same edge at several
+            # trial lengths) go out in pieces
+            cap = max(1, self.local.engine.result_capacity // 3)
+            out = np.empty((nodes.shape[0], 3))
+            for lo in range(0, nodes.shape[0], cap):
+                view = self.local.edge_derivatives_enqueue(nodes[lo:lo + cap], lengths[lo:lo + cap], chain_rule)
+                out[lo:lo + cap] = self._reduce_in_place(view.view(-1)).reshape(-1, 3)
+            return out
         part = self.local.edge_derivatives(nodes, lengths, chain_rule)
         if self.world > 1:
             self.collectives += 1

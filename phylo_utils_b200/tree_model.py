@@ -359,18 +359,25 @@ class TreeModel(object):
         return self.engine.result_tensor(1)
 
     def lnl_from_host_codes(self, packed_codes, node_a=None, node_b=None, n_chunks=0, enqueue_only=False):
-        """lnL of a NEW alignment over the same taxa, tree and models, starting from pinned HOST codes (two 4-bit codes
-        per byte, ``LikelihoodEngine.pack_codes``; rows in the order of the alignment given to ``set_tip_codes``):
-        the host-to-device copy is pipelined with the pruning (``phb_lnl_from_host_packed``).  lnL-only models
+        """lnL of a NEW alignment over the same taxa, tree and models, starting from pinned HOST codes: two 4-bit codes
+        per byte (``LikelihoodEngine.pack_codes``) or, as a ``(low, high)`` tuple, the 3-bit planes of
+        ``LikelihoodEngine.split_codes`` (look-up tables of at most 8 rows); rows in ``tip_row_order``.  The
+        host-to-device copy is pipelined with the pruning (``phb_lnl_from_host_packed`` / ``_split``).  lnL-only models
         (``store_partials=False``).  ``enqueue_only``: as ``lnl_enqueue``."""
         if self.store_partials or self.ascbias:
             raise ValueError("lnl_from_host_codes needs an lnL-only model (store_partials=False) without asc-bias correction")
         if node_a is None:
             node_a, node_b = self.traversal.root_edge
         length = self._edge_length(node_a, node_b)
+        split = isinstance(packed_codes, (tuple, list))
         if enqueue_only:
-            self.engine.lnl_from_host_packed_async(packed_codes, node_a, node_b, length, n_chunks)
+            if split:
+                self.engine.lnl_from_host_split_async(packed_codes, node_a, node_b, length, n_chunks)
+            else:
+                self.engine.lnl_from_host_packed_async(packed_codes, node_a, node_b, length, n_chunks)
             return self.engine.result_tensor(1)
+        if split:
+            return self.engine.lnl_from_host_split(packed_codes, node_a, node_b, length, n_chunks=n_chunks)[0]
         return self.engine.lnl_from_host(packed_codes, node_a, node_b, length, n_chunks=n_chunks, packed=True)[0]
 
     # ------------------------------------------------------------------------------------------

@@ -117,3 +117,22 @@ def test_compression_and_context_entry_points_fail_loudly_without_a_gpu():
     from phylo_utils_b200 import LikelihoodEngine
     with pytest.raises(RuntimeError):
         LikelihoodEngine(4, 10, 4, 4)
+
+
+def test_code_packing_helpers_round_trip():
+    import numpy as np
+    from phylo_utils_b200 import LikelihoodEngine
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 8, 9, 64, 1001):
+        codes = rng.integers(0, 8, size=(5, n)).astype(np.uint8)
+        low, high = LikelihoodEngine.split_codes(codes)
+        assert low.shape == (5, (n + 3) // 4) and high.shape == (5, (n + 7) // 8)
+        s = np.arange(n)
+        got = ((low[:, s // 4] >> (2 * (s % 4))) & 3) | (((high[:, s // 8] >> (s % 8)) & 1) << 2)
+        assert np.array_equal(got, codes)
+        packed = LikelihoodEngine.pack_codes(codes)
+        assert np.array_equal((packed[:, s // 2] >> (4 * (s % 2))) & 15, codes)
+    with pytest.raises(ValueError):
+        LikelihoodEngine.split_codes(np.full((2, 3), 8, dtype=np.uint8))
+    with pytest.raises(ValueError):
+        LikelihoodEngine.pack_codes(np.full((2, 3), 16, dtype=np.uint8))

@@ -69,9 +69,15 @@ def _worker(rank, world, port, out_dir, n_gpus):
     d = tm.edge_derivatives(nodes)
     d_host = tm.local.edge_derivatives(nodes)     # this rank's share only
     n_coll = tm.collectives
+    # more (edge, trial length) pairs than the device result buffer holds: goes out in pieces
+    reps = tm.local.engine.result_capacity // (3 * len(nodes)) + 2
+    d_long = tm.edge_derivatives(np.tile(nodes, reps))
+    assert np.array_equal(d_long, np.tile(d, (reps, 1))) and tm.collectives > n_coll + 1
 
     # lnL-only model: resident walk and the host-fed (pipelined, packed) evaluation of this rank's shard
     lo, hi = shard_bounds(codes.shape[1], rank, world)
+    used = np.unique(codes)                       # the look-up table restricted to the rows this alignment uses (4 or 5 of 15)
+    codes, lut = np.searchsorted(used, codes).astype(np.uint8), lut[used]
     tl = ShardedTreeModel(device=device, store_partials=False)
     tl.set_tree(tree(g))
     tl.set_tip_codes(codes, lut, names, sw, ii)
@@ -82,6 +88,9 @@ def _worker(rank, world, port, out_dir, n_gpus):
     order = tl.local.tip_row_order
     packed = phy.LikelihoodEngine.pack_codes(np.ascontiguousarray(codes[order][:, lo:hi]))
     total_from_host = tl.lnl_from_host_codes(packed, n_chunks=4)
+    planes = phy.LikelihoodEngine.split_codes(np.ascontiguousarray(codes[order][:, lo:hi]))
+    assert lut.shape[0] <= 8
+    assert tl.lnl_from_host_codes(planes, n_chunks=3) == total_from_host      # 3 bits per code in two planes: same bits out
 
     # Lewis ascertainment-bias correction under sharding: dummy patterns on every rank, no broadcast
     ga, _, codes_a, lut_a, sw_a, ii_a, names_a, model_a, rate_a = problem("ascbias_gtr_g4")

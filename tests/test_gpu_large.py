@@ -209,6 +209,19 @@ def test_pipelined_evaluation_from_host_codes_matches_resident():
     assert np.array_equal(p5, p2)
     with pytest.raises(RuntimeError):
         tm.engine.get_partials(tm.traversal.names[names[0]])
+    # three bits per code in two planes (look-up tables of at most 8 rows): same bits out, 3/8 of the bytes in
+    low, high = (torch.from_numpy(x).pin_memory().numpy() for x in phy.LikelihoodEngine.split_codes(other))
+    assert low.shape == (other.shape[0], other.shape[1] // 4) and high.shape == (other.shape[0], other.shape[1] // 8)
+    for chunks in (1, 5, 16):
+        t6, p6 = tm.engine.lnl_from_host_split((low, high), a, b, length, n_chunks=chunks, want_pattern=True)
+        assert np.array_equal(p6, p2)
+        assert_lnl_close(t6, t2)
+    t7, p7 = tm.engine.lnl_resident(a, b, length, want_pattern=True)       # the device keeps the split codes
+    assert np.array_equal(p7, p2)
+    assert tm.lnl_from_host_codes((low, high)) == t6                       # the TreeModel-level call
+    tm.engine.set_tips(codes, lut, tm._tip_rows()[1])                      # back to one byte per code
+    t8, p8 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
+    assert np.array_equal(p8, pattern)
 
 
 @pytest.mark.parametrize("n_pat", [1, 2, 63, 64, 65, 127, 4097])
@@ -232,6 +245,9 @@ def test_packed_codes_ragged_pattern_counts(n_pat):
         t, p = tm.engine.lnl_from_host(src, a, b, length, want_pattern=True, packed=packed)
         assert_lnl_close(p, want)
         assert_lnl_close(t, float(np.dot(want, w)))
+    t, p = tm.engine.lnl_from_host_split(phy.LikelihoodEngine.split_codes(codes), a, b, length, want_pattern=True)
+    assert_lnl_close(p, want)
+    assert_lnl_close(t, float(np.dot(want, w)))
 
 
 def test_four_patterns_per_lane_knob_gives_the_same_answer(monkeypatch):
@@ -256,6 +272,8 @@ def test_four_patterns_per_lane_knob_gives_the_same_answer(monkeypatch):
     t4, p4 = tm.engine.lnl_resident(a, b, length, want_pattern=True)
     packed = phy.LikelihoodEngine.pack_codes(codes)
     t4p, p4p = tm.engine.lnl_from_host(packed, a, b, length, n_chunks=7, want_pattern=True, packed=True)
+    t4s, p4s = tm.engine.lnl_from_host_split(phy.LikelihoodEngine.split_codes(codes), a, b, length, n_chunks=7, want_pattern=True)
+    assert np.array_equal(p4s, p4p)
     monkeypatch.delenv("PHB_PAIR_PPT")
     _lib.lib().phb_reload_tuning()
     assert_lnl_close(p4, p2)
