@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--patterns", type=int, default=1000000, help="site patterns of the WHOLE alignment (split over the GPUs)")
     ap.add_argument("--cpu-patterns", type=int, default=20000, help="pattern sample for the CPU baseline")
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--chunks", type=int, default=64, help="host->device pipeline depth of the e2e path")
+    ap.add_argument("--chunks", type=int, default=0, help="host->device pipeline depth of the e2e path (0: the library's rule, ~4 MB per chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-stored", action="store_true", help="skip the 'partials stored' measurements (HBM rooflines)")

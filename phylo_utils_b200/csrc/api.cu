@@ -846,7 +846,14 @@ static int lnl_from_host(phb_ctx* c, const uint8_t* codes, const uint8_t* codes_
     if (st) return st;
     c->have_partials = false;
     c->have_up = false;
-    if (n_chunks <= 0) n_chunks = 64;   // measured at 1000 x 1M: 16 -> 68.6, 64 -> 69.9 evaluations/s
+    if (n_chunks <= 0) {
+        // about 4 MB per chunk, between 4 and 64 chunks: at 1000 x 1M (0.5 GB of nibbles) 64 chunks beat 16 (69.9 vs 68.6
+        // evaluations/s); at an eighth of that per GPU with eight GPUs on one host, 64 chunks are 192 small copies per
+        // step and process, and their issue cost - not the bytes - bounds the evaluation
+        const size_t per_code_x8 = mode == 0 ? 8 : (mode == 1 ? 4 : 3);
+        const size_t bytes = (size_t)c->n_tips * (size_t)c->S * per_code_x8 / 8;
+        n_chunks = (int)std::min<size_t>(64, std::max<size_t>(4, bytes >> 22));
+    }
     st = dna_pair_from_host(c, codes, codes_hi, mode, n_chunks, node_a, node_b);
     if (st) return st;
     if (total == nullptr) return PHB_OK;   // stream-ordered form: phb_result_fetch / phb_sync complete the evaluation
