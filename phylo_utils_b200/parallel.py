@@ -79,7 +79,9 @@ class ShardedTreeModel(object):
     Every rank calls every method (SPMD); scalar results are identical on all ranks.
     """
 
-    def __init__(self, device=None, up_partials=False, mode="auto", store_partials=True):
+    def __init__(self, device=None, up_partials=False, mode="auto", store_partials=True, local_model=None):
+        """``local_model``: the per-rank model object (default: a ``TreeModel`` on this rank's GPU).  Anything with
+        TreeModel's methods will do - the CPU tests of the sharding logic plug in a stand-in."""
         dist = _dist()
         self.rank = dist.get_rank() if dist else 0
         self.world = dist.get_world_size() if dist else 1
@@ -87,7 +89,8 @@ class ShardedTreeModel(object):
             import os
             device = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = device
-        self.local = TreeModel(device=device, up_partials=up_partials, mode=mode, store_partials=store_partials)
+        self.local = local_model if local_model is not None else TreeModel(
+            device=device, up_partials=up_partials, mode=mode, store_partials=store_partials)
         self._torch_device = None
         self.n_patterns = None
         self.collectives = 0          # all-reduces / all-gathers issued so far (bench and tests read it)
@@ -163,7 +166,7 @@ class ShardedTreeModel(object):
     def _device_sums(self):
         """True when the local sums can stay on the device on their way through the collective."""
         m = self.local
-        return _dist() is not None and self.world > 1 and not m.ascbias and \
+        return _dist() is not None and self.world > 1 and not m.ascbias and hasattr(m, "lnl_enqueue") and \
             getattr(m.substitution_model, "has_real_eigensystem", True)
 
     def _reduce_in_place(self, view):
