@@ -112,16 +112,10 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     constexpr int HALF = (A - 1) / 2;                 // 16-byte pieces of an odd row
     static_assert(!ODD || (HALF + 2 <= 32 && A + 1 <= LDL), "one piece per lane; room for the shift");
     const bool fast = ODD && (p.K % 2 == 0) && p.pimg != nullptr;
-    // piece `lane` of a row whose first element is 16-byte aligned (sh == 0) or 8 bytes off (sh == 1)
-    auto piece_of = [&](int sh, int& j0, int& bytes) {
-        if (sh == 0) {
-            j0 = 2 * lane;
-            bytes = lane < HALF ? 16 : (lane == HALF ? 8 : 0);
-        } else {
-            j0 = lane == 0 ? 0 : 2 * lane - 1;
-            bytes = lane == 0 ? 8 : (lane <= HALF ? 16 : 0);
-        }
-    };
+    // A row = HALF 16-byte pieces (lane = piece, lanes 0 .. HALF-1, first element 2 lane + sh) + ONE 8-byte piece
+    // (element A-1 of an unshifted row, element 0 of a shifted one).  The 8-byte pieces of a warp's rows are moved by one
+    // instruction, lane = row - not by one lane walking the rows alone while 31 wait.
+    static_assert(!ODD || NT * 8 <= 16, "lane = row for the 8-byte pieces (rows 0..15), lane - 16 = row for the zeroing");
 
     // a P block or tip table -> the staging buffer: rows of A doubles, contiguous in shared memory too when LDP == A
     // (20 states: one 16-byte copy per two doubles instead of two 8-byte ones)
@@ -247,18 +241,18 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                 } else if (fast) {
                     const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
                     const double* g = p.clv + (((size_t)src_of(c) * S + wsite0) * K + k) * A;
-                    int j0, bytes;
-                    piece_of(sh, j0, bytes);
-                    const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld + j0 + sh);
-                    const double* q = g + j0;
-                    if (bytes == 16) {
+                    if (lane < HALF) {
+                        const int j0 = 2 * lane + sh;
+                        const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld + j0 + sh);
+                        const double* q = g + j0;
                         for (int n = 0; n < n_valid; ++n)
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + n * (LDL * 8)), "l"(q + (size_t)n * (K * A)) : "memory");
-                    } else if (bytes == 8) {
-                        for (int n = 0; n < n_valid; ++n)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst + n * (LDL * 8)), "l"(q + (size_t)n * (K * A)) : "memory");
-                    } else if (sh == 0 && lane == 31) {
-                        for (int n = 0; n < n_valid; ++n) Ld[n * LDL + A] = 0.0;   // stale element A-1 of a shifted row
+                    }
+                    if (lane < n_valid) {                     // the 8-byte piece of row `lane`
+                        const int j8 = sh == 0 ? A - 1 : 0;
+                        cp_async8(Ld + lane * LDL + j8 + sh, g + (size_t)lane * (K * A) + j8);
+                    } else if (sh == 0 && lane >= 16 && lane - 16 < n_valid) {
+                        Ld[(lane - 16) * LDL + A] = 0.0;      // column A may hold element A-1 of a shifted row
                     }
                 } else {
                     // rows of A doubles are 16-byte aligned when A is even (A = 20: ten 16-byte pieces per row)
@@ -365,15 +359,15 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     if (fast) {
                         // lane = piece, as on the way in: 16-byte loads from the shifted rows, 16-byte stores
                         const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
-                        int j0, bytes;
-                        piece_of(sh, j0, bytes);
-                        double* g = out + ((size_t)wsite0 * K + k) * A + j0;
-                        const double* src = myL + j0 + sh;
-                        if (bytes == 16) {
+                        double* g = out + ((size_t)wsite0 * K + k) * A;
+                        if (lane < HALF) {
+                            const int j0 = 2 * lane + sh;
                             for (int n = 0; n < n_valid; ++n)
-                                *reinterpret_cast<double2*>(g + (size_t)n * (K * A)) = *reinterpret_cast<const double2*>(src + n * LDL);
-                        } else if (bytes == 8) {
-                            for (int n = 0; n < n_valid; ++n) g[(size_t)n * (K * A)] = src[n * LDL];
+                                *reinterpret_cast<double2*>(g + (size_t)n * (K * A) + j0) = *reinterpret_cast<const double2*>(myL + n * LDL + j0 + sh);
+                        }
+                        if (lane < n_valid) {                 // the 8-byte piece of row `lane`
+                            const int j8 = sh == 0 ? A - 1 : 0;
+                            g[(size_t)lane * (K * A) + j8] = myL[lane * LDL + j8 + sh];
                         }
                     } else {
                         // coalesced: A contiguous doubles per pattern, in 16-byte pieces when A is even.  Columns >= A of
