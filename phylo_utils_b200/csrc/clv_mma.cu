@@ -261,12 +261,22 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     const unsigned char* g =
                         reinterpret_cast<const unsigned char*>(p.clv + (((size_t)src_of(c) * S + wsite0) * K + k) * A);
                     const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld);
-                    for (int e = lane; e < n_valid * PIECES; e += 32) {
-                        const int n = e / PIECES, piece = e - n * PIECES;
-                        const unsigned d = sdst + n * (LDL * 8) + piece * PB;
-                        const unsigned char* q = g + (size_t)n * (K * A * 8) + piece * PB;
-                        if (PB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
-                        else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
+                    if (PB == 16 && PIECES <= 16) {
+                        // a lane keeps its piece and walks the rows (32 / PIECES rows per trip): no index division per copy
+                        constexpr int RPT = 32 / PIECES;
+                        const int r0 = lane / PIECES, piece = lane - r0 * PIECES;
+                        if (r0 < RPT)
+                            for (int n = r0; n < n_valid; n += RPT)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + n * (LDL * 8) + piece * 16),
+                                             "l"(g + (size_t)n * (K * A * 8) + piece * 16) : "memory");
+                    } else {
+                        for (int e = lane; e < n_valid * PIECES; e += 32) {
+                            const int n = e / PIECES, piece = e - n * PIECES;
+                            const unsigned d = sdst + n * (LDL * 8) + piece * PB;
+                            const unsigned char* q = g + (size_t)n * (K * A * 8) + piece * PB;
+                            if (PB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q) : "memory");
+                            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(q) : "memory");
+                        }
                     }
                 }
                 cp_async_commit_all();
@@ -376,14 +386,23 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         const int n_valid = (int)min((int64_t)WR, p.S - wsite0);
                         unsigned char* g = reinterpret_cast<unsigned char*>(out + ((size_t)wsite0 * K + k) * A);
                         const unsigned char* src = reinterpret_cast<const unsigned char*>(myL);
-                        for (int e = lane; e < n_valid * PIECES; e += 32) {
-                            const int n = e / PIECES, piece = e - n * PIECES;
-                            if (PB == 16)
-                                *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
-                                    *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
-                            else
-                                *reinterpret_cast<double*>(g + (size_t)n * (K * A * 8) + piece * 8) =
-                                    *reinterpret_cast<const double*>(src + n * (LDL * 8) + piece * 8);
+                        if (PB == 16 && PIECES <= 16) {
+                            constexpr int RPT = 32 / PIECES;
+                            const int r0 = lane / PIECES, piece = lane - r0 * PIECES;
+                            if (r0 < RPT)
+                                for (int n = r0; n < n_valid; n += RPT)
+                                    *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
+                                        *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
+                        } else {
+                            for (int e = lane; e < n_valid * PIECES; e += 32) {
+                                const int n = e / PIECES, piece = e - n * PIECES;
+                                if (PB == 16)
+                                    *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
+                                        *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
+                                else
+                                    *reinterpret_cast<double*>(g + (size_t)n * (K * A * 8) + piece * 8) =
+                                        *reinterpret_cast<const double*>(src + n * (LDL * 8) + piece * 8);
+                            }
                         }
                     }
                     __syncwarp();
