@@ -237,6 +237,16 @@ int phb_lnl_from_host_packed_async(phb_ctx* ctx, const uint8_t* packed_codes, in
 int phb_lnl_from_host_split_async(phb_ctx* ctx, const uint8_t* low_plane, const uint8_t* high_plane, int n_chunks,
                                   int node_a, int node_b, double length);
 int phb_edge_derivatives_async(phb_ctx* ctx, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule);
+/* Pipelined host-fed evaluations (many alignments over one tree - bootstrap replicates, simulated data sets): up to TWO
+ * in flight.  phb_lnl_from_host_submit enqueues the copy of a new alignment (two codes per byte when high_plane is
+ * NULL, else the split 3-bit planes) into the code slot that is free and its walk behind whatever the stream holds;
+ * the copy engine works under the walk of the evaluation before.  The sum lands in device result[*slot_out] (an
+ * all-reduce may follow on the stream); phb_result_post enqueues its copy to the host, phb_result_wait blocks for
+ * that one evaluation only.  Post evaluation i before submitting i + 2 (its slot and result word are reused). */
+int phb_lnl_from_host_submit(phb_ctx* ctx, const uint8_t* codes, const uint8_t* high_plane, int n_chunks, int node_a,
+                             int node_b, double length, int* slot_out);
+int phb_result_post(phb_ctx* ctx, int slot);
+int phb_result_wait(phb_ctx* ctx, int slot, double* out);
 /* device address and capacity (in doubles) of the result buffer; it lies inside the caller's workspace when one
  * was given to phb_create */
 int phb_device_result(phb_ctx* ctx, void** device_ptr, int64_t* capacity_doubles);

@@ -66,6 +66,9 @@ SIGNATURES = {
     "phb_root_lnl_async": (c_int, [c_void_p, c_int, c_int, c_double]),
     "phb_lnl_from_host_packed_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double]),
     "phb_edge_derivatives_async": (c_int, [c_void_p, c_int, _ip, _dp, c_int]),
+    "phb_lnl_from_host_submit": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, POINTER(c_int)]),
+    "phb_result_post": (c_int, [c_void_p, c_int]),
+    "phb_result_wait": (c_int, [c_void_p, c_int, _dp]),
     "phb_device_result": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "phb_result_fetch": (c_int, [c_void_p, c_int, _dp]),
     "phb_op_clv": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

@@ -108,7 +108,7 @@ Plan make_plan(int n_tips, int64_t S, int K, int A, unsigned flags) {
     // parking area of the lnL-only resident kernel (4-state models): 160 SMs x 16 warps x 15 blocks
     p.scratch_size = A == 4 ? (size_t)160 * 16 * 15 * ((size_t)K * 1024 + 128) : 0;
     p.scratch = take(p.scratch_size);
-    p.flags = take((kMaxFlagChunks + 1) * sizeof(int));
+    p.flags = take(2 * (kMaxFlagChunks + 1) * sizeof(int));
     p.pattern_lnl = take((size_t)S * 8);
     p.cat_lnl = take((size_t)S * K * 8);
     p.partial = take((size_t)kPartialCap * 8);
@@ -381,7 +381,13 @@ int phb_destroy(phb_ctx* c) {
         cudaEventDestroy(c->start_event);
         cudaStreamDestroy(c->copy_stream);
     }
+    if (c->copy_stream)
+        for (int i = 0; i < 2; ++i) {
+            if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
+            if (c->result_event[i]) cudaEventDestroy(c->result_event[i]);
+        }
     if (c->h_epoch) cudaFreeHost(c->h_epoch);
+    if (c->h_results) cudaFreeHost(c->h_results);
     if (c->owns_ws && c->ws) cudaFree(c->ws);
     delete c;
     return PHB_OK;
@@ -1108,6 +1114,64 @@ int phb_root_lnl_async(phb_ctx* c, int node_a, int node_b, double length) {
 int phb_lnl_from_host_packed_async(phb_ctx* c, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
                                    double length) {
     return lnl_from_host(c, packed_codes, nullptr, 1, n_chunks, node_a, node_b, length, nullptr, nullptr);
+}
+
+// ---- pipelined host-fed evaluations: two in flight, the copy of one under the walk of the other ------------------
+int phb_lnl_from_host_submit(phb_ctx* c, const uint8_t* codes, const uint8_t* high_plane, int n_chunks, int node_a,
+                             int node_b, double length, int* slot_out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, codes != nullptr && slot_out != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host_submit: NULL argument");
+    PHB_REQUIRE(c, c->have_tips && c->have_schedule && c->have_model && c->have_lengths, PHB_ERR_STATE,
+                "phb_lnl_from_host_submit: tip layout (phb_set_tips), schedule, model and edge lengths must be set");
+    PHB_REQUIRE(c, dna_supported(c), PHB_ERR_UNSUPPORTED, "phb_lnl_from_host_submit: only 4-state models with K in {1,2,4,8}");
+    const int mode = high_plane != nullptr ? 2 : 1;
+    PHB_REQUIRE(c, c->n_codes <= (mode == 2 ? 8 : 16), PHB_ERR_UNSUPPORTED,
+                "phb_lnl_from_host_submit: the look-up table has too many rows for this code format");
+    st = build_eval_pmats(c, node_a, node_b, length);
+    if (st) return st;
+    c->have_partials = false;
+    c->have_up = false;
+    if (n_chunks <= 0) {
+        const size_t bytes = (size_t)c->n_tips * (size_t)c->S * (mode == 1 ? 4 : 3) / 8;
+        n_chunks = (int)std::min<size_t>(64, std::max<size_t>(4, bytes >> 22));
+    }
+    const int slot = c->next_slot;
+    st = dna_pair_from_host(c, codes, high_plane, mode, n_chunks, node_a, node_b, slot);
+    if (st) return st;
+    c->next_slot = 1 - slot;
+    *slot_out = slot;
+    return PHB_OK;
+}
+
+int phb_result_post(phb_ctx* c, int slot) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, (slot == 0 || slot == 1) && c->h_results != nullptr, PHB_ERR_INVALID, "phb_result_post: no such evaluation in flight");
+    PHB_CUDA(c, cudaMemcpyAsync(c->h_results + slot, c->d_result + slot, 8, cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaMemcpyAsync(reinterpret_cast<int*>(c->h_results + 2) + slot, c->d_flags + slot * (kMaxFlagChunks + 1) + kMaxFlagChunks,
+                                sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PHB_CUDA(c, cudaEventRecord(c->result_event[slot], c->stream));
+    return PHB_OK;
+}
+
+int phb_result_wait(phb_ctx* c, int slot, double* out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, (slot == 0 || slot == 1) && out != nullptr && c->h_results != nullptr, PHB_ERR_INVALID,
+                "phb_result_wait: no such evaluation in flight");
+    PHB_CUDA(c, cudaEventSynchronize(c->result_event[slot]));
+    int* const late = reinterpret_cast<int*>(c->h_results + 2) + slot;
+    if (*late) {
+        *late = 0;
+        cudaMemsetAsync(c->d_flags + slot * (kMaxFlagChunks + 1) + kMaxFlagChunks, 0, sizeof(int), c->stream);
+        return c->fail(PHB_ERR_CUDA, "phb_result_wait: a chunk of tip codes never arrived on the device");
+    }
+    *out = c->h_results[slot];
+    return PHB_OK;
 }
 
 int phb_edge_derivatives_async(phb_ctx* c, int n_edges, const int32_t* nodes, const double* lengths, int chain_rule) {

@@ -673,10 +673,11 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.S = c->S;
     a.tile_begin = tile_begin;
     a.tile_end = tile_end;
-    a.flags = c->d_flags;
+    int* const flags = c->d_flags_cur != nullptr ? c->d_flags_cur : c->d_flags;
+    a.flags = flags;
     a.epoch = c->flag_epoch;
     a.chunk_shift = chunk_shift;
-    a.error = c->d_flags + kMaxFlagChunks;
+    a.error = flags + kMaxFlagChunks;
     for (int i = 0; i < 4; ++i) a.ipi[i] = SYM ? 1.0 / c->h_freqs[i] : 1.0;
     auto kern = dna_pair_kernel<K, NC, PPT, CM, PIPE, SYM>;
     const size_t smem = L::WARP_BYTES + 256;   // + the per-lane running sums
@@ -955,8 +956,11 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
 // mode CODES_SPLIT3: codes_host is the plane of 2-bit values, rows of (S + 3) / 4 bytes, codes_hi_host the plane of high
 // bits, rows of (S + 7) / 8 bytes - 3 / 8 of a byte per code over PCIe.
 int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_hi_host, int mode, int n_chunks, int root_a,
-                       int root_b) {
+                       int root_b, int slot) {
     const bool packed = mode == CODES_NIBBLE;
+    const bool pipelined = slot >= 0;
+    const int s = pipelined ? slot : 0;
+    if (pipelined && mode == CODES_BYTE) return c->fail(PHB_ERR_UNSUPPORTED, "pipelined host-fed evaluations take packed codes (two slots must fit the code buffer)");
     int n_steps = 0, n_slots = 0;
     int st = cached_pair_plan(c, 1, root_a, root_b, &n_steps, &n_slots);
     if (st) return st;
@@ -964,10 +968,16 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_h
         PHB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < kMaxChunks; ++i) PHB_CUDA(c, cudaEventCreateWithFlags(&c->chunk_events[i], cudaEventDisableTiming));
         PHB_CUDA(c, cudaEventCreateWithFlags(&c->start_event, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            PHB_CUDA(c, cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming));
+            PHB_CUDA(c, cudaEventCreateWithFlags(&c->result_event[i], cudaEventDisableTiming));
+        }
     }
     if (c->h_epoch == nullptr) {
-        PHB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_epoch), 64, cudaHostAllocDefault));
-        PHB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, (kMaxFlagChunks + 1) * sizeof(int), c->stream));
+        PHB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_epoch), 128, cudaHostAllocDefault));   // one word per slot, 64 bytes apart
+        PHB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_results), 64, cudaHostAllocDefault));
+        PHB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * (kMaxFlagChunks + 1) * sizeof(int), c->stream));
+        PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // once per context: the copy stream must not race the reset
     }
     const int tile = 32 * pair_ppt(c);
     const int64_t n_tiles = (c->S + tile - 1) / tile;
@@ -977,37 +987,52 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_h
     const int64_t tpc = (int64_t)1 << chunk_shift;
     n_chunks = (int)((n_tiles + tpc - 1) / tpc);
     c->flag_epoch = c->flag_epoch >= (1 << 30) ? 1 : c->flag_epoch + 1;
-    *c->h_epoch = c->flag_epoch;
-    // the copy stream must not overtake work already queued on the compute stream (previous evaluation, flag reset)
-    PHB_CUDA(c, cudaEventRecord(c->start_event, c->stream));
-    PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
+    int* const h_epoch = c->h_epoch + 16 * s;      // the copy engine reads it when the flag copy executes: one word per slot
+    *h_epoch = c->flag_epoch;
+    int* const d_flags = c->d_flags + s * (kMaxFlagChunks + 1);
+    c->d_flags_cur = d_flags;
+    if (pipelined) {
+        // the copies may run ahead of the compute stream - that is the point - but not into a slot a queued walk still reads
+        PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->slot_done[s], 0));
+    } else {
+        // the copy stream must not overtake work already queued on the compute stream (previous evaluation, flag reset)
+        PHB_CUDA(c, cudaEventRecord(c->start_event, c->stream));
+        PHB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->start_event, 0));
+    }
     const bool split = mode == CODES_SPLIT3;
     const size_t host_row = split ? ((size_t)c->S + 3) / 4 : (packed ? ((size_t)c->S + 1) / 2 : (size_t)c->S);
     const size_t dev_pitch = split ? c->code_pitch / 4 : (packed ? c->code_pitch / 2 : c->code_pitch);
     const int per_tile = split ? tile / 4 : (packed ? tile / 2 : tile);   // bytes of one tile in a code row
     const size_t host_row_hi = ((size_t)c->S + 7) / 8, dev_pitch_hi = c->code_pitch / 8;
-    uint8_t* const d_hi = c->d_codes_ws + (size_t)c->n_tips * (c->code_pitch / 4);
+    uint8_t* const d_lo = c->d_codes_ws + (size_t)s * ((size_t)c->n_tips * c->code_pitch / 2);   // slot 1: the upper half
+    uint8_t* const d_hi = d_lo + (size_t)c->n_tips * (c->code_pitch / 4);
     c->codes_packed = mode != CODES_BYTE;
     c->codes_mode = mode;
-    c->d_codes = c->d_codes_ws;
+    c->d_codes = d_lo;
     for (int i = 0; i < n_chunks; ++i) {
         const int64_t b = tpc * i, e = std::min<int64_t>(tpc * (i + 1), n_tiles);
         const size_t c0 = (size_t)b * per_tile, c1 = std::min<size_t>((size_t)e * per_tile, host_row);
-        PHB_CUDA(c, cudaMemcpy2DAsync(c->d_codes_ws + c0, dev_pitch, codes_host + c0, host_row, c1 - c0, (size_t)c->n_tips,
+        PHB_CUDA(c, cudaMemcpy2DAsync(d_lo + c0, dev_pitch, codes_host + c0, host_row, c1 - c0, (size_t)c->n_tips,
                                       cudaMemcpyHostToDevice, c->copy_stream));
         if (split) {
             const size_t h0 = (size_t)b * (tile / 8), h1 = std::min<size_t>((size_t)e * (tile / 8), host_row_hi);
             PHB_CUDA(c, cudaMemcpy2DAsync(d_hi + h0, dev_pitch_hi, codes_hi_host + h0, host_row_hi, h1 - h0, (size_t)c->n_tips,
                                           cudaMemcpyHostToDevice, c->copy_stream));
         }
-        PHB_CUDA(c, cudaMemcpyAsync(c->d_flags + i, c->h_epoch, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+        PHB_CUDA(c, cudaMemcpyAsync(d_flags + i, h_epoch, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
     }
     int grid = 0;
     st = launch_pair_k(c, mode, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid, chunk_shift);
     if (st) return st;
     c->resident_slots = n_slots;
-    c->pipelined_pending = true;
-    return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
+    if (!pipelined) {
+        c->pipelined_pending = true;
+        return launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result);
+    }
+    st = launch_final_reduce(c, c->d_partial_sums, grid, 1, c->d_result + s);
+    if (st) return st;
+    PHB_CUDA(c, cudaEventRecord(c->slot_done[s], c->stream));
+    return PHB_OK;
 }
 
 }  // namespace phb

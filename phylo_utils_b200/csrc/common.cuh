@@ -152,7 +152,14 @@ struct Ctx {
     cudaEvent_t start_event = nullptr;
     // single-launch pipelining (clv_dna_pair.cu): per-chunk arrival flags + error word on the device, the epoch the
     // copy engine stamps them with (pinned host word), and whether an evaluation's error word is still unread
-    int* d_flags = nullptr;            // [kMaxFlagChunks + 1]
+    int* d_flags = nullptr;            // [2][kMaxFlagChunks + 1]: one set per code slot
+    int* d_flags_cur = nullptr;        // the set the next pair-kernel launch waits on
+    // pipelined host-fed evaluations (phb_lnl_from_host_submit): two code slots in the tip-code buffer (packed formats
+    // need at most half of it), so that the copy of evaluation i+1 runs under the walk of evaluation i
+    cudaEvent_t slot_done[2] = {};     // the walk that read slot s has finished (the copy stream waits for it)
+    cudaEvent_t result_event[2] = {};  // result s (and its error word) has reached h_results
+    double* h_results = nullptr;       // pinned: [2] sums, then [2] error words (as doubles' worth of ints)
+    int next_slot = 0;
     int* h_epoch = nullptr;
     int flag_epoch = 0;
     bool pipelined_pending = false;
@@ -241,8 +248,9 @@ int dna_root(Ctx* c, int a, int b, bool want_cat, bool store_root);
 // clv_dna_pair.cu: lnL-only walk, two patterns per lane (the default lnL-only path)
 int dna_pair_lnl(Ctx* c, int root_a, int root_b);
 int dna_pair_store(Ctx* c);   // all partials stored; PHB_ERR_UNSUPPORTED (no message) when the shape is not covered
+// slot < 0: immediate form (slot 0, ordered behind everything queued); slot 0 / 1: pipelined form, sum -> d_result[slot]
 int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_hi_host, int mode, int n_chunks, int root_a,
-                       int root_b);
+                       int root_b, int slot = -1);
 // up_dna_pair.cu: pre-order pass as one operand-resident walk; PHB_ERR_UNSUPPORTED (no message) when not covered
 int dna_up_walk(Ctx* c, int node_a, int node_b);
 // clv_generic.cu (any A <= 64, any K <= 16)

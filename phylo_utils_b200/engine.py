@@ -297,18 +297,45 @@ class LikelihoodEngine(object):
         self._ok(self._lib.phb_device_result(self._ctx, ctypes.byref(ptr), ctypes.byref(cap)))
         return int(cap.value)
 
-    def result_tensor(self, n):
-        """The first ``n`` doubles of the context's device result buffer as a torch tensor VIEW (no copy): what a
+    # ---- pipelined host-fed evaluations: two in flight ---------------------------------------------------
+    def host_fed_submit(self, codes, node_a, node_b, length, n_chunks=0):
+        """Enqueue the evaluation of a new alignment given as pinned host codes - ``pack_codes`` output, or the
+        ``(low, high)`` planes of ``split_codes`` - and return its slot (0 / 1).  Its copy runs under the walk of the
+        evaluation submitted before; ``result_post(slot)`` + ``result_wait(slot)`` deliver the sum."""
+        if isinstance(codes, (tuple, list)):
+            low, high = self._split_planes(codes)
+            hp = ctypes.c_void_p(high.ctypes.data)
+        else:
+            low = np.ascontiguousarray(codes, dtype=np.uint8)
+            if low.shape != (self.n_tips, (self.n_patterns + 1) // 2):
+                raise ValueError("packed codes must be {}".format((self.n_tips, (self.n_patterns + 1) // 2)))
+            high, hp = None, None
+        slot = ctypes.c_int(-1)
+        self._ok(self._lib.phb_lnl_from_host_submit(self._ctx, ctypes.c_void_p(low.ctypes.data), hp, int(n_chunks), int(node_a),
+                                                    int(node_b), float(length), ctypes.byref(slot)))
+        self._keep["host_codes_slot{}".format(slot.value)] = (low, high)      # read by the copy engine until the walk has run
+        return slot.value
+
+    def result_post(self, slot):
+        self._ok(self._lib.phb_result_post(self._ctx, int(slot)))
+
+    def result_wait(self, slot):
+        out = ctypes.c_double(0.0)
+        self._ok(self._lib.phb_result_wait(self._ctx, int(slot), ctypes.byref(out)))
+        return out.value
+
+    def result_tensor(self, n, offset=0):
+        """``n`` doubles of the context's device result buffer (from ``offset``) as a torch tensor VIEW (no copy): what a
         collective on the same stream reduces in place.  Needs the torch-owned workspace."""
         ws = self._keep.get("workspace")
         if ws is None:
             raise RuntimeError("result_tensor needs a torch-owned workspace (use_torch=True on a CUDA box)")
         ptr, cap = ctypes.c_void_p(), ctypes.c_int64(0)
         self._ok(self._lib.phb_device_result(self._ctx, ctypes.byref(ptr), ctypes.byref(cap)))
-        if not 0 <= n <= cap.value:
+        if not 0 <= n + offset <= cap.value:
             raise ValueError("the device result buffer holds {} doubles".format(cap.value))
         import torch
-        off = ptr.value - ws.data_ptr()
+        off = ptr.value - ws.data_ptr() + 8 * int(offset)
         return ws[off:off + 8 * int(n)].view(torch.float64)
 
     def result_fetch(self, n):

@@ -191,6 +191,19 @@ class ShardedTreeModel(object):
         return float(allreduce_sum([self.local.lnl_from_host_codes(packed_codes, node_a, node_b, n_chunks)],
                                    self._comm_device())[0])
 
+    def lnl_from_host_submit(self, packed_codes, node_a=None, node_b=None, n_chunks=0):
+        """Pipelined form of ``lnl_from_host_codes`` (``TreeModel.lnl_from_host_submit``): returns a handle whose
+        ``result()`` is the global lnL; the all-reduce of an evaluation is enqueued behind its walk when the next one is
+        submitted or its result is asked for."""
+        reduce = None
+        if self._device_sums():
+            def reduce(view):
+                _dist().all_reduce(view)
+                self.collectives += 1
+        elif self.world > 1:
+            raise ValueError("pipelined evaluations need the device-side reduction (a CUDA process group)")
+        return self.local.lnl_from_host_submit(packed_codes, node_a, node_b, n_chunks, reduce)
+
     def compute_likelihood_at_edge(self, node_a, node_b):
         _, pattern = self.local._pattern_lnl(node_a, node_b)
         pattern = pattern[:self.hi - self.lo]              # without the ascertainment-bias dummy patterns

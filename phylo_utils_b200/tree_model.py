@@ -38,6 +38,27 @@ logger = setup_logger()
 _TILE_MODE_MIN_PATTERNS = 16384
 
 
+class PendingLnl(object):
+    """One pipelined host-fed evaluation in flight (``TreeModel.lnl_from_host_submit``)."""
+
+    def __init__(self, model, slot, reduce=None):
+        self.model, self.slot, self._reduce, self._posted, self._value = model, slot, reduce, False, None
+
+    def post(self):
+        """Enqueue (not wait for) what follows the walk: the optional reduction over ranks, then the copy to the host."""
+        if not self._posted:
+            if self._reduce is not None:
+                self._reduce(self.model.engine.result_tensor(1, offset=self.slot))
+            self.model.engine.result_post(self.slot)
+            self._posted = True
+
+    def result(self):
+        if self._value is None:
+            self.post()
+            self._value = self.model.engine.result_wait(self.slot)
+        return self._value
+
+
 class TreeModel(object):
     alignment_codes = None
     ascbias = False
@@ -379,6 +400,28 @@ class TreeModel(object):
         if split:
             return self.engine.lnl_from_host_split(packed_codes, node_a, node_b, length, n_chunks=n_chunks)[0]
         return self.engine.lnl_from_host(packed_codes, node_a, node_b, length, n_chunks=n_chunks, packed=True)[0]
+
+    def lnl_from_host_submit(self, packed_codes, node_a=None, node_b=None, n_chunks=0, reduce=None):
+        """Pipelined ``lnl_from_host_codes``: enqueue the evaluation of one more alignment and return a ``PendingLnl``
+        whose ``result()`` delivers its lnL.  Up to two are in flight: the host-to-device copy of this one runs under the
+        walk of the one submitted before (many alignments over one tree - bootstrap replicates, simulated data).
+        ``reduce``: called with the device tensor view of the sum before it is copied back (``ShardedTreeModel`` passes
+        its all-reduce)."""
+        if self.store_partials or self.ascbias:
+            raise ValueError("lnl_from_host_submit needs an lnL-only model (store_partials=False) without asc-bias correction")
+        if node_a is None:
+            node_a, node_b = self.traversal.root_edge
+        length = self._edge_length(node_a, node_b)
+        pending = getattr(self, "_pending_lnl", None) or {}
+        for other in pending.values():
+            other.post()                              # their copies to the host go in front of the new walk
+        slot = self.engine.host_fed_submit(packed_codes, node_a, node_b, length, n_chunks)
+        if slot in pending:
+            pending[slot].result()                    # the slot's previous tenant: its value must be read before the word is reused
+        handle = PendingLnl(self, slot, reduce)
+        pending[slot] = handle
+        self._pending_lnl = pending
+        return handle
 
     # ------------------------------------------------------------------------------------------
     # attribute views of device state (reference attributes partials / scale / root_partials / root_scale)

@@ -91,6 +91,9 @@ def _worker(rank, world, port, out_dir, n_gpus):
     planes = phy.LikelihoodEngine.split_codes(np.ascontiguousarray(codes[order][:, lo:hi]))
     assert lut.shape[0] <= 8
     assert tl.lnl_from_host_codes(planes, n_chunks=3) == total_from_host      # 3 bits per code in two planes: same bits out
+    h0 = tl.lnl_from_host_submit(planes)                                       # two in flight, all-reduced on the device
+    h1 = tl.lnl_from_host_submit(packed)
+    assert h0.result() == total_from_host and h1.result() == total_from_host
 
     # Lewis ascertainment-bias correction under sharding: dummy patterns on every rank, no broadcast
     ga, _, codes_a, lut_a, sw_a, ii_a, names_a, model_a, rate_a = problem("ascbias_gtr_g4")

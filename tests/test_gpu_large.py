@@ -224,6 +224,59 @@ def test_pipelined_evaluation_from_host_codes_matches_resident():
     assert np.array_equal(p8, pattern)
 
 
+def test_two_host_fed_evaluations_in_flight():
+    """lnl_from_host_submit: alignments arrive one after the other on the host; the copy of one runs under the walk of the
+    one before.  Every result must be the bits the immediate call returns for that alignment, in order, whatever the mix of
+    code formats, and the two code slots / result words must not bleed into each other."""
+    import torch
+    tree, names, codes, lut = synthetic(90, 50021, 4, seed=31)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(store_partials=False)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    rng = np.random.default_rng(9)
+    aligns = [rng.integers(0, 5, size=codes.shape).astype(np.uint8) for _ in range(5)]
+    pin = lambda x: torch.from_numpy(x).pin_memory().numpy()        # noqa: E731
+    nibbles = [pin(phy.LikelihoodEngine.pack_codes(a)) for a in aligns]
+    planes = [tuple(pin(x) for x in phy.LikelihoodEngine.split_codes(a)) for a in aligns]
+    want = [tm.lnl_from_host_codes(n) for n in nibbles]
+    assert len(set(want)) == 5
+    # strictly alternating submit / result, depth two
+    got, pending = [], None
+    for i in range(5):
+        nxt = tm.lnl_from_host_submit(planes[i] if i % 2 else nibbles[i], n_chunks=(3, 0, 16)[i % 3])
+        if pending is not None:
+            got.append(pending.result())
+        pending = nxt
+    got.append(pending.result())
+    assert got == want
+    # results asked for late and out of order; a third submission forces the first slot's value out in time
+    h0 = tm.lnl_from_host_submit(planes[0])
+    h1 = tm.lnl_from_host_submit(planes[1])
+    h2 = tm.lnl_from_host_submit(nibbles[2])
+    assert (h2.result(), h0.result(), h1.result()) == (want[2], want[0], want[1])
+    # branch lengths may change between submissions
+    key = sorted(tm.traversal.brlens.keys())[4]
+    old = tm.traversal.brlens[key]
+    ha = tm.lnl_from_host_submit(planes[3])
+    tm.traversal.brlens[key] = old * 2.5
+    tm.compute_partials()
+    hb = tm.lnl_from_host_submit(planes[3])
+    assert ha.result() == want[3] and hb.result() == tm.lnl_from_host_codes(planes[3]) != want[3]
+    tm.traversal.brlens[key] = old
+    tm.compute_partials()
+    # afterwards the device holds the last alignment: the resident evaluation works on it
+    a, b = tm.traversal.root_edge
+    assert tm.lnl_from_host_submit(nibbles[4]).result() == want[4]
+    assert tm.engine.lnl_resident(a, b, tm.traversal.brlens[(a, b)])[0] == want[4]
+    with pytest.raises(ValueError):
+        tm.engine.host_fed_submit(aligns[0], a, b, 0.1)             # one byte per code: no room for two slots
+
+
 @pytest.mark.parametrize("n_pat", [1, 2, 63, 64, 65, 127, 4097])
 def test_packed_codes_ragged_pattern_counts(n_pat):
     tree, names, codes, lut = synthetic(33, n_pat, 4, seed=900 + n_pat)
