@@ -17,8 +17,11 @@ One "step" = one evaluation of the whole alignment through the product's own mul
             shard_bounds(1M, r, N)); the columns are generated in fixed blocks so the alignment - and hence lnL - is
             the same for every N.  `weak` (1M patterns PER GPU, what round 1 reported) is kept as an extra record.
   value     evaluations/s with the tip codes resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       the same evaluation starting from pinned HOST codes every step: ShardedTreeModel.lnl_from_host_codes
-            (C ABI phb_lnl_from_host_packed_async: two 4-bit codes per byte, copy pipelined with the pruning)
+  e2e       the same evaluation starting from pinned HOST codes every step (every step copies one alignment to the device
+            and reads one result back): ShardedTreeModel.lnl_from_host_submit / PendingLnl.result - C ABI
+            phb_lnl_from_host_submit: packed tip codes, the copy engine feeds the kernel chunk by chunk, and two
+            evaluations are in flight so that the copy of alignment i+1 runs under the walk of alignment i;
+            `e2e.one_at_a_time` is the same call sequence with the result on the host before the next evaluation is issued
   roofline  the dominant kernel timed alone.  The lnL-only walk keeps every intermediate on chip: it is bound by the
             fp64 / shared-memory pipes, NOT by HBM, and is reported as such (bound "fp64", denominator = the DFMA
             rate measured in this run); its algorithmic-byte rate is given for the record and labelled as what it
