@@ -407,7 +407,7 @@ def workload_config(args, world):
                     "split into {} pattern shard(s)".format(args.taxa, args.patterns, world),
         "taxa": args.taxa, "global_patterns": args.patterns, "patterns_per_gpu": args.patterns // world,
         "categories": NCAT, "states": 4, "tree": "random joins, seed {}".format(args.seed),
-        "parallelism": "pattern shards x{} (ShardedTreeModel, device all-reduce of the scalar)".format(world),
+        "parallelism": "pattern shards x{} (ShardedTreeModel, the scalar summed over ranks on the device)".format(world),
         "l2": "every evaluation re-reads its shard's tip codes ({} MB per GPU) and, in the stored-partials walks, streams "
               ">= 16 GB of node blocks: far beyond the 126 MB L2, no flush needed".format(args.taxa * (args.patterns // world) // 1000000),
     }
@@ -588,7 +588,7 @@ def main():
         e2e["bytes_are"] = "per GPU (its shard's tip codes + the branch lengths); x{} over the box".format(world)
         e2e["api"] = ("ShardedTreeModel.compute_partials() + lnl_from_host_submit(codes) / PendingLnl.result() -> TreeModel -> C ABI "
                       "phb_set_edge_lengths + phb_lnl_from_host_submit (pinned host tip codes, {} chunks, copied by the copy engine while "
-                      "the kernel already walks the first chunks and the previous alignment), device all-reduce, phb_result_post + "
+                      "the kernel already walks the first chunks and the previous alignment), sum over ranks on the device, phb_result_post + "
                       "phb_result_wait".format(args.chunks or "~4 MB"))
         e2e["other_format"] = other
         del packed, planes
@@ -660,7 +660,11 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "collectives_in_timed_region": int(collectives),
-            "path": "ShardedTreeModel(store_partials=False): lnL-only operand-resident walk per shard, device all-reduce",
+            "rank_sum": ("inside the reduction kernel: every rank stores its total into the peers' exchange buffers over NVLink "
+                         "(CUDA IPC) and adds what arrives in rank order - phb_peer_sum_next, no collective-library call"
+                         if getattr(tm, "peer_sums", False) else
+                         ("torch.distributed all_reduce in place on the device result buffer" if world > 1 else "single rank")),
+            "path": "ShardedTreeModel(store_partials=False): lnL-only operand-resident walk per shard, sum over ranks on the device",
             "with_stored_partials": stored, "weak_scaling": weak, "configs": configs, "sharded_parity": parity,
             "clocks": clocks.summary(), "lnl": lnl, "host_placement_rank0": numa,
             "site_node_updates_per_s": (n_taxa - 2) * n_pat * 1e3 / ms_per_step,

@@ -252,6 +252,21 @@ int phb_result_wait(phb_ctx* ctx, int slot, double* out);
 int phb_device_result(phb_ctx* ctx, void** device_ptr, int64_t* capacity_doubles);
 int phb_result_fetch(phb_ctx* ctx, int n, double* out);
 
+/* ---- the scalar sum over the ranks of ONE box inside the reduction kernel -----------------------------------------
+ * (no counterpart in the reference: it is one process, bin/phy.py:146.)  At 2 ms per evaluation on eight GPUs a
+ * collective-library call behind every evaluation is 2-3 % of the step.  Instead every rank owns a small exchange
+ * buffer (phb_peer_buffer returns its CUDA IPC handle, PHB_PEER_HANDLE_BYTES bytes), maps the buffers of all ranks
+ * (phb_peer_connect: `handles` = world handles in rank order, exchanged by the caller - e.g. one all_gather at set-up)
+ * and, when phb_peer_sum_next was called right before a stream-ordered scalar-lnL entry point (phb_lnl_resident_async,
+ * phb_root_lnl_async, phb_lnl_from_host_packed_async / _split_async / _submit), the kernel that reduces the per-CTA
+ * sums also stores the rank's total into every peer's buffer (NVLink), waits for the peers' totals and adds them in
+ * rank order: result[0] (or result[slot]) then holds the GLOBAL lnL, bit-identical on every rank.  Every rank must
+ * make the same sequence of such calls.  The wait is bounded (about a minute); a rank that never arrives yields NaN. */
+#define PHB_PEER_HANDLE_BYTES 64
+int phb_peer_buffer(phb_ctx* ctx, void* handle_out);
+int phb_peer_connect(phb_ctx* ctx, int rank, int world, const void* handles);
+int phb_peer_sum_next(phb_ctx* ctx);
+
 /* ---- stand-alone operators (host arrays in, host arrays out; reference-exact semantics) ------ */
 /* clv gufunc (numba_likelihood_engine.py:10-46): per-(site,category) natural-log scalers, rescale by the
  * category maximum when 0 < max < 2^-128.  p1,p2 [K][A][A]; clv1,clv2,out [S][K][A]; scalers [S][K]. */

@@ -71,6 +71,9 @@ SIGNATURES = {
     "phb_result_wait": (c_int, [c_void_p, c_int, _dp]),
     "phb_device_result": (c_int, [c_void_p, POINTER(c_void_p), _lp]),
     "phb_result_fetch": (c_int, [c_void_p, c_int, _dp]),
+    "phb_peer_buffer": (c_int, [c_void_p, c_void_p]),
+    "phb_peer_connect": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "phb_peer_sum_next": (c_int, [c_void_p]),
     "phb_op_clv": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "phb_op_lnl_node": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp]),
     "phb_op_lnl_branch": (c_int, [c_int, c_int64, c_int, c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

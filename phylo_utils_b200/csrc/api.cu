@@ -371,6 +371,14 @@ int phb_create(int device, int n_tips, int64_t n_patterns, int n_cat, int n_stat
     return PHB_OK;
 }
 
+static void peer_close(phb_ctx* c) {
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (c->peer.cells[r] != nullptr && c->peer.cells[r] != c->peer.own) cudaIpcCloseMemHandle(c->peer.cells[r]);
+        c->peer.cells[r] = nullptr;
+    }
+    c->peer.connected = false;
+}
+
 int phb_destroy(phb_ctx* c) {
     if (!c) return PHB_OK;
     cudaSetDevice(c->device);
@@ -386,6 +394,8 @@ int phb_destroy(phb_ctx* c) {
             if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
             if (c->result_event[i]) cudaEventDestroy(c->result_event[i]);
         }
+    peer_close(c);
+    if (c->peer.own) cudaFree(c->peer.own);
     if (c->h_epoch) cudaFreeHost(c->h_epoch);
     if (c->h_results) cudaFreeHost(c->h_results);
     if (c->owns_ws && c->ws) cudaFree(c->ws);
@@ -887,9 +897,13 @@ int phb_lnl_from_host_split(phb_ctx* c, const uint8_t* low_plane, const uint8_t*
 
 int phb_lnl_from_host_split_async(phb_ctx* c, const uint8_t* low_plane, const uint8_t* high_plane, int n_chunks, int node_a,
                                   int node_b, double length) {
-    return lnl_from_host(c, low_plane, high_plane, 2, n_chunks, node_a, node_b, length, nullptr, nullptr);
+    if (!c) return PHB_ERR_INVALID;
+    c->peer.use_now = c->peer.armed;   // (the guard type is defined further down; lnl_from_host ends with the reduction)
+    c->peer.armed = false;
+    const int st_ = lnl_from_host(c, low_plane, high_plane, 2, n_chunks, node_a, node_b, length, nullptr, nullptr);
+    c->peer.use_now = false;
+    return st_;
 }
-
 int phb_split_codes(const uint8_t* codes, int n_tips, int64_t n_patterns, uint8_t* low_plane, uint8_t* high_plane) {
     if (codes == nullptr || low_plane == nullptr || high_plane == nullptr || n_tips < 0 || n_patterns < 0) {
         set_thread_error("phb_split_codes: bad argument");
@@ -1101,25 +1115,100 @@ int phb_branch_derivatives(phb_ctx* c, int node_a, int node_b, int n_lengths, co
 }
 
 // ---- stream-ordered forms ------------------------------------------------------------------------------------
+// phb_peer_sum_next arms exactly the next stream-ordered scalar-lnL entry point, whether it succeeds or not
+namespace {
+struct PeerUse {
+    phb_ctx* c;
+    explicit PeerUse(phb_ctx* ctx) : c(ctx) {
+        c->peer.use_now = c->peer.armed;
+        c->peer.armed = false;
+    }
+    ~PeerUse() { c->peer.use_now = false; }
+};
+}  // namespace
+
 int phb_lnl_resident_async(phb_ctx* c, int node_a, int node_b, double length) {
     if (!c) return PHB_ERR_INVALID;
+    PeerUse peer(c);
     return lnl_resident_enqueue(c, node_a, node_b, length);
 }
 
 int phb_root_lnl_async(phb_ctx* c, int node_a, int node_b, double length) {
     if (!c) return PHB_ERR_INVALID;
+    PeerUse peer(c);
     return root_lnl_enqueue(c, node_a, node_b, length, nullptr, false);
 }
 
 int phb_lnl_from_host_packed_async(phb_ctx* c, const uint8_t* packed_codes, int n_chunks, int node_a, int node_b,
                                    double length) {
+    if (!c) return PHB_ERR_INVALID;
+    PeerUse peer(c);
     return lnl_from_host(c, packed_codes, nullptr, 1, n_chunks, node_a, node_b, length, nullptr, nullptr);
+}
+
+// ---- sum over the ranks of one box inside the reduction kernel (no collective library call) --------------------------
+int phb_peer_buffer(phb_ctx* c, void* handle_out) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, handle_out != nullptr, PHB_ERR_INVALID, "phb_peer_buffer: NULL handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PHB_PEER_HANDLE_BYTES, "handle size is part of the ABI");
+    if (c->peer.own == nullptr) {
+        const size_t bytes = 2 * kMaxPeers * 16;
+        PHB_CUDA(c, cudaMalloc(&c->peer.own, bytes));
+        PHB_CUDA(c, cudaMemset(c->peer.own, 0, bytes));
+        PHB_CUDA(c, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    PHB_CUDA(c, cudaIpcGetMemHandle(&h, c->peer.own));
+    std::memcpy(handle_out, &h, sizeof h);
+    return PHB_OK;
+}
+
+int phb_peer_connect(phb_ctx* c, int rank, int world, const void* handles) {
+    if (!c) return PHB_ERR_INVALID;
+    int st = activate(c);
+    if (st) return st;
+    PHB_REQUIRE(c, handles != nullptr && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, PHB_ERR_INVALID,
+                "phb_peer_connect: bad rank / world (at most 16 ranks) or NULL handles");
+    PHB_REQUIRE(c, c->peer.own != nullptr, PHB_ERR_STATE, "phb_peer_connect: call phb_peer_buffer first");
+    PHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    peer_close(c);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            c->peer.cells[r] = c->peer.own;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)r * sizeof h, sizeof h);
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            peer_close(c);
+            return c->fail(PHB_ERR_CUDA, std::string("phb_peer_connect: cannot map the buffer of rank ") + std::to_string(r) + " (" +
+                                             cudaGetErrorString(e) + ")");
+        }
+        c->peer.cells[r] = ptr;
+    }
+    c->peer.rank = rank;
+    c->peer.world = world;
+    c->peer.connected = true;
+    return PHB_OK;
+}
+
+int phb_peer_sum_next(phb_ctx* c) {
+    if (!c) return PHB_ERR_INVALID;
+    PHB_REQUIRE(c, c->peer.connected, PHB_ERR_STATE, "phb_peer_sum_next: no peers connected (phb_peer_connect)");
+    c->peer.armed = true;
+    return PHB_OK;
 }
 
 // ---- pipelined host-fed evaluations: two in flight, the copy of one under the walk of the other ------------------
 int phb_lnl_from_host_submit(phb_ctx* c, const uint8_t* codes, const uint8_t* high_plane, int n_chunks, int node_a,
                              int node_b, double length, int* slot_out) {
     if (!c) return PHB_ERR_INVALID;
+    PeerUse peer(c);
     int st = activate(c);
     if (st) return st;
     PHB_REQUIRE(c, codes != nullptr && slot_out != nullptr, PHB_ERR_INVALID, "phb_lnl_from_host_submit: NULL argument");

@@ -195,6 +195,63 @@ __global__ void final_reduce_kernel(const double* __restrict__ parts, int n_part
     if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
+// The same reduction followed by the sum over the ranks of one box, in the same kernel: the rank's total goes straight
+// into every peer's exchange buffer (mapped through CUDA IPC: stores over NVLink), then the kernel waits for the peers'
+// values in its own buffer and adds them in rank order - every rank ends with the same bits, no collective library call,
+// no second launch.  Cell = {value, sequence number}; the number is stored with release semantics at system scope behind
+// the value and read with acquire semantics, so a matching number implies a visible value.  Two parities of cells: a
+// rank can be at most one exchange ahead of a peer that has not read its cells yet (it needs that peer's value to get
+// further).  The wait is bounded (about a minute): a rank that never shows up yields NaN, not a hung GPU.
+struct PeerCell {
+    double value;
+    unsigned long long seq;
+};
+struct PeerArgs {
+    PeerCell* cells[kMaxPeers];
+    int rank, world, parity;
+    unsigned long long seq;
+};
+
+__global__ void final_reduce_peer_kernel(const double* __restrict__ parts, int n_parts, double* __restrict__ out,
+                                         const __grid_constant__ PeerArgs a) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_parts; i += 256) acc += parts[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double mine = s[0];
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < a.world) {
+        PeerCell* dst = a.cells[r] + a.parity * kMaxPeers + a.rank;
+        asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(&dst->value), "d"(mine) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->seq), "l"(a.seq) : "memory");
+        const PeerCell* src = a.cells[a.rank] + a.parity * kMaxPeers + r;
+        double v = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll 1
+        for (int spin = 0; spin < (1 << 26); ++spin) {
+            unsigned long long have;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(have) : "l"(&src->seq) : "memory");
+            if (have == a.seq) {
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(&src->value) : "memory");
+                break;
+            }
+            __nanosleep(spin < 4096 ? 20 : 1000);
+        }
+        s[r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int i = 0; i < a.world; ++i) total += s[i];
+        out[0] = total;
+    }
+}
+
 // largest byte of an array: validates tip codes without a host pass over N x S bytes.
 // `head` bytes are handled one by one until the pointer is 16-byte aligned, then 16 at a time.
 __global__ void max_code_kernel(const uint8_t* __restrict__ codes, size_t n, size_t head, int* __restrict__ out) {
@@ -349,6 +406,20 @@ int launch_max_code(Ctx* c, const uint8_t* d_codes, size_t n, int* worst) {
 }
 
 int launch_final_reduce(Ctx* c, const double* d_parts, int n_parts, int n_out, double* d_out) {
+    if (n_out == 1 && c->peer.use_now) {
+        c->peer.use_now = false;
+        if (!c->peer.connected) return c->fail(PHB_ERR_STATE, "phb_peer_sum_next: no peers connected (phb_peer_connect)");
+        PeerArgs a;
+        for (int r = 0; r < kMaxPeers; ++r) a.cells[r] = static_cast<PeerCell*>(c->peer.cells[r]);
+        a.rank = c->peer.rank;
+        a.world = c->peer.world;
+        a.seq = ++c->peer.epoch;
+        a.parity = (int)(a.seq & 1);
+        final_reduce_peer_kernel<<<1, 256, 0, c->stream>>>(d_parts, n_parts, d_out, a);
+        c->launches++;
+        PHB_CUDA(c, cudaGetLastError());
+        return PHB_OK;
+    }
     final_reduce_kernel<<<n_out, 256, 0, c->stream>>>(d_parts, n_parts, d_out);
     c->launches++;
     PHB_CUDA(c, cudaGetLastError());

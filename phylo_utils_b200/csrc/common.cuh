@@ -163,6 +163,17 @@ struct Ctx {
     int* h_epoch = nullptr;
     int flag_epoch = 0;
     bool pipelined_pending = false;
+    // sum of a scalar result over the ranks of one box INSIDE the reduction kernel (phb_peer_*): every rank owns a small
+    // exchange buffer, has the peers' buffers mapped (CUDA IPC over NVLink) and writes its value into all of them
+    struct PeerLink {
+        void* own = nullptr;            // [2 parities][kMaxPeers] cells {value, sequence number} in this device's memory
+        void* cells[16] = {};           // rank r's buffer as this process sees it (own for r == rank)
+        int rank = 0, world = 0;
+        unsigned long long epoch = 0;   // exchanges done; every rank runs the same sequence of them
+        bool connected = false;
+        bool armed = false;             // phb_peer_sum_next: the next scalar-lnL entry point uses the exchange
+        bool use_now = false;           // ... and this is that entry point
+    } peer;
     double* d_pattern_lnl = nullptr;   // [S]
     double* d_cat_lnl = nullptr;       // [S][K]
     double* d_partial_sums = nullptr;  // [kPartialCap]
@@ -215,6 +226,7 @@ struct Ctx {
 constexpr int kMaxReduceBlocks = 4096;
 constexpr int kPartialCap = 65536;   // doubles in the block-sum buffer
 constexpr int kMaxEdgeBatch = 64;
+constexpr int kMaxPeers = 16;
 constexpr int kMaxChunks = 32;
 constexpr int kMaxFlagChunks = 255;
 constexpr int kTipTabCodes = 16;     // tip tables cover look-up tables of up to 16 rows (IUPAC DNA has 15)

@@ -290,6 +290,28 @@ class LikelihoodEngine(object):
                                                       1 if chain_rule else 0))
         return nodes.shape[0]
 
+    # ---- the scalar sum over the ranks of one box inside the reduction kernel ---------------------------
+    PEER_HANDLE_BYTES = 64
+
+    def peer_buffer(self):
+        """Allocate this rank's exchange buffer (once) and return its CUDA IPC handle (``PEER_HANDLE_BYTES`` bytes)."""
+        handle = ctypes.create_string_buffer(self.PEER_HANDLE_BYTES)
+        self._ok(self._lib.phb_peer_buffer(self._ctx, handle))
+        return handle.raw
+
+    def peer_connect(self, rank, world, handles):
+        """Map the exchange buffers of all ``world`` ranks (``handles``: their IPC handles concatenated in rank order)."""
+        handles = bytes(handles)
+        if len(handles) != self.PEER_HANDLE_BYTES * int(world):
+            raise ValueError("need {} bytes of handles".format(self.PEER_HANDLE_BYTES * int(world)))
+        self._ok(self._lib.phb_peer_connect(self._ctx, int(rank), int(world), handles))
+        self.peer_world = int(world)
+
+    def peer_sum_next(self):
+        """The next stream-ordered scalar-lnL call leaves the sum over all connected ranks in the result buffer (every
+        rank must make the same call)."""
+        self._ok(self._lib.phb_peer_sum_next(self._ctx))
+
     @property
     def result_capacity(self):
         """Doubles the context's device result buffer holds (3 per edge of the tree, at least 256)."""

@@ -94,6 +94,8 @@ class ShardedTreeModel(object):
         self._torch_device = None
         self.n_patterns = None
         self.collectives = 0          # all-reduces / all-gathers issued so far (bench and tests read it)
+        self.peer_sums = False        # scalar lnL sums run inside the reduction kernel over peer memory (initialise())
+        self.peer_exchanges = 0       # ... how many of the `collectives` were such exchanges
 
     def _comm_device(self):
         dist = _dist()
@@ -154,6 +156,49 @@ class ShardedTreeModel(object):
 
     def initialise(self):
         self.local.initialise()
+        self._connect_peers()
+
+    def _connect_peers(self):
+        """Map every rank's exchange buffer into every other rank (CUDA IPC; the ranks of ONE box), so that the scalar lnL
+        sum runs inside the kernel that reduces the per-CTA sums (``phb_peer_sum_next``): no collective-library call on
+        the evaluation path.  All ranks agree on the outcome; if any of them cannot map a peer (ranks on different
+        nodes, IPC unavailable, ``PHB_PEER_SUM=0``) all of them stay with the in-place ``all_reduce``."""
+        import os
+        self.peer_sums = False
+        dist = _dist()
+        engine = getattr(self.local, "engine", None)
+        if dist is None or self.world < 2 or self.world > 16 or engine is None or not hasattr(engine, "peer_buffer"):
+            return
+        import torch
+        dev = self._comm_device() or torch.device("cpu")
+        n = engine.PEER_HANDLE_BYTES
+        ok, handle = 1, bytes(n)
+        if os.environ.get("PHB_PEER_SUM", "1") == "0":
+            ok = 0
+        else:
+            try:
+                handle = engine.peer_buffer()
+            except RuntimeError:
+                ok = 0
+        mine = torch.tensor(list(handle) + [ok], dtype=torch.uint8, device=dev)
+        got = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(got, mine)
+        got = [bytes(t.cpu().tolist()) for t in got]
+        if all(g[n] == 1 for g in got):
+            try:
+                engine.peer_connect(self.rank, self.world, b"".join(g[:n] for g in got))
+            except RuntimeError:
+                ok = 0
+        else:
+            ok = 0
+        agreed = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+        self.peer_sums = bool(int(agreed.item()))
+
+    def _peer_value(self, value):
+        if value != value:
+            raise RuntimeError("peer sum: a rank never delivered its value (ranks out of step, or one of them died)")
+        return float(value)
 
     def compute_partials(self):
         self.local.compute_partials()
@@ -176,6 +221,11 @@ class ShardedTreeModel(object):
         return self.local.engine.result_fetch(view.numel())
 
     def lnl(self, node_a=None, node_b=None):
+        if self._device_sums() and self.peer_sums:
+            self.local.lnl_enqueue(node_a, node_b, peer_sum=True)      # the global sum is formed by the reduction kernel
+            self.collectives += 1
+            self.peer_exchanges += 1
+            return self._peer_value(self.local.engine.result_fetch(1)[0])
         if self._device_sums():
             return float(self._reduce_in_place(self.local.lnl_enqueue(node_a, node_b))[0])
         if self.world > 1:
@@ -185,6 +235,11 @@ class ShardedTreeModel(object):
     def lnl_from_host_codes(self, packed_codes, node_a=None, node_b=None, n_chunks=0):
         """``TreeModel.lnl_from_host_codes`` on this rank's shard of a new alignment (pinned host memory, two codes
         per byte), summed over the ranks on the device."""
+        if self._device_sums() and self.peer_sums:
+            self.local.lnl_from_host_codes(packed_codes, node_a, node_b, n_chunks, enqueue_only=True, peer_sum=True)
+            self.collectives += 1
+            self.peer_exchanges += 1
+            return self._peer_value(self.local.engine.result_fetch(1)[0])
         if self._device_sums():
             view = self.local.lnl_from_host_codes(packed_codes, node_a, node_b, n_chunks, enqueue_only=True)
             return float(self._reduce_in_place(view)[0])
@@ -196,6 +251,12 @@ class ShardedTreeModel(object):
         ``result()`` is the global lnL; the all-reduce of an evaluation is enqueued behind its walk when the next one is
         submitted or its result is asked for."""
         reduce = None
+        if self._device_sums() and self.peer_sums:
+            self.collectives += 1
+            self.peer_exchanges += 1
+            handle = self.local.lnl_from_host_submit(packed_codes, node_a, node_b, n_chunks, None, peer_sum=True)
+            handle.check = self._peer_value
+            return handle
         if self._device_sums():
             def reduce(view):
                 _dist().all_reduce(view)

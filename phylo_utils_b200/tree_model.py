@@ -43,6 +43,7 @@ class PendingLnl(object):
 
     def __init__(self, model, slot, reduce=None):
         self.model, self.slot, self._reduce, self._posted, self._value = model, slot, reduce, False, None
+        self.check = None     # optional: validates / converts the value when it arrives
 
     def post(self):
         """Enqueue (not wait for) what follows the walk: the optional reduction over ranks, then the copy to the host."""
@@ -56,6 +57,8 @@ class PendingLnl(object):
         if self._value is None:
             self.post()
             self._value = self.model.engine.result_wait(self.slot)
+            if self.check is not None:
+                self._value = self.check(self._value)
         return self._value
 
 
@@ -363,7 +366,7 @@ class TreeModel(object):
         total, _ = self._pattern_lnl(node_a, node_b, want_pattern=False)   # the per-pattern vector stays on the device
         return total
 
-    def lnl_enqueue(self, node_a=None, node_b=None):
+    def lnl_enqueue(self, node_a=None, node_b=None, peer_sum=False):
         """Stream-ordered ``lnl``: the evaluation is only enqueued and its sum stays on the device; returns a
         one-element torch tensor VIEW of it (``engine.result_tensor``) that a collective on the same stream can
         reduce in place.  No host synchronisation.  Not available with the ascertainment-bias correction or a
@@ -373,13 +376,15 @@ class TreeModel(object):
         if self.ascbias or not getattr(self.substitution_model, "has_real_eigensystem", True):
             raise ValueError("lnl_enqueue: this model composes its likelihood on the host; use lnl()")
         length = self._edge_length(node_a, node_b)
+        if peer_sum:                                  # arms exactly the next call (phb_peer_sum_next)
+            self.engine.peer_sum_next()
         if self.store_partials:
             self.engine.root_lnl_async(node_a, node_b, length)
         else:
             self.engine.lnl_resident_async(node_a, node_b, length)
         return self.engine.result_tensor(1)
 
-    def lnl_from_host_codes(self, packed_codes, node_a=None, node_b=None, n_chunks=0, enqueue_only=False):
+    def lnl_from_host_codes(self, packed_codes, node_a=None, node_b=None, n_chunks=0, enqueue_only=False, peer_sum=False):
         """lnL of a NEW alignment over the same taxa, tree and models, starting from pinned HOST codes: two 4-bit codes
         per byte (``LikelihoodEngine.pack_codes``) or, as a ``(low, high)`` tuple, the 3-bit planes of
         ``LikelihoodEngine.split_codes`` (look-up tables of at most 8 rows); rows in ``tip_row_order``.  The
@@ -392,6 +397,8 @@ class TreeModel(object):
         length = self._edge_length(node_a, node_b)
         split = isinstance(packed_codes, (tuple, list))
         if enqueue_only:
+            if peer_sum:
+                self.engine.peer_sum_next()
             if split:
                 self.engine.lnl_from_host_split_async(packed_codes, node_a, node_b, length, n_chunks)
             else:
@@ -401,7 +408,7 @@ class TreeModel(object):
             return self.engine.lnl_from_host_split(packed_codes, node_a, node_b, length, n_chunks=n_chunks)[0]
         return self.engine.lnl_from_host(packed_codes, node_a, node_b, length, n_chunks=n_chunks, packed=True)[0]
 
-    def lnl_from_host_submit(self, packed_codes, node_a=None, node_b=None, n_chunks=0, reduce=None):
+    def lnl_from_host_submit(self, packed_codes, node_a=None, node_b=None, n_chunks=0, reduce=None, peer_sum=False):
         """Pipelined ``lnl_from_host_codes``: enqueue the evaluation of one more alignment and return a ``PendingLnl``
         whose ``result()`` delivers its lnL.  Up to two are in flight: the host-to-device copy of this one runs under the
         walk of the one submitted before (many alignments over one tree - bootstrap replicates, simulated data).
@@ -415,6 +422,8 @@ class TreeModel(object):
         pending = getattr(self, "_pending_lnl", None) or {}
         for other in pending.values():
             other.post()                              # their copies to the host go in front of the new walk
+        if peer_sum:
+            self.engine.peer_sum_next()
         slot = self.engine.host_fed_submit(packed_codes, node_a, node_b, length, n_chunks)
         if slot in pending:
             pending[slot].result()                    # the slot's previous tenant: its value must be read before the word is reused

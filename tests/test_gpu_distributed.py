@@ -4,7 +4,8 @@ Two-rank runs of the sharded TreeModel on the GPU box.
 With two or more GPUs the group is NCCL, one rank per GPU (the product configuration).  On a one-GPU box - the
 driver's test box - both ranks share cuda:0 and the group is gloo, which accepts CUDA tensors: ShardedTreeModel's
 device-side reduction path (stream-ordered evaluation -> in-place all-reduce of a tensor view of the engine's result
-buffer -> one fetch) runs unchanged, only the transport differs.  Either way the checks are the reference's golden
+buffer -> one fetch) runs unchanged, only the transport differs.  The scalar lnL sums do not go through the group at
+all where the ranks can map each other's memory: they are formed inside the reduction kernel (phb_peer_*).  Either way the checks are the reference's golden
 outputs (tests/golden/, written by the unmodified reference).
 """
 import os
@@ -94,6 +95,21 @@ def _worker(rank, world, port, out_dir, n_gpus):
     h0 = tl.lnl_from_host_submit(planes)                                       # two in flight, all-reduced on the device
     h1 = tl.lnl_from_host_submit(packed)
     assert h0.result() == total_from_host and h1.result() == total_from_host
+    # Where the ranks can map each other's exchange buffers (CUDA IPC: the ranks of one box) the scalar sums above were
+    # formed INSIDE the reduction kernel (phb_peer_sum_next), not by the process group.  The same model over the
+    # group's all_reduce must give the same bits (two addends: the order cannot matter).
+    assert tl.peer_exchanges == (5 if tl.peer_sums else 0) and tm.peer_sums == tl.peer_sums
+    print("peer_sums rank {}: {} ({} exchanges)".format(rank, tl.peer_sums, tl.peer_exchanges), flush=True)
+    os.environ["PHB_PEER_SUM"] = "0"
+    tn = ShardedTreeModel(device=device, store_partials=False)
+    tn.set_tree(tree(g))
+    tn.set_tip_codes(codes, lut, names, sw, ii)
+    tn.set_rate_model(rate)
+    tn.set_substitution_model(model)
+    tn.initialise()
+    del os.environ["PHB_PEER_SUM"]
+    assert not tn.peer_sums and tn.lnl() == total_lnl_only and tn.peer_exchanges == 0
+    assert tn.lnl_from_host_submit(packed).result() == total_from_host
 
     # Lewis ascertainment-bias correction under sharding: dummy patterns on every rank, no broadcast
     ga, _, codes_a, lut_a, sw_a, ii_a, names_a, model_a, rate_a = problem("ascbias_gtr_g4")
@@ -108,6 +124,7 @@ def _worker(rank, world, port, out_dir, n_gpus):
     asc_site = ta.compute_likelihood_at_edge(*ta.traversal.root_edge)
 
     np.savez(os.path.join(out_dir, "rank{}.npz".format(rank)), total=total, site=site, d=d, d_host=d_host, n_coll=n_coll,
+             peer=int(tl.peer_sums),
              total_lnl_only=total_lnl_only, total_from_host=total_from_host, asc_total=asc_total, asc_site=asc_site)
     dist.destroy_process_group()
 
@@ -129,6 +146,7 @@ def test_two_rank_sharded_tree_model(tmp_path):
         assert int(z["n_coll"]) == 3                                   # lnl, per-site gather, derivatives
         assert abs(float(z["asc_total"]) - float(ga["total_lnl"])) <= 1e-10 * abs(float(ga["total_lnl"]))
         assert np.allclose(z["asc_site"], ga["site_lnl"], rtol=1e-10, atol=0)
+    assert int(outs[0]["peer"]) == int(outs[1]["peer"])                # the ranks agreed on how the scalar sums are formed
     assert np.array_equal(outs[0]["d"], outs[1]["d"])                  # every rank holds the same global sums
     assert np.allclose(outs[0]["d_host"] + outs[1]["d_host"], outs[0]["d"], rtol=1e-12, atol=1e-9)
     assert not np.allclose(outs[0]["d_host"][:, 0], outs[0]["d"][:, 0])   # a shard alone is not the total
