@@ -485,6 +485,7 @@ def main():
     codes_host = torch.from_numpy(make_codes(n_taxa, lo, hi, args.seed)).pin_memory()
     tm = sharded_model(codes_host.numpy(), n_pat, store_partials=False)
     eng = tm.local.engine
+    peer_sums = bool(getattr(tm, "peer_sums", False))
     root_a, root_b = tm.traversal.root_edge
 
     def evaluate():
@@ -662,7 +663,7 @@ def main():
             "collectives_in_timed_region": int(collectives),
             "rank_sum": ("inside the reduction kernel: every rank stores its total into the peers' exchange buffers over NVLink "
                          "(CUDA IPC) and adds what arrives in rank order - phb_peer_sum_next, no collective-library call"
-                         if getattr(tm, "peer_sums", False) else
+                         if peer_sums else
                          ("torch.distributed all_reduce in place on the device result buffer" if world > 1 else "single rank")),
             "path": "ShardedTreeModel(store_partials=False): lnL-only operand-resident walk per shard, sum over ranks on the device",
             "with_stored_partials": stored, "weak_scaling": weak, "configs": configs, "sharded_parity": parity,

@@ -28,6 +28,9 @@ static Tuning read_tuning() {
         v.pair_ctas = num("PHB_PAIR_CTAS");
         v.pair_ppt = num("PHB_PAIR_PPT");
         v.pair_grid = num("PHB_PAIR_GRID");
+        v.pair_one_warp_ctas = num("PHB_PAIR_ONE_WARP_CTAS") != 0;
+        v.pair_cta_rounds = num("PHB_PAIR_CTA_ROUNDS");
+        v.pair_stagger = num("PHB_PAIR_STAGGER");
         v.pair_full_p = flag("PHB_PAIR_FULL_P");
         v.up_ppt = num("PHB_UP_PPT");
         v.up_warps = num("PHB_UP_WARPS");
@@ -393,6 +396,7 @@ int phb_destroy(phb_ctx* c) {
         for (int i = 0; i < 2; ++i) {
             if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
             if (c->result_event[i]) cudaEventDestroy(c->result_event[i]);
+            if (c->copies_done[i]) cudaEventDestroy(c->copies_done[i]);
         }
     peer_close(c);
     if (c->peer.own) cudaFree(c->peer.own);

@@ -69,6 +69,7 @@ struct PairArgs {
     int epoch, chunk_shift;       // tiles per chunk = 1 << chunk_shift
     int* error;                   // set to 1 if a chunk never arrived (bounded wait)
     double ipi[4];                // SYM: 1 / pi_i
+    int stagger_ns;               // multi-warp CTA form: worker w starts (w mod 32) * stagger_ns late (0 = together)
 };
 
 
@@ -115,7 +116,7 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
 #pragma unroll
         for (int p = 0; p < PPT; ++p) e[p] += *reinterpret_cast<const int*>(opin + (lane + 32 * p) * ROWB + K * 32);   // in the row's padding
     } else if (KB == KIND_SLOT) {
-        const int* x = reinterpret_cast<const int*>(opin + L::BLOCK_BYTES + lane * (4 * PPT));
+        const int* x = reinterpret_cast<const int*>(opin + L::BLOCK_BYTES + lane * L::EXP_STRIDE);
         if (PPT == 2) {
             const int2 v = *reinterpret_cast<const int2*>(x);
             e[0] += v.x;
@@ -124,8 +125,8 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
             const int4 v = *reinterpret_cast<const int4*>(x);
             e[0] += v.x;
             e[1] += v.y;
-            e[PPT - 2] += v.z;
-            e[PPT - 1] += v.w;
+            e[2] += v.z;
+            if (PPT == 4) e[PPT - 1] += v.w;
         }
     }
     int ra[PPT], rb[PPT];
@@ -259,18 +260,20 @@ __device__ __noinline__ void wait_for_chunk(const int* flags, int chunk_shift, i
     *error = 1;
 }
 
+// The walk of ONE warp: `worker` of `n_workers` takes the tiles tile_begin + worker, + n_workers, ... below tile_end (tiles
+// of 32 PPT patterns), parks in its own stripe `my_scratch`, works in its own `smem` (WARP_BYTES + 256) and leaves the
+// weighted sum of its tiles' lnL in *sum_out.
 template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
-__global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair_kernel(const __grid_constant__ PairArgs p) {
+__device__ __forceinline__ void pair_walk(const PairArgs& p, unsigned char* const smem, const int lane, const int worker,
+                                          const int n_workers, const int tile_begin, const int tile_end,
+                                          unsigned char* const my_scratch, double* const sum_out) {
     using L = PairLayout<K, NC, PPT>;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x;
     PairRow* const s_desc = reinterpret_cast<PairRow*>(smem);
     unsigned char* const s_stage = smem + L::DESC_BYTES;
     unsigned char* const s_opin = s_stage + 2 * L::STAGE_BYTES;
-    const int wstride = gridDim.x, n_steps = p.n_steps, tile_end = (int)p.tile_end;
+    const int wstride = n_workers, n_steps = p.n_steps;
     double* const s_acc = reinterpret_cast<double*>(smem + L::WARP_BYTES);   // per-lane running sum of weight * lnL
     s_acc[lane] = 0.0;
-    unsigned char* const my_scratch = p.scratch + (size_t)blockIdx.x * p.n_slots * L::SLOT_BYTES;
 
     // parked block `slot` -> the operand tile (the lane's own chunks, in the layout it wrote them)
     auto fetch_slot = [&](int slot) {
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
         }
     };
 
-    int tile = (int)p.tile_begin + blockIdx.x;
+    int tile = tile_begin + worker;
     if (tile < tile_end) {
         // prologue: descriptors of rows 0 and 1, then the inputs of row 0
         if (lane < 2) cp_async16(&s_desc[lane], &p.rows[lane < n_steps ? lane : 0]);
@@ -393,9 +396,9 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
                             *reinterpret_cast<double2*>(dst + ((h * K + k) * 2) * 512) = make_double2(prev[h][k][0], prev[h][k][1]);
                             *reinterpret_cast<double2*>(dst + ((h * K + k) * 2 + 1) * 512) = make_double2(prev[h][k][2], prev[h][k][3]);
                         }
-                    int* ex = reinterpret_cast<int*>(my_scratch + (size_t)dst_slot * L::SLOT_BYTES + L::BLOCK_BYTES + lane * (4 * PPT));
+                    int* ex = reinterpret_cast<int*>(my_scratch + (size_t)dst_slot * L::SLOT_BYTES + L::BLOCK_BYTES + lane * L::EXP_STRIDE);
                     if (PPT == 2) *reinterpret_cast<int2*>(ex) = make_int2(pe[0], pe[1]);
-                    else *reinterpret_cast<int4*>(ex) = make_int4(pe[0], pe[1], pe[PPT - 2], pe[PPT - 1]);
+                    else *reinterpret_cast<int4*>(ex) = make_int4(pe[0], pe[1], pe[2], PPT == 4 ? pe[PPT - 1] : 0);
                 }
             } else {
                 // root pseudo-row: pi-dot, Gamma mixture, log, weighted sum (tree_model.py:200-217)
@@ -415,9 +418,9 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
                     lnl[h] = mix > 0 ? log(mix) + (double)pe[h] * kLn2 : -INFINITY;
                 }
                 double acc = s_acc[lane];
-                if (s0 + PPT <= p.S) {
+                if (PPT % 2 == 0 && s0 + PPT <= p.S) {
 #pragma unroll
-                    for (int h = 0; h < PPT; h += 2) {
+                    for (int h = 0; h + 1 < PPT; h += 2) {
                         *reinterpret_cast<double2*>(p.pattern_lnl + s0 + h) = make_double2(lnl[h], lnl[h + 1]);
                         if (p.weights) {
                             const double2 w = *reinterpret_cast<const double2*>(p.weights + s0 + h);
@@ -447,7 +450,33 @@ __global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair
         cp_async_wait_all();
     }
     const double total = warp_sum(s_acc[lane]);
-    if (lane == 0) p.partial_sums[blockIdx.x] = total;
+    if (lane == 0) *sum_out = total;
+}
+
+// one warp per CTA: the CTAs of an SM spread over its four sub-partitions
+template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
+__global__ void __launch_bounds__(32, PairLayout<K, NC, PPT>::MIN_CTAS) dna_pair_kernel(const __grid_constant__ PairArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    pair_walk<K, NC, PPT, CM, PIPE, SYM>(p, smem, threadIdx.x, blockIdx.x, gridDim.x, (int)p.tile_begin, (int)p.tile_end,
+                                         p.scratch + (size_t)blockIdx.x * p.n_slots * PairLayout<K, NC, PPT>::SLOT_BYTES,
+                                         p.partial_sums + blockIdx.x);
+}
+
+// All the warps an SM can hold in ONE CTA.  Warp w of a CTA runs on sub-partition w mod 4, so every sub-partition gets
+// the same number of walks (twelve 1-warp CTAs leave that to the block scheduler), and the warps of a CTA start together
+// and stay close to each other in the row loop: they fetch the same instructions and the same P blocks at about the
+// same time (1M patterns: 13.9 ms against 14.5 ms for the 1-warp CTAs on the same box, profiles/r02g_*).  Worker ids
+// are interleaved over the CTAs - worker = warp * CTAs + CTA - so that a last, partial round of tiles spreads over all
+// SMs instead of filling the first few.
+template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
+__global__ void __launch_bounds__(32 * PairLayout<K, NC, PPT>::MIN_CTAS, 1) dna_pair_cta_kernel(const __grid_constant__ PairArgs p) {
+    using L = PairLayout<K, NC, PPT>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int worker = warp * gridDim.x + blockIdx.x, n_workers = (int)(blockDim.x >> 5) * gridDim.x;
+    if (p.stagger_ns > 0) __nanosleep((unsigned)((worker * 7) & 31) * (unsigned)p.stagger_ns);
+    pair_walk<K, NC, PPT, CM, PIPE, SYM>(p, smem + (size_t)warp * (L::WARP_BYTES + 256), lane, worker, n_workers, (int)p.tile_begin,
+                                         (int)p.tile_end, p.scratch + (size_t)worker * p.n_slots * L::SLOT_BYTES, p.partial_sums + worker);
 }
 
 // ---- the same walk with every node block written to the caller-visible partials array --------------------------
@@ -651,10 +680,8 @@ int launch_pair_store(Ctx* c, int n_steps) {
     return PHB_OK;
 }
 
-template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
-int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
-                int max_grid, int* grid_out, int chunk_shift) {
-    using L = PairLayout<K, NC, PPT>;
+template <int CM, bool SYM>
+PairArgs pair_args(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums, int chunk_shift) {
     PairArgs a;
     a.rows = static_cast<const PairRow*>(c->d_res_rows);
     a.n_steps = n_steps;
@@ -679,6 +706,49 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
     a.chunk_shift = chunk_shift;
     a.error = flags + kMaxFlagChunks;
     for (int i = 0; i < 4; ++i) a.ipi[i] = SYM ? 1.0 / c->h_freqs[i] : 1.0;
+    a.stagger_ns = tuning().pair_stagger;
+    return a;
+}
+
+template <int K, int NC, int PPT, int CM, bool PIPE, bool SYM>
+int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t tile_end, double* partial_sums,
+                int max_grid, int* grid_out, int chunk_shift) {
+    using L = PairLayout<K, NC, PPT>;
+    PairArgs a = pair_args<CM, SYM>(c, n_steps, n_slots, tile_begin, tile_end, partial_sums, chunk_shift);
+    // Which form?  Measured on one box (profiles/r02g_cta_form_ab.jsonl, 1-warp CTAs -> one CTA per SM): 8.8 rounds of
+    // tiles 14.56 -> 13.78 ms, 4.4 rounds 7.20 -> 7.25, 2.2 rounds 3.68 -> 3.94, one wave 1.96 -> 2.21: the big CTAs win
+    // where every warp walks many tiles, the independent 1-warp CTAs (launched one after the other, out of step from
+    // the start) where it walks one or two.
+    const int64_t rounds_x10 = 10 * (tile_end - tile_begin) / ((int64_t)c->sm_count * L::MIN_CTAS);
+    const int min_rounds_x10 = tuning().pair_cta_rounds != 0 ? 10 * tuning().pair_cta_rounds : 60;
+    if (!tuning().pair_one_warp_ctas && rounds_x10 >= min_rounds_x10) {
+        // one CTA per SM that carries all the warps the tiles need (whole rounds of the four sub-partitions)
+        auto kern = dna_pair_cta_kernel<K, NC, PPT, CM, PIPE, SYM>;
+        const size_t per_warp = L::WARP_BYTES + 256;   // + the per-lane running sums
+        const int64_t n_tiles = tile_end - tile_begin;
+        int warps = (int)std::min<int64_t>(L::MIN_CTAS, (n_tiles + c->sm_count - 1) / c->sm_count);
+        warps = warps <= 1 ? 1 : std::min<int>(L::MIN_CTAS, (warps + 3) / 4 * 4);
+        if (tuning().pair_ctas > 0) warps = std::min(warps, tuning().pair_ctas);
+        warps = (int)std::min<size_t>((size_t)warps, c->smem_optin / per_warp);
+        if (warps < 1) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
+        int64_t ctas = std::min<int64_t>(c->sm_count, (n_tiles + warps - 1) / warps);
+        // every warp needs its own scratch stripe and its own partial sum
+        const int64_t cap = std::min<int64_t>((int64_t)(c->scratch_bytes / ((size_t)n_slots * L::SLOT_BYTES)), max_grid);
+        if (cap < 1) return c->fail(PHB_ERR_NOMEM, "pair kernel: scratch area too small");
+        if (ctas * warps > cap) {
+            warps = (int)std::max<int64_t>(1, std::min<int64_t>(warps, cap / std::max<int64_t>(1, ctas)));
+            ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, cap / warps));
+        }
+        const size_t smem = (size_t)warps * per_warp;
+        PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        kern<<<(int)ctas, 32 * warps, smem, c->stream>>>(a);
+        c->launches++;
+        PHB_CUDA(c, cudaGetLastError());
+        c->resident_warps = warps;
+        *grid_out = (int)(ctas * warps);
+        return PHB_OK;
+    }
     auto kern = dna_pair_kernel<K, NC, PPT, CM, PIPE, SYM>;
     const size_t smem = L::WARP_BYTES + 256;   // + the per-lane running sums
     if (smem > c->smem_optin) return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel: does not fit in shared memory");
@@ -711,14 +781,19 @@ int launch_pair(Ctx* c, int n_steps, int n_slots, int64_t tile_begin, int64_t ti
 // the lnL-only walk reads the symmetric form of the P blocks (10 numbers instead of 16) when the model is reversible
 bool pair_sym(const Ctx* c) { return c->reversible && c->d_rmats != nullptr && !tuning().pair_full_p; }
 
-// patterns per lane: 2 everywhere; 4 is built for K = 4 and selected with PHB_PAIR_PPT=4 (tuning knob)
-int pair_ppt(const Ctx* c) {
+// patterns per lane: 2 everywhere; 4 is built for K = 4 (PHB_PAIR_PPT forces it)
+int pair_ppt(const Ctx* c, int mode) {
+    (void)mode;
     if (c->K != 4) return 2;
     if (tuning().pair_ppt == 2 || tuning().pair_ppt == 4) return tuning().pair_ppt;
     // A tile is one long sequential job (a walk over the whole tree), so what counts is the number of WAVES: when the
     // 64-pattern tiles need a second, nearly empty wave of warps but the 128-pattern tiles fit in one, the bigger
     // tiles win (125k patterns - the 8-GPU shard of the 1M-pattern alignment: 2.19 vs 2.36 ms); otherwise the
     // 64-pattern tiles do (250k: 4.00 vs 4.47 ms; 1M: 15.3 vs 15.8 ms on the same box).
+    // (Tried and dropped, profiles/r02g_tile_mix_ab.jsonl: 96-pattern tiles, nine warps per SM - the walk is bound per
+    // sub-partition and nine warps put three on one of them, 2.09 vs 1.96 ms; and 64- and 96-pattern walks mixed in
+    // one CTA so that every sub-partition holds 224 patterns - two loop bodies competing for the instruction cache,
+    // 2.64 ms.)
     const int64_t t64 = (c->S + 63) / 64, t128 = (c->S + 127) / 128;
     const int64_t wave2 = (int64_t)c->sm_count * PairLayout<4, 8, 2>::MIN_CTAS, wave4 = (int64_t)c->sm_count * PairLayout<4, 8, 4>::MIN_CTAS;
     return (t64 > wave2 && t128 <= wave4) ? 4 : 2;
@@ -753,7 +828,7 @@ int launch_pair_v(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t
 int launch_pair_k(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
                   int* grid_out, int chunk_shift = -1) {
     static_assert(kTipTabCodes == 16, "tip tables are staged with 8 or 16 rows per category");
-    const int key = c->K * 1000 + tip_table_rows(c) * 10 + pair_ppt(c);
+    const int key = c->K * 1000 + tip_table_rows(c) * 10 + pair_ppt(c, mode);
     switch (key) {
 #define PHB_PAIR_CASE(K_, NC_, PPT_) \
     case K_ * 1000 + NC_ * 10 + PPT_: \
@@ -938,7 +1013,7 @@ int dna_pair_lnl(Ctx* c, int root_a, int root_b) {
     int st = cached_pair_plan(c, 1, root_a, root_b, &n_steps, &n_slots);
     if (st) return st;
     int grid = 0;
-    const int tile = 32 * pair_ppt(c);
+    const int tile = 32 * pair_ppt(c, c->codes_mode);
     const int64_t n_tiles = (c->S + tile - 1) / tile;
     st = launch_pair_k(c, c->codes_mode, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid);
     if (st) return st;
@@ -971,6 +1046,7 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_h
         for (int i = 0; i < 2; ++i) {
             PHB_CUDA(c, cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming));
             PHB_CUDA(c, cudaEventCreateWithFlags(&c->result_event[i], cudaEventDisableTiming));
+            PHB_CUDA(c, cudaEventCreateWithFlags(&c->copies_done[i], cudaEventDisableTiming));
         }
     }
     if (c->h_epoch == nullptr) {
@@ -979,7 +1055,7 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_h
         PHB_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * (kMaxFlagChunks + 1) * sizeof(int), c->stream));
         PHB_CUDA(c, cudaStreamSynchronize(c->stream));   // once per context: the copy stream must not race the reset
     }
-    const int tile = 32 * pair_ppt(c);
+    const int tile = 32 * pair_ppt(c, mode);
     const int64_t n_tiles = (c->S + tile - 1) / tile;
     n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_chunks, kMaxFlagChunks), n_tiles));
     int chunk_shift = 0;   // chunks are a power of two of tiles: the kernel finds a tile's flag with a shift
@@ -988,6 +1064,9 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_h
     n_chunks = (int)((n_tiles + tpc - 1) / tpc);
     c->flag_epoch = c->flag_epoch >= (1 << 30) ? 1 : c->flag_epoch + 1;
     int* const h_epoch = c->h_epoch + 16 * s;      // the copy engine reads it when the flag copy executes: one word per slot
+    // ... so the flag copies of the slot's previous evaluation must have executed before the word changes (they have,
+    // unless the caller submits a third evaluation while the copies of the first are still queued)
+    if (pipelined) PHB_CUDA(c, cudaEventSynchronize(c->copies_done[s]));
     *h_epoch = c->flag_epoch;
     int* const d_flags = c->d_flags + s * (kMaxFlagChunks + 1);
     c->d_flags_cur = d_flags;
@@ -1021,6 +1100,7 @@ int dna_pair_from_host(Ctx* c, const uint8_t* codes_host, const uint8_t* codes_h
         }
         PHB_CUDA(c, cudaMemcpyAsync(d_flags + i, h_epoch, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
     }
+    if (pipelined) PHB_CUDA(c, cudaEventRecord(c->copies_done[s], c->copy_stream));
     int grid = 0;
     st = launch_pair_k(c, mode, n_steps, n_slots, 0, n_tiles, c->d_partial_sums, kPartialCap, &grid, chunk_shift);
     if (st) return st;

@@ -48,6 +48,9 @@ struct Tuning {
     bool compress_timing = false;    // PHB_COMPRESS_TIMING: per-phase wall clock of phb_compress_patterns on stderr
     int pair_ctas = 0;               // PHB_PAIR_CTAS: cap on resident warps per SM of the pair kernel
     int pair_ppt = 0;                // PHB_PAIR_PPT: patterns per lane of the lnL-only pair kernel (0 = choose)
+    bool pair_one_warp_ctas = false; // PHB_PAIR_ONE_WARP_CTAS: the lnL-only walk always as 1-warp CTAs (12 per SM), never one CTA of 12 warps per SM
+    int pair_cta_rounds = 0;         // PHB_PAIR_CTA_ROUNDS: rounds of tiles from which on the one-CTA-per-SM form is used (0 = 6; -1 = always)
+    int pair_stagger = 0;            // PHB_PAIR_STAGGER: start offset between the warps of the one-CTA-per-SM form, ns (experiment)
     int pair_grid = 0;               // PHB_PAIR_GRID: 0 = choose, 1 = every resident warp, 2 = equal tiles per warp
     bool pair_full_p = false;        // PHB_PAIR_FULL_P: the lnL-only walk reads full P blocks even for reversible models
     int up_ppt = 0;                  // PHB_UP_PPT: patterns per lane of the pre-order walk
@@ -158,6 +161,7 @@ struct Ctx {
     // need at most half of it), so that the copy of evaluation i+1 runs under the walk of evaluation i
     cudaEvent_t slot_done[2] = {};     // the walk that read slot s has finished (the copy stream waits for it)
     cudaEvent_t result_event[2] = {};  // result s (and its error word) has reached h_results
+    cudaEvent_t copies_done[2] = {};   // every copy of the evaluation in slot s (and its flags) has executed
     double* h_results = nullptr;       // pinned: [2] sums, then [2] error words (as doubles' worth of ints)
     int next_slot = 0;
     int* h_epoch = nullptr;

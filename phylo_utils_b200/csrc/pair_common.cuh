@@ -31,12 +31,14 @@ struct PairLayout {
     static constexpr int DESC_BYTES = 4 * 16;                     // descriptor ring: rows r .. r+2 in flight
     static constexpr int CHUNKS = PPT * K * 2;                    // 16-byte chunks per lane in a parked block
     static constexpr int BLOCK_BYTES = CHUNKS * 512;              // [pattern of the lane][k][half][lane]
-    static constexpr int SLOT_BYTES = BLOCK_BYTES + 128 * PPT;    // + PPT exponents per lane
+    static constexpr int EXP_STRIDE = PPT == 1 ? 4 : (PPT == 2 ? 8 : 16);   // bytes of exponents per lane (PPT = 3: one word unused)
+    static constexpr int SLOT_BYTES = BLOCK_BYTES + 32 * EXP_STRIDE;        // + PPT exponents per lane
     static constexpr int WARP_BYTES = DESC_BYTES + 2 * STAGE_BYTES + SLOT_BYTES;
     // CTAs (= warps) per SM the register file is budgeted for.  A warp lives in one of the four SM
     // sub-partitions with 16384 registers each: 12 CTAs = 3 warps per sub-partition = 168 registers.
     // Four patterns per lane (K <= 4) double the register footprint: 8 CTAs = 2 warps per sub-partition = 255 registers.
-    static constexpr int MIN_CTAS = PPT == 2 ? (K <= 2 ? 16 : (K <= 4 ? 12 : 4)) : (K <= 1 ? 16 : (K <= 2 ? 12 : 8));
+    // Three patterns per lane (96-pattern tiles, K = 4): 9 CTAs = 224 registers.
+    static constexpr int MIN_CTAS = PPT == 2 ? (K <= 2 ? 16 : (K <= 4 ? 12 : 4)) : (PPT == 3 ? 9 : (K <= 1 ? 16 : (K <= 2 ? 12 : 8)));
 };
 
 // Which patterns of its tile a lane owns, and how a parked operand tile is laid out in shared memory:
@@ -70,7 +72,15 @@ __device__ __forceinline__ void table_rows(const unsigned char* codes, int lane,
     }
     constexpr bool PACKED = CM == CODES_NIBBLE;
     unsigned raw;
-    if (PACKED) raw = PPT == 2 ? (unsigned)codes[lane] : (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane);
+    if (PPT == 3) {
+        // patterns 3 lane .. 3 lane + 2: three bytes, or three nibbles starting at nibble 3 lane (two bytes cover them)
+        if (PACKED) {
+            const int n0 = 3 * lane;
+            raw = ((unsigned)codes[n0 >> 1] | ((unsigned)codes[(n0 >> 1) + 1] << 8)) >> (4 * (n0 & 1));
+        } else {
+            raw = (unsigned)codes[3 * lane] | ((unsigned)codes[3 * lane + 1] << 8) | ((unsigned)codes[3 * lane + 2] << 16);
+        }
+    } else if (PACKED) raw = PPT == 2 ? (unsigned)codes[lane] : (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane);
     else raw = PPT == 2 ? (unsigned)*reinterpret_cast<const unsigned short*>(codes + 2 * lane)
                         : *reinterpret_cast<const unsigned*>(codes + 4 * lane);
 #pragma unroll
