@@ -102,9 +102,12 @@ __device__ __forceinline__ void sym_matvec(const unsigned char* blk, const doubl
     }
 }
 
+// pair_product: the products, the operands' exponents summed into pe, mh <- high word of the largest entry per pattern;
+// pair_rescale: the threshold test on mh and the rescaling.  The lnL-only walk runs the second step once behind its
+// four row shapes (one copy of the rare path, and the shapes end where their last product is written).
 template <int K, int NC, int PPT, int CM, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE, bool SYM = false>
-__device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
-                                            double (&prev)[PPT][K][4], int (&pe)[PPT], const double* ipi = nullptr) {
+__device__ __forceinline__ void pair_product(const unsigned char* st, const unsigned char* opin, int lane,
+                                             double (&prev)[PPT][K][4], int (&pe)[PPT], int (&mh)[PPT], const double* ipi = nullptr) {
     constexpr int PB = SYM ? 80 : 128;   // bytes of one category's P block (SYM: the upper triangle of diag(pi) P)
     using L = PairLayout<K, NC, PPT>;
     constexpr int ROWB = K * 32 + 16;   // LAYOUT_ARRAY: one pattern's row of the operand tile
@@ -134,7 +137,6 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
     for (int p = 0; p < PPT; ++p) ra[p] = rb[p] = 0;
     if (KA == KIND_TIP) table_rows<NC, PPT, CM, LAYOUT>(st + L::CODES_OFF, lane, ra);
     if (KB == KIND_TIP) table_rows<NC, PPT, CM, LAYOUT>(st + L::CODES_OFF + L::TILE, lane, rb);
-    int mh[PPT];
 #pragma unroll
     for (int p = 0; p < PPT; ++p) mh[p] = 0;
 #pragma unroll
@@ -221,7 +223,13 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
                 mh[p] = max(mh[p], __double2hiint(x[p][i]));   // partials are >= 0: the high word orders them
             }
     }
-    // 0 < max < 2^-128: multiply by the exact power of two that brings the maximum into [1, 2)
+#pragma unroll
+    for (int p = 0; p < PPT; ++p) pe[p] = e[p];
+}
+
+// 0 < max < 2^-128: multiply by the exact power of two that brings the maximum into [1, 2)
+template <int K, int PPT>
+__device__ __forceinline__ void pair_rescale(double (&prev)[PPT][K][4], int (&pe)[PPT], const int (&mh)[PPT]) {
     bool small[PPT], any = false;
 #pragma unroll
     for (int p = 0; p < PPT; ++p) {
@@ -238,12 +246,19 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
                 for (int k = 0; k < K; ++k)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) prev[p][k][i] *= f;
-                e[p] -= shift;
+                pe[p] -= shift;
             }
         }
     }
-#pragma unroll
-    for (int p = 0; p < PPT; ++p) pe[p] = e[p];
+}
+
+
+template <int K, int NC, int PPT, int CM, int KA, int KB, int LAYOUT = LAYOUT_PRIVATE, bool SYM = false>
+__device__ __forceinline__ void pair_update(const unsigned char* st, const unsigned char* opin, int lane,
+                                            double (&prev)[PPT][K][4], int (&pe)[PPT], const double* ipi = nullptr) {
+    int mh[PPT];
+    pair_product<K, NC, PPT, CM, KA, KB, LAYOUT, SYM>(st, opin, lane, prev, pe, mh, ipi);
+    pair_rescale<K, PPT>(prev, pe, mh);
 }
 
 // Block (politely, and not forever) until the copy engine has delivered the chunk that holds tile t.
@@ -373,14 +388,16 @@ __device__ __forceinline__ void pair_walk(const PairArgs& p, unsigned char* cons
             // four row shapes (canonical operand order); a short if-chain instead of a jump table: no table load and
             // indirect branch on the row's critical path
             const int kind_a = kinds & 3, kind_b = kinds >> 2;
+            int mh[PPT];
             if (kind_b == KIND_SLOT) {
-                if (kind_a == KIND_PREV) pair_update<K, NC, PPT, CM, KIND_PREV, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
-                else pair_update<K, NC, PPT, CM, KIND_TIP, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                if (kind_a == KIND_PREV) pair_product<K, NC, PPT, CM, KIND_PREV, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, mh, p.ipi);
+                else pair_product<K, NC, PPT, CM, KIND_TIP, KIND_SLOT, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, mh, p.ipi);
             } else if (kind_b == KIND_PREV) {
-                pair_update<K, NC, PPT, CM, KIND_TIP, KIND_PREV, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                pair_product<K, NC, PPT, CM, KIND_TIP, KIND_PREV, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, mh, p.ipi);
             } else {
-                pair_update<K, NC, PPT, CM, KIND_TIP, KIND_TIP, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, p.ipi);
+                pair_product<K, NC, PPT, CM, KIND_TIP, KIND_TIP, LAYOUT_PRIVATE, SYM>(st, s_opin, lane, prev, pe, mh, p.ipi);
             }
+            pair_rescale<K, PPT>(prev, pe, mh);
             if (fetch_late) {   // the operand tile is free now (a lane only ever touches its own chunks of it)
                 fetch_slot(slot_n);
                 cp_async_commit();
@@ -807,8 +824,12 @@ int launch_pair_v(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t
     switch (flavour) {
 #define PHB_PAIR_FLAVOUR(F_, CM_, PIPE_, SYM_) \
     case F_: return launch_pair<K, NC, PPT, CM_, PIPE_, SYM_>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
-        PHB_PAIR_FLAVOUR(0, CODES_BYTE, false, false)
         PHB_PAIR_FLAVOUR(1, CODES_BYTE, false, true)
+#ifdef PHB_PAIR_PROBE_ONLY   // developer builds: only the headline instantiation (SASS inspection in seconds)
+    }
+    return PHB_ERR_UNSUPPORTED;
+#else
+        PHB_PAIR_FLAVOUR(0, CODES_BYTE, false, false)
         PHB_PAIR_FLAVOUR(2, CODES_BYTE, true, false)
         PHB_PAIR_FLAVOUR(3, CODES_BYTE, true, true)
         PHB_PAIR_FLAVOUR(4, CODES_NIBBLE, false, false)
@@ -823,6 +844,7 @@ int launch_pair_v(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t
         if (flavour == 11) return launch_pair<K, NC, PPT, CODES_SPLIT3, true, true>(c, n_steps, n_slots, b, e, ps, max_grid, grid_out, cs);
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "split 3-bit tip codes need a look-up table of at most 8 rows and a reversible model");
+#endif
 }
 
 int launch_pair_k(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t e, double* ps, int max_grid,
@@ -833,16 +855,18 @@ int launch_pair_k(Ctx* c, int mode, int n_steps, int n_slots, int64_t b, int64_t
 #define PHB_PAIR_CASE(K_, NC_, PPT_) \
     case K_ * 1000 + NC_ * 10 + PPT_: \
         return launch_pair_v<K_, NC_, PPT_>(c, mode, n_steps, n_slots, b, e, ps, max_grid, grid_out, chunk_shift);
+        PHB_PAIR_CASE(4, 8, 2)
+#ifndef PHB_PAIR_PROBE_ONLY
         PHB_PAIR_CASE(1, 8, 2)
         PHB_PAIR_CASE(1, 16, 2)
         PHB_PAIR_CASE(2, 8, 2)
         PHB_PAIR_CASE(2, 16, 2)
-        PHB_PAIR_CASE(4, 8, 2)
         PHB_PAIR_CASE(4, 16, 2)
         PHB_PAIR_CASE(8, 8, 2)
         PHB_PAIR_CASE(8, 16, 2)
         PHB_PAIR_CASE(4, 8, 4)
         PHB_PAIR_CASE(4, 16, 4)
+#endif
 #undef PHB_PAIR_CASE
     }
     return c->fail(PHB_ERR_UNSUPPORTED, "pair kernel needs K in {1,2,4,8}");
@@ -994,15 +1018,17 @@ int dna_pair_store(Ctx* c) {
     if (st) return st;
     if (n_steps == 0) return PHB_OK;
     switch (c->K * 100 + tip_table_rows(c)) {
+        case 408: return launch_pair_store<4, 8, 2>(c, n_steps);
+#ifndef PHB_PAIR_PROBE_ONLY
         case 108: return launch_pair_store<1, 8, 2>(c, n_steps);
         case 116: return launch_pair_store<1, 16, 2>(c, n_steps);
         case 208: return launch_pair_store<2, 8, 2>(c, n_steps);
         case 216: return launch_pair_store<2, 16, 2>(c, n_steps);
-        case 408: return launch_pair_store<4, 8, 2>(c, n_steps);
         case 416: return launch_pair_store<4, 16, 2>(c, n_steps);
         // eight categories: one pattern per lane (two would need 128 registers for the block alone)
         case 808: return launch_pair_store<8, 8, 1>(c, n_steps);
         case 816: return launch_pair_store<8, 16, 1>(c, n_steps);
+#endif
     }
     return PHB_ERR_UNSUPPORTED;
 }

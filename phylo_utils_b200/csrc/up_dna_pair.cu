@@ -240,24 +240,41 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
         __syncwarp();
     }
 
+    // A warp-wide copy round moves 32 pieces of 16 bytes = PPR patterns; the lane's piece of round j of a block tile sits
+    // at lane_off + j * PPR * ROWB in the padded tile and at lane * 16 + j * 512 in the block.  Every tile but the
+    // alignment's last one is whole: its copies carry no per-piece bounds and no per-piece address arithmetic (the
+    // per-piece form was 90 - 115 instructions per block moved, a quarter of the walk's instructions:
+    // profiles/r02i_up_walk_sass_profile.txt); the ragged last tile goes through compact loops.
+    constexpr int PPR = 32 / PIECES;
+    static_assert(32 % PIECES == 0, "a copy round covers whole patterns");
+    const int lane_off = (lane / PIECES) * ROWB + (lane % PIECES) * 16;
+    const size_t block_bytes = S * (size_t)(K * 32);
+    unsigned char* const clv_bytes = reinterpret_cast<unsigned char*>(p.clv);
+
     // block `blk` of tile t -> a pattern-major operand tile (exponents into the row padding)
     auto fetch_block = [&](int blk, int t, unsigned char* dst) {
         const size_t site0 = (size_t)t * L::TILE;
-        const int valid = (int)min((int64_t)L::TILE, p.S - (int64_t)site0);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.clv + ((size_t)blk * S + site0) * (K * 4));
-#pragma unroll
-        for (int j = 0; j < ROUNDS; ++j) {
-            const int c = lane + 32 * j;
-            if (c < valid * PIECES) cp_async16(dst + (c / PIECES) * ROWB + (c % PIECES) * 16, src + (size_t)c * 16);
-        }
+        const unsigned char* src = clv_bytes + (size_t)blk * block_bytes + site0 * (K * 32);
         const int32_t* ex = p.scale + (size_t)blk * S + site0;
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+        if (site0 + L::TILE <= S) {
+            const unsigned d = d0 + lane_off;
+            const unsigned char* g = src + lane * 16;
 #pragma unroll
-        for (int q = 0; q < PPT; ++q)
-            if (lane + 32 * q < valid)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(
-                                                                                dst + (lane + 32 * q) * ROWB + K * 32)),
-                             "l"(ex + lane + 32 * q)
-                             : "memory");
+            for (int j = 0; j < ROUNDS; ++j)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + j * (PPR * ROWB)), "l"(g + j * 512) : "memory");
+#pragma unroll
+            for (int q = 0; q < PPT; ++q)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + (lane + 32 * q) * ROWB + K * 32), "l"(ex + lane + 32 * q) : "memory");
+            return;
+        }
+        const int valid = (int)(S - site0);
+#pragma unroll 1
+        for (int c = lane; c < valid * PIECES; c += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (c / PIECES) * ROWB + (c % PIECES) * 16), "l"(src + (size_t)c * 16) : "memory");
+#pragma unroll 1
+        for (int r = lane; r < valid; r += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + r * ROWB + K * 32), "l"(ex + r) : "memory");
     };
     // everything step `d` reads at tile t -> buffer b: operand P blocks / tip tables, tip codes, down-block tiles
     auto stage_step = [&](const UpStep d, int t, int b) {
@@ -302,8 +319,10 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
     // registers -> padded staging tile (a dead operand tile) -> coalesced streaming stores into block `blk`
     auto store_block = [&](const double (&v)[PPT][K][4], const int (&e)[PPT], int blk, int t, unsigned char* s_out) {
         const size_t site0 = (size_t)t * L::TILE;
-        const int valid = (int)min((int64_t)L::TILE, p.S - (int64_t)site0);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(p.clv + ((size_t)blk * S + site0) * (K * 4));
+        const bool whole = site0 + L::TILE <= S;
+        const int valid = whole ? L::TILE : (int)(S - site0);
+        unsigned char* dst = clv_bytes + (size_t)blk * block_bytes + site0 * (K * 32);
+        int32_t* ex = p.scale + (size_t)blk * S + site0;
 #pragma unroll
         for (int h = 0; h < PPT; ++h) {   // 32 patterns at a time
             __syncwarp();                 // the staging tile's previous readers are done
@@ -314,40 +333,55 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
                 *reinterpret_cast<double2*>(d + 16) = make_double2(v[h][k][2], v[h][k][3]);
             }
             __syncwarp();
+            if (whole) {
+                const unsigned char* sl = s_out + lane_off;
+                unsigned char* g = dst + (size_t)h * (32 * PIECES * 16) + lane * 16;
 #pragma unroll
-            for (int j = 0; j < PIECES; ++j) {
-                const int c = lane + 32 * j;
-                if (c + h * 32 * PIECES < valid * PIECES) {
+                for (int j = 0; j < PIECES; ++j)
+                    __stcs(reinterpret_cast<int4*>(g + j * 512), *reinterpret_cast<const int4*>(sl + j * (PPR * ROWB)));
+                ex[lane + 32 * h] = e[h];
+            } else {
+#pragma unroll 1
+                for (int c = lane; c + h * 32 * PIECES < valid * PIECES && c < 32 * PIECES; c += 32) {
                     const int4 w = *reinterpret_cast<const int4*>(s_out + (c / PIECES) * ROWB + (c % PIECES) * 16);
                     __stcs(reinterpret_cast<int4*>(dst + (size_t)(c + h * 32 * PIECES) * 16), w);
                 }
+                if (lane + 32 * h < valid) ex[lane + 32 * h] = e[h];
             }
         }
-#pragma unroll
-        for (int h = 0; h < PPT; ++h)
-            if (lane + 32 * h < valid) p.scale[(size_t)blk * S + site0 + lane + 32 * h] = e[h];
     };
 
     // v <- (V^-1 down[c]) * (V^T (pi * v)) per category, v = up[c]: the edge's sum table (derivs.cu)
+    // (`tip` is warp-uniform: a tip child's first factor is one table row for all categories, and its K products
+    // V^-1 . down are skipped by a real branch - half of all children are tips; with the staging code above at a third of
+    // its former size the two bodies fit the instruction cache.)
     auto sum_table = [&](double (&v)[PPT][K][4], bool tip, const unsigned char* tl, const unsigned char* codes) {
 #pragma unroll
         for (int h = 0; h < PPT; ++h) {
-            double xt[4] = {0.0, 0.0, 0.0, 0.0};
-            if (tip) lds32(s_xtab + (int)(codes[lane + 32 * h] & (NC - 1)) * 32, xt);
+            double y[K][4];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                double a[4] = {0.0, 0.0, 0.0, 0.0};
-                if (!tip) lds32(tl + (lane + 32 * h) * ROWB + k * 32, a);
-                double r[4];
+            for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    double x = fma(p.m1[4 * m + 3], a[3], fma(p.m1[4 * m + 2], a[2], fma(p.m1[4 * m + 1], a[1], p.m1[4 * m] * a[0])));
-                    if (tip) x = xt[m];
-                    const double y = fma(p.m2[4 * m + 3], v[h][k][3], fma(p.m2[4 * m + 2], v[h][k][2], fma(p.m2[4 * m + 1], v[h][k][1], p.m2[4 * m] * v[h][k][0])));
-                    r[m] = x * y;
+                for (int m = 0; m < 4; ++m)
+                    y[k][m] = fma(p.m2[4 * m + 3], v[h][k][3], fma(p.m2[4 * m + 2], v[h][k][2], fma(p.m2[4 * m + 1], v[h][k][1], p.m2[4 * m] * v[h][k][0])));
+            if (tip) {
+                double xt[4];
+                lds32(s_xtab + (int)(codes[lane + 32 * h] & (NC - 1)) * 32, xt);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) v[h][k][m] = xt[m] * y[k][m];
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double a[4];
+                    lds32(tl + (lane + 32 * h) * ROWB + k * 32, a);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const double x = fma(p.m1[4 * m + 3], a[3], fma(p.m1[4 * m + 2], a[2], fma(p.m1[4 * m + 1], a[1], p.m1[4 * m] * a[0])));
+                        v[h][k][m] = x * y[k][m];
+                    }
                 }
-#pragma unroll
-                for (int m = 0; m < 4; ++m) v[h][k][m] = r[m];
             }
         }
     };
