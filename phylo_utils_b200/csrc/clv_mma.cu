@@ -83,7 +83,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // one P buffer and one child-row buffer, the P block and the child rows of phase ph+1 stream into the other
 // pair with cp.async (8-byte pieces: rows of 20 or 61 doubles are only 8-byte aligned).  Padding rows and
 // columns are zeroed once and never touched again.
-template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL, bool FUSED>
+// KK: the category count when it is known at compile time (4: every configuration BASELINE.json names), 0 = p.K.  With it
+// the byte distance between two patterns' rows of a block, K * A * 8, is a constant, and the per-row copies below become
+// one instruction with an immediate offset each; as a run-time value every copy paid a 64-bit multiply-add chain (the
+// copy loops were 37 % of the 20-state kernel's instructions: profiles/r02i_mma_sass_profile.txt).
+template <int AA, int MT, int KS, int NT, int WARPS, bool LEVEL, bool FUSED, int KK = 0>
 __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) {
     constexpr int MROWS = MT * 8, KCOLS = KS * 4;
     constexpr int LDP = pad_pitch(KCOLS);
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
     int* s_shift = s_exp + 3 * TS;                           // [TS] binary shift a pattern of the output is rescaled by
     static_assert(WR <= 32, "one pattern per lane in the per-pattern bookkeeping");
     constexpr int A = AA;   // compile-time: the staging loops divide by it
-    const int K = p.K;
+    const int K = KK != 0 ? KK : p.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fr = lane >> 2, fc = lane & 3;          // fragment row / column
     const size_t S = (size_t)p.S;
@@ -245,8 +249,11 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         const int j0 = 2 * lane + sh;
                         const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld + j0 + sh);
                         const double* q = g + j0;
-                        for (int n = 0; n < n_valid; ++n)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + n * (LDL * 8)), "l"(q + (size_t)n * (K * A)) : "memory");
+                        asm volatile("" : "+l"(q));   // one base register: ptxas otherwise rebuilds the address from the kernel parameters inside every predicated copy
+#pragma unroll
+                        for (int n = 0; n < WR; ++n)
+                            if (n < n_valid)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + n * (LDL * 8)), "l"(q + (size_t)n * (K * A)) : "memory");
                     }
                     if (lane < n_valid) {                     // the 8-byte piece of row `lane`
                         const int j8 = sh == 0 ? A - 1 : 0;
@@ -263,12 +270,18 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                     const unsigned sdst = (unsigned)__cvta_generic_to_shared(Ld);
                     if (PB == 16 && PIECES <= 16) {
                         // a lane keeps its piece and walks the rows (32 / PIECES rows per trip): no index division per copy
-                        constexpr int RPT = 32 / PIECES;
+                        constexpr int RPT = 32 / PIECES > 0 ? 32 / PIECES : 1, TRIPS = (WR + RPT - 1) / RPT;   // (PIECES > 32: this branch is not taken)
                         const int r0 = lane / PIECES, piece = lane - r0 * PIECES;
-                        if (r0 < RPT)
-                            for (int n = r0; n < n_valid; n += RPT)
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + n * (LDL * 8) + piece * 16),
-                                             "l"(g + (size_t)n * (K * A * 8) + piece * 16) : "memory");
+                        if (r0 < RPT) {
+                            const unsigned d0 = sdst + r0 * (LDL * 8) + piece * 16;
+                            const unsigned char* q0 = g + (size_t)r0 * (K * A * 8) + piece * 16;
+                            asm volatile("" : "+l"(q0));
+#pragma unroll
+                            for (int i = 0; i < TRIPS; ++i)
+                                if (r0 + RPT * i < n_valid)
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * (RPT * LDL * 8)),
+                                                 "l"(q0 + (size_t)i * (RPT * K * A * 8)) : "memory");
+                        }
                     } else {
                         for (int e = lane; e < n_valid * PIECES; e += 32) {
                             const int n = e / PIECES, piece = e - n * PIECES;
@@ -372,8 +385,13 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         double* g = out + ((size_t)wsite0 * K + k) * A;
                         if (lane < HALF) {
                             const int j0 = 2 * lane + sh;
-                            for (int n = 0; n < n_valid; ++n)
-                                *reinterpret_cast<double2*>(g + (size_t)n * (K * A) + j0) = *reinterpret_cast<const double2*>(myL + n * LDL + j0 + sh);
+                            double* gq = g + j0;
+                            const double* sq = myL + j0 + sh;
+                            asm volatile("" : "+l"(gq));
+#pragma unroll
+                            for (int n = 0; n < WR; ++n)
+                                if (n < n_valid)
+                                    *reinterpret_cast<double2*>(gq + (size_t)n * (K * A)) = *reinterpret_cast<const double2*>(sq + n * LDL);
                         }
                         if (lane < n_valid) {                 // the 8-byte piece of row `lane`
                             const int j8 = sh == 0 ? A - 1 : 0;
@@ -387,12 +405,18 @@ __global__ void __launch_bounds__(WARPS * 32) mma_prune_kernel(const MmaArgs p) 
                         unsigned char* g = reinterpret_cast<unsigned char*>(out + ((size_t)wsite0 * K + k) * A);
                         const unsigned char* src = reinterpret_cast<const unsigned char*>(myL);
                         if (PB == 16 && PIECES <= 16) {
-                            constexpr int RPT = 32 / PIECES;
+                            constexpr int RPT = 32 / PIECES > 0 ? 32 / PIECES : 1, TRIPS = (WR + RPT - 1) / RPT;   // (PIECES > 32: this branch is not taken)
                             const int r0 = lane / PIECES, piece = lane - r0 * PIECES;
-                            if (r0 < RPT)
-                                for (int n = r0; n < n_valid; n += RPT)
-                                    *reinterpret_cast<int4*>(g + (size_t)n * (K * A * 8) + piece * 16) =
-                                        *reinterpret_cast<const int4*>(src + n * (LDL * 8) + piece * 16);
+                            if (r0 < RPT) {
+                                unsigned char* g0 = g + (size_t)r0 * (K * A * 8) + piece * 16;
+                                const unsigned char* s0 = src + r0 * (LDL * 8) + piece * 16;
+                                asm volatile("" : "+l"(g0));
+#pragma unroll
+                                for (int i = 0; i < TRIPS; ++i)
+                                    if (r0 + RPT * i < n_valid)
+                                        *reinterpret_cast<int4*>(g0 + (size_t)i * (RPT * K * A * 8)) =
+                                            *reinterpret_cast<const int4*>(s0 + i * (RPT * LDL * 8));
+                            }
                         } else {
                             for (int e = lane; e < n_valid * PIECES; e += 32) {
                                 const int n = e / PIECES, piece = e - n * PIECES;
@@ -544,7 +568,8 @@ int launch_mma(Ctx* c, const OpRow* d_rows, int row_begin, int row_end, const Mm
     a.A = c->A;
     a.K = c->K;
     const size_t smem = (2 * (size_t)MROWS * LDP + 2 * (size_t)TS * LDL) * sizeof(double) + 4 * TS + 4 * TS * sizeof(int);
-    auto kern = d_frows != nullptr ? mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, true> : mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, false>;
+    auto kern = d_frows != nullptr ? (c->K == 4 ? mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, true, 4> : mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, true>)
+                                   : (c->K == 4 ? mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, false, 4> : mma_prune_kernel<AA, MT, KS, NT, WARPS, LEVEL, false>);
     PHB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     PHB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
