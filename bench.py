@@ -517,22 +517,30 @@ def main():
     dfma_peak = fp64_peak(local_rank)
     prune_bytes, _ = algorithmic_bytes(n_taxa, n_local)
     flops = algorithmic_flops(n_taxa, n_local)
-    ncu = ncu_record("dna_pair_kernel_lnl_only_1000x1M") or {}
-    # the launch's own rule (clv_dna_pair.cu: pair_ppt): 128-pattern tiles when the 64-pattern tiles need a second wave
+    # the launch's own rules (clv_dna_pair.cu): 128-pattern tiles when the 64-pattern tiles need a second wave (pair_ppt);
+    # one CTA of all resident warps per SM from six rounds of tiles on, independent one-warp CTAs below that (launch_pair)
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     ppt = 4 if ((n_local + 63) // 64 > 12 * sms and (n_local + 127) // 128 <= 8 * sms) else 2
+    warps_per_sm = 12 if ppt == 2 else 8
+    cta_form = 10 * ((n_local + 32 * ppt - 1) // (32 * ppt)) // (sms * warps_per_sm) >= 60
+    kernel_name = "dna_pair_cta_kernel" if cta_form else "dna_pair_kernel"
+    ncu = ncu_record("dna_pair_cta_kernel_lnl_only_1000x1M" if cta_form else "dna_pair_kernel_lnl_only_1000x1M") or {}
     achieved_tf = flops / (kernel_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": dfma_peak, "unit": "TFLOP/s", "frac": achieved_tf / dfma_peak,
         "traffic": ncu.get("dram_bytes_per_launch"),
-        "kernel": "dna_pair_kernel<K=4,NC=8,PPT={},SYM> ({} patterns per lane, whole post-order walk + root + reduction in one "
-                  "launch, operands on chip, symmetric P blocks, no partials stored)".format(ppt, {2: "two", 4: "four"}[ppt]),
+        "kernel": "{}<K=4,NC=8,PPT={},SYM> ({} patterns per lane, {}; whole post-order walk + root + reduction in one "
+                  "launch, operands on chip, symmetric P blocks, no partials stored)".format(
+                      kernel_name, ppt, {2: "two", 4: "four"}[ppt],
+                      "one CTA of {} warps per SM".format(warps_per_sm) if cta_form else "one-warp CTAs, {} per SM".format(warps_per_sm)),
         "kernel_ms": kernel_ms, "patterns_per_launch": n_local, "share_of_step": kernel_ms / ms_per_step,
         "algorithmic_flops_per_launch": flops,
         "flops_per_unit": "272 fp64 flop per site-node update (SURVEY.md 8(d): K (4 A^2 + A)), x (N-2) x patterns of the shard",
         "peak_source": "measured in this run: phb_op_fp64_peak (8 independent DFMA chains per thread on every SM); "
                        "nominal 64 FMA/clk/SM x 148 x 1.965 GHz = 37.2",
-        "limiter": "shared-memory (LSU) data pipe, then the fp64 pipe; DRAM is idle (see `ncu`)",
+        "limiter": "per-warp latency at three warps per scheduler (168 registers): 20 % fewer shared-memory wavefronts changed "
+                   "nothing, 6 % fewer instructions bought 1.3 % (DESIGN.md 3.1); the busiest units are the shared-memory (LSU) data "
+                   "pipe and the fp64 pipe; DRAM is idle (see `ncu`)",
         "ncu": ncu or None,
         "hbm_algorithmic": {
             "bytes_per_launch": prune_bytes, "gbs": prune_bytes / (kernel_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak_hbm,

@@ -425,3 +425,38 @@ def test_derivative_configs_full_size_properties(shape):
     assert np.allclose(tm.edge_derivatives(nodes, lengths * 1.5), other, rtol=rtol, atol=1e-6)   # first pass again
     res = optimise_branch_lengths(tm, max_sweeps=1, inner_iterations=2, tol=0.0)
     assert res["lnl"] >= total
+
+
+@pytest.mark.parametrize("tree_fn,n_taxa,n_pat,mode", [
+    (random_tree, 300, 6000, "auto"),         # deep enough that every pattern is rescaled many times on the way up
+    (caterpillar_tree, 200, 3000, "tile"),
+    (random_tree, 300, 20000, "resident"),    # the stored operand-resident walk (one binary exponent per pattern)
+])
+def test_per_category_lnl_vs_oracle_where_rescaling_is_routine(tree_fn, n_taxa, n_pat, mode):
+    """The engine keeps ONE binary exponent per pattern, the reference one natural-log scaler per (site,
+    category) (numba_likelihood_engine.py:37-44).  Per-category root values (`lnl_node`, :82-87) must still agree wherever
+    the reference's value is representable next to the pattern's best category: checked here at sizes where the 2^-128
+    threshold fires at most levels of the tree, not only on the 10-taxon golden cases."""
+    tree, names, codes, lut = synthetic(n_taxa, n_pat, 4, seed=7 * n_taxa + n_pat, tree_fn=tree_fn)
+    model = phy.substitution_models.GTR([6., 5., 4., 3., 2., 1.], [0.1, 0.2, 0.3, 0.4])
+    rate = phy.rate_models.GammaRateModel(4, 0.5)
+    tm = phy.TreeModel(mode=mode)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    a, b = tm.traversal.root_edge
+    length = tm.traversal.brlens[(a, b)]
+    _, pattern, cat = tm.engine.root_lnl(a, b, length, want_pattern=True, want_cat=True, root_pmats=tm._root_pmats(length))
+    assert tm.scale.min() < -128                      # the rescaling branch ran, repeatedly
+    tips = {tm.traversal.names[n]: np.ascontiguousarray(lut[codes[i]]) for i, n in enumerate(names)}
+    _, ot = oracle.tree_lnl(tm.traversal, tips, model.p, model.freqs, rate.rates, rate.weights, return_tree=True)
+    root_pm = np.stack([model.p(0, rate.rates), model.p(length, rate.rates)])
+    want_pattern, want_cat = ot.likelihood_at_edge(a, b, root_pm, model.freqs, rate.weights, want_cat=True)
+    assert_lnl_close(pattern, want_pattern)
+    # a category more than 2^-900 below the pattern's best one may have been flushed (documented quirk); none is here
+    spread = want_cat.max(axis=1, keepdims=True) - want_cat
+    assert spread.max() < 600
+    assert_lnl_close(cat, want_cat, what="per-category lnL")
+    assert_lnl_close(oracle.mix_categories(cat, rate.weights), pattern, rtol=1e-13)

@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "phylo_utils_b200", "libphylo_b200.so")
-HOT = [r"dna_pair_kernel", r"dna_pair_store_kernel", r"dna_up_kernel", r"dna_edge_st_kernel", r"dna_edge_sumtable_kernel",
+HOT = [r"dna_pair_cta_kernel", r"dna_pair_kernel", r"dna_pair_store_kernel", r"dna_up_kernel", r"dna_edge_st_kernel", r"dna_edge_sumtable_kernel",
        r"mma_prune_kernel", r"mma_edge_deriv_kernel", r"edge_st_kernel", r"dna_prune_kernel", r"dna_root_kernel",
        r"pmatrix_kernel", r"tip_table_kernel"]
 
