@@ -455,8 +455,44 @@ def test_per_category_lnl_vs_oracle_where_rescaling_is_routine(tree_fn, n_taxa, 
     root_pm = np.stack([model.p(0, rate.rates), model.p(length, rate.rates)])
     want_pattern, want_cat = ot.likelihood_at_edge(a, b, root_pm, model.freqs, rate.weights, want_cat=True)
     assert_lnl_close(pattern, want_pattern)
-    # a category more than 2^-900 below the pattern's best one may have been flushed (documented quirk); none is here
+    # One exponent per pattern: the rescaling fires when the pattern's largest entry drops below 2^-128, and a product of
+    # two such operands can reach 2^-256 before it is rescaled - so a category more than ~2^-766 (530 nats) below the
+    # pattern's best one can run into the denormal range or flush to zero (documented quirk; its weight in the
+    # mixture is < 1e-230).  Everything within 500 nats must match to 1e-10; beyond that: -inf, or the value to within a nat.
     spread = want_cat.max(axis=1, keepdims=True) - want_cat
-    assert spread.max() < 600
-    assert_lnl_close(cat, want_cat, what="per-category lnL")
+    near = spread < 500
+    assert near.mean() > 0.95 and spread.max() > 200          # the slow category really is hundreds of nats down
+    assert_lnl_close(cat[near], want_cat[near], what="per-category lnL")
+    far = ~near
+    assert np.all(np.isneginf(cat[far]) | (np.abs(cat[far] - want_cat[far]) <= 1.0))
     assert_lnl_close(oracle.mix_categories(cat, rate.weights), pattern, rtol=1e-13)
+
+
+@pytest.mark.parametrize("n_states,K", [(20, 2), (20, 5), (61, 2)])
+def test_dmma_kernels_with_a_run_time_category_count(n_states, K):
+    """The FP64 tensor-core kernels are specialised for K = 4 (category count as a template parameter, clv_mma.cu); every other
+    count goes through the instantiation that reads K at run time - post-order walk in both launch modes against the oracle,
+    and the pre-order pass + derivative passes through the pulley principle (lnL from any edge = lnL at the root)."""
+    if n_states == 20:
+        model = phy.substitution_models.WAG()
+        tree, names, codes, lut = synthetic(40, 1500, 20, seed=11 + K)
+    else:
+        from phylo_utils_b200.substitution_models.codon import f3x4
+        model = phy.substitution_models.GY94(2.0, 0.3, f3x4(np.random.default_rng(5).dirichlet(np.ones(4) * 5, size=3)))
+        tree, names, codes, lut = synthetic(16, 300, 61, seed=13)
+    rate = phy.rate_models.GammaRateModel(K, 0.6)
+    for mode in ("tile", "level"):
+        _, total, pattern, want = run_both(tree, names, codes, lut, model, rate, mode)
+        assert_lnl_close(pattern, want)
+    tm = phy.TreeModel(up_partials=True)
+    tm.set_tree(tree)
+    tm.set_tip_codes(codes, lut, {n: i for i, n in enumerate(names)})
+    tm.set_rate_model(rate)
+    tm.set_substitution_model(model)
+    tm.initialise()
+    root = tm.lnl()
+    tm.compute_up_partials()
+    nodes = [n for n in range(2 * len(names) - 2) if n != tm.traversal.root_edge[1]][::3][:12]
+    for _ in range(2):                      # first pass (writes the sum tables) and a later one (reads them)
+        d = tm.edge_derivatives(nodes)
+        assert_lnl_close(d[:, 0], np.full(len(nodes), root), rtol=1e-9, what="lnL across an edge")
