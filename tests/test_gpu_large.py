@@ -461,7 +461,7 @@ def test_per_category_lnl_vs_oracle_where_rescaling_is_routine(tree_fn, n_taxa, 
     # mixture is < 1e-230).  Everything within 500 nats must match to 1e-10; beyond that: -inf, or the value to within a nat.
     spread = want_cat.max(axis=1, keepdims=True) - want_cat
     near = spread < 500
-    assert near.mean() > 0.95 and spread.max() > 200          # the slow category really is hundreds of nats down
+    assert near.mean() > 0.7 and spread.max() > 200           # three categories in full, the slowest one hundreds of nats down
     assert_lnl_close(cat[near], want_cat[near], what="per-category lnL")
     far = ~near
     assert np.all(np.isneginf(cat[far]) | (np.abs(cat[far] - want_cat[far]) <= 1.0))
