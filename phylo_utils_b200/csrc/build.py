@@ -51,8 +51,21 @@ def _run(cmd, verbose):
     return res.stdout
 
 
-def build(force=False, verbose=False, ptxas_info=False):
+def build(force=False, verbose=False, ptxas_info=False, checks=False):
+    """checks=True: the same sources with -DPHB_DEVICE_CHECKS (device-side invariant asserts, common.cuh) into
+    libphylo_b200_checks.so - a developer build the parity tests can be pointed at through PHB_LIBRARY."""
     nvcc = _nvcc()
+    global OBJ, OUT
+    saved = OBJ, OUT
+    if checks:
+        OBJ, OUT = os.path.join(HERE, "_obj_checks"), os.path.join(PKG, "libphylo_b200_checks.so")
+    try:
+        return _build(nvcc, force, verbose, ptxas_info, ["-DPHB_DEVICE_CHECKS"] if checks else [])
+    finally:
+        OBJ, OUT = saved
+
+
+def _build(nvcc, force, verbose, ptxas_info, defines):
     os.makedirs(OBJ, exist_ok=True)
     headers = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
     headers.append(os.path.abspath(__file__))
@@ -64,7 +77,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         objs.append(o)
         if force or _stale(o, [s] + headers):
             if src.endswith(".cu"):
-                cmd = [nvcc] + ARCH + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
+                cmd = [nvcc] + ARCH + NVCC_FLAGS + defines + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", s, "-o", o]
             else:
                 cmd = [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
                        "-Xcompiler", "-ffp-contract=off", "-c", s, "-o", o]
@@ -79,7 +92,8 @@ def build(force=False, verbose=False, ptxas_info=False):
 
 
 if __name__ == "__main__":
-    out, logs = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_info="--ptxas" in sys.argv)
+    out, logs = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ptxas_info="--ptxas" in sys.argv,
+                      checks="--checks" in sys.argv)
     if "--ptxas" in sys.argv:
         print("\n".join(logs))
     print(out)

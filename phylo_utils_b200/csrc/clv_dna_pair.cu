@@ -264,6 +264,7 @@ __device__ __forceinline__ void pair_update(const unsigned char* st, const unsig
 // Block (politely, and not forever) until the copy engine has delivered the chunk that holds tile t.
 // Deliberately NOT inlined: it runs once per tile, and as a call its registers stay out of the row loop's allocation.
 __device__ __noinline__ void wait_for_chunk(const int* flags, int chunk_shift, int epoch, int* error, int t) {
+    PHB_DCHECK((t >> chunk_shift) < kMaxFlagChunks);
     const int* f = flags + (t >> chunk_shift);
 #pragma unroll 1
     for (int spin = 0; spin < (1 << 23); ++spin) {   // ~10 s of 1 us naps: the copies were never issued - report, do not hang
@@ -292,6 +293,7 @@ __device__ __forceinline__ void pair_walk(const PairArgs& p, unsigned char* cons
 
     // parked block `slot` -> the operand tile (the lane's own chunks, in the layout it wrote them)
     auto fetch_slot = [&](int slot) {
+        PHB_DCHECK(slot >= 0 && slot < p.n_slots);
         const unsigned char* src = my_scratch + (size_t)slot * L::SLOT_BYTES;
 #pragma unroll
         for (int j = 0; j < L::CHUNKS; ++j) cp_async16(s_opin + j * 512 + lane * 16, src + j * 512 + lane * 16);
@@ -315,8 +317,10 @@ __device__ __forceinline__ void pair_walk(const PairArgs& p, unsigned char* cons
         constexpr int CL = (CM == CODES_BYTE ? L::TILE : (CM == CODES_NIBBLE ? L::TILE / 2 : L::TILE / 4)) / 16;
         const int which = lane >> 3, piece = lane & 7;
         const bool tip = which == 0 ? kind_a == KIND_TIP : kind_b == KIND_TIP;
+        PHB_DCHECK(kind_a != KIND_SLOT && t >= tile_begin && t < tile_end);
         if (which < 2 && tip) {
             const int tip_row = which == 0 ? d.src_a : (int)(d.packed & 0xffffff);
+            PHB_DCHECK(tip_row >= 0 && (piece >= CL || (size_t)t * (CL * 16) + piece * 16 + 16 <= p.pitch));   // inside the tip's code row
             if (piece < CL)
                 cp_async16(st + L::CODES_OFF + which * L::TILE + piece * 16,
                            p.codes + (size_t)tip_row * p.pitch + (size_t)t * (CL * 16) + piece * 16);
@@ -404,6 +408,7 @@ __device__ __forceinline__ void pair_walk(const PairArgs& p, unsigned char* cons
             }
             if (row != n_steps - 1) {
                 if (dst_slot != 15) {
+                    PHB_DCHECK(dst_slot < p.n_slots);
                     // park: coalesced 128-bit stores straight from registers into the warp's own stripe
                     unsigned char* dst = my_scratch + (size_t)dst_slot * L::SLOT_BYTES + lane * 16;
 #pragma unroll
@@ -420,6 +425,7 @@ __device__ __forceinline__ void pair_walk(const PairArgs& p, unsigned char* cons
             } else {
                 // root pseudo-row: pi-dot, Gamma mixture, log, weighted sum (tree_model.py:200-217)
                 const int64_t s0 = (int64_t)tile * L::TILE + PPT * lane;
+                PHB_DCHECK((int64_t)tile * L::TILE < p.S);
                 double lnl[PPT];
 #pragma unroll
                 for (int h = 0; h < PPT; ++h) {
@@ -609,6 +615,7 @@ __global__ void __launch_bounds__(32, 11) dna_pair_store_kernel(const PairStoreA
             stage_row(dn, tile_n, (q + 1) & 1);
             if (((dn.packed >> 26) & 3) == KIND_SLOT) {
                 slot_n = dn.packed & 0xffffff;       // producer row of the parked operand
+                PHB_DCHECK(slot_n < row_n && tile_n < n_tiles);   // written by this warp, for this tile, in an earlier row
                 if (opin_busy) fetch_late = true;
                 else fetch_block(slot_n, tile_n);
             }

@@ -15,6 +15,17 @@ namespace phb {
 // Partials smaller than this get rescaled (same threshold as the reference's SCALE_THRESHOLD,
 // likelihood/numba_likelihood_engine.py:7); rescaling multiplies by an exact power of two.
 constexpr double kScaleThreshold = 2.938735877055718769921841343056e-39;  // 2^-128
+// Device-side invariant checks of the walks (slot indices, tile ranges, code-row bounds, producer-before-consumer order):
+// compiled in by `python phylo_utils_b200/csrc/build.py --checks` (-DPHB_DEVICE_CHECKS -> libphylo_b200_checks.so), nothing
+// in the shipped build.  compute-sanitizer is closed on this pool; the parity tests are run once per round against the
+// checked build instead (PHB_LIBRARY=.../libphylo_b200_checks.so python -m pytest tests -m gpu).
+#ifdef PHB_DEVICE_CHECKS
+#include <cassert>
+#define PHB_DCHECK(cond) assert(cond)
+#else
+#define PHB_DCHECK(cond) ((void)0)
+#endif
+
 constexpr int kScaleThresholdHi = 0x37F00000;                              // high word of 2^-128
 constexpr double kLn2 = 0.693147180559945309417232121458;
 

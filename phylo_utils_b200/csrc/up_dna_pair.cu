@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
 
     // block `blk` of tile t -> a pattern-major operand tile (exponents into the row padding)
     auto fetch_block = [&](int blk, int t, unsigned char* dst) {
+        PHB_DCHECK(blk >= 0 && t >= 0 && t < n_tiles);
         const size_t site0 = (size_t)t * L::TILE;
         const unsigned char* src = clv_bytes + (size_t)blk * block_bytes + site0 * (K * 32);
         const int32_t* ex = p.scale + (size_t)blk * S + site0;
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
             return;
         }
         if (mode == UP_LOAD_SLOT) {   // the lane's own chunks of a parked block, in the layout it wrote them
+            PHB_DCHECK(ST && d.src_x >= 0 && d.src_x < p.n_slots);
             const unsigned char* src = my_scratch + (size_t)d.src_x * U::SLOT_BYTES;
 #pragma unroll
             for (int j = 0; j < U::CHUNKS; ++j) cp_async16(tl + j * 512 + lane * 16, src + j * 512 + lane * 16);
@@ -318,6 +320,7 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
     };
     // registers -> padded staging tile (a dead operand tile) -> coalesced streaming stores into block `blk`
     auto store_block = [&](const double (&v)[PPT][K][4], const int (&e)[PPT], int blk, int t, unsigned char* s_out) {
+        PHB_DCHECK(blk >= 0 && t >= 0 && t < n_tiles);
         const size_t site0 = (size_t)t * L::TILE;
         const bool whole = site0 + L::TILE <= S;
         const int valid = whole ? L::TILE : (int)(S - site0);
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(32, PPT == 1 ? 8 : 4) dna_up_kernel(const __gr
     };
     // park: coalesced 128-bit stores straight from registers into the warp's own stripe
     auto park_block = [&](const double (&v)[PPT][K][4], const int (&e)[PPT], int slot) {
+        PHB_DCHECK(slot >= 0 && slot < p.n_slots);
         unsigned char* dst = my_scratch + (size_t)slot * U::SLOT_BYTES + lane * 16;
 #pragma unroll
         for (int h = 0; h < PPT; ++h)
