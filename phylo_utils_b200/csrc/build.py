@@ -17,9 +17,10 @@ ROOT = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libphylo_b200.so")
 OBJ = os.path.join(HERE, "_obj")
 
-CUDA_SOURCES = ["api.cu", "pmatrix.cu", "clv_dna.cu", "clv_dna_pair.cu", "up_dna_pair.cu", "clv_generic.cu", "clv_mma.cu", "ops.cu", "derivs.cu", "compress.cu"]
+CUDA_SOURCES = ["api.cu", "pmatrix.cu", "clv_dna.cu", "clv_dna_pair.cu", "clv_dna_pair_k4n8.cu", "clv_dna_pair_k4n16.cu", "clv_dna_pair_k12.cu",
+                "clv_dna_pair_k8.cu", "up_dna_pair.cu", "clv_generic.cu", "clv_mma.cu", "ops.cu", "derivs.cu", "compress.cu"]
 HOST_SOURCES = ["discrete_gamma.cpp"]
-HEADERS = ["common.cuh", "resident_plan.cuh", "pair_common.cuh", os.path.join(ROOT, "include", "phylo_b200.h")]
+HEADERS = ["common.cuh", "resident_plan.cuh", "pair_common.cuh", "pair_walk.cuh", os.path.join(ROOT, "include", "phylo_b200.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
