@@ -136,3 +136,18 @@ def test_code_packing_helpers_round_trip():
         LikelihoodEngine.split_codes(np.full((2, 3), 8, dtype=np.uint8))
     with pytest.raises(ValueError):
         LikelihoodEngine.pack_codes(np.full((2, 3), 16, dtype=np.uint8))
+
+
+def test_build_script_lists_every_source_and_header():
+    """A translation unit or header that exists under csrc/ but is missing from build.py would silently drop kernels from the
+    library (the lnL-only walk is instantiated in four units) or leave stale objects after a header edit."""
+    import importlib.util
+    csrc = os.path.join(ROOT, "phylo_utils_b200", "csrc")
+    spec = importlib.util.spec_from_file_location("phb_build", os.path.join(csrc, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    on_disk = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cpp")))
+    assert on_disk == sorted(mod.CUDA_SOURCES + mod.HOST_SOURCES)
+    headers = sorted(f for f in os.listdir(csrc) if f.endswith(".cuh"))
+    assert headers == sorted(h for h in mod.HEADERS if not os.path.isabs(h))
+    assert "-lineinfo" in mod.NVCC_FLAGS and "arch=compute_100a,code=sm_100a" in mod.ARCH
