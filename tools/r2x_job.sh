@@ -1,4 +1,5 @@
 #!/bin/bash
+# (record of a dropped experiment: the one-category-per-lane layout and its PHB_PAIR_NO_CAT switch are not in the tree - DESIGN.md 3.1, profiles/r02h_cat_layout_experiment.txt)
 # one category per lane (CAT) against the round-2a layout: GPU tests, then the shard-size probe with and without it
 python -m pytest tests -m gpu -x -q > gpurun_out/r2x_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/r2x_pytest.log
 for cat in 0 1; do
